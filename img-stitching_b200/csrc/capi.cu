@@ -1,0 +1,715 @@
+// C ABI implementation (include/panob200.h): context, init-time table build + upload,
+// wave scheduling of the kernels, host<->device pipelining.  No CPU compute fallback exists:
+// every process entry point launches CUDA kernels or fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/panob200.h"
+#include "geometry.hpp"
+#include "pano_dev.h"
+
+using namespace pano;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct ProfEntry {
+    const char *name;
+    cudaEvent_t e0, e1;
+    double bytes;
+};
+
+constexpr int kPipeDepth = 3;
+
+}  // namespace
+
+struct pano_ctx {
+    pano_config cfg{};
+    std::vector<float> K, R;
+    int device = 0;
+    int n = 0;
+    int blender = PANO_BLEND_MULTIBAND;
+    std::string err;
+
+    // geometry
+    std::vector<Rect> rois;            // warped roi per camera (corner + size)
+    Rect dst_roi;
+    int nb = 0, pad_w = 0, pad_h = 0;
+    std::vector<FeedRect> feed;
+    std::vector<std::vector<float>> xmap, ymap;   // float maps (host, kept for inspection)
+    std::vector<std::vector<uint8_t>> mask;       // current blend masks (sizes[cam])
+    bool map64 = false;
+
+    // device tables
+    PanoTables host{};
+    PanoTables *dev = nullptr;
+    bool tables_dirty = true;
+    std::vector<void *> owned;                    // device allocations to free
+    std::vector<void *> cam_mask0, cam_gain;      // per camera, re-uploadable
+    std::vector<std::vector<void *>> cam_wt;      // per camera per level
+
+    // staging for host entry points
+    uint8_t *stage_in[kPipeDepth] = {nullptr, nullptr, nullptr};
+    uint8_t *stage_out[kPipeDepth] = {nullptr, nullptr, nullptr};
+    cudaStream_t s_h2d = nullptr, s_compute = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_in[kPipeDepth]{}, ev_done[kPipeDepth]{}, ev_out[kPipeDepth]{};
+
+    // profiling
+    bool profiling = false;
+    std::vector<ProfEntry> prof;
+    int last_launches = 0;
+
+    size_t frame_bytes() const { return (size_t)cfg.src_width * cfg.src_height * 3; }
+    size_t set_bytes() const { return frame_bytes() * n; }
+    size_t out_bytes() const { return (size_t)host.cut_w * host.cut_h * 3; }
+};
+
+namespace {
+
+int fail(pano_ctx *h, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    else g_create_error = buf;
+    return PANO_ERR;
+}
+
+#define CK(h, call)                                                                        \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return fail(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+inline int roundUp(int v, int m) { return (v + m - 1) / m * m; }
+
+int reflectIdx(int p, int n)  // BORDER_REFLECT
+{
+    if (n == 1) return 0;
+    while ((unsigned)p >= (unsigned)n) p = p < 0 ? -p - 1 : 2 * n - 1 - p;
+    return p;
+}
+
+template <typename T>
+int devAlloc(pano_ctx *h, T **p, size_t count, bool zero = true)
+{
+    CK(h, cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T)));
+    if (zero) CK(h, cudaMemset(*p, 0, std::max<size_t>(count, 1) * sizeof(T)));
+    h->owned.push_back(*p);
+    return PANO_OK;
+}
+
+// upload a w x h host array into a pitched device array
+template <typename T>
+int upload2d(pano_ctx *h, T *dst, int dpitch, const T *src, int spitch, int w, int hh)
+{
+    CK(h, cudaMemcpy2D(dst, (size_t)dpitch * sizeof(T), src, (size_t)spitch * sizeof(T), (size_t)w * sizeof(T), hh,
+                       cudaMemcpyHostToDevice));
+    return PANO_OK;
+}
+
+int buildWeights(pano_ctx *h, int cam)
+{
+    CamTables &C = h->host.cam[cam];
+    const Rect &img = h->rois[cam];
+    const FeedRect &fr = h->feed[cam];
+    const std::vector<uint8_t> &m = h->mask[cam];
+    if (h->blender == PANO_BLEND_FEATHER) {
+        std::vector<float> w((size_t)img.w * img.h);
+        featherWeight(m.data(), img.w, img.h, img.w, h->cfg.sharpness, w.data());
+        if (upload2d(h, (float *)h->cam_wt[cam][0], C.wt_pitch[0], w.data(), img.w, img.w, img.h)) return PANO_ERR;
+        C.use_wt0 = 1;
+        return PANO_OK;
+    }
+    // level 0: padded 8-bit mask, zero outside the image (copyMakeBorder CONSTANT)
+    const int W = fr.rect.w, H = fr.rect.h;
+    std::vector<uint8_t> m0((size_t)W * H, 0);
+    for (int y = 0; y < img.h; ++y)
+        std::memcpy(&m0[(size_t)(y + fr.top) * W + fr.left], &m[(size_t)y * img.w], img.w);
+    if (upload2d(h, (uint8_t *)h->cam_mask0[cam], C.mask_pitch, m0.data(), W, W, H)) return PANO_ERR;
+    C.use_wt0 = 0;
+    if (h->blender != PANO_BLEND_MULTIBAND) return PANO_OK;
+    // float weight pyramid (MultiBandBlender::feed: convertTo(CV_32F, 1/255) + pyrDown chain)
+    std::vector<float> cur((size_t)W * H);
+    for (size_t i = 0; i < cur.size(); ++i) cur[i] = (float)m0[i] * (1.f / 255.f);
+    int cw = W, ch = H;
+    for (int l = 1; l <= h->nb; ++l) {
+        std::vector<float> nxt((size_t)((cw + 1) / 2) * ((ch + 1) / 2));
+        pyrDownF32(cur.data(), cw, ch, nxt.data());
+        cw = (cw + 1) / 2; ch = (ch + 1) / 2;
+        if (upload2d(h, (float *)h->cam_wt[cam][l], C.wt_pitch[l], nxt.data(), cw, cw, ch)) return PANO_ERR;
+        cur.swap(nxt);
+    }
+    return PANO_OK;
+}
+
+int syncTables(pano_ctx *h)
+{
+    if (!h->tables_dirty) return PANO_OK;
+    CK(h, cudaMemcpy(h->dev, &h->host, sizeof(PanoTables), cudaMemcpyHostToDevice));
+    h->tables_dirty = false;
+    return PANO_OK;
+}
+
+struct Launch {
+    pano_ctx *h;
+    cudaStream_t st;
+    int idx = 0;
+    void begin(const char *name, double bytes)
+    {
+        if (!h->profiling) return;
+        ProfEntry pe;
+        pe.name = name; pe.bytes = bytes;
+        cudaEventCreate(&pe.e0); cudaEventCreate(&pe.e1);
+        cudaEventRecord(pe.e0, st);
+        h->prof.push_back(pe);
+    }
+    void end()
+    {
+        ++h->last_launches;
+        if (!h->profiling) return;
+        cudaEventRecord(h->prof.back().e1, st);
+    }
+};
+
+void clearProf(pano_ctx *h)
+{
+    for (auto &p : h->prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+    h->prof.clear();
+}
+
+// algorithmic bytes per kernel (DESIGN.md "roofline accounting")
+double warpBytes(const pano_ctx *h, int slots)
+{
+    double b = 0;
+    for (int i = 0; i < h->n; ++i) {
+        const CamTables &C = h->host.cam[i];
+        b += (double)C.rw * C.rh * ((h->map64 ? 8 : 4) + 6 + (C.gain_mode == 1 ? 4 : 0)) + (double)h->frame_bytes();
+    }
+    return b * slots;
+}
+double pyrdownBytes(const pano_ctx *h, int l, int slots)
+{
+    double b = 0;
+    for (int i = 0; i < h->n; ++i) {
+        const CamTables &C = h->host.cam[i];
+        b += 6.0 * (C.rw >> l) * (C.rh >> l) + 6.0 * (C.rw >> (l + 1)) * (C.rh >> (l + 1));
+    }
+    return b * slots;
+}
+double collapseBytes(const pano_ctx *h, int l, int slots)
+{
+    double b = 0;
+    const int nb = h->nb;
+    for (int i = 0; i < h->n; ++i) {
+        const CamTables &C = h->host.cam[i];
+        const double px = (double)(C.rw >> l) * (C.rh >> l);
+        b += px * (6 + ((l == 0 && !C.use_wt0) ? 1 : 4));
+        if (l < nb) b += 6.0 * (C.rw >> (l + 1)) * (C.rh >> (l + 1));
+    }
+    if (l < nb) b += 6.0 * (h->pad_w >> (l + 1)) * (h->pad_h >> (l + 1));
+    if (l == 0) b += (double)h->out_bytes();
+    else b += 6.0 * (h->pad_w >> l) * (h->pad_h >> l);
+    return b * slots;
+}
+double directBytes(const pano_ctx *h, int slots)
+{
+    double b = (double)h->out_bytes() + (double)h->set_bytes();
+    for (int i = 0; i < h->n; ++i) {
+        const CamTables &C = h->host.cam[i];
+        b += (double)C.rw * C.rh * ((h->map64 ? 8 : 4) + (h->blender == PANO_BLEND_FEATHER ? 4 : 1) + (C.gain_mode == 1 ? 4 : 0));
+    }
+    return b * slots;
+}
+
+// one wave = up to max_batch frame-sets through the whole kernel chain
+int runWave(pano_ctx *h, const uint8_t *frames_dev, uint8_t *out_dev, int slots, cudaStream_t st)
+{
+    Launch L{h, st};
+    static const char *kDown[] = {"pyrdown_l0", "pyrdown_l1", "pyrdown_l2", "pyrdown_l3", "pyrdown_l4",
+                                  "pyrdown_l5", "pyrdown_l6", "pyrdown_l7", "pyrdown_l8"};
+    static const char *kCol[] = {"collapse_l0", "collapse_l1", "collapse_l2", "collapse_l3", "collapse_l4",
+                                 "collapse_l5", "collapse_l6", "collapse_l7", "collapse_l8"};
+    if (h->blender != PANO_BLEND_MULTIBAND) {
+        L.begin("direct_blend", directBytes(h, slots));
+        launch_direct_blend(h->dev, h->host, h->blender, frames_dev, out_dev, slots, st);
+        L.end();
+    } else {
+        L.begin("warp", warpBytes(h, slots));
+        launch_warp(h->dev, h->host, frames_dev, slots, st);
+        L.end();
+        for (int l = 0; l < h->nb; ++l) {
+            L.begin(kDown[l], pyrdownBytes(h, l, slots));
+            launch_pyrdown(h->dev, h->host, l, slots, st);
+            L.end();
+        }
+        L.begin("coarsest", collapseBytes(h, h->nb, slots));
+        launch_coarsest(h->dev, h->host, out_dev, slots, st);
+        L.end();
+        for (int l = h->nb - 1; l >= 0; --l) {
+            L.begin(kCol[l], collapseBytes(h, l, slots));
+            launch_collapse(h->dev, h->host, l, out_dev, slots, st);
+            L.end();
+        }
+    }
+    CK(h, cudaGetLastError());
+    return PANO_OK;
+}
+
+int ensureStaging(pano_ctx *h)
+{
+    if (h->stage_in[0]) return PANO_OK;
+    const size_t S = h->cfg.max_batch;
+    for (int i = 0; i < kPipeDepth; ++i) {
+        if (devAlloc(h, &h->stage_in[i], h->set_bytes() * S, false)) return PANO_ERR;
+        if (devAlloc(h, &h->stage_out[i], h->out_bytes() * S, false)) return PANO_ERR;
+        CK(h, cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+        CK(h, cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+        CK(h, cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+    }
+    CK(h, cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    CK(h, cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+    CK(h, cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    return PANO_OK;
+}
+
+}  // namespace
+
+// =========================================================================== C ABI
+
+extern "C" {
+
+const char *pano_version(void) { return "panob200 0.1 sm_100a"; }
+
+const char *pano_last_error(pano_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int pano_create(const pano_config *cfg, pano_handle *out)
+{
+    if (!cfg || !out) return fail(nullptr, "pano_create: null argument");
+    *out = nullptr;
+    if (cfg->num_images < 1 || cfg->num_images > kMaxCams) return fail(nullptr, "num_images must be 1..%d", kMaxCams);
+    if (cfg->src_width < 2 || cfg->src_height < 2) return fail(nullptr, "bad source size");
+    if (!cfg->K || !cfg->R) return fail(nullptr, "K/R missing");
+    if (cfg->blender < PANO_BLEND_NO || cfg->blender > PANO_BLEND_MULTIBAND) return fail(nullptr, "bad blender kind");
+    if (cfg->warp_kind != PANO_WARP_SPHERICAL && cfg->warp_kind != PANO_WARP_CYLINDRICAL) return fail(nullptr, "bad warp kind");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, "no CUDA device: this library has no CPU path");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, "bad device ordinal %d", cfg->device);
+
+    pano_ctx *h = new pano_ctx();
+    auto bail = [&](int) { g_create_error = h->err; pano_destroy(h); return PANO_ERR; };
+    h->cfg = *cfg;
+    h->cfg.max_batch = std::max(1, cfg->max_batch);
+    h->n = cfg->num_images;
+    h->blender = cfg->blender;
+    h->device = cfg->device;
+    h->K.assign(cfg->K, cfg->K + 9 * h->n);
+    h->R.assign(cfg->R, cfg->R + 9 * h->n);
+    h->cfg.K = h->K.data();
+    h->cfg.R = h->R.data();
+    if (cudaSetDevice(h->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(0); }
+
+    const int W = cfg->src_width, H = cfg->src_height, n = h->n;
+    h->map64 = (32 * (W - 1) + 31 > 65535) || (32 * (H - 1) + 31 > 65535);
+
+    // ---- warp tables (RotationWarperBase::warpRoi / buildMaps) ----
+    h->rois.resize(n); h->xmap.resize(n); h->ymap.resize(n); h->mask.resize(n);
+    for (int i = 0; i < n; ++i) {
+        RotationWarper wp(cfg->warp_kind, cfg->warped_image_scale);
+        wp.setCamera(&h->K[9 * i], &h->R[9 * i]);
+        Rect r = wp.warpRoi(W, H);
+        if (r.w <= 0 || r.h <= 0 || (double)r.w * r.h > 4e8) { h->err = "degenerate warp roi (check K/R/scale)"; return bail(0); }
+        h->rois[i] = r;
+        h->xmap[i].resize((size_t)r.w * r.h);
+        h->ymap[i].resize((size_t)r.w * r.h);
+        wp.buildMaps(W, H, r, h->xmap[i].data(), h->ymap[i].data());
+        // default mask = warp of an all-255 mask with INTER_NEAREST / BORDER_CONSTANT (:1085)
+        h->mask[i].resize((size_t)r.w * r.h);
+        for (size_t p = 0; p < h->mask[i].size(); ++p) {
+            const int ix = std::max(-32768, std::min(32767, (int)lrintf(h->xmap[i][p])));
+            const int iy = std::max(-32768, std::min(32767, (int)lrintf(h->ymap[i][p])));
+            h->mask[i][p] = ((unsigned)ix < (unsigned)W && (unsigned)iy < (unsigned)H) ? 255 : 0;
+        }
+    }
+    h->dst_roi = resultRoi(h->rois);
+
+    // ---- blender geometry ----
+    PanoTables &T = h->host;
+    T.num_cams = n; T.src_w = W; T.src_h = H;
+    T.roi_w = h->dst_roi.w; T.roi_h = h->dst_roi.h;
+    h->feed.resize(n);
+    if (h->blender == PANO_BLEND_MULTIBAND) {
+        h->nb = multibandPrepare(h->dst_roi, std::max(0, cfg->num_bands), h->pad_w, h->pad_h);
+        if (h->nb + 1 > kMaxLevels) { h->err = "too many bands"; return bail(0); }
+        for (int i = 0; i < n; ++i) h->feed[i] = multibandFeedRect(h->dst_roi, h->pad_w, h->pad_h, h->nb, h->rois[i]);
+    } else {
+        h->nb = 0; h->pad_w = h->dst_roi.w; h->pad_h = h->dst_roi.h;
+        for (int i = 0; i < n; ++i) {
+            FeedRect fr{};
+            fr.rect.x = h->rois[i].x - h->dst_roi.x; fr.rect.y = h->rois[i].y - h->dst_roi.y;
+            fr.rect.w = h->rois[i].w; fr.rect.h = h->rois[i].h;
+            h->feed[i] = fr;
+        }
+    }
+    T.nb = h->nb; T.pad_w = h->pad_w; T.pad_h = h->pad_h;
+    if (cfg->cut[2] > 0 && cfg->cut[3] > 0) {
+        T.cut_x = cfg->cut[0]; T.cut_y = cfg->cut[1]; T.cut_w = cfg->cut[2]; T.cut_h = cfg->cut[3];
+    } else {
+        T.cut_x = 0; T.cut_y = 0; T.cut_w = T.roi_w; T.cut_h = T.roi_h;
+    }
+    if (T.cut_x < 0 || T.cut_y < 0 || T.cut_x + T.cut_w > T.roi_w || T.cut_y + T.cut_h > T.roi_h) {
+        h->err = "cut rectangle lies outside the dst roi";  // cv::Mat::operator()(Rect) would assert (:1210)
+        return bail(0);
+    }
+
+    // ---- per-camera device tables ----
+    const int S = h->cfg.max_batch;
+    h->cam_mask0.assign(n, nullptr); h->cam_gain.assign(n, nullptr);
+    h->cam_wt.assign(n, std::vector<void *>(kMaxLevels, nullptr));
+    for (int i = 0; i < n; ++i) {
+        CamTables &C = T.cam[i];
+        const FeedRect &fr = h->feed[i];
+        const Rect &img = h->rois[i];
+        C.rx = fr.rect.x; C.ry = fr.rect.y; C.rw = fr.rect.w; C.rh = fr.rect.h;
+        C.map_pitch = roundUp(C.rw, 64);
+        // folded map over the feed rect: copyMakeBorder(BORDER_REFLECT) of the warped image is a
+        // re-read of the warp at the mirrored coordinate
+        std::vector<uint32_t> m32;
+        std::vector<uint2> m64;
+        if (h->map64) m64.assign((size_t)C.map_pitch * C.rh, make_uint2(0, 0));
+        else m32.assign((size_t)C.map_pitch * C.rh, 0u);
+        for (int Y = 0; Y < C.rh; ++Y) {
+            const int y = reflectIdx(Y - fr.top, img.h);
+            for (int X = 0; X < C.rw; ++X) {
+                const int x = reflectIdx(X - fr.left, img.w);
+                const FixedCoord fc = toFixed(h->xmap[i][(size_t)y * img.w + x], h->ymap[i][(size_t)y * img.w + x]);
+                const uint32_t sx = foldReflect(fc.ix, fc.fx, W), sy = foldReflect(fc.iy, fc.fy, H);
+                if (h->map64) m64[(size_t)Y * C.map_pitch + X] = make_uint2(sx, sy);
+                else m32[(size_t)Y * C.map_pitch + X] = sx | (sy << 16);
+            }
+        }
+        if (h->map64) {
+            uint2 *d = nullptr;
+            if (devAlloc(h, &d, m64.size(), false)) return bail(0);
+            if (cudaMemcpy(d, m64.data(), m64.size() * sizeof(uint2), cudaMemcpyHostToDevice) != cudaSuccess) { h->err = "map upload failed"; return bail(0); }
+            C.map64 = d; C.map32 = nullptr;
+        } else {
+            uint32_t *d = nullptr;
+            if (devAlloc(h, &d, m32.size(), false)) return bail(0);
+            if (cudaMemcpy(d, m32.data(), m32.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) { h->err = "map upload failed"; return bail(0); }
+            C.map32 = d; C.map64 = nullptr;
+        }
+        C.gain_mode = 0; C.gain_map = nullptr; C.gain_scalar = 1.0;
+        // weights
+        C.mask_pitch = roundUp(C.rw, 64);
+        uint8_t *m0 = nullptr;
+        if (devAlloc(h, &m0, (size_t)C.mask_pitch * C.rh)) return bail(0);
+        h->cam_mask0[i] = m0; C.mask0 = m0;
+        const int wl0 = (h->blender == PANO_BLEND_MULTIBAND) ? 0 : 0;
+        for (int l = wl0; l <= h->nb; ++l) {
+            C.wt_pitch[l] = roundUp(std::max(1, C.rw >> l), 32);
+            float *w = nullptr;
+            if (devAlloc(h, &w, (size_t)C.wt_pitch[l] * std::max(1, C.rh >> l))) return bail(0);
+            h->cam_wt[i][l] = w; C.wt[l] = w;
+        }
+        // pyramid workspace
+        if (h->blender == PANO_BLEND_MULTIBAND) {
+            for (int l = 0; l <= h->nb; ++l) {
+                const int lw = C.rw >> l, lh = C.rh >> l;
+                C.g_pitch[l] = roundUp(lw, 64);
+                C.g_plane[l] = (size_t)C.g_pitch[l] * lh;
+                C.g_slot[l] = 3 * C.g_plane[l];
+                int16_t *g = nullptr;
+                if (devAlloc(h, &g, C.g_slot[l] * S)) return bail(0);
+                C.g[l] = g;
+            }
+        }
+    }
+    if (h->blender == PANO_BLEND_MULTIBAND) {
+        for (int l = 1; l <= h->nb; ++l) {
+            const int lw = h->pad_w >> l, lh = h->pad_h >> l;
+            T.out_pitch[l] = roundUp(lw, 64);
+            T.out_plane[l] = (size_t)T.out_pitch[l] * lh;
+            T.out_slot[l] = 3 * T.out_plane[l];
+            int16_t *o = nullptr;
+            if (devAlloc(h, &o, T.out_slot[l] * S)) return bail(0);
+            T.outp[l] = o;
+        }
+    }
+    if (devAlloc(h, &h->dev, 1)) return bail(0);
+    for (int i = 0; i < n; ++i)
+        if (buildWeights(h, i)) return bail(0);
+    h->tables_dirty = true;
+    *out = h;
+    return PANO_OK;
+}
+
+int pano_destroy(pano_handle h)
+{
+    if (!h) return PANO_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    clearProf(h);
+    for (void *p : h->owned) cudaFree(p);
+    for (int i = 0; i < kPipeDepth; ++i) {
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+        if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+    }
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_compute) cudaStreamDestroy(h->s_compute);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    delete h;
+    return PANO_OK;
+}
+
+int pano_get_geometry(pano_handle h, int *corners, int *sizes, int *dst_roi, int *out_wh)
+{
+    if (!h) return PANO_ERR;
+    for (int i = 0; i < h->n; ++i) {
+        if (corners) { corners[2 * i] = h->rois[i].x; corners[2 * i + 1] = h->rois[i].y; }
+        if (sizes) { sizes[2 * i] = h->rois[i].w; sizes[2 * i + 1] = h->rois[i].h; }
+    }
+    if (dst_roi) { dst_roi[0] = h->dst_roi.x; dst_roi[1] = h->dst_roi.y; dst_roi[2] = h->dst_roi.w; dst_roi[3] = h->dst_roi.h; }
+    if (out_wh) { out_wh[0] = h->host.cut_w; out_wh[1] = h->host.cut_h; }
+    return PANO_OK;
+}
+
+int pano_get_blend_geometry(pano_handle h, int *num_bands, int *padded_wh, int *feed_rects)
+{
+    if (!h) return PANO_ERR;
+    if (num_bands) *num_bands = h->nb;
+    if (padded_wh) { padded_wh[0] = h->pad_w; padded_wh[1] = h->pad_h; }
+    if (feed_rects)
+        for (int i = 0; i < h->n; ++i) {
+            feed_rects[4 * i] = h->feed[i].rect.x; feed_rects[4 * i + 1] = h->feed[i].rect.y;
+            feed_rects[4 * i + 2] = h->feed[i].rect.w; feed_rects[4 * i + 3] = h->feed[i].rect.h;
+        }
+    return PANO_OK;
+}
+
+int pano_get_warp_maps(pano_handle h, int cam, float *xmap, float *ymap)
+{
+    if (!h || cam < 0 || cam >= h->n) return fail(h, "bad camera index");
+    if (xmap) std::memcpy(xmap, h->xmap[cam].data(), h->xmap[cam].size() * sizeof(float));
+    if (ymap) std::memcpy(ymap, h->ymap[cam].data(), h->ymap[cam].size() * sizeof(float));
+    return PANO_OK;
+}
+
+int pano_get_fixed_maps(pano_handle h, int cam, int16_t *ixy, uint16_t *frac)
+{
+    if (!h || cam < 0 || cam >= h->n) return fail(h, "bad camera index");
+    const size_t cnt = h->xmap[cam].size();
+    for (size_t p = 0; p < cnt; ++p) {
+        const FixedCoord fc = toFixed(h->xmap[cam][p], h->ymap[cam][p]);
+        if (ixy) { ixy[2 * p] = (int16_t)fc.ix; ixy[2 * p + 1] = (int16_t)fc.iy; }
+        if (frac) frac[p] = (uint16_t)(fc.fy * 32 + fc.fx);
+    }
+    return PANO_OK;
+}
+
+int pano_set_mask(pano_handle h, int cam, const uint8_t *mask, int width, int height, int stride)
+{
+    if (!h || cam < 0 || cam >= h->n || !mask) return fail(h, "pano_set_mask: bad argument");
+    const Rect &img = h->rois[cam];
+    if (width != img.w || height != img.h || stride < width)
+        return fail(h, "pano_set_mask: mask must be %dx%d (got %dx%d)", img.w, img.h, width, height);
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());  // tables may be in use by an in-flight wave
+    for (int y = 0; y < height; ++y) std::memcpy(&h->mask[cam][(size_t)y * width], mask + (size_t)y * stride, width);
+    if (buildWeights(h, cam)) return PANO_ERR;
+    h->tables_dirty = true;
+    return PANO_OK;
+}
+
+int pano_set_weight_level(pano_handle h, int cam, int level, const float *w, int width, int height)
+{
+    if (!h || cam < 0 || cam >= h->n || !w) return fail(h, "pano_set_weight_level: bad argument");
+    if (h->blender != PANO_BLEND_MULTIBAND || level < 0 || level > h->nb) return fail(h, "pano_set_weight_level: bad level");
+    CamTables &C = h->host.cam[cam];
+    if (width != (C.rw >> level) || height != (C.rh >> level))
+        return fail(h, "pano_set_weight_level: level %d must be %dx%d", level, C.rw >> level, C.rh >> level);
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());
+    if (upload2d(h, (float *)h->cam_wt[cam][level], C.wt_pitch[level], w, width, width, height)) return PANO_ERR;
+    if (level == 0) C.use_wt0 = 1;
+    h->tables_dirty = true;
+    return PANO_OK;
+}
+
+int pano_set_feather_weight(pano_handle h, int cam, const float *w, int width, int height)
+{
+    if (!h || cam < 0 || cam >= h->n || !w) return fail(h, "pano_set_feather_weight: bad argument");
+    if (h->blender != PANO_BLEND_FEATHER) return fail(h, "pano_set_feather_weight: blender is not feather");
+    CamTables &C = h->host.cam[cam];
+    if (width != C.rw || height != C.rh) return fail(h, "pano_set_feather_weight: must be %dx%d", C.rw, C.rh);
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());
+    if (upload2d(h, (float *)h->cam_wt[cam][0], C.wt_pitch[0], w, width, width, height)) return PANO_ERR;
+    C.use_wt0 = 1;
+    h->tables_dirty = true;
+    return PANO_OK;
+}
+
+int pano_set_gain_map(pano_handle h, int cam, const float *gain, int width, int height)
+{
+    if (!h || cam < 0 || cam >= h->n) return fail(h, "pano_set_gain_map: bad argument");
+    CamTables &C = h->host.cam[cam];
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());
+    h->tables_dirty = true;
+    if (!gain) { C.gain_mode = 0; return PANO_OK; }
+    const Rect &img = h->rois[cam];
+    const FeedRect &fr = h->feed[cam];
+    if (width != img.w || height != img.h) return fail(h, "pano_set_gain_map: must be %dx%d", img.w, img.h);
+    std::vector<float> g((size_t)C.map_pitch * C.rh, 1.f);
+    for (int Y = 0; Y < C.rh; ++Y) {
+        const int y = reflectIdx(Y - fr.top, img.h);
+        for (int X = 0; X < C.rw; ++X) g[(size_t)Y * C.map_pitch + X] = gain[(size_t)y * img.w + reflectIdx(X - fr.left, img.w)];
+    }
+    if (!h->cam_gain[cam]) {
+        float *d = nullptr;
+        if (devAlloc(h, &d, g.size(), false)) return PANO_ERR;
+        h->cam_gain[cam] = d;
+    }
+    CK(h, cudaMemcpy(h->cam_gain[cam], g.data(), g.size() * sizeof(float), cudaMemcpyHostToDevice));
+    C.gain_map = (const float *)h->cam_gain[cam];
+    C.gain_mode = 1;
+    return PANO_OK;
+}
+
+int pano_set_gain_scalar(pano_handle h, int cam, double gain)
+{
+    if (!h || cam < 0 || cam >= h->n) return fail(h, "pano_set_gain_scalar: bad argument");
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());
+    h->host.cam[cam].gain_mode = 2;
+    h->host.cam[cam].gain_scalar = gain;
+    h->tables_dirty = true;
+    return PANO_OK;
+}
+
+int pano_process_device(pano_handle h, const uint8_t *frames_dev, uint8_t *out_dev, int batch, void *stream)
+{
+    if (!h || !frames_dev || !out_dev || batch < 1) return fail(h, "pano_process_device: bad argument");
+    CK(h, cudaSetDevice(h->device));
+    if (syncTables(h)) return PANO_ERR;
+    cudaStream_t st = (cudaStream_t)stream;
+    h->last_launches = 0;
+    if (h->profiling) clearProf(h);
+    const int S = h->cfg.max_batch;
+    for (int b0 = 0; b0 < batch; b0 += S) {
+        const int slots = std::min(S, batch - b0);
+        if (runWave(h, frames_dev + (size_t)b0 * h->set_bytes(), out_dev + (size_t)b0 * h->out_bytes(), slots, st)) return PANO_ERR;
+    }
+    return PANO_OK;
+}
+
+int pano_process(pano_handle h, const uint8_t *const *frames, const int *strides, uint8_t *out, int out_stride)
+{
+    if (!h || !frames || !out) return fail(h, "pano_process: bad argument");
+    CK(h, cudaSetDevice(h->device));
+    if (ensureStaging(h) || syncTables(h)) return PANO_ERR;
+    const int W3 = h->cfg.src_width * 3, H = h->cfg.src_height;
+    if (out_stride < h->host.cut_w * 3) return fail(h, "pano_process: out_stride too small");
+    for (int i = 0; i < h->n; ++i) {
+        const int st = strides ? strides[i] : W3;
+        if (!frames[i] || st < W3) return fail(h, "pano_process: bad frame %d", i);
+        CK(h, cudaMemcpy2DAsync(h->stage_in[0] + (size_t)i * h->frame_bytes(), W3, frames[i], st, W3, H,
+                                cudaMemcpyHostToDevice, h->s_compute));
+    }
+    h->last_launches = 0;
+    if (h->profiling) clearProf(h);
+    if (runWave(h, h->stage_in[0], h->stage_out[0], 1, h->s_compute)) return PANO_ERR;
+    CK(h, cudaMemcpy2DAsync(out, out_stride, h->stage_out[0], (size_t)h->host.cut_w * 3, (size_t)h->host.cut_w * 3,
+                            h->host.cut_h, cudaMemcpyDeviceToHost, h->s_compute));
+    CK(h, cudaStreamSynchronize(h->s_compute));
+    return PANO_OK;
+}
+
+int pano_process_batch(pano_handle h, const uint8_t *frames_host, uint8_t *out_host, int batch)
+{
+    if (!h || !frames_host || !out_host || batch < 1) return fail(h, "pano_process_batch: bad argument");
+    CK(h, cudaSetDevice(h->device));
+    if (ensureStaging(h) || syncTables(h)) return PANO_ERR;
+    const int S = h->cfg.max_batch;
+    h->last_launches = 0;
+    const bool prof = h->profiling;
+    h->profiling = false;
+    int wave = 0;
+    for (int b0 = 0; b0 < batch; b0 += S, ++wave) {
+        const int slots = std::min(S, batch - b0);
+        const int q = wave % kPipeDepth;
+        // staging slot q is free once its previous D2H has finished
+        if (wave >= kPipeDepth) CK(h, cudaStreamWaitEvent(h->s_h2d, h->ev_out[q], 0));
+        CK(h, cudaMemcpyAsync(h->stage_in[q], frames_host + (size_t)b0 * h->set_bytes(), h->set_bytes() * slots,
+                              cudaMemcpyHostToDevice, h->s_h2d));
+        CK(h, cudaEventRecord(h->ev_in[q], h->s_h2d));
+        CK(h, cudaStreamWaitEvent(h->s_compute, h->ev_in[q], 0));
+        if (wave >= kPipeDepth) CK(h, cudaStreamWaitEvent(h->s_compute, h->ev_out[q], 0));
+        if (runWave(h, h->stage_in[q], h->stage_out[q], slots, h->s_compute)) { h->profiling = prof; return PANO_ERR; }
+        CK(h, cudaEventRecord(h->ev_done[q], h->s_compute));
+        CK(h, cudaStreamWaitEvent(h->s_d2h, h->ev_done[q], 0));
+        CK(h, cudaMemcpyAsync(out_host + (size_t)b0 * h->out_bytes(), h->stage_out[q], h->out_bytes() * slots,
+                              cudaMemcpyDeviceToHost, h->s_d2h));
+        CK(h, cudaEventRecord(h->ev_out[q], h->s_d2h));
+    }
+    h->profiling = prof;
+    CK(h, cudaStreamSynchronize(h->s_d2h));
+    CK(h, cudaStreamSynchronize(h->s_compute));
+    CK(h, cudaStreamSynchronize(h->s_h2d));
+    return PANO_OK;
+}
+
+int pano_profile_enable(pano_handle h, int on)
+{
+    if (!h) return PANO_ERR;
+    h->profiling = on != 0;
+    if (!on) clearProf(h);
+    return PANO_OK;
+}
+
+int pano_profile_read(pano_handle h, int max, const char **names, float *ms, int *launches, double *alg_bytes)
+{
+    if (!h) return PANO_ERR;
+    // aggregate by name, preserving first-seen order
+    std::vector<const char *> order;
+    std::vector<float> tms;
+    std::vector<int> cnt;
+    std::vector<double> bytes;
+    for (auto &p : h->prof) {
+        if (cudaEventSynchronize(p.e1) != cudaSuccess) return fail(h, "profile event sync failed");
+        float t = 0.f;
+        cudaEventElapsedTime(&t, p.e0, p.e1);
+        size_t k = 0;
+        for (; k < order.size(); ++k)
+            if (!std::strcmp(order[k], p.name)) break;
+        if (k == order.size()) { order.push_back(p.name); tms.push_back(0.f); cnt.push_back(0); bytes.push_back(0.0); }
+        tms[k] += t; cnt[k] += 1; bytes[k] += p.bytes;
+    }
+    const int nout = std::min<int>(max, (int)order.size());
+    for (int k = 0; k < nout; ++k) {
+        if (names) names[k] = order[k];
+        if (ms) ms[k] = tms[k];
+        if (launches) launches[k] = cnt[k];
+        if (alg_bytes) alg_bytes[k] = bytes[k];
+    }
+    return nout;
+}
+
+int pano_last_launch_count(pano_handle h) { return h ? h->last_launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,331 @@
+// nvCam front end (include/nvcam.hpp:898-929 + getFrame :1092-1094) on sm_100a:
+//   resize(8UC4, bilinear) -> drop alpha -> remap INTER_CUBIC (border 0) -> crop rect
+//   -> resize(bilinear) -> resize to the stitcher input size.
+// Identity resizes are skipped (cv::resize with equal sizes is a copy); dropping the alpha
+// channel is folded into whichever kernel reads the camera frame.  Arithmetic follows
+// SURVEY.md A4 (15-bit bicubic table with OpenCV's tap-adjust rule) and A5 (11-bit bilinear
+// resize coefficients, rows clipped / columns clamped) exactly.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/panob200.h"
+#include "geometry.hpp"
+
+using namespace pano;
+
+namespace {
+
+struct ResizeTab {
+    int sw = 0, sh = 0, dw = 0, dh = 0;
+    int *xofs = nullptr, *yofs = nullptr;
+    short2 *xa = nullptr, *ya = nullptr;   // (a0, a1)
+};
+
+__device__ __forceinline__ int sat_u8(int v) { return max(0, min(255, v)); }
+
+// cv::resize INTER_LINEAR u8: one thread = one output pixel (3 channels out, CIN in)
+template <int CIN>
+__global__ void __launch_bounds__(256) resize_kernel(const uint8_t *__restrict__ src, size_t src_img, int sstride,
+                                                     uint8_t *__restrict__ dst, size_t dst_img, int dstride,
+                                                     ResizeTab t)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= t.dw || y >= t.dh) return;
+    const uint8_t *s = src + (size_t)blockIdx.z * src_img;
+    uint8_t *d = dst + (size_t)blockIdx.z * dst_img + (size_t)y * dstride + (size_t)x * 3;
+    const int sx0 = t.xofs[x], sx1 = min(sx0 + 1, t.sw - 1);
+    const int yo = t.yofs[y];
+    const int sy0 = min(max(yo, 0), t.sh - 1), sy1 = min(max(yo + 1, 0), t.sh - 1);
+    const short2 ax = t.xa[x], ay = t.ya[y];
+    const uint8_t *r0 = s + (size_t)sy0 * sstride, *r1 = s + (size_t)sy1 * sstride;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int t0 = __ldg(r0 + sx0 * CIN + c) * ax.x + __ldg(r0 + sx1 * CIN + c) * ax.y;
+        const int t1 = __ldg(r1 + sx0 * CIN + c) * ax.x + __ldg(r1 + sx1 * CIN + c) * ax.y;
+        d[c] = (uint8_t)sat_u8((((ay.x * (t0 >> 4)) >> 16) + ((ay.y * (t1 >> 4)) >> 16) + 2) >> 2);
+    }
+}
+
+// drop alpha only (camera size == undistort size and no undistort): 4 -> 3 channels
+__global__ void __launch_bounds__(256) drop_alpha_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                         size_t npx)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npx) return;
+    const uchar4 p = __ldg(reinterpret_cast<const uchar4 *>(src) + i);
+    dst[3 * i] = p.x; dst[3 * i + 1] = p.y; dst[3 * i + 2] = p.z;
+}
+
+// cv::remap INTER_CUBIC, BORDER_CONSTANT(0), restricted to the crop rect.
+// map: per undistorted pixel {sx, sy} = cvRound(32*map) with the integer part saturated to int16.
+template <int CIN>
+__global__ void __launch_bounds__(256) cubic_kernel(const uint8_t *__restrict__ src, size_t src_img, int sw, int sh,
+                                                    int sstride, const int2 *__restrict__ map, int map_w,
+                                                    const short *__restrict__ tab, int rx, int ry, int rw, int rh,
+                                                    uint8_t *__restrict__ dst, size_t dst_img)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= rw || y >= rh) return;
+    const int2 m = __ldg(map + (size_t)(y + ry) * map_w + (x + rx));
+    const int ix = (m.x >> 5) - 1, iy = (m.y >> 5) - 1;
+    const short *w = tab + (((m.y & 31) << 5) | (m.x & 31)) * 16;
+    const uint8_t *s = src + (size_t)blockIdx.z * src_img;
+    int acc[3] = {0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int py = iy + r;
+        if ((unsigned)py >= (unsigned)sh) continue;
+        const uint8_t *row = s + (size_t)py * sstride;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int px = ix + q;
+            if ((unsigned)px >= (unsigned)sw) continue;
+            const int wt = __ldg(w + r * 4 + q);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[c] += wt * __ldg(row + px * CIN + c);
+        }
+    }
+    uint8_t *d = dst + (size_t)blockIdx.z * dst_img + ((size_t)y * rw + x) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) d[c] = (uint8_t)sat_u8((acc[c] + 16384) >> 15);
+}
+
+thread_local std::string g_front_error;
+
+}  // namespace
+
+struct pano_frontend_ctx {
+    pano_frontend_config cfg{};
+    std::string err;
+    std::vector<float> mapx, mapy;
+    std::vector<void *> owned;
+    int2 *dmap = nullptr;
+    short *dtab = nullptr;
+    ResizeTab r_in, r_mid, r_out;       // cam->undist, rect->undist, undist->out
+    bool use_r_in = false, use_r_mid = false, use_r_out = false;
+    uint8_t *buf_a = nullptr, *buf_b = nullptr, *buf_c = nullptr;  // intermediates, max_batch deep
+    uint8_t *stage_in = nullptr, *stage_out = nullptr;
+    int launches = 0;
+};
+
+namespace {
+
+int ffail(pano_frontend_ctx *h, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    else g_front_error = buf;
+    return PANO_ERR;
+}
+
+#define FCK(h, call)                                                                              \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) return ffail(h, "%s failed: %s", #call, cudaGetErrorString(e_));   \
+    } while (0)
+
+template <typename T>
+int falloc(pano_frontend_ctx *h, T **p, size_t count)
+{
+    FCK(h, cudaMalloc((void **)p, std::max<size_t>(1, count) * sizeof(T)));
+    h->owned.push_back(*p);
+    return PANO_OK;
+}
+
+int makeResize(pano_frontend_ctx *h, ResizeTab &t, int sw, int sh, int dw, int dh)
+{
+    t.sw = sw; t.sh = sh; t.dw = dw; t.dh = dh;
+    std::vector<int> xo, yo;
+    std::vector<int16_t> xa0, xa1, ya0, ya1;
+    resizeAxis(sw, dw, true, xo, xa0, xa1);
+    resizeAxis(sh, dh, false, yo, ya0, ya1);
+    std::vector<short2> xa(dw), ya(dh);
+    for (int i = 0; i < dw; ++i) xa[i] = make_short2(xa0[i], xa1[i]);
+    for (int i = 0; i < dh; ++i) ya[i] = make_short2(ya0[i], ya1[i]);
+    if (falloc(h, &t.xofs, dw) || falloc(h, &t.yofs, dh) || falloc(h, &t.xa, dw) || falloc(h, &t.ya, dh)) return PANO_ERR;
+    FCK(h, cudaMemcpy(t.xofs, xo.data(), dw * sizeof(int), cudaMemcpyHostToDevice));
+    FCK(h, cudaMemcpy(t.yofs, yo.data(), dh * sizeof(int), cudaMemcpyHostToDevice));
+    FCK(h, cudaMemcpy(t.xa, xa.data(), dw * sizeof(short2), cudaMemcpyHostToDevice));
+    FCK(h, cudaMemcpy(t.ya, ya.data(), dh * sizeof(short2), cudaMemcpyHostToDevice));
+    return PANO_OK;
+}
+
+inline dim3 grid2(int w, int hh, dim3 b, int z) { return dim3((w + b.x - 1) / b.x, (hh + b.y - 1) / b.y, z); }
+
+}  // namespace
+
+extern "C" {
+
+const char *pano_frontend_last_error(pano_frontend_handle h) { return h ? h->err.c_str() : g_front_error.c_str(); }
+
+int pano_frontend_create(const pano_frontend_config *cfg, pano_frontend_handle *out)
+{
+    if (!cfg || !out) return ffail(nullptr, "pano_frontend_create: null argument");
+    *out = nullptr;
+    if (cfg->cam_src_width < 2 || cfg->cam_src_height < 2 || cfg->undist_width < 2 || cfg->undist_height < 2 ||
+        cfg->out_width < 2 || cfg->out_height < 2)
+        return ffail(nullptr, "bad sizes");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return ffail(nullptr, "no CUDA device: this library has no CPU path");
+    if (cfg->device < 0 || cfg->device >= ndev) return ffail(nullptr, "bad device ordinal");
+    pano_frontend_ctx *h = new pano_frontend_ctx();
+    h->cfg = *cfg;
+    h->cfg.max_batch = std::max(1, cfg->max_batch);
+    auto bail = [&]() { g_front_error = h->err; pano_frontend_destroy(h); return PANO_ERR; };
+    if (cudaSetDevice(cfg->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(); }
+    const int S = h->cfg.max_batch;
+    const int uw = cfg->undist_width, uh = cfg->undist_height;
+    if (cfg->undistort) {
+        const int *rc = cfg->rect;
+        if (rc[0] < 0 || rc[1] < 0 || rc[2] < 1 || rc[3] < 1 || rc[0] + rc[2] > uw || rc[1] + rc[3] > uh) {
+            h->err = "crop rect outside the undistorted image";
+            return bail();
+        }
+        h->mapx.resize((size_t)uw * uh);
+        h->mapy.resize((size_t)uw * uh);
+        if (cfg->mapx && cfg->mapy) {
+            std::memcpy(h->mapx.data(), cfg->mapx, h->mapx.size() * sizeof(float));
+            std::memcpy(h->mapy.data(), cfg->mapy, h->mapy.size() * sizeof(float));
+        } else {
+            undistortMaps(cfg->K, cfg->D, cfg->newK, uw, uh, h->mapx.data(), h->mapy.data());
+        }
+        std::vector<int2> fm((size_t)uw * uh);
+        for (size_t i = 0; i < fm.size(); ++i) {
+            const FixedCoord fc = toFixed(h->mapx[i], h->mapy[i]);
+            fm[i] = make_int2(fc.ix * 32 + fc.fx, fc.iy * 32 + fc.fy);
+        }
+        std::vector<int16_t> tab(1024 * 16);
+        cubicTable(tab.data());
+        if (falloc(h, &h->dmap, fm.size()) || falloc(h, &h->dtab, tab.size())) return bail();
+        if (cudaMemcpy(h->dmap, fm.data(), fm.size() * sizeof(int2), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(h->dtab, tab.data(), tab.size() * sizeof(short), cudaMemcpyHostToDevice) != cudaSuccess) {
+            h->err = "front-end table upload failed";
+            return bail();
+        }
+        h->use_r_in = !(cfg->cam_src_width == uw && cfg->cam_src_height == uh);
+        h->use_r_mid = !(rc[2] == uw && rc[3] == uh);
+        if (h->use_r_in && makeResize(h, h->r_in, cfg->cam_src_width, cfg->cam_src_height, uw, uh)) return bail();
+        if (h->use_r_mid && makeResize(h, h->r_mid, rc[2], rc[3], uw, uh)) return bail();
+    } else {
+        h->use_r_in = !(cfg->cam_src_width == uw && cfg->cam_src_height == uh);
+        if (h->use_r_in && makeResize(h, h->r_in, cfg->cam_src_width, cfg->cam_src_height, uw, uh)) return bail();
+    }
+    h->use_r_out = !(cfg->out_width == uw && cfg->out_height == uh);
+    if (h->use_r_out && makeResize(h, h->r_out, uw, uh, cfg->out_width, cfg->out_height)) return bail();
+    const size_t ubytes = (size_t)uw * uh * 3 * S;
+    if (falloc(h, &h->buf_a, ubytes) || falloc(h, &h->buf_b, ubytes) || falloc(h, &h->buf_c, ubytes)) return bail();
+    *out = h;
+    return PANO_OK;
+}
+
+int pano_frontend_destroy(pano_frontend_handle h)
+{
+    if (!h) return PANO_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    for (void *p : h->owned) cudaFree(p);
+    delete h;
+    return PANO_OK;
+}
+
+int pano_frontend_get_maps(pano_frontend_handle h, float *mapx, float *mapy)
+{
+    if (!h || h->mapx.empty()) return ffail(h, "no undistort maps");
+    if (mapx) std::memcpy(mapx, h->mapx.data(), h->mapx.size() * sizeof(float));
+    if (mapy) std::memcpy(mapy, h->mapy.data(), h->mapy.size() * sizeof(float));
+    return PANO_OK;
+}
+
+int pano_frontend_process_device(pano_frontend_handle h, const uint8_t *argb, uint8_t *out, int batch, void *stream)
+{
+    if (!h || !argb || !out || batch < 1) return ffail(h, "pano_frontend_process_device: bad argument");
+    FCK(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const pano_frontend_config &c = h->cfg;
+    const int S = c.max_batch, uw = c.undist_width, uh = c.undist_height;
+    const size_t in_img = (size_t)c.cam_src_width * c.cam_src_height * 4;
+    const size_t u_img = (size_t)uw * uh * 3, o_img = (size_t)c.out_width * c.out_height * 3;
+    const dim3 blk(32, 8);
+    h->launches = 0;
+    for (int b0 = 0; b0 < batch; b0 += S) {
+        const int nb = std::min(S, batch - b0);
+        const uint8_t *src = argb + (size_t)b0 * in_img;
+        uint8_t *final_dst = out + (size_t)b0 * o_img;
+        // stage 1: camera frame -> undist-sized 3-channel "tmp" (:903-904 / :924-927)
+        const uint8_t *cur = src; int cur_c = 4; int cw = c.cam_src_width, chh = c.cam_src_height; size_t cur_img = in_img;
+        auto target = [&](bool last, uint8_t *scratch) { return last ? final_dst : scratch; };
+        if (c.undistort) {
+            if (h->use_r_in) {
+                resize_kernel<4><<<grid2(uw, uh, blk, nb), blk, 0, st>>>(cur, cur_img, cw * 4, h->buf_a, u_img, uw * 3, h->r_in);
+                ++h->launches;
+                cur = h->buf_a; cur_c = 3; cw = uw; chh = uh; cur_img = u_img;
+            }
+            // stage 2: cubic remap restricted to the crop rect (:909-916)
+            const int *rc = c.rect;
+            const bool last2 = !h->use_r_mid && !h->use_r_out;
+            uint8_t *d2 = target(last2, h->buf_b);
+            const size_t d2_img = (size_t)rc[2] * rc[3] * 3;
+            if (cur_c == 4)
+                cubic_kernel<4><<<grid2(rc[2], rc[3], blk, nb), blk, 0, st>>>(cur, cur_img, cw, chh, cw * 4, h->dmap, uw, h->dtab,
+                                                                              rc[0], rc[1], rc[2], rc[3], d2, d2_img);
+            else
+                cubic_kernel<3><<<grid2(rc[2], rc[3], blk, nb), blk, 0, st>>>(cur, cur_img, cw, chh, cw * 3, h->dmap, uw, h->dtab,
+                                                                              rc[0], rc[1], rc[2], rc[3], d2, d2_img);
+            ++h->launches;
+            cur = d2; cur_c = 3; cw = rc[2]; chh = rc[3]; cur_img = d2_img;
+            // stage 3: resize the crop back to the undistort size (:917)
+            if (h->use_r_mid) {
+                uint8_t *d3 = target(!h->use_r_out, h->buf_c);
+                resize_kernel<3><<<grid2(uw, uh, blk, nb), blk, 0, st>>>(cur, cur_img, cw * 3, d3, u_img, uw * 3, h->r_mid);
+                ++h->launches;
+                cur = d3; cw = uw; chh = uh; cur_img = u_img;
+            }
+        } else {
+            uint8_t *d1 = target(!h->use_r_out, h->buf_a);
+            if (h->use_r_in) {
+                resize_kernel<4><<<grid2(uw, uh, blk, nb), blk, 0, st>>>(cur, cur_img, cw * 4, d1, u_img, uw * 3, h->r_in);
+            } else {
+                const size_t npx = (size_t)uw * uh * nb;
+                drop_alpha_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(cur, d1, npx);
+            }
+            ++h->launches;
+            cur = d1; cur_c = 3; cw = uw; chh = uh; cur_img = u_img;
+        }
+        // stage 4: getFrame(.., src=false) resize to the stitcher input (:1094)
+        if (h->use_r_out) {
+            resize_kernel<3><<<grid2(c.out_width, c.out_height, blk, nb), blk, 0, st>>>(cur, cur_img, cw * 3, final_dst, o_img,
+                                                                                         c.out_width * 3, h->r_out);
+            ++h->launches;
+        }
+    }
+    FCK(h, cudaGetLastError());
+    return PANO_OK;
+}
+
+int pano_frontend_process(pano_frontend_handle h, const uint8_t *argb_host, int stride, uint8_t *out_host, int out_stride)
+{
+    if (!h || !argb_host || !out_host) return ffail(h, "pano_frontend_process: bad argument");
+    FCK(h, cudaSetDevice(h->cfg.device));
+    const pano_frontend_config &c = h->cfg;
+    const size_t in_row = (size_t)c.cam_src_width * 4, out_row = (size_t)c.out_width * 3;
+    if (stride < (int)in_row || out_stride < (int)out_row) return ffail(h, "stride too small");
+    if (!h->stage_in) {
+        if (falloc(h, &h->stage_in, in_row * c.cam_src_height) || falloc(h, &h->stage_out, out_row * c.out_height)) return PANO_ERR;
+    }
+    FCK(h, cudaMemcpy2D(h->stage_in, in_row, argb_host, stride, in_row, c.cam_src_height, cudaMemcpyHostToDevice));
+    if (pano_frontend_process_device(h, h->stage_in, h->stage_out, 1, nullptr)) return PANO_ERR;
+    FCK(h, cudaMemcpy2D(out_host, out_stride, h->stage_out, out_row, out_row, c.out_height, cudaMemcpyDeviceToHost));
+    return PANO_OK;
+}
+
+}  // extern "C"

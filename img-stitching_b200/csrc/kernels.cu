@@ -1,0 +1,446 @@
+// sm_100a kernels of the per-frame compose path.
+//
+// All kernels are HBM-bound integer/byte work (no dense contraction -> no tensor cores).
+// Internal pyramids are channel-PLANAR int16 with 128-byte aligned rows so that every
+// stencil row is a run of aligned 16-byte vectors; the interleaved BGR layout only exists at
+// the two ends (camera frames in, panorama out).  Exactness rules:
+// integer fixed point everywhere OpenCV uses it; the three float steps
+// (lap*w, sum of w, acc/(w+1e-5f)) use explicit round-to-nearest intrinsics so that neither
+// FMA contraction nor fast division can change a bit.
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "pano_dev.h"
+
+namespace pano {
+
+namespace {
+
+__device__ __forceinline__ int sat_s16(int v) { return max(-32768, min(32767, v)); }
+__device__ __forceinline__ int sat_u8(int v) { return max(0, min(255, v)); }
+__device__ __forceinline__ int wrap_s16(int v) { return (int)(short)v; }
+
+__device__ __forceinline__ int reflect101(int p, int n)
+{
+    if ((unsigned)p < (unsigned)n) return p;
+    if (n == 1) return 0;
+    do {
+        p = p < 0 ? -p : 2 * n - 2 - p;
+    } while ((unsigned)p >= (unsigned)n);
+    return p;
+}
+
+// cv::pyrUp source index rule: reflect-101 on the low side, replicate on the high side
+__device__ __forceinline__ int up_index(int i, int n) { return i < 0 ? (n > 1 ? 1 : 0) : (i >= n ? n - 1 : i); }
+
+// (short)(float) as x86 does it for in-range values: truncate toward zero, keep low 16 bits
+__device__ __forceinline__ int trunc_s16(float f) { return (int)(short)__float2int_rz(f); }
+
+// ------------------------------------------------------------------ K1: rotation warp
+// cv::remap(INTER_LINEAR, BORDER_REFLECT) of blender_warper->warp (ocvstitcher.hpp:1171)
+// + compensator->apply (stitching_detailed.cpp:841) + convertTo(CV_16S) (:1180)
+// + copyMakeBorder(BORDER_REFLECT) of MultiBandBlender::feed, in one gather.
+// One thread = 4 consecutive pixels of one row of one camera's feed rect.
+__device__ __forceinline__ void bilinear_bgr(const uint8_t *__restrict__ src, int W, int H, uint32_t sx, uint32_t sy,
+                                             int out[3])
+{
+    const int ix = sx >> 5, fx = sx & 31, iy = sy >> 5, fy = sy & 31;
+    const int ix1 = min(ix + 1, W - 1), iy1 = min(iy + 1, H - 1);
+    const uint8_t *r0 = src + ((size_t)iy * W) * 3, *r1 = src + ((size_t)iy1 * W) * 3;
+    const int w00 = (32 - fy) * (32 - fx), w01 = (32 - fy) * fx, w10 = fy * (32 - fx), w11 = fy * fx;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int s = w00 * __ldg(r0 + ix * 3 + c) + w01 * __ldg(r0 + ix1 * 3 + c) +
+                      w10 * __ldg(r1 + ix * 3 + c) + w11 * __ldg(r1 + ix1 * 3 + c);
+        out[c] = (s + 512) >> 10;  // == (sum(w*32*p) + 16384) >> 15
+    }
+}
+
+__device__ __forceinline__ int apply_gain(int v, int mode, float g, double gs)
+{
+    if (mode == 1) return sat_u8(__float2int_rn(__fmul_rn((float)v, g)));
+    if (mode == 2) return sat_u8(__double2int_rn(__dmul_rn((double)v, gs)));
+    return v;
+}
+
+template <bool kMap64>
+__global__ void __launch_bounds__(256) warp_kernel(const PanoTables *__restrict__ T, const uint8_t *__restrict__ frames)
+{
+    const int ncam = T->num_cams;
+    const int cam = blockIdx.z % ncam, slot = blockIdx.z / ncam;
+    const CamTables &C = T->cam[cam];
+    const int X = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int Y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (X >= C.rw || Y >= C.rh) return;
+    const int W = T->src_w, H = T->src_h;
+    const uint8_t *src = frames + ((size_t)slot * ncam + cam) * ((size_t)W * H * 3);
+    uint32_t sx[4], sy[4];
+    if (kMap64) {
+        const uint2 *m = C.map64 + (size_t)Y * C.map_pitch + X;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint2 e = __ldg(m + j);
+            sx[j] = e.x; sy[j] = e.y;
+        }
+    } else {
+        const uint4 e = __ldg(reinterpret_cast<const uint4 *>(C.map32 + (size_t)Y * C.map_pitch + X));
+        sx[0] = e.x & 0xffffu; sy[0] = e.x >> 16;
+        sx[1] = e.y & 0xffffu; sy[1] = e.y >> 16;
+        sx[2] = e.z & 0xffffu; sy[2] = e.z >> 16;
+        sx[3] = e.w & 0xffffu; sy[3] = e.w >> 16;
+    }
+    float g[4] = {1.f, 1.f, 1.f, 1.f};
+    if (C.gain_mode == 1) {
+        const float4 gv = __ldg(reinterpret_cast<const float4 *>(C.gain_map + (size_t)Y * C.map_pitch + X));
+        g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
+    }
+    short px[3][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int v[3];
+        bilinear_bgr(src, W, H, sx[j], sy[j], v);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) px[c][j] = (short)apply_gain(v[c], C.gain_mode, g[j], C.gain_scalar);
+    }
+    int16_t *dst = C.g[0] + (size_t)slot * C.g_slot[0] + (size_t)Y * C.g_pitch[0] + X;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        uint2 o;
+        o.x = (uint16_t)px[c][0] | ((uint32_t)(uint16_t)px[c][1] << 16);
+        o.y = (uint16_t)px[c][2] | ((uint32_t)(uint16_t)px[c][3] << 16);
+        *reinterpret_cast<uint2 *>(dst + (size_t)c * C.g_plane[0]) = o;
+    }
+}
+
+// ------------------------------------------------------------------ K2: pyrDown int16
+// cv::pyrDown on CV_16S (MultiBandBlender::feed): 5x5 [1 4 6 4 1]^2, reflect-101,
+// (sum + 128) >> 8.  One thread = 4 x 2 outputs of one plane.
+__device__ __forceinline__ void load_row11(const int16_t *__restrict__ row, int x0, int w, int v[11])
+{
+    if (x0 >= 0 && x0 + 10 < w) {
+        // x0 = 8t-2: 4-byte aligned; x0+2 = 8t: 16-byte aligned (rows are 128-byte aligned)
+        const uint32_t a = *reinterpret_cast<const uint32_t *>(row + x0);
+        const uint4 b = *reinterpret_cast<const uint4 *>(row + x0 + 2);
+        v[0] = (short)(a & 0xffff); v[1] = (short)(a >> 16);
+        v[2] = (short)(b.x & 0xffff); v[3] = (short)(b.x >> 16);
+        v[4] = (short)(b.y & 0xffff); v[5] = (short)(b.y >> 16);
+        v[6] = (short)(b.z & 0xffff); v[7] = (short)(b.z >> 16);
+        v[8] = (short)(b.w & 0xffff); v[9] = (short)(b.w >> 16);
+        v[10] = row[x0 + 10];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 11; ++j) v[j] = row[reflect101(x0 + j, w)];
+    }
+}
+
+__global__ void __launch_bounds__(256) pyrdown_kernel(const PanoTables *__restrict__ T, int level)
+{
+    const int ncam = T->num_cams;
+    int z = blockIdx.z;
+    const int plane = z % 3; z /= 3;
+    const int cam = z % ncam, slot = z / ncam;
+    const CamTables &C = T->cam[cam];
+    const int sw = C.rw >> level, sh = C.rh >> level;
+    const int dw = (sw + 1) >> 1, dh = (sh + 1) >> 1;
+    const int ox = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int oy = (blockIdx.y * blockDim.y + threadIdx.y) * 2;
+    if (ox >= dw || oy >= dh) return;
+    const int16_t *src = C.g[level] + (size_t)slot * C.g_slot[level] + (size_t)plane * C.g_plane[level];
+    int16_t *dst = C.g[level + 1] + (size_t)slot * C.g_slot[level + 1] + (size_t)plane * C.g_plane[level + 1];
+    const int sp = C.g_pitch[level], dp = C.g_pitch[level + 1];
+    int acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+        const int sy = reflect101(2 * oy - 2 + r, sh);
+        int v[11];
+        load_row11(src + (size_t)sy * sp, 2 * ox - 2, sw, v);
+        const int k0 = (r == 0 || r == 4) ? 1 : ((r == 1 || r == 3) ? 4 : (r == 2 ? 6 : 0));
+        const int k1 = (r == 2 || r == 6) ? 1 : ((r == 3 || r == 5) ? 4 : (r == 4 ? 6 : 0));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int h = v[2 * j] + 4 * v[2 * j + 1] + 6 * v[2 * j + 2] + 4 * v[2 * j + 3] + v[2 * j + 4];
+            acc0[j] += k0 * h;
+            acc1[j] += k1 * h;
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        if (oy + rr >= dh) break;
+        const int *a = rr ? acc1 : acc0;
+        int16_t *d = dst + (size_t)(oy + rr) * dp + ox;
+        if (ox + 3 < dw) {
+            uint2 o;
+            o.x = (uint16_t)(short)((a[0] + 128) >> 8) | ((uint32_t)(uint16_t)(short)((a[1] + 128) >> 8) << 16);
+            o.y = (uint16_t)(short)((a[2] + 128) >> 8) | ((uint32_t)(uint16_t)(short)((a[3] + 128) >> 8) << 16);
+            *reinterpret_cast<uint2 *>(d) = o;
+        } else {
+            for (int j = 0; j < 4 && ox + j < dw; ++j) d[j] = (short)((a[j] + 128) >> 8);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K3: blend + collapse
+// pyrUp of one coarse plane around coarse pixel (k, m) -> the 2x2 fine block (2k..2k+1, 2m..2m+1)
+__device__ __forceinline__ void pyrup_2x2(const int16_t *__restrict__ p, int pitch, int cw, int ch, int k, int m, int up[4])
+{
+    const int k0 = up_index(k - 1, cw), k2 = up_index(k + 1, cw);
+    int he[3], ho[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int mm = up_index(m - 1 + r, ch);
+        const int16_t *row = p + (size_t)mm * pitch;
+        const int a = row[k0], b = row[k], c = row[k2];
+        he[r] = a + 6 * b + c;
+        ho[r] = 4 * (b + c);
+    }
+    up[0] = (he[0] + 6 * he[1] + he[2] + 32) >> 6;
+    up[1] = (ho[0] + 6 * ho[1] + ho[2] + 32) >> 6;
+    up[2] = (4 * (he[1] + he[2]) + 32) >> 6;
+    up[3] = (4 * (ho[1] + ho[2]) + 32) >> 6;
+}
+
+__device__ __forceinline__ void store_pano_px(const PanoTables *__restrict__ T, uint8_t *__restrict__ pano, int slot,
+                                              int X, int Y, const int v[3], bool valid)
+{
+    const int cx = X - T->cut_x, cy = Y - T->cut_y;
+    if ((unsigned)cx >= (unsigned)T->cut_w || (unsigned)cy >= (unsigned)T->cut_h) return;
+    uint8_t *o = pano + ((size_t)slot * T->cut_h + cy) * ((size_t)T->cut_w * 3) + (size_t)cx * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = valid ? (uint8_t)sat_u8(v[c]) : 0;
+}
+
+// Coarsest level nb: dst = normalize(sum_i trunc(g_i * w_i)).  One thread = one pixel.
+__global__ void __launch_bounds__(256) coarsest_kernel(const PanoTables *__restrict__ T, uint8_t *__restrict__ pano)
+{
+    const int L = T->nb;
+    const int W = T->pad_w >> L, H = T->pad_h >> L;
+    const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int slot = blockIdx.z;
+    if (X >= W || Y >= H) return;
+    int acc[3] = {0, 0, 0};
+    float wsum = 0.f;
+    for (int i = 0; i < T->num_cams; ++i) {
+        const CamTables &C = T->cam[i];
+        const int x = X - (C.rx >> L), y = Y - (C.ry >> L);
+        if ((unsigned)x >= (unsigned)(C.rw >> L) || (unsigned)y >= (unsigned)(C.rh >> L)) continue;
+        float w;
+        if (L == 0 && !C.use_wt0) w = __fmul_rn((float)C.mask0[(size_t)y * C.mask_pitch + x], 1.f / 255.f);
+        else w = C.wt[L][(size_t)y * C.wt_pitch[L] + x];
+        const int16_t *g = C.g[L] + (size_t)slot * C.g_slot[L] + (size_t)y * C.g_pitch[L] + x;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            acc[c] += trunc_s16(__fmul_rn((float)g[(size_t)c * C.g_plane[L]], w));
+        wsum = __fadd_rn(wsum, w);
+    }
+    const float den = __fadd_rn(wsum, 1e-5f);
+    int res[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) res[c] = trunc_s16(__fdiv_rn((float)wrap_s16(acc[c]), den));
+    if (L == 0) {
+        if (X < T->roi_w && Y < T->roi_h) store_pano_px(T, pano, slot, X, Y, res, wsum > 1e-5f);
+    } else {
+        int16_t *o = T->outp[L] + (size_t)slot * T->out_slot[L] + (size_t)Y * T->out_pitch[L] + X;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o[(size_t)c * T->out_plane[L]] = (short)res[c];
+    }
+}
+
+// Level l < nb: out[l] = sat_add(pyrUp(out[l+1]), normalize(sum_i trunc(sat_sub(g_i[l], pyrUp(g_i[l+1])) * w_i[l]))).
+// At level 0 the result is cropped / masked / saturated into the 8-bit panorama.
+// One thread = one coarse pixel (k, m) of level l+1 = a 2x2 block of level l.
+__global__ void __launch_bounds__(256) collapse_kernel(const PanoTables *__restrict__ T, int L, uint8_t *__restrict__ pano)
+{
+    const int Wc = T->pad_w >> (L + 1), Hc = T->pad_h >> (L + 1);
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y * blockDim.y + threadIdx.y;
+    const int slot = blockIdx.z;
+    if (k >= Wc || m >= Hc) return;
+    const int X = 2 * k, Y = 2 * m;
+    int acc[3][4];
+    float wsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[c][j] = 0;
+
+    for (int i = 0; i < T->num_cams; ++i) {
+        const CamTables &C = T->cam[i];
+        const int x = X - (C.rx >> L), y = Y - (C.ry >> L);
+        const int fw = C.rw >> L, fh = C.rh >> L;
+        if ((unsigned)x >= (unsigned)fw || (unsigned)y >= (unsigned)fh) continue;
+        float w[4];
+        if (L == 0 && !C.use_wt0) {
+            const uint8_t *mrow = C.mask0 + (size_t)y * C.mask_pitch + x;
+            const uchar2 a = *reinterpret_cast<const uchar2 *>(mrow);
+            const uchar2 b = *reinterpret_cast<const uchar2 *>(mrow + C.mask_pitch);
+            w[0] = __fmul_rn((float)a.x, 1.f / 255.f); w[1] = __fmul_rn((float)a.y, 1.f / 255.f);
+            w[2] = __fmul_rn((float)b.x, 1.f / 255.f); w[3] = __fmul_rn((float)b.y, 1.f / 255.f);
+        } else {
+            const float *wrow = C.wt[L] + (size_t)y * C.wt_pitch[L] + x;
+            const float2 a = *reinterpret_cast<const float2 *>(wrow);
+            const float2 b = *reinterpret_cast<const float2 *>(wrow + C.wt_pitch[L]);
+            w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y;
+        }
+        const int16_t *gf = C.g[L] + (size_t)slot * C.g_slot[L] + (size_t)y * C.g_pitch[L] + x;
+        const int16_t *gc = C.g[L + 1] + (size_t)slot * C.g_slot[L + 1];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            int up[4];
+            pyrup_2x2(gc + (size_t)c * C.g_plane[L + 1], C.g_pitch[L + 1], fw >> 1, fh >> 1, x >> 1, y >> 1, up);
+            const int16_t *f = gf + (size_t)c * C.g_plane[L];
+            const uint32_t r0 = *reinterpret_cast<const uint32_t *>(f);
+            const uint32_t r1 = *reinterpret_cast<const uint32_t *>(f + C.g_pitch[L]);
+            const int fine[4] = {(short)(r0 & 0xffff), (short)(r0 >> 16), (short)(r1 & 0xffff), (short)(r1 >> 16)};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int lap = sat_s16(fine[j] - up[j]);
+                acc[c][j] += trunc_s16(__fmul_rn((float)lap, w[j]));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) wsum[j] = __fadd_rn(wsum[j], w[j]);
+    }
+
+    int res[3][4];
+    const int16_t *oc = T->outp[L + 1] + (size_t)slot * T->out_slot[L + 1];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        int up[4];
+        pyrup_2x2(oc + (size_t)c * T->out_plane[L + 1], T->out_pitch[L + 1], Wc, Hc, k, m, up);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int nrm = trunc_s16(__fdiv_rn((float)wrap_s16(acc[c][j]), __fadd_rn(wsum[j], 1e-5f)));
+            res[c][j] = sat_s16(up[j] + nrm);
+        }
+    }
+    if (L == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int px = X + (j & 1), py = Y + (j >> 1);
+            if (px < T->roi_w && py < T->roi_h) {
+                const int v[3] = {res[0][j], res[1][j], res[2][j]};
+                store_pano_px(T, pano, slot, px, py, v, wsum[j] > 1e-5f);
+            }
+        }
+    } else {
+        int16_t *o = T->outp[L] + (size_t)slot * T->out_slot[L] + (size_t)Y * T->out_pitch[L] + X;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            int16_t *oc2 = o + (size_t)c * T->out_plane[L];
+            *reinterpret_cast<uint32_t *>(oc2) = (uint16_t)(short)res[c][0] | ((uint32_t)(uint16_t)(short)res[c][1] << 16);
+            *reinterpret_cast<uint32_t *>(oc2 + T->out_pitch[L]) =
+                (uint16_t)(short)res[c][2] | ((uint32_t)(uint16_t)(short)res[c][3] << 16);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K4: single-pass blenders
+// FeatherBlender (stitching_detailed.cpp:865-869) and Blender::NO (ocvstitcher.hpp:1190-1191):
+// no pyramid, so warp + gain + weight + accumulate + normalise + 8-bit + crop is ONE gather per
+// output pixel.  One thread = one panorama pixel inside the cut rectangle.
+template <bool kMap64>
+__global__ void __launch_bounds__(256) direct_blend_kernel(const PanoTables *__restrict__ T, int blender,
+                                                           const uint8_t *__restrict__ frames, uint8_t *__restrict__ pano)
+{
+    const int cx = blockIdx.x * blockDim.x + threadIdx.x, cy = blockIdx.y * blockDim.y + threadIdx.y;
+    const int slot = blockIdx.z;
+    if (cx >= T->cut_w || cy >= T->cut_h) return;
+    const int X = cx + T->cut_x, Y = cy + T->cut_y;
+    const int W = T->src_w, H = T->src_h, ncam = T->num_cams;
+    int acc[3] = {0, 0, 0};
+    float wsum = 0.f;
+    int any = 0;
+    for (int i = 0; i < ncam; ++i) {
+        const CamTables &C = T->cam[i];
+        const int x = X - C.rx, y = Y - C.ry;
+        if ((unsigned)x >= (unsigned)C.rw || (unsigned)y >= (unsigned)C.rh) continue;
+        uint32_t sx, sy;
+        if (kMap64) {
+            const uint2 e = __ldg(C.map64 + (size_t)y * C.map_pitch + x);
+            sx = e.x; sy = e.y;
+        } else {
+            const uint32_t e = __ldg(C.map32 + (size_t)y * C.map_pitch + x);
+            sx = e & 0xffffu; sy = e >> 16;
+        }
+        const uint8_t *src = frames + ((size_t)slot * ncam + i) * ((size_t)W * H * 3);
+        int v[3];
+        bilinear_bgr(src, W, H, sx, sy, v);
+        const float g = C.gain_mode == 1 ? __ldg(C.gain_map + (size_t)y * C.map_pitch + x) : 1.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = apply_gain(v[c], C.gain_mode, g, C.gain_scalar);
+        if (blender == 1) {  // feather
+            const float w = __ldg(C.wt[0] + (size_t)y * C.wt_pitch[0] + x);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[c] += trunc_s16(__fmul_rn((float)v[c], w));
+            wsum = __fadd_rn(wsum, w);
+        } else {             // no blending: later images overwrite where their mask is set
+            const int mk = C.mask0[(size_t)y * C.mask_pitch + x];
+            if (mk) { acc[0] = v[0]; acc[1] = v[1]; acc[2] = v[2]; }
+            any |= mk;
+        }
+    }
+    uint8_t *o = pano + ((size_t)slot * T->cut_h + cy) * ((size_t)T->cut_w * 3) + (size_t)cx * 3;
+    if (blender == 1) {
+        const float den = __fadd_rn(wsum, 1e-5f);
+        const bool valid = wsum > 1e-5f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            o[c] = valid ? (uint8_t)sat_u8(trunc_s16(__fdiv_rn((float)wrap_s16(acc[c]), den))) : 0;
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o[c] = any ? (uint8_t)sat_u8(acc[c]) : 0;
+    }
+}
+
+inline dim3 grid2d(int w, int h, dim3 block, int z) { return dim3((w + block.x - 1) / block.x, (h + block.y - 1) / block.y, z); }
+
+}  // namespace
+
+void launch_warp(const PanoTables *dev, const PanoTables &host, const uint8_t *frames, int nslots, cudaStream_t stream)
+{
+    int maxw = 0, maxh = 0;
+    for (int i = 0; i < host.num_cams; ++i) {
+        maxw = max(maxw, host.cam[i].rw);
+        maxh = max(maxh, host.cam[i].rh);
+    }
+    const dim3 block(32, 8);
+    const dim3 grid = grid2d((maxw + 3) / 4, maxh, block, host.num_cams * nslots);
+    if (host.cam[0].map64) warp_kernel<true><<<grid, block, 0, stream>>>(dev, frames);
+    else warp_kernel<false><<<grid, block, 0, stream>>>(dev, frames);
+}
+
+void launch_pyrdown(const PanoTables *dev, const PanoTables &host, int level, int nslots, cudaStream_t stream)
+{
+    int maxw = 0, maxh = 0;
+    for (int i = 0; i < host.num_cams; ++i) {
+        maxw = max(maxw, ((host.cam[i].rw >> level) + 1) / 2);
+        maxh = max(maxh, ((host.cam[i].rh >> level) + 1) / 2);
+    }
+    const dim3 block(32, 8);
+    const dim3 grid = grid2d((maxw + 3) / 4, (maxh + 1) / 2, block, host.num_cams * nslots * 3);
+    pyrdown_kernel<<<grid, block, 0, stream>>>(dev, level);
+}
+
+void launch_coarsest(const PanoTables *dev, const PanoTables &host, uint8_t *pano, int nslots, cudaStream_t stream)
+{
+    const dim3 block(32, 8);
+    const dim3 grid = grid2d(host.pad_w >> host.nb, host.pad_h >> host.nb, block, nslots);
+    coarsest_kernel<<<grid, block, 0, stream>>>(dev, pano);
+}
+
+void launch_collapse(const PanoTables *dev, const PanoTables &host, int level, uint8_t *pano, int nslots, cudaStream_t stream)
+{
+    const dim3 block(32, 8);
+    const dim3 grid = grid2d(host.pad_w >> (level + 1), host.pad_h >> (level + 1), block, nslots);
+    collapse_kernel<<<grid, block, 0, stream>>>(dev, level, pano);
+}
+
+void launch_direct_blend(const PanoTables *dev, const PanoTables &host, int blender, const uint8_t *frames,
+                         uint8_t *pano, int nslots, cudaStream_t stream)
+{
+    const dim3 block(32, 8);
+    const dim3 grid = grid2d(host.cut_w, host.cut_h, block, nslots);
+    if (host.cam[0].map64) direct_blend_kernel<true><<<grid, block, 0, stream>>>(dev, blender, frames, pano);
+    else direct_blend_kernel<false><<<grid, block, 0, stream>>>(dev, blender, frames, pano);
+}
+
+}  // namespace pano

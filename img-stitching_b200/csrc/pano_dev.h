@@ -1,0 +1,66 @@
+// Device-side table layout shared by the kernels (kernels.cu) and the C ABI (capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace pano {
+
+constexpr int kMaxCams = 8;
+constexpr int kMaxLevels = 10;  // num_bands + 1 <= kMaxLevels
+
+// One camera's static tables and per-wave pyramid workspace.  All "pitch" values are in
+// ELEMENTS of the array they describe.  Pyramid planes are channel-planar int16:
+// g[l] -> [slot][3 planes][h_l rows][g_pitch[l]].
+struct CamTables {
+    // feed rect of MultiBandBlender::feed at level 0, in padded-dst coordinates
+    // (for feather / no-blend: the image rect itself, borders = 0)
+    int rx, ry, rw, rh;
+    // folded fixed-point remap table over the feed rect: (sy' << 16) | sx'   (map32)
+    // or {sx', sy'} pairs (map64) when 32*src_dim does not fit 16 bits
+    const uint32_t *map32;
+    const uint2 *map64;
+    int map_pitch;
+    // exposure gain: mode 0 off, 1 per-pixel float map (feed-rect layout, pitch = map_pitch),
+    // 2 scalar (double, GainCompensator)
+    int gain_mode;
+    const float *gain_map;
+    double gain_scalar;
+    // weights: level 0 = 8-bit mask (weight = mask * (1/255.f)), levels >= 1 float
+    const uint8_t *mask0;
+    int mask_pitch;
+    const float *wt[kMaxLevels];
+    int wt_pitch[kMaxLevels];
+    int use_wt0;  // 1: level-0 weights come from wt[0] (caller override / feather) instead of mask0
+    // pyramid workspace
+    int16_t *g[kMaxLevels];
+    int g_pitch[kMaxLevels];
+    size_t g_plane[kMaxLevels];  // elements per plane
+    size_t g_slot[kMaxLevels];   // elements per frame-set slot (= 3 planes)
+};
+
+struct PanoTables {
+    int num_cams;
+    int src_w, src_h;
+    int nb;                  // effective band count (levels 0..nb)
+    int pad_w, pad_h;        // padded dst size (level 0)
+    int roi_w, roi_h;        // unpadded dst roi size
+    int cut_x, cut_y, cut_w, cut_h;
+    // collapsed dst pyramid, levels 1..nb: [slot][3][h_l][out_pitch[l]]
+    int16_t *outp[kMaxLevels];
+    int out_pitch[kMaxLevels];
+    size_t out_plane[kMaxLevels];
+    size_t out_slot[kMaxLevels];
+    CamTables cam[kMaxCams];
+};
+
+// launchers (kernels.cu) -- all asynchronous on `stream`
+void launch_warp(const PanoTables *dev, const PanoTables &host, const uint8_t *frames, int nslots, cudaStream_t stream);
+void launch_pyrdown(const PanoTables *dev, const PanoTables &host, int level, int nslots, cudaStream_t stream);
+void launch_coarsest(const PanoTables *dev, const PanoTables &host, uint8_t *pano, int nslots, cudaStream_t stream);
+void launch_collapse(const PanoTables *dev, const PanoTables &host, int level, uint8_t *pano, int nslots, cudaStream_t stream);
+void launch_direct_blend(const PanoTables *dev, const PanoTables &host, int blender, const uint8_t *frames,
+                         uint8_t *pano, int nslots, cudaStream_t stream);
+
+}  // namespace pano

@@ -1,0 +1,180 @@
+/*
+ * panob200.h -- C ABI of the B200-native per-frame compose path of Img-Stitching.
+ *
+ * The reference has no FFI: its hot path is a header-only C++ class compiled into every
+ * executable (`ocvStitcher`, /root/reference/include/ocvstitcher.hpp:254-1306, and the
+ * `nvCam` pixel pipeline, include/nvcam.hpp:898-929,1083-1100).  This header is the
+ * boundary a maintainer binds instead; each entry point cites the reference interface it
+ * replaces.  Plain pointers and sizes only; no exceptions cross it; every call returns
+ * PANO_OK (0) or PANO_ERR (-1), mirroring RET_OK / RET_ERR
+ * (include/stitcherglobal.h:13-14).  There is no CPU fallback: without a CUDA device every
+ * compute entry point fails with PANO_ERR.
+ *
+ * Image conventions (same as the reference's cv::Mat usage): 8-bit, interleaved, row-major,
+ * BGR order as delivered by nvCam::getFrame; strides in bytes.
+ */
+#ifndef PANOB200_H
+#define PANOB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PANO_OK 0
+#define PANO_ERR (-1)
+
+/* warper kinds: cv::SphericalWarper (include/ocvstitcher.hpp:1000) and
+ * cv::CylindricalWarper (src/stitching_detailed.cpp:652-653; ocvstitcher.hpp:999 commented) */
+#define PANO_WARP_SPHERICAL 0
+#define PANO_WARP_CYLINDRICAL 1
+
+/* blender kinds: Blender::NO (include/ocvstitcher.hpp:1190-1191), FeatherBlender
+ * (src/stitching_detailed.cpp:865-869), MultiBandBlender (include/ocvstitcher.hpp:1186-1199) */
+#define PANO_BLEND_NO 0
+#define PANO_BLEND_FEATHER 1
+#define PANO_BLEND_MULTIBAND 2
+
+typedef struct pano_ctx *pano_handle;
+typedef struct pano_frontend_ctx *pano_frontend_handle;
+
+/* Static configuration = the members ocvStitcher keeps after init
+ * (include/ocvstitcher.hpp:1266-1299: camK, cameraR, warped_image_scale, m_cutParams) plus
+ * the stStitcherCfg fields that shape the compose (include/stitcherglobal.h:68-81). */
+typedef struct pano_config {
+    int num_images;            /* stStitcherCfg::num_images */
+    int src_width, src_height; /* stStitcherCfg::width/height (outPutWidth/outPutHeight) */
+    int warp_kind;             /* PANO_WARP_* */
+    float warped_image_scale;  /* ocvStitcher::warped_image_scale */
+    const float *K;            /* num_images x 9, row-major float32 (camK[i]) */
+    const float *R;            /* num_images x 9, row-major float32 (cameraR[i]) */
+    int blender;               /* PANO_BLEND_* */
+    int num_bands;             /* MultiBandBlender::setNumBands argument (:1195) */
+    float sharpness;           /* FeatherBlender::setSharpness argument */
+    int cut[4];                /* m_cutParams x,y,w,h in dst-roi coordinates; w<=0 -> whole dst roi */
+    int device;                /* CUDA device ordinal */
+    int max_batch;             /* frame-sets resident per launch wave (workspace sizing), >=1 */
+} pano_config;
+
+/* Error text of the last failing call on this thread (create) or handle. */
+const char *pano_last_error(pano_handle h);
+
+/* ocvStitcher::init + the geometry half of initSeam (:1054-1063, :1110): builds the
+ * rotation-warp tables on the host (bit-exact with RotationWarperBase::buildMaps), the dst
+ * roi, and the blender geometry; allocates all device memory.  Masks default to the warped
+ * all-255 mask (what NoSeamFinder would leave, :1034). */
+int pano_create(const pano_config *cfg, pano_handle *out);
+int pano_destroy(pano_handle h);
+
+/* m_corners / m_sizes / resultRoi (include/ocvstitcher.hpp:1055-1063,1110).
+ * corners, sizes: 2*num_images ints; dst_roi: x,y,w,h; out_wh: size process() writes. */
+int pano_get_geometry(pano_handle h, int *corners, int *sizes, int *dst_roi, int *out_wh);
+/* effective band count and the padded dst size after MultiBandBlender::prepare */
+int pano_get_blend_geometry(pano_handle h, int *num_bands, int *padded_wh, int *feed_rects /*4 per image*/);
+
+/* The remap tables RotationWarperBase::buildMaps would produce for camera `cam` (float32,
+ * sizes[cam] large), and their fixed-point form as cv::remap consumes them
+ * (ixy: int16 pairs, frac: (fy<<5)|fx) -- the parity tests check these bit-exactly. */
+int pano_get_warp_maps(pano_handle h, int cam, float *xmap, float *ymap);
+int pano_get_fixed_maps(pano_handle h, int cam, int16_t *ixy, uint16_t *frac);
+
+/* m_blenderMask[cam] (include/ocvstitcher.hpp:1101,1257).  Re-callable at run time: this is
+ * how updateMask (:1218-1261) lands.  mask is sizes[cam] large, 8-bit, soft (0..255). */
+int pano_set_mask(pano_handle h, int cam, const uint8_t *mask, int width, int height, int stride);
+/* Optional: override the float weight pyramid level the library derives from the mask
+ * (MultiBandBlender::feed builds it with cv::pyrDown on CV_32F, which is only ~1-ulp
+ * reproducible outside OpenCV).  level in [0, num_bands]; size = feed rect >> level. */
+int pano_set_weight_level(pano_handle h, int cam, int level, const float *w, int width, int height);
+/* Optional: FeatherBlender weight map (distanceTransform-derived, static); sizes[cam] large.
+ * Without it the library derives it from the mask. */
+int pano_set_feather_weight(pano_handle h, int cam, const float *w, int width, int height);
+/* compensator->apply (src/stitching_detailed.cpp:841; ocvstitcher.hpp:1178 commented):
+ * full-resolution float gain map (BlocksGainCompensator) or scalar gain (GainCompensator).
+ * gain == NULL switches gain apply off for the camera. */
+int pano_set_gain_map(pano_handle h, int cam, const float *gain, int width, int height);
+int pano_set_gain_scalar(pano_handle h, int cam, double gain);
+
+/* ocvStitcher::process (include/ocvstitcher.hpp:1141-1216) for one frame-set held in HOST
+ * memory: frames[i] -> src_height rows of strides[i] bytes; out receives the cut rectangle,
+ * out_stride bytes per row (>= 3*cut_w).  Synchronous. */
+int pano_process(pano_handle h, const uint8_t *const *frames, const int *strides,
+                 uint8_t *out, int out_stride);
+/* Same for `batch` frame-sets already resident in DEVICE memory, packed
+ * [batch][num_images][src_height][src_width][3]; out packed [batch][cut_h][cut_w][3].
+ * Asynchronous on `stream` (a cudaStream_t; NULL = legacy default stream). */
+int pano_process_device(pano_handle h, const uint8_t *frames_dev, uint8_t *out_dev, int batch, void *stream);
+/* Host-memory batch (packed as above): H2D, compose and D2H are pipelined on internal
+ * streams.  Pinned host memory gives full PCIe rate.  Synchronous. */
+int pano_process_batch(pano_handle h, const uint8_t *frames_host, uint8_t *out_host, int batch);
+
+/* Per-kernel device time of the last pano_process_device call made while profiling was
+ * enabled (CUDA events on the launching stream).  names: up to max entries. */
+int pano_profile_enable(pano_handle h, int on);
+int pano_profile_read(pano_handle h, int max, const char **names, float *ms, int *launches, double *alg_bytes);
+/* number of kernel launches issued by the last process call */
+int pano_last_launch_count(pano_handle h);
+
+/* ---------------------------------------------------------------- nvCam front end
+ * nvCam::read_frame's pixel pipeline (include/nvcam.hpp:898-929): resize(8UC4) -> drop alpha
+ * -> remap INTER_CUBIC over initUndistortRectifyMap maps -> crop rect -> resize, followed by
+ * getFrame(.., src=false)'s resize to the stitcher input (:1092-1094). */
+typedef struct pano_frontend_config {
+    int cam_src_width, cam_src_height;   /* stCamCfg::camSrcWidth/Height: 8UC4 input */
+    int undist_width, undist_height;     /* stCamCfg::undistoredWidth/Height */
+    int out_width, out_height;           /* stCamCfg::outPutWidth/Height */
+    int undistort;                       /* stCamCfg::undistor */
+    double K[9];                         /* m_cameraK */
+    double D[4];                         /* m_cameraDistorParams k1,k2,p1,p2 */
+    double newK[9];                      /* getOptimalNewCameraMatrix(K,D,size,1,size,0) (:831) */
+    int rect[4];                         /* m_rectPara x,y,w,h (:916) */
+    const float *mapx, *mapy;            /* optional: caller-supplied m_mapx/m_mapy (undist size) */
+    int device;
+    int max_batch;
+} pano_frontend_config;
+
+int pano_frontend_create(const pano_frontend_config *cfg, pano_frontend_handle *out);
+int pano_frontend_destroy(pano_frontend_handle h);
+const char *pano_frontend_last_error(pano_frontend_handle h);
+/* m_mapx / m_mapy as prepareUndistorMap builds them (include/nvcam.hpp:823-833) */
+int pano_frontend_get_maps(pano_frontend_handle h, float *mapx, float *mapy);
+/* frames: [batch][cam_src_height][cam_src_width][4] -> out [batch][out_height][out_width][3] */
+int pano_frontend_process_device(pano_frontend_handle h, const uint8_t *argb_dev, uint8_t *out_dev,
+                                 int batch, void *stream);
+int pano_frontend_process(pano_frontend_handle h, const uint8_t *argb_host, int stride,
+                          uint8_t *out_host, int out_stride);
+
+/* ---------------------------------------------------------------- host-only table builders
+ * The init-time products of ocvStitcher::initSeam / nvCam::prepareUndistorMap, computed on the
+ * host exactly as the handle does internally.  None of these needs a CUDA device. */
+/* blender_warper->warpRoi (include/ocvstitcher.hpp:1057): roi = x,y,w,h */
+int pano_host_warp_roi(int warp_kind, float scale, const float *K, const float *R, int src_w, int src_h, int *roi);
+/* RotationWarperBase::buildMaps: xmap/ymap sized roi.h x roi.w */
+int pano_host_build_maps(int warp_kind, float scale, const float *K, const float *R, int src_w, int src_h,
+                         float *xmap, float *ymap);
+/* resultRoi + MultiBandBlender::prepare/feed rectangle arithmetic (reached from :1198,:1202).
+ * feed_rects: x,y,w,h in padded-dst coordinates; borders: top,bottom,left,right */
+int pano_host_blend_geometry(int n, const int *corners, const int *sizes, int num_bands, int *dst_roi,
+                             int *eff_bands, int *padded_wh, int *feed_rects, int *borders);
+/* BORDER_REFLECT folded into an in-range sample position 32*i'+f' (map folding) */
+unsigned pano_host_fold_reflect(int i, int f, int n);
+/* cv::convertMaps view of float maps (what cv::remap uses internally) */
+int pano_host_fixed_maps(const float *xmap, const float *ymap, size_t count, int16_t *ixy, uint16_t *frac);
+/* cv::pyrDown on CV_32F as the handle evaluates it for the weight pyramids */
+int pano_host_pyrdown_f32(const float *src, int w, int h, float *dst);
+/* FeatherBlender weight: min(distanceTransform(mask, DIST_L1, 3) * sharpness, 1) */
+int pano_host_feather_weight(const uint8_t *mask, int w, int h, int stride, float sharpness, float *out);
+/* cv::initUndistortRectifyMap(K, D, I, newK, size, CV_32FC1) (include/nvcam.hpp:832) */
+int pano_host_undistort_maps(const double *K, const double *D, const double *newK, int w, int h, float *mapx, float *mapy);
+/* cv::remap's INTER_CUBIC 15-bit table (1024 x 16) and cv::resize's INTER_LINEAR axis tables */
+int pano_host_cubic_table(int16_t *tab);
+int pano_host_resize_axis(int ssize, int dsize, int clamp_frac, int *ofs, int16_t *a0, int16_t *a1);
+
+/* library / build identification: returns e.g. "panob200 sm_100a" */
+const char *pano_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANOB200_H */

@@ -1,0 +1,276 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the oracle and the
+committed cv2 golden vectors.  Integer/byte work -> the bar is BIT-EXACT (max|d| = 0) whenever
+the float weight tables are the reference's own (golden / oracle-built); with library-built
+weight pyramids vs cv2's SIMD float pyrDown the stated tolerance is max|d| <= 1 LSB."""
+import os
+
+import numpy as np
+import pytest
+
+import panob200
+import util
+from golden import calib
+from oracle import compose, oracle as orc
+
+pytestmark = pytest.mark.gpu
+SC = panob200.StitcherConfig
+
+
+def load(name):
+    return np.load(os.path.join(util.GOLDEN, name + ".npz"))
+
+
+def make(Ks, Rs, scale, W, H, warp="spherical", blender="multiband", num_bands=5, cut=None, max_batch=1, sharp=None):
+    st = panob200.ocvStitcher(SC(width=W, height=H, num_images=len(Rs), Ks=Ks, Rs=Rs, warped_image_scale=scale,
+                                 warp=warp, blender=blender, num_bands=num_bands, cut=cut, max_batch=max_batch,
+                                 sharpness=sharp))
+    return st
+
+
+def golden_setup(name, warp, blender="multiband", gains=False):
+    g = load(name)
+    W, H = int(g["width"]), int(g["height"])
+    Ks, Rs, scale = calib.rig("2222", W)
+    n = len(Rs)
+    nb = int(g["num_bands"])
+    st = make(Ks, Rs, scale, W, H, warp, blender, nb, cut=[int(v) for v in g["cut"]],
+              sharp=float(g["sharpness"]) if "sharpness" in g.files else None)
+    masks = [g["mask%d" % i] for i in range(n)]
+    wl = [{l: g["w%d_%d" % (i, l)] for l in range(1, nb + 1)} for i in range(n)] if blender == "multiband" else None
+    fw = [g["fw%d" % i] for i in range(n)] if blender == "feather" else None
+    assert st.initTables(masks, wl, fw) == 0, st.last_error
+    if gains:
+        st.set_gain_maps([g["gain%d" % i] for i in range(n)])
+    return g, st, util.synth_set(n, H, W, int(g["seed"]))
+
+
+def assert_equal(name, got, want):
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert np.array_equal(got, want), util.report(name, got, want)
+
+
+# ------------------------------------------------------------------ golden vectors (cv2 4.13)
+
+@pytest.mark.parametrize("name,warp", [("cfg1_small", "spherical"), ("cfg1_cyl_small", "cylindrical")])
+def test_multiband_golden_bit_exact(name, warp):
+    g, st, imgs = golden_setup(name, warp)
+    assert np.array_equal(np.array(st.m_corners), g["corners"]) and np.array_equal(np.array(st.m_sizes), g["sizes"])
+    assert st.dst_roi == tuple(g["dst_roi"])
+    assert_equal(name, st.process(imgs), g["pano_multiband"])
+    assert st.last_launch_count() >= 3
+
+
+def test_multiband_library_weights_within_1lsb():
+    g = load("cfg1_small")
+    Ks, Rs, scale = calib.rig("2222", 240)
+    st = make(Ks, Rs, scale, 240, 135, num_bands=5, cut=[int(v) for v in g["cut"]])
+    assert st.initTables([g["mask%d" % i] for i in range(4)]) == 0, st.last_error
+    out = st.process(util.synth_set(4, 135, 240, int(g["seed"])))
+    d = np.abs(out.astype(int) - g["pano_multiband"].astype(int))
+    assert d.max() <= 1, util.report("library weights", out, g["pano_multiband"])   # tolerance: 1 LSB
+
+
+def test_feather_no_gain_golden_bit_exact():
+    g, st, imgs = golden_setup("cfg1_small", "spherical", "feather")
+    assert_equal("feather", st.process(imgs), g["pano_feather"])
+    st.set_gain_maps([g["gain%d" % i] for i in range(4)])
+    assert_equal("gain+feather", st.process(imgs), g["pano_gain_feather"])
+    st.set_gain_maps([None] * 4)
+    assert_equal("feather again", st.process(imgs), g["pano_feather"])
+    g, st, imgs = golden_setup("cfg1_small", "spherical", "no")
+    assert_equal("no", st.process(imgs), g["pano_no"])
+    g, st, imgs = golden_setup("cfg1_small", "spherical", "multiband", gains=True)
+    assert_equal("gain+multiband", st.process(imgs), g["pano_gain_multiband"])
+
+
+# ------------------------------------------------------------------ against the oracle
+
+def oracle_case(Ks, Rs, scale, W, H, warp, blender, nb, seed, masks="soft", cut=None, gains=None, sharp=0.05):
+    t = compose.build_tables(Ks, Rs, scale, (W, H), warp)
+    if masks == "soft":
+        t.blend_masks = util.soft_masks(t)
+    imgs = util.synth_set(len(Rs), H, W, seed)
+    st = make(Ks, Rs, scale, W, H, warp, blender, nb, cut=cut, sharp=sharp)
+    fw = None
+    if blender == "feather":
+        fw = [panob200.capi.host_feather_weight(m, sharp) for m in t.blend_masks]
+    assert st.initTables(t.blend_masks if masks == "soft" else None, None, None) == 0, st.last_error
+    if gains is not None:
+        t.gain_maps = gains
+        st.set_gain_maps(gains)
+    want = compose.process(t, imgs, blender, nb, feather_weights=fw, cut=cut)
+    return t, st, imgs, want
+
+
+@pytest.mark.parametrize("nb", [0, 1, 2, 4, 7])
+def test_band_counts_vs_oracle(nb):
+    Ks, Rs, scale = calib.rig("2222", 320)
+    t, st, imgs, want = oracle_case(Ks, Rs, scale, 320, 180, "spherical", "multiband", nb, seed=10 + nb)
+    assert_equal("nb=%d" % nb, st.process(imgs), want)
+
+
+def test_default_masks_and_fixed_maps_vs_oracle():
+    Ks, Rs, scale = calib.rig("424", 320)
+    t, st, imgs, want = oracle_case(Ks, Rs, scale, 320, 180, "spherical", "multiband", 3, seed=3, masks="default")
+    assert_equal("default masks", st.process(imgs), want)
+    for i in range(len(Rs)):
+        ixy, fr = st.fixed_maps(i)
+        oixy, ofr = orc.convert_maps(*t.maps[i])
+        assert np.array_equal(ixy, oixy) and np.array_equal(fr, ofr)        # remap index maps: bit-exact
+        xm, ym = st.warp_maps(i)
+        assert np.array_equal(xm, t.maps[i][0]) and np.array_equal(ym, t.maps[i][1])
+
+
+def test_odd_geometry_three_cameras_cylindrical():
+    Ks, Rs, scale = calib.ring(3, 333, 187, 70.0, 38.0)
+    t, st, imgs, want = oracle_case(Ks, Rs, scale, 333, 187, "cylindrical", "multiband", 4, seed=21, cut=[7, 5, 600, 150])
+    assert_equal("odd cyl", st.process(imgs), want)
+
+
+def test_feather_and_no_blend_vs_oracle_with_scalar_gain():
+    Ks, Rs, scale = calib.rig("2222", 320)
+    gains = [1.0, 0.83, 1.21, 1.07]
+    t, st, imgs, want = oracle_case(Ks, Rs, scale, 320, 180, "spherical", "feather", 0, seed=5, gains=gains, sharp=0.04)
+    assert_equal("feather scalar gain", st.process(imgs), want)
+    t, st, imgs, want = oracle_case(Ks, Rs, scale, 320, 180, "spherical", "no", 0, seed=6)
+    assert_equal("no blend", st.process(imgs), want)
+
+
+def test_wide_source_uses_64bit_map_entries():
+    Ks, Rs, scale = calib.ring(2, 2300, 96, 80.0, 50.0)
+    t, st, imgs, want = oracle_case(Ks, Rs, scale, 2300, 96, "cylindrical", "multiband", 3, seed=8)
+    assert_equal("map64", st.process(imgs), want)
+
+
+def test_mask_update_at_runtime():
+    Ks, Rs, scale = calib.rig("2222", 240)
+    t, st, imgs, want = oracle_case(Ks, Rs, scale, 240, 135, "spherical", "multiband", 3, seed=4)
+    assert_equal("before", st.process(imgs), want)
+    new = [np.minimum(m, np.uint8(200)) for m in t.blend_masks]
+    new[1][:, : new[1].shape[1] // 2] = 0
+    for i, m in enumerate(new):
+        st.set_mask(i, m)                       # the updateMask landing (ocvstitcher.hpp:1257)
+    t.blend_masks = new
+    want2 = compose.process(t, imgs, "multiband", 3)
+    assert_equal("after", st.process(imgs), want2)
+    assert not np.array_equal(want, want2)
+
+
+def test_batched_device_and_host_apis():
+    import torch
+    Ks, Rs, scale = calib.rig("2222", 240)
+    t = compose.build_tables(Ks, Rs, scale, (240, 135), "spherical")
+    t.blend_masks = util.soft_masks(t)
+    st = panob200.ocvStitcher(SC(width=240, height=135, num_images=4, Ks=Ks, Rs=Rs, warped_image_scale=scale,
+                                 blender="multiband", num_bands=4, cut_height=100, max_batch=2))
+    assert st.initTables(t.blend_masks) == 0, st.last_error
+    B = 5
+    sets = [util.synth_set(4, 135, 240, 50 + b) for b in range(B)]
+    cut = st.m_cutParams
+    want = [compose.process(t, s, "multiband", 4, cut=cut) for s in sets]
+    host = torch.from_numpy(np.stack([np.stack(s) for s in sets])).pin_memory()
+    ow, oh = st.out_size
+    out_dev = torch.empty((B, oh, ow, 3), dtype=torch.uint8, device="cuda")
+    st.process_device(host.cuda(), out_dev)
+    torch.cuda.synchronize()
+    got = out_dev.cpu().numpy()
+    for b in range(B):
+        assert_equal("device batch %d" % b, got[b], want[b])
+    out_host = torch.empty((B, oh, ow, 3), dtype=torch.uint8).pin_memory()
+    st.process_batch(host, out_host)
+    for b in range(B):
+        assert_equal("host batch %d" % b, out_host.numpy()[b], want[b])
+    # idempotence: same inputs, same bytes; and strided host frames through pano_process
+    st.process_device(host.cuda(), out_dev)
+    torch.cuda.synchronize()
+    assert np.array_equal(out_dev.cpu().numpy(), got)
+    padded = [np.ascontiguousarray(np.pad(f, ((0, 0), (0, 5), (0, 0))))[:, :240] for f in sets[0]]
+    assert_equal("strided", st.process(padded), want[0])
+
+
+def test_error_behaviour():
+    Ks, Rs, scale = calib.rig("2222", 240)
+    st = make(Ks, Rs, scale, 240, 135, num_bands=3, cut=[0, 0, 5000, 50])
+    assert st.initTables() == -1 and "cut" in st.last_error          # cv::Mat ROI would assert (:1210)
+    st = make(Ks, Rs, scale, 240, 135, num_bands=3)
+    assert st.initTables() == 0
+    with pytest.raises(panob200.PanoError):
+        st.set_mask(0, np.zeros((10, 10), np.uint8))
+    with pytest.raises(panob200.PanoError):
+        st.process([np.zeros((135, 240, 3), np.uint8)] * 3)
+    with pytest.raises(panob200.PanoError):
+        st.process([np.zeros((100, 240, 3), np.uint8)] * 4)
+
+
+# ------------------------------------------------------------------ BASELINE full sizes
+
+def test_config1_full_size_vs_oracle_and_properties():
+    """4 x 1920x1080 spherical, 5 bands (BASELINE config 1 shape) against the scalar oracle, plus
+    size-independent properties: batch slots are independent and deterministic."""
+    import torch
+    Ks, Rs, scale = calib.rig("2222", 1920)
+    t = compose.build_tables(Ks, Rs, scale, (1920, 1080), "spherical")
+    t.blend_masks = util.soft_masks(t)
+    cut = [0, 64, 5336, 896]
+    st = panob200.ocvStitcher(SC(width=1920, height=1080, num_images=4, Ks=Ks, Rs=Rs, warped_image_scale=scale,
+                                 blender="multiband", num_bands=5, cut=cut, max_batch=2))
+    assert st.initTables(t.blend_masks) == 0, st.last_error
+    assert st.dst_roi == (-4486, 1903, 5336, 1025)
+    imgs = util.synth_set(4, 1080, 1920, 7)
+    want = compose.process(t, imgs, "multiband", 5, cut=cut)
+    got = st.process(imgs)
+    assert_equal("config1 full", got, want)
+    other = util.synth_set(4, 1080, 1920, 8)
+    batch = torch.from_numpy(np.stack([np.stack(imgs), np.stack(other), np.stack(imgs)])).cuda()
+    out = torch.empty((3, 896, 5336, 3), dtype=torch.uint8, device="cuda")
+    st.process_device(batch, out)
+    torch.cuda.synchronize()
+    o = out.cpu().numpy()
+    assert np.array_equal(o[0], got) and np.array_equal(o[2], got) and not np.array_equal(o[1], got)
+    # uncovered panorama pixels read as 0 (the reference zero-fills dst every frame)
+    full, mask = compose.process(t, imgs, "multiband", 5, return_s16=True)
+    hole = mask[64:960] == 0
+    assert (got[hole] == 0).all()
+
+
+# ------------------------------------------------------------------ nvCam front end
+
+def test_front_end_golden_bit_exact():
+    g = np.load(os.path.join(util.GOLDEN, "frontend_small.npz"))
+    CamConfig = panob200.pkg.nvcam.CamConfig
+    rect = [int(v) for v in g["rect"]]
+    base = dict(K=g["K"].reshape(-1), distorParams=g["D"], rect=rect, newK=g["newK"])
+    fe = panob200.nvCamFrontEnd(CamConfig(camSrcWidth=480, camSrcHeight=270, undistoredWidth=480, undistoredHeight=270,
+                                          outPutWidth=480, outPutHeight=270, undistor=True, **base))
+    mx, my = fe.maps()
+    ixy, fr = orc.convert_maps(mx, my)
+    omx, omy = orc.init_undistort_map(g["K"], g["D"], g["newK"], 480, 270)
+    oixy, ofr = orc.convert_maps(omx, omy)
+    assert np.array_equal(ixy, oixy) and np.array_equal(fr, ofr)
+    assert_equal("same size", fe.getFrame(util.synth_frame(270, 480, 77, channels=4)), g["out_same"])
+    big = util.synth_frame(540, 960, 78, channels=4)
+    fe = panob200.nvCamFrontEnd(CamConfig(camSrcWidth=960, camSrcHeight=540, undistoredWidth=480, undistoredHeight=270,
+                                          outPutWidth=360, outPutHeight=203, undistor=True, **base))
+    assert_equal("down", fe.getFrame(big), g["out_down"])
+    fe = panob200.nvCamFrontEnd(CamConfig(camSrcWidth=960, camSrcHeight=540, undistoredWidth=480, undistoredHeight=270,
+                                          outPutWidth=360, outPutHeight=203, undistor=False, **base))
+    assert_equal("no undistort", fe.getFrame(big), g["out_noud"])
+
+
+def test_front_end_config2_shape_vs_oracle():
+    """1920x1080 8UC4 -> cubic undistort -> crop [69,103,1782,889] -> resize 1920x1080 (config 2)."""
+    import torch
+    cam = calib.CAM_LIJING_390_FOV60_1920
+    newK = np.array([[1627.5076, 0, 943.1681], [0, 1622.9720, 571.5369], [0, 0, 1]])
+    CamConfig = panob200.pkg.nvcam.CamConfig
+    fe = panob200.nvCamFrontEnd(CamConfig(K=cam["K"], distorParams=cam["distorParams"], rect=cam["rect"], newK=newK, max_batch=2))
+    mx, my = fe.maps()
+    frames = [util.synth_frame(1080, 1920, 90 + i, channels=4) for i in range(3)]
+    want = [compose.front_end(f, (1920, 1080), mx, my, cam["rect"], (1920, 1080)) for f in frames]
+    assert_equal("config2 front end", fe.getFrame(frames[0]), want[0])
+    dev = torch.from_numpy(np.stack(frames)).cuda()
+    out = torch.empty((3, 1080, 1920, 3), dtype=torch.uint8, device="cuda")
+    fe.process_device(dev, out)
+    torch.cuda.synchronize()
+    for i in range(3):
+        assert_equal("batch %d" % i, out[i].cpu().numpy(), want[i])
