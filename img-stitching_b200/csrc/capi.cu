@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -51,6 +52,7 @@ struct pano_ctx {
     // device tables
     PanoTables host{};
     PanoTables *dev = nullptr;
+    KernelChoice kc;
     bool tables_dirty = true;
     std::vector<void *> owned;                    // device allocations to free
     std::vector<void *> cam_mask0, cam_gain;      // per camera, re-uploadable
@@ -248,11 +250,11 @@ int runWave(pano_ctx *h, const uint8_t *frames_dev, uint8_t *out_dev, int slots,
         L.end();
     } else {
         L.begin("warp", warpBytes(h, slots));
-        launch_warp(h->dev, h->host, frames_dev, slots, st);
+        launch_warp(h->dev, h->host, h->kc, frames_dev, slots, st);
         L.end();
         for (int l = 0; l < h->nb; ++l) {
             L.begin(kDown[l], pyrdownBytes(h, l, slots));
-            launch_pyrdown(h->dev, h->host, l, slots, st);
+            launch_pyrdown(h->dev, h->host, h->kc, l, slots, st);
             L.end();
         }
         L.begin("coarsest", collapseBytes(h, h->nb, slots));
@@ -260,7 +262,7 @@ int runWave(pano_ctx *h, const uint8_t *frames_dev, uint8_t *out_dev, int slots,
         L.end();
         for (int l = h->nb - 1; l >= 0; --l) {
             L.begin(kCol[l], collapseBytes(h, l, slots));
-            launch_collapse(h->dev, h->host, l, out_dev, slots, st);
+            launch_collapse(h->dev, h->host, h->kc, l, out_dev, slots, st);
             L.end();
         }
     }
@@ -412,6 +414,38 @@ int pano_create(const pano_config *cfg, pano_handle *out)
             if (cudaMemcpy(d, m32.data(), m32.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) { h->err = "map upload failed"; return bail(0); }
             C.map32 = d; C.map64 = nullptr;
         }
+        // source footprint of every 128x8 output tile (staged-gather warp kernel)
+        C.tiles_x = (C.rw + kWarpTileW - 1) / kWarpTileW;
+        C.tiles_y = (C.rh + kWarpTileH - 1) / kWarpTileH;
+        {
+            std::vector<int4> tl((size_t)C.tiles_x * C.tiles_y);
+            const int W3 = W * 3;
+            for (int ty = 0; ty < C.tiles_y; ++ty)
+                for (int tx = 0; tx < C.tiles_x; ++tx) {
+                    int x0 = INT32_MAX, x1 = -1, y0 = INT32_MAX, y1 = -1;
+                    // the kernel samples all 4-pixel groups that start inside the rect
+                    const int xe = std::min(roundUp(C.rw, 4), (tx + 1) * kWarpTileW);
+                    for (int Y = ty * kWarpTileH; Y < std::min(C.rh, (ty + 1) * kWarpTileH); ++Y)
+                        for (int X = tx * kWarpTileW; X < xe; ++X) {
+                            uint32_t sx, sy;
+                            if (h->map64) { sx = m64[(size_t)Y * C.map_pitch + X].x; sy = m64[(size_t)Y * C.map_pitch + X].y; }
+                            else { sx = m32[(size_t)Y * C.map_pitch + X] & 0xffffu; sy = m32[(size_t)Y * C.map_pitch + X] >> 16; }
+                            const int ix = sx >> 5, iy = sy >> 5;
+                            x0 = std::min(x0, ix); x1 = std::max(x1, std::min(ix + 1, W - 1));
+                            y0 = std::min(y0, iy); y1 = std::max(y1, std::min(iy + 1, H - 1));
+                        }
+                    const int b0 = (x0 * 3) / 16 * 16, b1 = roundUp(x1 * 3 + 3, 16);
+                    const int rows = y1 - y0 + 1, chunks = (b1 - b0) / 16;
+                    int4 d = make_int4(0, 0, 0, 0);
+                    if (W3 % 16 == 0 && rows <= kWarpSmemRows && chunks * 16 <= kWarpSmemRowBytes && b1 <= W3)
+                        d = make_int4(b0, y0, rows, chunks);
+                    tl[(size_t)ty * C.tiles_x + tx] = d;
+                }
+            int4 *dt = nullptr;
+            if (devAlloc(h, &dt, tl.size(), false)) return bail(0);
+            if (cudaMemcpy(dt, tl.data(), tl.size() * sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess) { h->err = "tile table upload failed"; return bail(0); }
+            C.tiles = dt;
+        }
         C.gain_mode = 0; C.gain_map = nullptr; C.gain_scalar = 1.0;
         // weights
         C.mask_pitch = roundUp(C.rw, 64);
@@ -429,7 +463,7 @@ int pano_create(const pano_config *cfg, pano_handle *out)
         if (h->blender == PANO_BLEND_MULTIBAND) {
             for (int l = 0; l <= h->nb; ++l) {
                 const int lw = C.rw >> l, lh = C.rh >> l;
-                C.g_pitch[l] = roundUp(lw, 64);
+                C.g_pitch[l] = roundUp(lw + 24, 64);   // packed kernels over-read up to 18 samples past a row
                 C.g_plane[l] = (size_t)C.g_pitch[l] * lh;
                 C.g_slot[l] = 3 * C.g_plane[l];
                 int16_t *g = nullptr;
@@ -441,12 +475,22 @@ int pano_create(const pano_config *cfg, pano_handle *out)
     if (h->blender == PANO_BLEND_MULTIBAND) {
         for (int l = 1; l <= h->nb; ++l) {
             const int lw = h->pad_w >> l, lh = h->pad_h >> l;
-            T.out_pitch[l] = roundUp(lw, 64);
+            T.out_pitch[l] = roundUp(lw + 8, 64);
             T.out_plane[l] = (size_t)T.out_pitch[l] * lh;
             T.out_slot[l] = 3 * T.out_plane[l];
             int16_t *o = nullptr;
             if (devAlloc(h, &o, T.out_slot[l] * S)) return bail(0);
             T.outp[l] = o;
+        }
+    }
+    // which fast kernels this geometry admits (the generic ones cover everything else)
+    h->kc.warp_tiled = ((W * 3) % 16 == 0);
+    if (h->blender == PANO_BLEND_MULTIBAND) {
+        for (int l = 0; l < h->nb; ++l) {
+            bool ok = true;
+            for (int i = 0; i < n; ++i) ok = ok && ((T.cam[i].rw >> l) % 4 == 0) && ((T.cam[i].rh >> l) % 2 == 0) && ((T.cam[i].rw >> l) >= 16);
+            h->kc.pyrdown8[l] = ok;
+            h->kc.collapse8[l] = (h->nb - l >= 3);
         }
     }
     if (devAlloc(h, &h->dev, 1)) return bail(0);

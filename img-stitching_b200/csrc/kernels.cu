@@ -333,6 +333,305 @@ __global__ void __launch_bounds__(256) collapse_kernel(const PanoTables *__restr
     }
 }
 
+
+// ================================================================== packed (DP2A) kernels
+// The planar int16 pyramids arrive from memory as 32-bit words holding two neighbouring
+// samples.  IDP.2A (dp2a: two 16-bit x 8-bit products + accumulate) evaluates the separable
+// stencils directly on those words, so no sample is ever unpacked before filtering.
+#define COEF(lo, hi) (((hi) << 8) | (lo))
+
+// ---- K2': pyrDown, one thread = 8 x 2 outputs of one plane (sw % 4 == 0, sh % 2 == 0)
+__global__ void __launch_bounds__(256) pyrdown8_kernel(const PanoTables *__restrict__ T, int level)
+{
+    const int ncam = T->num_cams;
+    int z = blockIdx.z;
+    const int plane = z % 3; z /= 3;
+    const int cam = z % ncam, slot = z / ncam;
+    const CamTables &C = T->cam[cam];
+    const int sw = C.rw >> level, sh = C.rh >> level;
+    const int dw = sw >> 1, dh = sh >> 1;
+    const int ox = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    const int oy = (blockIdx.y * blockDim.y + threadIdx.y) * 2;
+    if (ox >= dw || oy >= dh) return;
+    const int sp = C.g_pitch[level], dp = C.g_pitch[level + 1];
+    const int16_t *src = C.g[level] + (size_t)slot * C.g_slot[level] + (size_t)plane * C.g_plane[level];
+    int16_t *dst = C.g[level + 1] + (size_t)slot * C.g_slot[level + 1] + (size_t)plane * C.g_plane[level + 1];
+    const int edge = dw - ox + 1;            // local index of the pair that starts at column sw (reflect-101)
+    int acc0[8], acc1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc0[j] = 0; acc1[j] = 0; }
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+        const int sy = reflect101(2 * oy - 2 + r, sh);
+        const int16_t *row = src + sy * sp + 2 * ox;
+        int q[10];
+        const uint4 a = *reinterpret_cast<const uint4 *>(row);
+        const uint4 b = *reinterpret_cast<const uint4 *>(row + 8);
+        q[1] = a.x; q[2] = a.y; q[3] = a.z; q[4] = a.w; q[5] = b.x; q[6] = b.y; q[7] = b.z; q[8] = b.w;
+        q[9] = *reinterpret_cast<const int *>(row + 16);          // rows carry >= 24 samples of padding
+        if (ox > 0) q[0] = *reinterpret_cast<const int *>(row - 2);
+        else q[0] = __byte_perm(q[2], q[1], 0x7610);              // (v[-2], v[-1]) := (v[2], v[1])
+        if (edge <= 9) {
+#pragma unroll
+            for (int k = 1; k <= 9; ++k)
+                if (k == edge) q[k] = q[k - 1];                   // v[sw] := v[sw-2]
+        }
+        const int k0 = (r == 0 || r == 4) ? 1 : ((r == 1 || r == 3) ? 4 : (r == 2 ? 6 : 0));
+        const int k1 = (r == 2 || r == 6) ? 1 : ((r == 3 || r == 5) ? 4 : (r == 4 ? 6 : 0));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int h = __dp2a_lo(q[j], COEF(1, 4), __dp2a_lo(q[j + 1], COEF(6, 4), __dp2a_lo(q[j + 2], COEF(1, 0), 0)));
+            if (k0) acc0[j] += k0 * h;
+            if (k1) acc1[j] += k1 * h;
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        if (oy + rr >= dh) break;
+        const int *a = rr ? acc1 : acc0;
+        int16_t *d = dst + (oy + rr) * dp + ox;
+        if (ox + 8 <= dw) {
+            uint4 o;
+            o.x = (uint16_t)((a[0] + 128) >> 8) | ((uint32_t)((a[1] + 128) >> 8) << 16);
+            o.y = (uint16_t)((a[2] + 128) >> 8) | ((uint32_t)((a[3] + 128) >> 8) << 16);
+            o.z = (uint16_t)((a[4] + 128) >> 8) | ((uint32_t)((a[5] + 128) >> 8) << 16);
+            o.w = (uint16_t)((a[6] + 128) >> 8) | ((uint32_t)((a[7] + 128) >> 8) << 16);
+            *reinterpret_cast<uint4 *>(d) = o;
+        } else {
+            for (int j = 0; j < 8 && ox + j < dw; ++j) d[j] = (short)((a[j] + 128) >> 8);
+        }
+    }
+}
+
+// ---- pyrUp of one coarse row segment: coarse columns k0..k0+3 -> 8 fine columns (before the
+// vertical pass).  k0 % 4 == 0, cw % 4 == 0.
+__device__ __forceinline__ void up_row8(const int16_t *__restrict__ row, int k0, int cw, int h[8])
+{
+    const uint2 p = *reinterpret_cast<const uint2 *>(row + k0);
+    const int P0 = p.x, P1 = p.y;
+    const int Pm = k0 > 0 ? *reinterpret_cast<const int *>(row + k0 - 2) : P0;              // c[-1] := c[1]
+    const int P2 = k0 + 4 < cw ? *reinterpret_cast<const int *>(row + k0 + 4) : (P1 >> 16);  // c[cw] := c[cw-1]
+    h[0] = __dp2a_lo(P0, COEF(6, 1), __dp2a_lo(Pm, COEF(0, 1), 0));
+    h[1] = __dp2a_lo(P0, COEF(4, 4), 0);
+    h[2] = __dp2a_lo(P0, COEF(1, 6), __dp2a_lo(P1, COEF(1, 0), 0));
+    h[3] = __dp2a_lo(P0, COEF(0, 4), __dp2a_lo(P1, COEF(4, 0), 0));
+    h[4] = __dp2a_lo(P1, COEF(6, 1), __dp2a_lo(P0, COEF(0, 1), 0));
+    h[5] = __dp2a_lo(P1, COEF(4, 4), 0);
+    h[6] = __dp2a_lo(P1, COEF(1, 6), __dp2a_lo(P2, COEF(1, 0), 0));
+    h[7] = __dp2a_lo(P1, COEF(0, 4), __dp2a_lo(P2, COEF(4, 0), 0));
+}
+
+// 8 x 2 fine block (rows 2m, 2m+1; columns 2k0..2k0+7) of pyrUp(plane)
+__device__ __forceinline__ void pyrup_8x2(const int16_t *__restrict__ plane, int pitch, int cw, int ch, int k0, int m,
+                                          int up[16])
+{
+    int ha[8], hb[8], hc[8];
+    up_row8(plane + up_index(m - 1, ch) * pitch, k0, cw, ha);
+    up_row8(plane + m * pitch, k0, cw, hb);
+    up_row8(plane + up_index(m + 1, ch) * pitch, k0, cw, hc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        up[j] = (ha[j] + 6 * hb[j] + hc[j] + 32) >> 6;
+        up[8 + j] = (hb[j] + hc[j] + 8) >> 4;          // == (4*(hb+hc) + 32) >> 6
+    }
+}
+
+__device__ __forceinline__ void unpack8(const uint4 v, int o[8])
+{
+    o[0] = (short)(v.x & 0xffff); o[1] = (int)v.x >> 16;
+    o[2] = (short)(v.y & 0xffff); o[3] = (int)v.y >> 16;
+    o[4] = (short)(v.z & 0xffff); o[5] = (int)v.z >> 16;
+    o[6] = (short)(v.w & 0xffff); o[7] = (int)v.w >> 16;
+}
+
+// ---- K3': blend + collapse, one thread = 8 x 2 pixels of ONE plane (threadIdx.z = plane).
+// Cameras whose 16 weights are all zero contribute exactly nothing ((short)(lap*0) == 0,
+// w_sum + 0 == w_sum) and are skipped before any of their pyramid data is touched.
+// Level 0 stages the three planes through shared memory so the interleaved 8-bit panorama
+// leaves in aligned 8-byte stores.
+template <bool kLevel0>
+__global__ void __launch_bounds__(384) collapse8_kernel(const PanoTables *__restrict__ T, int L, uint8_t *__restrict__ pano)
+{
+    __shared__ __align__(16) uint8_t tile[8][256 * 3];
+    const int plane = threadIdx.z;
+    const int X0 = (blockIdx.x * 32 + threadIdx.x) * 8, Y0 = (blockIdx.y * 4 + threadIdx.y) * 2;
+    const int slot = blockIdx.z;
+    const int Wf = T->pad_w >> L, Hf = T->pad_h >> L;
+    const bool active = X0 < Wf && Y0 < Hf;
+    int res[16];
+    float wsum[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { res[j] = 0; wsum[j] = 0.f; }
+    if (active) {
+        int acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = 0;
+        const int ncam = T->num_cams;
+        for (int i = 0; i < ncam; ++i) {
+            const CamTables &C = T->cam[i];
+            const int x = X0 - (C.rx >> L), y = Y0 - (C.ry >> L);
+            const int fw = C.rw >> L, fh = C.rh >> L;
+            if ((unsigned)x >= (unsigned)fw || (unsigned)y >= (unsigned)fh) continue;
+            float w[16];
+            if (kLevel0 && !C.use_wt0) {
+                const uint8_t *mrow = C.mask0 + y * C.mask_pitch + x;
+                const uint2 a = *reinterpret_cast<const uint2 *>(mrow);
+                const uint2 b = *reinterpret_cast<const uint2 *>(mrow + C.mask_pitch);
+                if ((a.x | a.y | b.x | b.y) == 0u) continue;
+                const uint32_t mw[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    w[j] = __fmul_rn((float)((mw[j >> 2] >> (8 * (j & 3))) & 0xffu), 1.f / 255.f);
+            } else {
+                const float *wrow = C.wt[L] + y * C.wt_pitch[L] + x;
+                const float4 a0 = *reinterpret_cast<const float4 *>(wrow), a1 = *reinterpret_cast<const float4 *>(wrow + 4);
+                const float4 b0 = *reinterpret_cast<const float4 *>(wrow + C.wt_pitch[L]);
+                const float4 b1 = *reinterpret_cast<const float4 *>(wrow + C.wt_pitch[L] + 4);
+                w[0] = a0.x; w[1] = a0.y; w[2] = a0.z; w[3] = a0.w; w[4] = a1.x; w[5] = a1.y; w[6] = a1.z; w[7] = a1.w;
+                w[8] = b0.x; w[9] = b0.y; w[10] = b0.z; w[11] = b0.w; w[12] = b1.x; w[13] = b1.y; w[14] = b1.z; w[15] = b1.w;
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) any |= (w[j] != 0.f);
+                if (!any) continue;
+            }
+            int up[16], fine[16];
+            pyrup_8x2(C.g[L + 1] + (size_t)slot * C.g_slot[L + 1] + (size_t)plane * C.g_plane[L + 1], C.g_pitch[L + 1],
+                      fw >> 1, fh >> 1, x >> 1, y >> 1, up);
+            const int16_t *f = C.g[L] + (size_t)slot * C.g_slot[L] + (size_t)plane * C.g_plane[L] + y * C.g_pitch[L] + x;
+            unpack8(*reinterpret_cast<const uint4 *>(f), fine);
+            unpack8(*reinterpret_cast<const uint4 *>(f + C.g_pitch[L]), fine + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int lap = sat_s16(fine[j] - up[j]);
+                acc[j] += trunc_s16(__fmul_rn((float)lap, w[j]));
+                wsum[j] = __fadd_rn(wsum[j], w[j]);
+            }
+        }
+        int up[16];
+        pyrup_8x2(T->outp[L + 1] + (size_t)slot * T->out_slot[L + 1] + (size_t)plane * T->out_plane[L + 1],
+                  T->out_pitch[L + 1], Wf >> 1, Hf >> 1, X0 >> 1, Y0 >> 1, up);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int a = wrap_s16(acc[j]);
+            const int nrm = a == 0 ? 0 : trunc_s16(__fdiv_rn((float)a, __fadd_rn(wsum[j], 1e-5f)));
+            res[j] = sat_s16(up[j] + nrm);
+        }
+    }
+    if (!kLevel0) {
+        if (!active) return;
+        int16_t *o = T->outp[L] + (size_t)slot * T->out_slot[L] + (size_t)plane * T->out_plane[L] + Y0 * T->out_pitch[L] + X0;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int *v = res + 8 * r;
+            uint4 q;
+            q.x = (uint16_t)v[0] | ((uint32_t)v[1] << 16); q.y = (uint16_t)v[2] | ((uint32_t)v[3] << 16);
+            q.z = (uint16_t)v[4] | ((uint32_t)v[5] << 16); q.w = (uint16_t)v[6] | ((uint32_t)v[7] << 16);
+            *reinterpret_cast<uint4 *>(o + r * T->out_pitch[L]) = q;
+        }
+        return;
+    }
+    // level 0: mask (dst_w > 1e-5), saturate to 8 bits, interleave through shared memory
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int v = wsum[j] > 1e-5f ? sat_u8(res[j]) : 0;
+        tile[threadIdx.y * 2 + (j >> 3)][(threadIdx.x * 8 + (j & 7)) * 3 + plane] = (uint8_t)v;
+    }
+    __syncthreads();
+    const int tid = (threadIdx.z * 4 + threadIdx.y) * 32 + threadIdx.x;   // 0..383: one 16-byte chunk each
+    const int row = tid / 48, col = (tid % 48) * 16;
+    const int Y = blockIdx.y * 8 + row - T->cut_y;
+    if ((unsigned)Y >= (unsigned)T->cut_h) return;
+    const int xbyte = (blockIdx.x * 256 - T->cut_x) * 3 + col;            // byte offset inside the output row
+    const int row_bytes = T->cut_w * 3;
+    uint8_t *orow = pano + ((size_t)slot * T->cut_h + Y) * (size_t)row_bytes;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        const int b0 = xbyte + 8 * hh;
+        const uint8_t *s = &tile[row][col + 8 * hh];
+        if (b0 >= 0 && b0 + 8 <= row_bytes && ((reinterpret_cast<uintptr_t>(orow + b0) & 7) == 0)) {
+            *reinterpret_cast<uint2 *>(orow + b0) = *reinterpret_cast<const uint2 *>(s);
+        } else {
+            for (int k = 0; k < 8; ++k)
+                if (b0 + k >= 0 && b0 + k < row_bytes) orow[b0 + k] = s[k];
+        }
+    }
+}
+
+// ---- K1': rotation warp with the source footprint of each 128 x 8 output tile staged in
+// shared memory (coalesced 16-byte loads), then gathered with bank-conflict-free byte reads.
+template <bool kMap64>
+__global__ void __launch_bounds__(256) warp_tile_kernel(const PanoTables *__restrict__ T, const uint8_t *__restrict__ frames)
+{
+    __shared__ __align__(16) uint8_t sm[kWarpSmemRows * kWarpSmemRowBytes];
+    const int ncam = T->num_cams;
+    const int cam = blockIdx.z % ncam, slot = blockIdx.z / ncam;
+    const CamTables &C = T->cam[cam];
+    if ((int)blockIdx.x >= C.tiles_x || (int)blockIdx.y >= C.tiles_y) return;
+    const int W = T->src_w, H = T->src_h, W3 = W * 3;
+    const uint8_t *src = frames + ((size_t)slot * ncam + cam) * ((size_t)W3 * H);
+    const int4 td = __ldg(C.tiles + blockIdx.y * C.tiles_x + blockIdx.x);   // {xbyte0, y0, rows, chunks}
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int stride = td.w * 16;
+    if (td.z > 0) {
+        const int total = td.z * td.w;
+        for (int i = tid; i < total; i += 256) {
+            const int r = i / td.w, c = i - r * td.w;
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)(td.y + r) * W3 + td.x) + c);
+            *reinterpret_cast<uint4 *>(sm + r * stride + c * 16) = v;
+        }
+    }
+    __syncthreads();
+    const int X = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int Y = blockIdx.y * 8 + threadIdx.y;
+    if (X >= C.rw || Y >= C.rh) return;
+    uint32_t sx[4], sy[4];
+    if (kMap64) {
+        const uint2 *m = C.map64 + (size_t)Y * C.map_pitch + X;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint2 e = __ldg(m + j);
+            sx[j] = e.x; sy[j] = e.y;
+        }
+    } else {
+        const uint4 e = __ldg(reinterpret_cast<const uint4 *>(C.map32 + (size_t)Y * C.map_pitch + X));
+        sx[0] = e.x & 0xffffu; sy[0] = e.x >> 16;
+        sx[1] = e.y & 0xffffu; sy[1] = e.y >> 16;
+        sx[2] = e.z & 0xffffu; sy[2] = e.z >> 16;
+        sx[3] = e.w & 0xffffu; sy[3] = e.w >> 16;
+    }
+    float g[4] = {1.f, 1.f, 1.f, 1.f};
+    if (C.gain_mode == 1) {
+        const float4 gv = __ldg(reinterpret_cast<const float4 *>(C.gain_map + (size_t)Y * C.map_pitch + X));
+        g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
+    }
+    short px[3][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int v[3];
+        if (td.z > 0) {
+            const int ix = sx[j] >> 5, fx = sx[j] & 31, iy = sy[j] >> 5, fy = sy[j] & 31;
+            const int ix1 = min(ix + 1, W - 1), iy1 = min(iy + 1, H - 1);
+            const uint8_t *r0 = sm + (iy - td.y) * stride - td.x, *r1 = sm + (iy1 - td.y) * stride - td.x;
+            const int w00 = (32 - fy) * (32 - fx), w01 = (32 - fy) * fx, w10 = fy * (32 - fx), w11 = fy * fx;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                v[c] = (w00 * r0[ix * 3 + c] + w01 * r0[ix1 * 3 + c] + w10 * r1[ix * 3 + c] + w11 * r1[ix1 * 3 + c] + 512) >> 10;
+        } else {
+            bilinear_bgr(src, W, H, sx[j], sy[j], v);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) px[c][j] = (short)apply_gain(v[c], C.gain_mode, g[j], C.gain_scalar);
+    }
+    int16_t *dst = C.g[0] + (size_t)slot * C.g_slot[0] + (size_t)Y * C.g_pitch[0] + X;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        uint2 o;
+        o.x = (uint16_t)px[c][0] | ((uint32_t)(uint16_t)px[c][1] << 16);
+        o.y = (uint16_t)px[c][2] | ((uint32_t)(uint16_t)px[c][3] << 16);
+        *reinterpret_cast<uint2 *>(dst + (size_t)c * C.g_plane[0]) = o;
+    }
+}
+
 // ------------------------------------------------------------------ K4: single-pass blenders
 // FeatherBlender (stitching_detailed.cpp:865-869) and Blender::NO (ocvstitcher.hpp:1190-1191):
 // no pyramid, so warp + gain + weight + accumulate + normalise + 8-bit + crop is ONE gather per
@@ -395,8 +694,20 @@ inline dim3 grid2d(int w, int h, dim3 block, int z) { return dim3((w + block.x -
 
 }  // namespace
 
-void launch_warp(const PanoTables *dev, const PanoTables &host, const uint8_t *frames, int nslots, cudaStream_t stream)
+void launch_warp(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, const uint8_t *frames, int nslots,
+                 cudaStream_t stream)
 {
+    if (kc.warp_tiled) {
+        int tx = 0, ty = 0;
+        for (int i = 0; i < host.num_cams; ++i) {
+            tx = max(tx, host.cam[i].tiles_x);
+            ty = max(ty, host.cam[i].tiles_y);
+        }
+        const dim3 block(32, 8), grid(tx, ty, host.num_cams * nslots);
+        if (host.cam[0].map64) warp_tile_kernel<true><<<grid, block, 0, stream>>>(dev, frames);
+        else warp_tile_kernel<false><<<grid, block, 0, stream>>>(dev, frames);
+        return;
+    }
     int maxw = 0, maxh = 0;
     for (int i = 0; i < host.num_cams; ++i) {
         maxw = max(maxw, host.cam[i].rw);
@@ -408,7 +719,8 @@ void launch_warp(const PanoTables *dev, const PanoTables &host, const uint8_t *f
     else warp_kernel<false><<<grid, block, 0, stream>>>(dev, frames);
 }
 
-void launch_pyrdown(const PanoTables *dev, const PanoTables &host, int level, int nslots, cudaStream_t stream)
+void launch_pyrdown(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, int level, int nslots,
+                    cudaStream_t stream)
 {
     int maxw = 0, maxh = 0;
     for (int i = 0; i < host.num_cams; ++i) {
@@ -416,6 +728,11 @@ void launch_pyrdown(const PanoTables *dev, const PanoTables &host, int level, in
         maxh = max(maxh, ((host.cam[i].rh >> level) + 1) / 2);
     }
     const dim3 block(32, 8);
+    if (kc.pyrdown8[level]) {
+        const dim3 grid8 = grid2d((maxw + 7) / 8, (maxh + 1) / 2, block, host.num_cams * nslots * 3);
+        pyrdown8_kernel<<<grid8, block, 0, stream>>>(dev, level);
+        return;
+    }
     const dim3 grid = grid2d((maxw + 3) / 4, (maxh + 1) / 2, block, host.num_cams * nslots * 3);
     pyrdown_kernel<<<grid, block, 0, stream>>>(dev, level);
 }
@@ -427,8 +744,16 @@ void launch_coarsest(const PanoTables *dev, const PanoTables &host, uint8_t *pan
     coarsest_kernel<<<grid, block, 0, stream>>>(dev, pano);
 }
 
-void launch_collapse(const PanoTables *dev, const PanoTables &host, int level, uint8_t *pano, int nslots, cudaStream_t stream)
+void launch_collapse(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, int level, uint8_t *pano,
+                     int nslots, cudaStream_t stream)
 {
+    if (kc.collapse8[level]) {
+        const int wf = host.pad_w >> level, hf = host.pad_h >> level;
+        const dim3 block(32, 4, 3), grid((wf + 255) / 256, (hf + 7) / 8, nslots);
+        if (level == 0) collapse8_kernel<true><<<grid, block, 0, stream>>>(dev, level, pano);
+        else collapse8_kernel<false><<<grid, block, 0, stream>>>(dev, level, pano);
+        return;
+    }
     const dim3 block(32, 8);
     const dim3 grid = grid2d(host.pad_w >> (level + 1), host.pad_h >> (level + 1), block, nslots);
     collapse_kernel<<<grid, block, 0, stream>>>(dev, level, pano);

@@ -22,6 +22,10 @@ struct CamTables {
     const uint32_t *map32;
     const uint2 *map64;
     int map_pitch;
+    // per 128x8 output tile: source bounding box of the gather {x byte offset (16B aligned),
+    // first row, rows, 16-byte chunks per row}; rows == 0 -> tile gathers straight from global
+    const int4 *tiles;
+    int tiles_x, tiles_y;
     // exposure gain: mode 0 off, 1 per-pixel float map (feed-rect layout, pitch = map_pitch),
     // 2 scalar (double, GainCompensator)
     int gain_mode;
@@ -56,10 +60,22 @@ struct PanoTables {
 };
 
 // launchers (kernels.cu) -- all asynchronous on `stream`
-void launch_warp(const PanoTables *dev, const PanoTables &host, const uint8_t *frames, int nslots, cudaStream_t stream);
-void launch_pyrdown(const PanoTables *dev, const PanoTables &host, int level, int nslots, cudaStream_t stream);
+constexpr int kWarpTileW = 128, kWarpTileH = 8;       // output pixels per warp-kernel block
+constexpr int kWarpSmemRows = 24, kWarpSmemRowBytes = 640;
+
+struct KernelChoice {
+    bool warp_tiled = false;                 // staged-gather warp kernel usable (row bytes % 16 == 0)
+    bool pyrdown8[kMaxLevels] = {};          // packed 8-wide pyrDown usable at this source level
+    bool collapse8[kMaxLevels] = {};         // packed 8x2 collapse usable at this level
+};
+
+void launch_warp(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, const uint8_t *frames, int nslots,
+                 cudaStream_t stream);
+void launch_pyrdown(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, int level, int nslots,
+                    cudaStream_t stream);
 void launch_coarsest(const PanoTables *dev, const PanoTables &host, uint8_t *pano, int nslots, cudaStream_t stream);
-void launch_collapse(const PanoTables *dev, const PanoTables &host, int level, uint8_t *pano, int nslots, cudaStream_t stream);
+void launch_collapse(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, int level, uint8_t *pano,
+                     int nslots, cudaStream_t stream);
 void launch_direct_blend(const PanoTables *dev, const PanoTables &host, int blender, const uint8_t *frames,
                          uint8_t *pano, int nslots, cudaStream_t stream);
 

@@ -1,0 +1,161 @@
+"""Pins the oracle (oracle/pano_oracle.c) LIVE against cv2 -- the reference's own OpenCV classes --
+on random + adversarial inputs.  Skipped where cv2 is not importable; the committed fixtures in
+tests/golden/ (test_oracle_golden.py) carry the same pin without cv2."""
+import numpy as np
+import pytest
+
+import util
+from golden import calib
+from oracle import oracle as orc, cv2_reference as ref  # noqa: F401  (cv2_reference imports cv2)
+
+cv2 = pytest.importorskip("cv2")
+
+
+def eq(a, b, what):
+    assert np.array_equal(a, b), util.report(what, a, b)
+
+
+@pytest.mark.parametrize("name,kind", [("spherical", 0), ("cylindrical", 1)])
+def test_rotation_warper_maps(name, kind):
+    Ks, Rs, sc = calib.rig("2222", 960)
+    for K, R in zip(Ks, Rs):
+        w = cv2.PyRotationWarper(name, np.float32(sc))
+        assert tuple(w.warpRoi((960, 540), K, R)) == orc.warp_roi(kind, np.float32(sc), K, R, 960, 540)
+        _, xm, ym = w.buildMaps((960, 540), K, R)
+        _, oxm, oym = orc.build_maps(kind, np.float32(sc), K, R, 960, 540)
+        assert np.array_equal(xm, oxm) and np.array_equal(ym, oym)
+
+
+def test_remap_variants_and_convert_maps():
+    rng = np.random.default_rng(1)
+    src = rng.integers(0, 256, (97, 131, 3), np.uint8)
+    xm = (rng.random((80, 120), np.float32) * 180 - 25).astype(np.float32)
+    ym = (rng.random((80, 120), np.float32) * 150 - 25).astype(np.float32)
+    xm[0, :10] = -1; ym[0, :10] = -1
+    xm[1, :5] = 1e6; ym[1, :5] = -1e7; xm[2, :5] = 5e9; xm[3, :3] = 40000; ym[3, :3] = -40000
+    eq(cv2.remap(src, xm, ym, cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT), orc.remap_bilinear_u8(src, xm, ym, "reflect"), "linear reflect")
+    eq(cv2.remap(src, xm, ym, cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT), orc.remap_bilinear_u8(src, xm, ym, "const"), "linear const")
+    m = rng.integers(0, 256, (97, 131), np.uint8)
+    eq(cv2.remap(m, xm, ym, cv2.INTER_NEAREST, borderMode=cv2.BORDER_CONSTANT), orc.remap_nearest_u8(m, xm, ym), "nearest")
+    eq(cv2.remap(src, xm, ym, cv2.INTER_CUBIC), orc.remap_cubic_u8(src, xm, ym), "cubic")
+    ixy, fr = cv2.convertMaps(xm, ym, cv2.CV_16SC2)
+    oixy, ofr = orc.convert_maps(xm, ym)
+    eq(ixy, oixy, "convertMaps ixy"); eq(fr, ofr, "convertMaps frac")
+
+
+@pytest.mark.parametrize("sw,sh,dw,dh,c", [(131, 97, 64, 40, 3), (1920, 1080, 960, 540, 4), (1782, 889, 1920, 1080, 3),
+                                           (100, 100, 257, 33, 3), (640, 360, 1920, 1080, 4), (960, 540, 1920, 1080, 3),
+                                           (1920, 1080, 720, 405, 3), (50, 60, 50, 60, 3)])
+def test_resize_bilinear(sw, sh, dw, dh, c):
+    s = np.random.default_rng(sw + dw).integers(0, 256, (sh, sw, c), np.uint8)
+    eq(cv2.resize(s, (dw, dh)), orc.resize_bilinear_u8(s, (dw, dh)), "resize")
+
+
+@pytest.mark.parametrize("w,h", [(64, 32), (33, 17), (5, 3), (2, 2), (1, 1), (128, 7), (57, 33)])
+def test_pyramids_s16(w, h):
+    rng = np.random.default_rng(w * 100 + h)
+    for lo, hi in ((-600, 600), (-32768, 32767)):
+        s = rng.integers(lo, hi, (h, w, 3)).astype(np.int16)
+        eq(cv2.pyrDown(s), orc.pyrdown_s16(s), "pyrDown")
+        eq(cv2.pyrUp(s), orc.pyrup_s16(s, (2 * w, 2 * h)), "pyrUp even")
+        if w > 1 and h > 1:
+            eq(cv2.pyrUp(s, dstsize=(2 * w - 1, 2 * h - 1)), orc.pyrup_s16(s, (2 * w - 1, 2 * h - 1)), "pyrUp odd")
+
+
+def test_float_pyrdown_is_within_one_ulp():
+    f = np.random.default_rng(0).random((132, 228), np.float32)
+    a, b = cv2.pyrDown(f), orc.pyrdown_f32(f)
+    assert np.max(np.abs(a - b)) <= np.spacing(np.float32(1.0))     # documented: not bit-reproducible
+
+
+def _blend_inputs():
+    corners = [(-100, 20), (60, 33), (230, 25)]
+    sizes = [(200, 150), (210, 140), (190, 155)]
+    imgs = [util.synth_frame(s[1], s[0], 40 + i).astype(np.int16) for i, s in enumerate(sizes)]
+    masks = []
+    for s in sizes:
+        m = np.zeros((s[1], s[0]), np.uint8)
+        m[5:-7, 10:-4] = 255
+        masks.append(cv2.GaussianBlur(m, (9, 9), 0))
+    return corners, sizes, imgs, masks
+
+
+@pytest.mark.parametrize("nb", [1, 3, 5, 7])
+def test_multiband_blender(nb):
+    corners, sizes, imgs, masks = _blend_inputs()
+    roi = cv2.detail.resultRoi(corners=corners, sizes=sizes)
+    bl = cv2.detail_MultiBandBlender(0, nb)
+    bl.prepare(roi)
+    for i in range(3):
+        bl.feed(imgs[i], masks[i], corners[i])
+    r, rm = bl.blend(None, None)
+    nbe, pwh = orc.mb_prepare(roi, nb)
+    ew = []
+    for i in range(3):
+        _, bd = orc.mb_feed_rect(roi, pwh, nbe, corners[i], sizes[i])
+        ws = [cv2.copyMakeBorder(masks[i].astype(np.float32) * np.float32(1 / 255.), bd[0], bd[1], bd[2], bd[3], cv2.BORDER_CONSTANT)]
+        for _ in range(nbe):
+            ws.append(cv2.pyrDown(ws[-1]))
+        ew.append(ws)
+    o, om = orc.multiband_blend(imgs, masks, corners, sizes, nb, ew)
+    eq(r, o, "multiband"); eq(rm, om, "multiband mask")
+
+
+def test_feather_no_blend_and_gain():
+    corners, sizes, imgs, masks = _blend_inputs()
+    roi = cv2.detail.resultRoi(corners=corners, sizes=sizes)
+    for sharp in (0.02, 0.1, 1 / 37.3):
+        fb = cv2.detail_FeatherBlender(sharp)
+        fb.prepare(roi)
+        for i in range(3):
+            fb.feed(imgs[i], masks[i], corners[i])
+        r, rm = fb.blend(None, None)
+        o, om = orc.feather_blend(imgs, [ref._feather_weight(m, sharp) for m in masks], corners, sizes)
+        eq(r, o, "feather"); eq(rm, om, "feather mask")
+    nbl = cv2.detail.Blender_createDefault(cv2.detail.Blender_NO)
+    nbl.prepare(roi)
+    for i in range(3):
+        nbl.feed(imgs[i], masks[i], corners[i])
+    r, rm = nbl.blend(None, None)
+    o, om = orc.no_blend(imgs, masks, corners, sizes)
+    eq(r, o, "no blend"); eq(rm, om, "no blend mask")
+    img = util.synth_frame(50, 60, 3)
+    gc = cv2.detail_BlocksGainCompensator(32, 32, 1)
+    gains = [(np.random.default_rng(2).random((2, 2)).astype(np.float32) + 0.5)]
+    gc.setMatGains(gains)
+    got = gc.apply(0, (0, 0), img.copy(), np.full((50, 60), 255, np.uint8))
+    eq(got, orc.gain_apply_u8(img, cv2.resize(gains[0], (60, 50), interpolation=cv2.INTER_LINEAR)), "blocks gain")
+    gs = cv2.detail_GainCompensator(1)
+    gs.setMatGains([np.array([[1.2345]], np.float64)])
+    eq(gs.apply(0, (0, 0), img.copy(), np.full((50, 60), 255, np.uint8)), orc.gain_apply_u8(img, None, 1.2345), "scalar gain")
+
+
+def test_undistort_maps_fixed_point_identical():
+    cam = calib.CAM_LIJING_390_FOV60_1920
+    K = np.array(cam["K"]).reshape(3, 3)
+    D = np.array(cam["distorParams"])
+    newK, mx, my = ref.undistort_tables(K, D, (1920, 1080))
+    ox, oy = orc.init_undistort_map(K, D, newK, 1920, 1080)
+    assert (mx != ox).sum() + (my != oy).sum() <= 16          # AVX2/FMA path of cv2: a few 1-ulp floats
+    a, af = cv2.convertMaps(mx, my, cv2.CV_16SC2)
+    b, bf = orc.convert_maps(ox, oy)
+    assert np.array_equal(a, b) and np.array_equal(af, bf)    # what remap consumes is identical
+
+
+def test_full_call_sequence_matches_cv2_reference():
+    """oracle/compose.process == cv2-driven ocvStitcher::process restatement (GraphCut masks)."""
+    Ks, Rs, sc = calib.rig("2222", 480)
+    imgs = util.synth_set(4, 270, 480, 3)
+    t = ref.init_seam(imgs, Ks, Rs, sc)
+    from oracle import compose
+    ot = compose.build_tables(Ks, Rs, sc, (480, 270))
+    assert ot.corners == t.corners and ot.sizes == t.sizes and ot.dst_roi == tuple(t.dst_roi)
+    for a, b in zip(ot.warped_masks, t.warped_masks):
+        eq(a, b, "warped mask")
+    ot.blend_masks = t.blend_masks
+    cut = ref.default_cut(t.dst_roi, 200)
+    want = ref.process(t, imgs, "multiband", 4, cut=cut)
+    got = compose.process(ot, imgs, "multiband", 4, cut=cut)
+    d = np.abs(got.astype(int) - want.astype(int))
+    assert d.max() <= 1, util.report("compose", got, want)     # own float weight pyramid: <= 1 LSB
+    eq(ref.process(t, imgs, "no", cut=cut), compose.process(ot, imgs, "no", cut=cut), "no-blend compose")
