@@ -62,9 +62,9 @@ def rig(name, width):
     return out_k, Rs, float(np.float32(d["scale"]) * f)
 
 
-def ring(n, width, height, hfov_deg, step_deg):
+def ring(n, width, height, hfov_deg, step_deg, focal=None):
     """Synthetic cylindrical ring of BASELINE config 4: R_i = R_y((i-(n-1)/2)*step)."""
-    f = np.float32((width / 2.0) / np.tan(np.radians(hfov_deg) / 2.0))
+    f = np.float32(focal if focal is not None else (width / 2.0) / np.tan(np.radians(hfov_deg) / 2.0))
     K = np.array([[f, 0, width / 2.0], [0, f, height / 2.0], [0, 0, 1]], np.float32)
     Rs = []
     for i in range(n):

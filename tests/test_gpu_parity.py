@@ -235,6 +235,48 @@ def test_config1_full_size_vs_oracle_and_properties():
     assert (got[hole] == 0).all()
 
 
+def test_config3_shape_gain_feather_and_no_blend():
+    """BASELINE config 3: imx424 rig x3 (1920x1080), warp -> block-gain apply on 8U -> 16S ->
+    FeatherBlender(sharpness = 1/blend_width); plus Blender::NO (what the yaml's strength 0 selects)."""
+    Ks, Rs, scale = calib.rig("424", 1920)
+    t = compose.build_tables(Ks, Rs, scale, (1920, 1080), "spherical")
+    t.blend_masks = util.soft_masks(t)
+    assert t.dst_roi[2:] == (6383, 1131)                       # SURVEY 8d geometry
+    bw = compose.blend_width(t.dst_roi, 5.0)
+    sharp = float(np.float32(1.0) / np.float32(bw))
+    gains = []
+    for i, (w, h) in enumerate(t.sizes):                       # smooth per-pixel gain tables (static after init)
+        yy, xx = np.mgrid[0:h, 0:w]
+        gains.append((0.85 + 0.3 * ((xx * (i + 3) + yy * 7) % 997) / 997.0).astype(np.float32))
+    imgs = util.synth_set(4, 1080, 1920, 31)
+    fw = [panob200.capi.host_feather_weight(m, sharp) for m in t.blend_masks]
+    st = make(Ks, Rs, scale, 1920, 1080, "spherical", "feather", 0, sharp=sharp)
+    assert st.initTables(t.blend_masks) == 0, st.last_error
+    st.set_gain_maps(gains)
+    t.gain_maps = gains
+    assert_equal("config3 gain+feather", st.process(imgs), compose.process(t, imgs, "feather", feather_weights=fw))
+    st = make(Ks, Rs, scale, 1920, 1080, "spherical", "no", 0)
+    assert st.initTables(t.blend_masks) == 0, st.last_error
+    t.gain_maps = None
+    assert_equal("config3 no-blend", st.process(imgs), compose.process(t, imgs, "no"))
+
+
+def test_config4_full_size_8cam_4k_cylindrical_7_bands():
+    """BASELINE config 4 on ONE GPU: 8 x 3840x2160, cylindrical ring, 7 bands, 64-bit map entries."""
+    Ks, Rs, scale = calib.ring(8, 3840, 2160, 65.2, 40.0, focal=3000.0)
+    t = compose.build_tables(Ks, Rs, scale, (3840, 2160), "cylindrical")
+    t.blend_masks = util.soft_masks(t)
+    assert t.dst_roi[2:] == (18076, 2160) and t.corners[0] == (-9038, -1080)        # SURVEY 8d
+    st = make(Ks, Rs, scale, 3840, 2160, "cylindrical", "multiband", 7)
+    assert st.initTables(t.blend_masks) == 0, st.last_error
+    nb, padded, rects = st.blend_geometry()
+    assert nb == 7 and padded == (18176, 2176)
+    imgs = [util.synth_frame(2160, 3840, 400 + i, cell=64) for i in range(8)]
+    got = st.process(imgs)
+    assert_equal("config4 full", got, compose.process(t, imgs, "multiband", 7))
+    assert np.array_equal(st.process(imgs), got)               # idempotent
+
+
 # ------------------------------------------------------------------ nvCam front end
 
 def test_front_end_golden_bit_exact():
