@@ -12,3 +12,4 @@ from .capi import PanoError, build_library, library_path  # noqa: F401
 from .stitcher import ocvStitcher, StitcherConfig  # noqa: F401
 from .nvcam import nvCamFrontEnd  # noqa: F401
 from . import sharding  # noqa: F401
+from . import strips  # noqa: F401

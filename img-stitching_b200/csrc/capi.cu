@@ -54,6 +54,7 @@ struct pano_ctx {
     PanoTables *dev = nullptr;
     KernelChoice kc;
     bool tables_dirty = true;
+    int strip_x0 = 0, strip_x1 = 0;               // own dst columns (level 0, padded coords); full width = no split
     std::vector<void *> owned;                    // device allocations to free
     std::vector<void *> cam_mask0, cam_gain;      // per camera, re-uploadable
     std::vector<std::vector<void *>> cam_wt;      // per camera per level
@@ -236,38 +237,72 @@ double directBytes(const pano_ctx *h, int slots)
     return b * slots;
 }
 
-// one wave = up to max_batch frame-sets through the whole kernel chain
-int runWave(pano_ctx *h, const uint8_t *frames_dev, uint8_t *out_dev, int slots, cudaStream_t st)
+// The kernel chain is a sequence of PHASES (one wave = all phases for up to max_batch frame-sets):
+//   multiband:  p in [0, nb): (p == 0: warp) + pyrDown level p     -> produces g[p+1]
+//               p == nb: coarsest level                            -> produces out[nb]
+//               p in (nb, 2nb]: collapse level 2nb - p             -> produces out[L] / the panorama
+//   feather / no-blend: a single phase.
+// The strip split (pano_strip_*) runs them one at a time with halo exchanges in between.
+int phaseCount(const pano_ctx *h) { return h->blender == PANO_BLEND_MULTIBAND ? 2 * h->nb + 1 : 1; }
+
+int runPhase(pano_ctx *h, int p, const uint8_t *frames_dev, uint8_t *out_dev, int slots, cudaStream_t st)
 {
     Launch L{h, st};
     static const char *kDown[] = {"pyrdown_l0", "pyrdown_l1", "pyrdown_l2", "pyrdown_l3", "pyrdown_l4",
                                   "pyrdown_l5", "pyrdown_l6", "pyrdown_l7", "pyrdown_l8"};
     static const char *kCol[] = {"collapse_l0", "collapse_l1", "collapse_l2", "collapse_l3", "collapse_l4",
                                  "collapse_l5", "collapse_l6", "collapse_l7", "collapse_l8"};
+    const int nb = h->nb;
     if (h->blender != PANO_BLEND_MULTIBAND) {
         L.begin("direct_blend", directBytes(h, slots));
         launch_direct_blend(h->dev, h->host, h->blender, frames_dev, out_dev, slots, st);
         L.end();
-    } else {
-        L.begin("warp", warpBytes(h, slots));
-        launch_warp(h->dev, h->host, h->kc, frames_dev, slots, st);
-        L.end();
-        for (int l = 0; l < h->nb; ++l) {
-            L.begin(kDown[l], pyrdownBytes(h, l, slots));
-            launch_pyrdown(h->dev, h->host, h->kc, l, slots, st);
+    } else if (p < nb) {
+        if (p == 0) {
+            L.begin("warp", warpBytes(h, slots));
+            launch_warp(h->dev, h->host, h->kc, frames_dev, slots, st);
             L.end();
         }
-        L.begin("coarsest", collapseBytes(h, h->nb, slots));
+        L.begin(kDown[p], pyrdownBytes(h, p, slots));
+        launch_pyrdown(h->dev, h->host, h->kc, p, slots, st);
+        L.end();
+    } else if (p == nb) {
+        if (nb == 0) {
+            L.begin("warp", warpBytes(h, slots));
+            launch_warp(h->dev, h->host, h->kc, frames_dev, slots, st);
+            L.end();
+        }
+        L.begin("coarsest", collapseBytes(h, nb, slots));
         launch_coarsest(h->dev, h->host, out_dev, slots, st);
         L.end();
-        for (int l = h->nb - 1; l >= 0; --l) {
-            L.begin(kCol[l], collapseBytes(h, l, slots));
-            launch_collapse(h->dev, h->host, h->kc, l, out_dev, slots, st);
-            L.end();
-        }
+    } else {
+        const int l = 2 * nb - p;
+        L.begin(kCol[l], collapseBytes(h, l, slots));
+        launch_collapse(h->dev, h->host, h->kc, l, out_dev, slots, st);
+        L.end();
     }
+    return PANO_OK;
+}
+
+int runWave(pano_ctx *h, const uint8_t *frames_dev, uint8_t *out_dev, int slots, cudaStream_t st)
+{
+    const int np = phaseCount(h);
+    for (int p = 0; p < np; ++p)
+        if (runPhase(h, p, frames_dev, out_dev, slots, st)) return PANO_ERR;
     CK(h, cudaGetLastError());
     return PANO_OK;
+}
+
+// halo exchanged after phase p: kind (0 = camera pyramids g, 1 = collapsed pyramid out), level, columns
+bool phaseHalo(const pano_ctx *h, int p, int &kind, int &level, int &ncols)
+{
+    if (h->blender != PANO_BLEND_MULTIBAND) return false;
+    const int nb = h->nb;
+    if (p < nb) { kind = 0; level = p + 1; ncols = 2; return true; }
+    if (p == nb) { kind = 1; level = nb; ncols = 1; return nb > 0; }
+    const int l = 2 * nb - p;
+    kind = 1; level = l; ncols = 1;
+    return l >= 1;
 }
 
 int ensureStaging(pano_ctx *h)
@@ -367,6 +402,8 @@ int pano_create(const pano_config *cfg, pano_handle *out)
         }
     }
     T.nb = h->nb; T.pad_w = h->pad_w; T.pad_h = h->pad_h;
+    for (int l = 0; l < kMaxLevels; ++l) { T.win_lo[l] = 0; T.win_hi[l] = INT_MAX; }
+    h->strip_x0 = 0; h->strip_x1 = h->pad_w;
     if (cfg->cut[2] > 0 && cfg->cut[3] > 0) {
         T.cut_x = cfg->cut[0]; T.cut_y = cfg->cut[1]; T.cut_w = cfg->cut[2]; T.cut_h = cfg->cut[3];
     } else {
@@ -716,6 +753,71 @@ int pano_process_batch(pano_handle h, const uint8_t *frames_host, uint8_t *out_h
     CK(h, cudaStreamSynchronize(h->s_compute));
     CK(h, cudaStreamSynchronize(h->s_h2d));
     return PANO_OK;
+}
+
+int pano_strip_set_window(pano_handle h, int x0, int x1, int margin)
+{
+    if (!h) return PANO_ERR;
+    const int unit = 1 << h->nb;
+    if (x0 < 0 || x1 > h->pad_w || x0 >= x1 || x0 % unit || x1 % unit || margin < 0)
+        return fail(h, "pano_strip_set_window: [%d,%d) must be a non-empty multiple-of-%d range inside [0,%d)", x0, x1, unit, h->pad_w);
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());
+    h->strip_x0 = x0; h->strip_x1 = x1;
+    const bool full = (x0 == 0 && x1 == h->pad_w);
+    for (int l = 0; l <= h->nb; ++l) {
+        h->host.win_lo[l] = full ? 0 : std::max(0, x0 - margin) >> l;
+        h->host.win_hi[l] = full ? INT_MAX : ((std::min(h->pad_w, x1 + margin) + (1 << l) - 1) >> l);
+    }
+    h->tables_dirty = true;
+    return PANO_OK;
+}
+
+int pano_strip_phase_count(pano_handle h) { return h ? phaseCount(h) : 0; }
+
+int pano_strip_run_phase(pano_handle h, int phase, const uint8_t *frames_dev, uint8_t *pano_dev, void *stream)
+{
+    if (!h || phase < 0 || phase >= phaseCount(h) || !frames_dev || !pano_dev) return fail(h, "pano_strip_run_phase: bad argument");
+    CK(h, cudaSetDevice(h->device));
+    if (syncTables(h)) return PANO_ERR;
+    if (phase == 0) h->last_launches = 0;
+    if (runPhase(h, phase, frames_dev, pano_dev, 1, (cudaStream_t)stream)) return PANO_ERR;
+    CK(h, cudaGetLastError());
+    return PANO_OK;
+}
+
+size_t pano_strip_halo_bytes(pano_handle h, int phase)
+{
+    int kind, level, ncols;
+    if (!h || !phaseHalo(h, phase, kind, level, ncols)) return 0;
+    return halo_elems(h->host, kind, level, ncols) * sizeof(int16_t);
+}
+
+static int haloCopy(pano_handle h, int phase, int side, void *buf, void *stream, bool unpack)
+{
+    int kind, level, ncols;
+    if (!h || !buf || (side != 0 && side != 1) || !phaseHalo(h, phase, kind, level, ncols))
+        return fail(h, "pano_strip_halo: bad argument / no halo after phase %d", phase);
+    CK(h, cudaSetDevice(h->device));
+    if (syncTables(h)) return PANO_ERR;
+    const int lo = h->strip_x0 >> level, hi = h->strip_x1 >> level;
+    int col;
+    if (!unpack) col = side == 0 ? lo : hi - ncols;          // my own edge columns, for that neighbour
+    else col = side == 0 ? lo - ncols : hi;                  // the neighbour's edge columns, into my halo
+    launch_halo_copy(h->dev, h->host, kind, level, col, ncols, (int16_t *)buf, unpack, 0, (cudaStream_t)stream);
+    ++h->last_launches;
+    CK(h, cudaGetLastError());
+    return PANO_OK;
+}
+
+int pano_strip_halo_pack(pano_handle h, int phase, int side, void *buf_dev, void *stream)
+{
+    return haloCopy(h, phase, side, buf_dev, stream, false);
+}
+
+int pano_strip_halo_unpack(pano_handle h, int phase, int side, const void *buf_dev, void *stream)
+{
+    return haloCopy(h, phase, side, const_cast<void *>(buf_dev), stream, true);
 }
 
 int pano_profile_enable(pano_handle h, int on)

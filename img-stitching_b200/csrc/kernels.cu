@@ -36,6 +36,12 @@ __device__ __forceinline__ int up_index(int i, int n) { return i < 0 ? (n > 1 ? 
 // (short)(float) as x86 does it for in-range values: truncate toward zero, keep low 16 bits
 __device__ __forceinline__ int trunc_s16(float f) { return (int)(short)__float2int_rz(f); }
 
+// strip split: true when dst columns [c0, c1) of level l miss this rank's column window
+__device__ __forceinline__ bool outside_window(const PanoTables *__restrict__ T, int l, int c0, int c1)
+{
+    return c1 <= T->win_lo[l] || c0 >= T->win_hi[l];
+}
+
 // ------------------------------------------------------------------ K1: rotation warp
 // cv::remap(INTER_LINEAR, BORDER_REFLECT) of blender_warper->warp (ocvstitcher.hpp:1171)
 // + compensator->apply (stitching_detailed.cpp:841) + convertTo(CV_16S) (:1180)
@@ -72,6 +78,7 @@ __global__ void __launch_bounds__(256) warp_kernel(const PanoTables *__restrict_
     const int X = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int Y = blockIdx.y * blockDim.y + threadIdx.y;
     if (X >= C.rw || Y >= C.rh) return;
+    if (outside_window(T, 0, C.rx + blockIdx.x * blockDim.x * 4, C.rx + (blockIdx.x + 1) * blockDim.x * 4)) return;
     const int W = T->src_w, H = T->src_h;
     const uint8_t *src = frames + ((size_t)slot * ncam + cam) * ((size_t)W * H * 3);
     uint32_t sx[4], sy[4];
@@ -145,6 +152,10 @@ __global__ void __launch_bounds__(256) pyrdown_kernel(const PanoTables *__restri
     const int ox = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int oy = (blockIdx.y * blockDim.y + threadIdx.y) * 2;
     if (ox >= dw || oy >= dh) return;
+    {
+        const int c0 = (C.rx >> (level + 1)) + blockIdx.x * blockDim.x * 4;
+        if (outside_window(T, level + 1, c0, c0 + blockDim.x * 4)) return;
+    }
     const int16_t *src = C.g[level] + (size_t)slot * C.g_slot[level] + (size_t)plane * C.g_plane[level];
     int16_t *dst = C.g[level + 1] + (size_t)slot * C.g_slot[level + 1] + (size_t)plane * C.g_plane[level + 1];
     const int sp = C.g_pitch[level], dp = C.g_pitch[level + 1];
@@ -217,6 +228,7 @@ __global__ void __launch_bounds__(256) coarsest_kernel(const PanoTables *__restr
     const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y * blockDim.y + threadIdx.y;
     const int slot = blockIdx.z;
     if (X >= W || Y >= H) return;
+    if (outside_window(T, L, blockIdx.x * blockDim.x, (blockIdx.x + 1) * blockDim.x)) return;
     int acc[3] = {0, 0, 0};
     float wsum = 0.f;
     for (int i = 0; i < T->num_cams; ++i) {
@@ -254,6 +266,7 @@ __global__ void __launch_bounds__(256) collapse_kernel(const PanoTables *__restr
     const int k = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y * blockDim.y + threadIdx.y;
     const int slot = blockIdx.z;
     if (k >= Wc || m >= Hc) return;
+    if (outside_window(T, L, 2 * blockIdx.x * blockDim.x, 2 * (blockIdx.x + 1) * blockDim.x)) return;
     const int X = 2 * k, Y = 2 * m;
     int acc[3][4];
     float wsum[4] = {0.f, 0.f, 0.f, 0.f};
@@ -353,6 +366,10 @@ __global__ void __launch_bounds__(256) pyrdown8_kernel(const PanoTables *__restr
     const int ox = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
     const int oy = (blockIdx.y * blockDim.y + threadIdx.y) * 2;
     if (ox >= dw || oy >= dh) return;
+    {
+        const int c0 = (C.rx >> (level + 1)) + blockIdx.x * blockDim.x * 8;
+        if (outside_window(T, level + 1, c0, c0 + blockDim.x * 8)) return;
+    }
     const int sp = C.g_pitch[level], dp = C.g_pitch[level + 1];
     const int16_t *src = C.g[level] + (size_t)slot * C.g_slot[level] + (size_t)plane * C.g_plane[level];
     int16_t *dst = C.g[level + 1] + (size_t)slot * C.g_slot[level + 1] + (size_t)plane * C.g_plane[level + 1];
@@ -457,7 +474,7 @@ __global__ void __launch_bounds__(384) collapse8_kernel(const PanoTables *__rest
     const int X0 = (blockIdx.x * 32 + threadIdx.x) * 8, Y0 = (blockIdx.y * 4 + threadIdx.y) * 2;
     const int slot = blockIdx.z;
     const int Wf = T->pad_w >> L, Hf = T->pad_h >> L;
-    const bool active = X0 < Wf && Y0 < Hf;
+    const bool active = X0 < Wf && Y0 < Hf && !outside_window(T, L, blockIdx.x * 256, blockIdx.x * 256 + 256);
     int res[16];
     float wsum[16];
 #pragma unroll
@@ -537,6 +554,7 @@ __global__ void __launch_bounds__(384) collapse8_kernel(const PanoTables *__rest
         tile[threadIdx.y * 2 + (j >> 3)][(threadIdx.x * 8 + (j & 7)) * 3 + plane] = (uint8_t)v;
     }
     __syncthreads();
+    if (outside_window(T, 0, blockIdx.x * 256, blockIdx.x * 256 + 256)) return;
     const int tid = (threadIdx.z * 4 + threadIdx.y) * 32 + threadIdx.x;   // 0..383: one 16-byte chunk each
     const int row = tid / 48, col = (tid % 48) * 16;
     const int Y = blockIdx.y * 8 + row - T->cut_y;
@@ -567,6 +585,7 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(const PanoTables *__rest
     const int cam = blockIdx.z % ncam, slot = blockIdx.z / ncam;
     const CamTables &C = T->cam[cam];
     if ((int)blockIdx.x >= C.tiles_x || (int)blockIdx.y >= C.tiles_y) return;
+    if (outside_window(T, 0, C.rx + blockIdx.x * kWarpTileW, C.rx + (blockIdx.x + 1) * kWarpTileW)) return;
     const int W = T->src_w, H = T->src_h, W3 = W * 3;
     const uint8_t *src = frames + ((size_t)slot * ncam + cam) * ((size_t)W3 * H);
     const int4 td = __ldg(C.tiles + blockIdx.y * C.tiles_x + blockIdx.x);   // {xbyte0, y0, rows, chunks}
@@ -644,6 +663,7 @@ __global__ void __launch_bounds__(256) direct_blend_kernel(const PanoTables *__r
     const int slot = blockIdx.z;
     if (cx >= T->cut_w || cy >= T->cut_h) return;
     const int X = cx + T->cut_x, Y = cy + T->cut_y;
+    if (X < T->win_lo[0] || X >= T->win_hi[0]) return;
     const int W = T->src_w, H = T->src_h, ncam = T->num_cams;
     int acc[3] = {0, 0, 0};
     float wsum = 0.f;
@@ -687,6 +707,39 @@ __global__ void __launch_bounds__(256) direct_blend_kernel(const PanoTables *__r
     } else {
 #pragma unroll
         for (int c = 0; c < 3; ++c) o[c] = any ? (uint8_t)sat_u8(acc[c]) : 0;
+    }
+}
+
+
+// ------------------------------------------------------------------ strip-split halo columns
+__global__ void __launch_bounds__(256) halo_copy_kernel(const PanoTables *__restrict__ T, int kind, int level, int col,
+                                                        int ncols, int16_t *__restrict__ buf, int unpack, int slot, int rows_max)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int plane = blockIdx.y % 3, cam = blockIdx.y / 3;
+    if (r >= rows_max) return;
+    int16_t *b = buf + (((size_t)cam * 3 + plane) * rows_max + r) * ncols;
+    if (kind == 1) {
+        const int h = T->pad_h >> level, w = T->pad_w >> level;
+        for (int c = 0; c < ncols; ++c) {
+            const int x = col + c;
+            const bool ok = r < h && x >= 0 && x < w;
+            int16_t *p = T->outp[level] + (size_t)slot * T->out_slot[level] + (size_t)plane * T->out_plane[level] +
+                         (size_t)r * T->out_pitch[level] + x;
+            if (unpack) { if (ok) *p = b[c]; }
+            else b[c] = ok ? *p : (int16_t)0;
+        }
+    } else {
+        const CamTables &C = T->cam[cam];
+        const int h = C.rh >> level, w = C.rw >> level, x0 = col - (C.rx >> level);
+        for (int c = 0; c < ncols; ++c) {
+            const int x = x0 + c;
+            const bool ok = r < h && x >= 0 && x < w;
+            int16_t *p = C.g[level] + (size_t)slot * C.g_slot[level] + (size_t)plane * C.g_plane[level] +
+                         (size_t)r * C.g_pitch[level] + x;
+            if (unpack) { if (ok) *p = b[c]; }
+            else b[c] = ok ? *p : (int16_t)0;
+        }
     }
 }
 
@@ -757,6 +810,27 @@ void launch_collapse(const PanoTables *dev, const PanoTables &host, const Kernel
     const dim3 block(32, 8);
     const dim3 grid = grid2d(host.pad_w >> (level + 1), host.pad_h >> (level + 1), block, nslots);
     collapse_kernel<<<grid, block, 0, stream>>>(dev, level, pano);
+}
+
+static int halo_rows(const PanoTables &host, int kind, int level)
+{
+    if (kind == 1) return host.pad_h >> level;
+    int r = 0;
+    for (int i = 0; i < host.num_cams; ++i) r = max(r, host.cam[i].rh >> level);
+    return r;
+}
+
+size_t halo_elems(const PanoTables &host, int kind, int level, int ncols)
+{
+    return (size_t)(kind == 1 ? 1 : host.num_cams) * 3 * halo_rows(host, kind, level) * ncols;
+}
+
+void launch_halo_copy(const PanoTables *dev, const PanoTables &host, int kind, int level, int col, int ncols,
+                      int16_t *buf, bool unpack, int slot, cudaStream_t stream)
+{
+    const int rows = halo_rows(host, kind, level);
+    const dim3 block(256), grid((rows + 255) / 256, 3 * (kind == 1 ? 1 : host.num_cams));
+    halo_copy_kernel<<<grid, block, 0, stream>>>(dev, kind, level, col, ncols, buf, unpack ? 1 : 0, slot, rows);
 }
 
 void launch_direct_blend(const PanoTables *dev, const PanoTables &host, int blender, const uint8_t *frames,

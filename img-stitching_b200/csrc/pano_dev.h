@@ -51,6 +51,9 @@ struct PanoTables {
     int pad_w, pad_h;        // padded dst size (level 0)
     int roi_w, roi_h;        // unpadded dst roi size
     int cut_x, cut_y, cut_w, cut_h;
+    // column window (spatial strip split): blocks whose dst columns at level l fall entirely
+    // outside [win_lo[l], win_hi[l]) are skipped.  Full range = no split.
+    int win_lo[kMaxLevels], win_hi[kMaxLevels];
     // collapsed dst pyramid, levels 1..nb: [slot][3][h_l][out_pitch[l]]
     int16_t *outp[kMaxLevels];
     int out_pitch[kMaxLevels];
@@ -78,5 +81,13 @@ void launch_collapse(const PanoTables *dev, const PanoTables &host, const Kernel
                      int nslots, cudaStream_t stream);
 void launch_direct_blend(const PanoTables *dev, const PanoTables &host, int blender, const uint8_t *frames,
                          uint8_t *pano, int nslots, cudaStream_t stream);
+
+// strip-split halo columns: pack / unpack `ncols` dst columns starting at dst column `col`
+// (level `level`) of either every camera's g[level] (kind 0) or out[level] (kind 1) into / from a
+// dense buffer laid out [cam][plane][row][ncols] int16 (cameras that do not cover the column
+// contribute zeros and ignore the incoming data).
+void launch_halo_copy(const PanoTables *dev, const PanoTables &host, int kind, int level, int col, int ncols,
+                      int16_t *buf, bool unpack, int slot, cudaStream_t stream);
+size_t halo_elems(const PanoTables &host, int kind, int level, int ncols);
 
 }  // namespace pano

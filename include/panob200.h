@@ -109,6 +109,23 @@ int pano_process_device(pano_handle h, const uint8_t *frames_dev, uint8_t *out_d
  * streams.  Pinned host memory gives full PCIe rate.  Synchronous. */
 int pano_process_batch(pano_handle h, const uint8_t *frames_host, uint8_t *out_host, int batch);
 
+/* ---------------------------------------------------------------- column-strip split
+ * Spatial decomposition of ONE large panorama across GPUs (BASELINE config 4): each
+ * rank owns the padded-dst columns [x0, x1) (multiples of 2^num_bands) and runs the compose as
+ * `pano_strip_phase_count()` phases; after every phase that reports halo bytes the ranks exchange
+ * the pyramid columns next to the strip edges (2 columns of every camera pyramid level, 1 column of
+ * every collapsed level) -- e.g. ncclSend/ncclRecv between neighbours -- and unpack them before the
+ * next phase.  `margin` = extra level-0 columns computed redundantly on each side (>= 8 with halo
+ * exchange; 3*2^num_bands makes the exchange unnecessary: the "redundant halo" variant).
+ * The panorama buffer has the full cut size; only the rank's own columns are meaningful.
+ * side: 0 = left neighbour, 1 = right neighbour.  One frame-set per call sequence. */
+int pano_strip_set_window(pano_handle h, int x0, int x1, int margin);
+int pano_strip_phase_count(pano_handle h);
+int pano_strip_run_phase(pano_handle h, int phase, const uint8_t *frames_dev, uint8_t *pano_dev, void *stream);
+size_t pano_strip_halo_bytes(pano_handle h, int phase);
+int pano_strip_halo_pack(pano_handle h, int phase, int side, void *buf_dev, void *stream);
+int pano_strip_halo_unpack(pano_handle h, int phase, int side, const void *buf_dev, void *stream);
+
 /* Per-kernel device time of the last pano_process_device call made while profiling was
  * enabled (CUDA events on the launching stream).  names: up to max entries. */
 int pano_profile_enable(pano_handle h, int on);

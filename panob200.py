@@ -26,4 +26,5 @@ ocvStitcher = pkg.ocvStitcher
 StitcherConfig = pkg.StitcherConfig
 nvCamFrontEnd = pkg.nvCamFrontEnd
 sharding = pkg.sharding
+strips = pkg.strips
 PanoError = pkg.PanoError

@@ -277,6 +277,50 @@ def test_config4_full_size_8cam_4k_cylindrical_7_bands():
     assert np.array_equal(st.process(imgs), got)               # idempotent
 
 
+# ------------------------------------------------------------------ column-strip split (config 4)
+
+def _strip_setup(nranks, mode, W=960, H=540, nb=5, ncam=8):
+    import torch
+    Ks, Rs, scale = calib.ring(ncam, W, H, 65.2, 40.0)
+    t = compose.build_tables(Ks, Rs, scale, (W, H), "cylindrical")
+    t.blend_masks = util.soft_masks(t)
+    imgs = [util.synth_frame(H, W, 700 + i, cell=32) for i in range(ncam)]
+    ref_st = make(Ks, Rs, scale, W, H, "cylindrical", "multiband", nb)
+    assert ref_st.initTables(t.blend_masks) == 0, ref_st.last_error
+    want = ref_st.process(imgs)
+    frames = torch.from_numpy(np.stack(imgs)).cuda()
+    ranks, panos = [], []
+    for r in range(nranks):
+        st = make(Ks, Rs, scale, W, H, "cylindrical", "multiband", nb)
+        assert st.initTables(t.blend_masks) == 0, st.last_error
+        ranks.append(panob200.strips.StripRank(st, r, nranks, mode))
+        panos.append(torch.full(want.shape, 77, dtype=torch.uint8, device="cuda"))
+    return t, imgs, want, frames, ranks, panos
+
+
+@pytest.mark.parametrize("nranks,mode", [(2, "exchange"), (4, "exchange"), (8, "exchange"), (4, "redundant")])
+def test_strip_split_equals_single_gpu(nranks, mode):
+    """Ranks emulated in lockstep on one GPU: the strip-split panorama (halo exchange or redundant
+    halo) must equal the undivided one byte for byte -- and that one equals the oracle."""
+    import torch
+    t, imgs, want, frames, ranks, panos = _strip_setup(nranks, mode)
+    assert_equal("undivided vs oracle", want, compose.process(t, imgs, "multiband", 5))
+    panob200.strips.compose_local(ranks, frames, panos)
+    torch.cuda.synchronize()
+    got = panob200.strips.assemble(ranks, panos).cpu().numpy()
+    assert_equal("strip split %d/%s" % (nranks, mode), got, want)
+    if mode == "exchange":
+        assert sum(ranks[0].halo_bytes(p) for p in range(ranks[0].phases)) > 0
+        # a rank that skipped the exchange must NOT reproduce the result (the halo matters)
+        for p_, r in zip(panos, ranks):
+            p_.fill_(0)
+        for r, p_ in zip(ranks, panos):
+            for ph in range(r.phases):
+                r.run_phase(ph, frames, p_, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert not np.array_equal(panob200.strips.assemble(ranks, panos).cpu().numpy(), want)
+
+
 # ------------------------------------------------------------------ nvCam front end
 
 def test_front_end_golden_bit_exact():
