@@ -55,6 +55,9 @@ struct pano_ctx {
     KernelChoice kc;
     bool tables_dirty = true;
     int strip_x0 = 0, strip_x1 = 0;               // own dst columns (level 0, padded coords); full width = no split
+    // [level][cam][tile] -> camera has a non-zero weight inside the 256x8 dst tile
+    std::vector<std::vector<std::vector<uint8_t>>> tile_flags;
+    std::vector<uint32_t *> d_tile_cams;
     std::vector<void *> owned;                    // device allocations to free
     std::vector<void *> cam_mask0, cam_gain;      // per camera, re-uploadable
     std::vector<std::vector<void *>> cam_wt;      // per camera per level
@@ -123,6 +126,41 @@ int upload2d(pano_ctx *h, T *dst, int dpitch, const T *src, int spitch, int w, i
     return PANO_OK;
 }
 
+inline int tilesX(const pano_ctx *h, int l) { return ((h->pad_w >> l) + 255) / 256; }
+inline int tilesY(const pano_ctx *h, int l) { return ((h->pad_h >> l) + 7) / 8; }
+
+// record which 256x8 dst tiles of level l see a non-zero weight of camera `cam`
+template <typename T>
+void markTiles(pano_ctx *h, int cam, int l, const T *data, int w, int hh, int pitch)
+{
+    if (h->tile_flags.empty()) return;
+    const CamTables &C = h->host.cam[cam];
+    const int ox = C.rx >> l, oy = C.ry >> l, tx = tilesX(h, l);
+    std::vector<uint8_t> &f = h->tile_flags[l][cam];
+    std::fill(f.begin(), f.end(), 0);
+    for (int y = 0; y < hh; ++y) {
+        const T *row = data + (size_t)y * pitch;
+        const int tyi = (oy + y) / 8;
+        for (int x = 0; x < w; ++x)
+            if (row[x] != (T)0) f[(size_t)tyi * tx + (ox + x) / 256] = 1;
+    }
+}
+
+int uploadTileCams(pano_ctx *h)
+{
+    if (h->tile_flags.empty()) return PANO_OK;
+    for (int l = 0; l <= h->nb; ++l) {
+        if (!h->d_tile_cams[l]) continue;
+        const size_t cnt = (size_t)tilesX(h, l) * tilesY(h, l);
+        std::vector<uint32_t> m(cnt, 0u);
+        for (int c = 0; c < h->n; ++c)
+            for (size_t t = 0; t < cnt; ++t)
+                if (h->tile_flags[l][c][t]) m[t] |= 1u << c;
+        CK(h, cudaMemcpy(h->d_tile_cams[l], m.data(), cnt * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    return PANO_OK;
+}
+
 int buildWeights(pano_ctx *h, int cam)
 {
     CamTables &C = h->host.cam[cam];
@@ -143,6 +181,7 @@ int buildWeights(pano_ctx *h, int cam)
         std::memcpy(&m0[(size_t)(y + fr.top) * W + fr.left], &m[(size_t)y * img.w], img.w);
     if (upload2d(h, (uint8_t *)h->cam_mask0[cam], C.mask_pitch, m0.data(), W, W, H)) return PANO_ERR;
     C.use_wt0 = 0;
+    markTiles(h, cam, 0, m0.data(), W, H, W);
     if (h->blender != PANO_BLEND_MULTIBAND) return PANO_OK;
     // float weight pyramid (MultiBandBlender::feed: convertTo(CV_32F, 1/255) + pyrDown chain)
     std::vector<float> cur((size_t)W * H);
@@ -153,6 +192,7 @@ int buildWeights(pano_ctx *h, int cam)
         pyrDownF32(cur.data(), cw, ch, nxt.data());
         cw = (cw + 1) / 2; ch = (ch + 1) / 2;
         if (upload2d(h, (float *)h->cam_wt[cam][l], C.wt_pitch[l], nxt.data(), cw, cw, ch)) return PANO_ERR;
+        markTiles(h, cam, l, nxt.data(), cw, ch, cw);
         cur.swap(nxt);
     }
     return PANO_OK;
@@ -161,6 +201,7 @@ int buildWeights(pano_ctx *h, int cam)
 int syncTables(pano_ctx *h)
 {
     if (!h->tables_dirty) return PANO_OK;
+    if (uploadTileCams(h)) return PANO_ERR;
     CK(h, cudaMemcpy(h->dev, &h->host, sizeof(PanoTables), cudaMemcpyHostToDevice));
     h->tables_dirty = false;
     return PANO_OK;
@@ -530,6 +571,32 @@ int pano_create(const pano_config *cfg, pano_handle *out)
             h->kc.collapse8[l] = (h->nb - l >= 3);
         }
     }
+    if (h->blender == PANO_BLEND_MULTIBAND) {
+        h->tile_flags.assign(h->nb + 1, std::vector<std::vector<uint8_t>>(n));
+        h->d_tile_cams.assign(h->nb + 1, nullptr);
+        for (int l = 0; l <= h->nb; ++l) {
+            const size_t cnt = (size_t)tilesX(h, l) * tilesY(h, l);
+            for (int c = 0; c < n; ++c) h->tile_flags[l][c].assign(cnt, 0);
+            uint32_t *d = nullptr;
+            if (devAlloc(h, &d, cnt)) return bail(0);
+            h->d_tile_cams[l] = d;
+            T.tile_cams[l] = d;
+        }
+    }
+    {
+        // exactness of the two kernel shortcuts under this host's IEEE arithmetic (always true on
+        // conforming hardware; the kernels fall back to the general path otherwise)
+        volatile float one = 1.0f, eps = 1e-5f, m255 = 255.f, inv = 1.f / 255.f;
+        const float den = one + eps;
+        bool ok = true;
+        for (int a = -32768; a <= 32767 && ok; ++a) {
+            if (a == 0) continue;
+            volatile float q = (float)a / den;
+            ok = ((int)(short)(int)q) == a - (a > 0 ? 1 : -1);
+        }
+        volatile float p = m255 * inv;
+        T.unit_norm_exact = (ok ? 1 : 0) | (p == 1.0f ? 2 : 0);
+    }
     if (devAlloc(h, &h->dev, 1)) return bail(0);
     for (int i = 0; i < n; ++i)
         if (buildWeights(h, i)) return bail(0);
@@ -627,6 +694,7 @@ int pano_set_weight_level(pano_handle h, int cam, int level, const float *w, int
     CK(h, cudaDeviceSynchronize());
     if (upload2d(h, (float *)h->cam_wt[cam][level], C.wt_pitch[level], w, width, width, height)) return PANO_ERR;
     if (level == 0) C.use_wt0 = 1;
+    markTiles(h, cam, level, w, width, height, width);
     h->tables_dirty = true;
     return PANO_OK;
 }

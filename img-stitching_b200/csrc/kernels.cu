@@ -9,6 +9,7 @@
 // FMA contraction nor fast division can change a bit.
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 
 #include "pano_dev.h"
 
@@ -420,14 +421,26 @@ __global__ void __launch_bounds__(256) pyrdown8_kernel(const PanoTables *__restr
     }
 }
 
-// ---- pyrUp of one coarse row segment: coarse columns k0..k0+3 -> 8 fine columns (before the
-// vertical pass).  k0 % 4 == 0, cw % 4 == 0.
-__device__ __forceinline__ void up_row8(const int16_t *__restrict__ row, int k0, int cw, int h[8])
+// ---- pyrUp of coarse columns k0..k0+3, rows m-1..m+1 -> the 8 x 2 fine block (rows 2m, 2m+1).
+// Split into an explicit LOAD step (12 words, issued early so several independent loads are in
+// flight) and a COMPUTE step.  k0 % 4 == 0, cw % 4 == 0.
+struct UpRaw { int pm[3], p0[3], p1[3], p2[3]; };
+
+__device__ __forceinline__ void up_load(const int16_t *__restrict__ plane, int pitch, int cw, int ch, int k0, int m, UpRaw &r)
 {
-    const uint2 p = *reinterpret_cast<const uint2 *>(row + k0);
-    const int P0 = p.x, P1 = p.y;
-    const int Pm = k0 > 0 ? *reinterpret_cast<const int *>(row + k0 - 2) : P0;              // c[-1] := c[1]
-    const int P2 = k0 + 4 < cw ? *reinterpret_cast<const int *>(row + k0 + 4) : (P1 >> 16);  // c[cw] := c[cw-1]
+    const int rows[3] = {up_index(m - 1, ch), m, up_index(m + 1, ch)};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int16_t *row = plane + rows[i] * pitch + k0;
+        const uint2 p = *reinterpret_cast<const uint2 *>(row);
+        r.p0[i] = p.x; r.p1[i] = p.y;
+        r.pm[i] = k0 > 0 ? *reinterpret_cast<const int *>(row - 2) : (int)p.x;              // c[-1] := c[1]
+        r.p2[i] = k0 + 4 < cw ? *reinterpret_cast<const int *>(row + 4) : ((int)p.y >> 16);  // c[cw] := c[cw-1]
+    }
+}
+
+__device__ __forceinline__ void up_hrow(int Pm, int P0, int P1, int P2, int h[8])
+{
     h[0] = __dp2a_lo(P0, COEF(6, 1), __dp2a_lo(Pm, COEF(0, 1), 0));
     h[1] = __dp2a_lo(P0, COEF(4, 4), 0);
     h[2] = __dp2a_lo(P0, COEF(1, 6), __dp2a_lo(P1, COEF(1, 0), 0));
@@ -438,14 +451,12 @@ __device__ __forceinline__ void up_row8(const int16_t *__restrict__ row, int k0,
     h[7] = __dp2a_lo(P1, COEF(0, 4), __dp2a_lo(P2, COEF(4, 0), 0));
 }
 
-// 8 x 2 fine block (rows 2m, 2m+1; columns 2k0..2k0+7) of pyrUp(plane)
-__device__ __forceinline__ void pyrup_8x2(const int16_t *__restrict__ plane, int pitch, int cw, int ch, int k0, int m,
-                                          int up[16])
+__device__ __forceinline__ void up_compute(const UpRaw &r, int up[16])
 {
     int ha[8], hb[8], hc[8];
-    up_row8(plane + up_index(m - 1, ch) * pitch, k0, cw, ha);
-    up_row8(plane + m * pitch, k0, cw, hb);
-    up_row8(plane + up_index(m + 1, ch) * pitch, k0, cw, hc);
+    up_hrow(r.pm[0], r.p0[0], r.p1[0], r.p2[0], ha);
+    up_hrow(r.pm[1], r.p0[1], r.p1[1], r.p2[1], hb);
+    up_hrow(r.pm[2], r.p0[2], r.p1[2], r.p2[2], hc);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         up[j] = (ha[j] + 6 * hb[j] + hc[j] + 32) >> 6;
@@ -462,19 +473,27 @@ __device__ __forceinline__ void unpack8(const uint4 v, int o[8])
 }
 
 // ---- K3': blend + collapse, one thread = 8 x 2 pixels of ONE plane (threadIdx.z = plane).
-// Cameras whose 16 weights are all zero contribute exactly nothing ((short)(lap*0) == 0,
-// w_sum + 0 == w_sum) and are skipped before any of their pyramid data is touched.
+// A static per-tile bitmask (built at init from the weights) lists the cameras with any non-zero
+// weight inside the block's 256 x 8 tile; the others contribute exactly nothing
+// ((short)(lap*0) == 0, w_sum + 0 == w_sum) and are never touched.  The loop over listed cameras
+// is block-uniform, so all of a camera's loads are in flight together.  Two exact shortcuts cover
+// the interior of every camera's region: all 16 weights == 1.0f -> (short)(lap*1.0f) == lap, and
+// w_sum == 1.0f -> (short)(a / 1.00001f) == a - sign(a) for every 16-bit a (checked on the host).
 // Level 0 stages the three planes through shared memory so the interleaved 8-bit panorama
 // leaves in aligned 8-byte stores.
-template <bool kLevel0>
-__global__ void __launch_bounds__(384) collapse8_kernel(const PanoTables *__restrict__ T, int L, uint8_t *__restrict__ pano)
+template <bool kLevel0, int TY>
+__global__ void __launch_bounds__(96 * TY, TY == 4 ? 2 : 3) collapse8_kernel(const PanoTables *__restrict__ T, int L,
+                                                                            uint8_t *__restrict__ pano)
 {
-    __shared__ __align__(16) uint8_t tile[8][256 * 3];
+    __shared__ __align__(16) uint8_t tile[2 * TY][256 * 3];
     const int plane = threadIdx.z;
-    const int X0 = (blockIdx.x * 32 + threadIdx.x) * 8, Y0 = (blockIdx.y * 4 + threadIdx.y) * 2;
+    const int X0 = (blockIdx.x * 32 + threadIdx.x) * 8, Y0 = (blockIdx.y * TY + threadIdx.y) * 2;
     const int slot = blockIdx.z;
     const int Wf = T->pad_w >> L, Hf = T->pad_h >> L;
-    const bool active = X0 < Wf && Y0 < Hf && !outside_window(T, L, blockIdx.x * 256, blockIdx.x * 256 + 256);
+    const bool in_window = !outside_window(T, L, blockIdx.x * 256, blockIdx.x * 256 + 256);
+    // level 0 only produces panorama pixels: rows outside the cut rectangle are never needed
+    const bool in_cut = !kLevel0 || (Y0 + 1 >= T->cut_y && Y0 < T->cut_y + T->cut_h);
+    const bool active = X0 < Wf && Y0 < Hf && in_window && in_cut;
     int res[16];
     float wsum[16];
 #pragma unroll
@@ -483,22 +502,38 @@ __global__ void __launch_bounds__(384) collapse8_kernel(const PanoTables *__rest
         int acc[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = 0;
-        const int ncam = T->num_cams;
-        for (int i = 0; i < ncam; ++i) {
+        UpRaw raw_out;     // loads issued now, consumed after the camera loop
+        up_load(T->outp[L + 1] + (size_t)slot * T->out_slot[L + 1] + (size_t)plane * T->out_plane[L + 1],
+                T->out_pitch[L + 1], Wf >> 1, Hf >> 1, X0 >> 1, Y0 >> 1, raw_out);
+        uint32_t cams = __ldg(T->tile_cams[L] + ((blockIdx.y * 2 * TY) >> 3) * gridDim.x + blockIdx.x);
+        while (cams) {
+            const int i = __ffs(cams) - 1;
+            cams &= cams - 1;
             const CamTables &C = T->cam[i];
             const int x = X0 - (C.rx >> L), y = Y0 - (C.ry >> L);
             const int fw = C.rw >> L, fh = C.rh >> L;
             if ((unsigned)x >= (unsigned)fw || (unsigned)y >= (unsigned)fh) continue;
+            // the camera is listed for this tile: fetch its pyramid data unconditionally, together
+            // with the weights, so that one memory round trip covers all of it
+            UpRaw raw;
+            up_load(C.g[L + 1] + (size_t)slot * C.g_slot[L + 1] + (size_t)plane * C.g_plane[L + 1], C.g_pitch[L + 1],
+                    fw >> 1, fh >> 1, x >> 1, y >> 1, raw);
+            const int16_t *f = C.g[L] + (size_t)slot * C.g_slot[L] + (size_t)plane * C.g_plane[L] + y * C.g_pitch[L] + x;
+            const uint4 f0 = *reinterpret_cast<const uint4 *>(f), f1 = *reinterpret_cast<const uint4 *>(f + C.g_pitch[L]);
             float w[16];
+            bool ones;
             if (kLevel0 && !C.use_wt0) {
                 const uint8_t *mrow = C.mask0 + y * C.mask_pitch + x;
                 const uint2 a = *reinterpret_cast<const uint2 *>(mrow);
                 const uint2 b = *reinterpret_cast<const uint2 *>(mrow + C.mask_pitch);
                 if ((a.x | a.y | b.x | b.y) == 0u) continue;
-                const uint32_t mw[4] = {a.x, a.y, b.x, b.y};
+                ones = (a.x & a.y & b.x & b.y) == 0xffffffffu && (T->unit_norm_exact & 2);   // 255 * (1/255.f) == 1.0f
+                if (!ones) {
+                    const uint32_t mw[4] = {a.x, a.y, b.x, b.y};
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    w[j] = __fmul_rn((float)((mw[j >> 2] >> (8 * (j & 3))) & 0xffu), 1.f / 255.f);
+                    for (int j = 0; j < 16; ++j)
+                        w[j] = __fmul_rn((float)((mw[j >> 2] >> (8 * (j & 3))) & 0xffu), 1.f / 255.f);
+                }
             } else {
                 const float *wrow = C.wt[L] + y * C.wt_pitch[L] + x;
                 const float4 a0 = *reinterpret_cast<const float4 *>(wrow), a1 = *reinterpret_cast<const float4 *>(wrow + 4);
@@ -507,31 +542,41 @@ __global__ void __launch_bounds__(384) collapse8_kernel(const PanoTables *__rest
                 w[0] = a0.x; w[1] = a0.y; w[2] = a0.z; w[3] = a0.w; w[4] = a1.x; w[5] = a1.y; w[6] = a1.z; w[7] = a1.w;
                 w[8] = b0.x; w[9] = b0.y; w[10] = b0.z; w[11] = b0.w; w[12] = b1.x; w[13] = b1.y; w[14] = b1.z; w[15] = b1.w;
                 bool any = false;
+                ones = true;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) any |= (w[j] != 0.f);
+                for (int j = 0; j < 16; ++j) { any |= (w[j] != 0.f); ones &= (w[j] == 1.0f); }
                 if (!any) continue;
             }
             int up[16], fine[16];
-            pyrup_8x2(C.g[L + 1] + (size_t)slot * C.g_slot[L + 1] + (size_t)plane * C.g_plane[L + 1], C.g_pitch[L + 1],
-                      fw >> 1, fh >> 1, x >> 1, y >> 1, up);
-            const int16_t *f = C.g[L] + (size_t)slot * C.g_slot[L] + (size_t)plane * C.g_plane[L] + y * C.g_pitch[L] + x;
-            unpack8(*reinterpret_cast<const uint4 *>(f), fine);
-            unpack8(*reinterpret_cast<const uint4 *>(f + C.g_pitch[L]), fine + 8);
+            up_compute(raw, up);
+            unpack8(f0, fine);
+            unpack8(f1, fine + 8);
+            if (ones) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int lap = sat_s16(fine[j] - up[j]);
-                acc[j] += trunc_s16(__fmul_rn((float)lap, w[j]));
-                wsum[j] = __fadd_rn(wsum[j], w[j]);
+                for (int j = 0; j < 16; ++j) {
+                    acc[j] += sat_s16(fine[j] - up[j]);
+                    wsum[j] = __fadd_rn(wsum[j], 1.0f);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int lap = sat_s16(fine[j] - up[j]);
+                    acc[j] += trunc_s16(__fmul_rn((float)lap, w[j]));
+                    wsum[j] = __fadd_rn(wsum[j], w[j]);
+                }
             }
         }
-        int up[16];
-        pyrup_8x2(T->outp[L + 1] + (size_t)slot * T->out_slot[L + 1] + (size_t)plane * T->out_plane[L + 1],
-                  T->out_pitch[L + 1], Wf >> 1, Hf >> 1, X0 >> 1, Y0 >> 1, up);
+        const bool unit_ok = (T->unit_norm_exact & 1) != 0;
+        int upo[16];
+        up_compute(raw_out, upo);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int a = wrap_s16(acc[j]);
-            const int nrm = a == 0 ? 0 : trunc_s16(__fdiv_rn((float)a, __fadd_rn(wsum[j], 1e-5f)));
-            res[j] = sat_s16(up[j] + nrm);
+            int nrm;
+            if (a == 0) nrm = 0;
+            else if (unit_ok && wsum[j] == 1.0f) nrm = a - ((a > 0) ? 1 : -1);
+            else nrm = trunc_s16(__fdiv_rn((float)a, __fadd_rn(wsum[j], 1e-5f)));
+            res[j] = sat_s16(upo[j] + nrm);
         }
     }
     if (!kLevel0) {
@@ -554,10 +599,10 @@ __global__ void __launch_bounds__(384) collapse8_kernel(const PanoTables *__rest
         tile[threadIdx.y * 2 + (j >> 3)][(threadIdx.x * 8 + (j & 7)) * 3 + plane] = (uint8_t)v;
     }
     __syncthreads();
-    if (outside_window(T, 0, blockIdx.x * 256, blockIdx.x * 256 + 256)) return;
-    const int tid = (threadIdx.z * 4 + threadIdx.y) * 32 + threadIdx.x;   // 0..383: one 16-byte chunk each
+    if (!in_window) return;
+    const int tid = (threadIdx.z * TY + threadIdx.y) * 32 + threadIdx.x;  // one 16-byte chunk of the tile each
     const int row = tid / 48, col = (tid % 48) * 16;
-    const int Y = blockIdx.y * 8 + row - T->cut_y;
+    const int Y = blockIdx.y * 2 * TY + row - T->cut_y;
     if ((unsigned)Y >= (unsigned)T->cut_h) return;
     const int xbyte = (blockIdx.x * 256 - T->cut_x) * 3 + col;            // byte offset inside the output row
     const int row_bytes = T->cut_w * 3;
@@ -802,9 +847,16 @@ void launch_collapse(const PanoTables *dev, const PanoTables &host, const Kernel
 {
     if (kc.collapse8[level]) {
         const int wf = host.pad_w >> level, hf = host.pad_h >> level;
-        const dim3 block(32, 4, 3), grid((wf + 255) / 256, (hf + 7) / 8, nslots);
-        if (level == 0) collapse8_kernel<true><<<grid, block, 0, stream>>>(dev, level, pano);
-        else collapse8_kernel<false><<<grid, block, 0, stream>>>(dev, level, pano);
+        static const int ty = getenv("PANO_C8_TY") ? atoi(getenv("PANO_C8_TY")) : 4;
+        if (ty == 4) {
+            const dim3 block(32, 4, 3), grid((wf + 255) / 256, (hf + 7) / 8, nslots);
+            if (level == 0) collapse8_kernel<true, 4><<<grid, block, 0, stream>>>(dev, level, pano);
+            else collapse8_kernel<false, 4><<<grid, block, 0, stream>>>(dev, level, pano);
+        } else {
+            const dim3 block(32, 2, 3), grid((wf + 255) / 256, (hf + 3) / 4, nslots);
+            if (level == 0) collapse8_kernel<true, 2><<<grid, block, 0, stream>>>(dev, level, pano);
+            else collapse8_kernel<false, 2><<<grid, block, 0, stream>>>(dev, level, pano);
+        }
         return;
     }
     const dim3 block(32, 8);

@@ -54,6 +54,10 @@ struct PanoTables {
     // column window (spatial strip split): blocks whose dst columns at level l fall entirely
     // outside [win_lo[l], win_hi[l]) are skipped.  Full range = no split.
     int win_lo[kMaxLevels], win_hi[kMaxLevels];
+    // per level: one u32 per 256 x 8 tile of the padded dst = bitmask of cameras that have any
+    // non-zero weight inside the tile (static; rebuilt whenever masks / weights change)
+    const uint32_t *tile_cams[kMaxLevels];
+    int unit_norm_exact;     // host verified (short)(a / (1.0f + 1e-5f)) == a - sign(a) for all int16 a
     // collapsed dst pyramid, levels 1..nb: [slot][3][h_l][out_pitch[l]]
     int16_t *outp[kMaxLevels];
     int out_pitch[kMaxLevels];
