@@ -492,7 +492,7 @@ int pano_create(const pano_config *cfg, pano_handle *out)
             if (cudaMemcpy(d, m32.data(), m32.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) { h->err = "map upload failed"; return bail(0); }
             C.map32 = d; C.map64 = nullptr;
         }
-        // source footprint of every 128x8 output tile (staged-gather warp kernel)
+        // source footprint of every 128x16 output tile (staged-gather warp kernel)
         C.tiles_x = (C.rw + kWarpTileW - 1) / kWarpTileW;
         C.tiles_y = (C.rh + kWarpTileH - 1) / kWarpTileH;
         {
@@ -501,8 +501,7 @@ int pano_create(const pano_config *cfg, pano_handle *out)
             for (int ty = 0; ty < C.tiles_y; ++ty)
                 for (int tx = 0; tx < C.tiles_x; ++tx) {
                     int x0 = INT32_MAX, x1 = -1, y0 = INT32_MAX, y1 = -1;
-                    // the kernel samples all 4-pixel groups that start inside the rect
-                    const int xe = std::min(roundUp(C.rw, 4), (tx + 1) * kWarpTileW);
+                    const int xe = std::min(C.rw, (tx + 1) * kWarpTileW);
                     for (int Y = ty * kWarpTileH; Y < std::min(C.rh, (ty + 1) * kWarpTileH); ++Y)
                         for (int X = tx * kWarpTileW; X < xe; ++X) {
                             uint32_t sx, sy;
@@ -512,11 +511,10 @@ int pano_create(const pano_config *cfg, pano_handle *out)
                             x0 = std::min(x0, ix); x1 = std::max(x1, std::min(ix + 1, W - 1));
                             y0 = std::min(y0, iy); y1 = std::max(y1, std::min(iy + 1, H - 1));
                         }
-                    const int b0 = (x0 * 3) / 16 * 16, b1 = roundUp(x1 * 3 + 3, 16);
-                    const int rows = y1 - y0 + 1, chunks = (b1 - b0) / 16;
+                    const int px0 = x0 / 16 * 16, groups = (x1 - px0) / 16 + 1;
+                    const int rows = y1 - y0 + 1;
                     int4 d = make_int4(0, 0, 0, 0);
-                    if (W3 % 16 == 0 && rows <= kWarpSmemRows && chunks * 16 <= kWarpSmemRowBytes && b1 <= W3)
-                        d = make_int4(b0, y0, rows, chunks);
+                    if (W % 16 == 0 && rows * groups * 16 <= kWarpSmemWords) d = make_int4(px0, y0, rows, groups);
                     tl[(size_t)ty * C.tiles_x + tx] = d;
                 }
             int4 *dt = nullptr;
@@ -562,7 +560,7 @@ int pano_create(const pano_config *cfg, pano_handle *out)
         }
     }
     // which fast kernels this geometry admits (the generic ones cover everything else)
-    h->kc.warp_tiled = ((W * 3) % 16 == 0);
+    h->kc.warp_tiled = (W % 16 == 0);
     if (h->blender == PANO_BLEND_MULTIBAND) {
         for (int l = 0; l < h->nb; ++l) {
             bool ok = true;

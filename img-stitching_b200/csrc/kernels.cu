@@ -496,10 +496,11 @@ __global__ void __launch_bounds__(96 * TY, TY == 4 ? 2 : 3) collapse8_kernel(con
     const bool active = X0 < Wf && Y0 < Hf && in_window && in_cut;
     int res[16];
     float wsum[16];
+    bool unit = false;
 #pragma unroll
     for (int j = 0; j < 16; ++j) { res[j] = 0; wsum[j] = 0.f; }
     if (active) {
-        int acc[16];
+        int acc[16], n_unit = 0, n_soft = 0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = 0;
         UpRaw raw_out;     // loads issued now, consumed after the camera loop
@@ -551,32 +552,40 @@ __global__ void __launch_bounds__(96 * TY, TY == 4 ? 2 : 3) collapse8_kernel(con
             up_compute(raw, up);
             unpack8(f0, fine);
             unpack8(f1, fine + 8);
+            // Gaussian-pyramid samples of 8-bit frames stay in [0, 255], so |lap| <= 255: the
+            // reference's saturating subtract, its (short) casts and the wrapping int16 adds can
+            // never clip here -- plain 32-bit arithmetic is bit-identical.
             if (ones) {
+                ++n_unit;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    acc[j] += sat_s16(fine[j] - up[j]);
-                    wsum[j] = __fadd_rn(wsum[j], 1.0f);
+                    acc[j] += fine[j] - up[j];
+                    wsum[j] = __fadd_rn(wsum[j], 1.0f);      // keep the reference's camera-order float sum
                 }
             } else {
+                ++n_soft;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int lap = sat_s16(fine[j] - up[j]);
-                    acc[j] += trunc_s16(__fmul_rn((float)lap, w[j]));
+                    acc[j] += __float2int_rz(__fmul_rn((float)(fine[j] - up[j]), w[j]));
                     wsum[j] = __fadd_rn(wsum[j], w[j]);
                 }
             }
         }
-        const bool unit_ok = (T->unit_norm_exact & 1) != 0;
         int upo[16];
         up_compute(raw_out, upo);
+        if (n_soft == 0 && n_unit == 1 && (T->unit_norm_exact & 1)) {
+            // exactly one camera, all weights 1.0f: dst_w == 1.0f and
+            // (short)(a / (1.0f + 1e-5f)) == a - sign(a) for every |a| <= 32768 (host-verified)
+            unit = true;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int a = wrap_s16(acc[j]);
-            int nrm;
-            if (a == 0) nrm = 0;
-            else if (unit_ok && wsum[j] == 1.0f) nrm = a - ((a > 0) ? 1 : -1);
-            else nrm = trunc_s16(__fdiv_rn((float)a, __fadd_rn(wsum[j], 1e-5f)));
-            res[j] = sat_s16(upo[j] + nrm);
+            for (int j = 0; j < 16; ++j) res[j] = upo[j] + acc[j] - max(-1, min(1, acc[j]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int a = acc[j];
+                const int nrm = a == 0 ? 0 : __float2int_rz(__fdiv_rn((float)a, __fadd_rn(wsum[j], 1e-5f)));
+                res[j] = upo[j] + nrm;      // |out| <= 255 * (levels): cannot reach the int16 limits
+            }
         }
     }
     if (!kLevel0) {
@@ -595,7 +604,7 @@ __global__ void __launch_bounds__(96 * TY, TY == 4 ? 2 : 3) collapse8_kernel(con
     // level 0: mask (dst_w > 1e-5), saturate to 8 bits, interleave through shared memory
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-        const int v = wsum[j] > 1e-5f ? sat_u8(res[j]) : 0;
+        const int v = (unit || wsum[j] > 1e-5f) ? sat_u8(res[j]) : 0;
         tile[threadIdx.y * 2 + (j >> 3)][(threadIdx.x * 8 + (j & 7)) * 3 + plane] = (uint8_t)v;
     }
     __syncthreads();
@@ -620,12 +629,19 @@ __global__ void __launch_bounds__(96 * TY, TY == 4 ? 2 : 3) collapse8_kernel(con
     }
 }
 
-// ---- K1': rotation warp with the source footprint of each 128 x 8 output tile staged in
-// shared memory (coalesced 16-byte loads), then gathered with bank-conflict-free byte reads.
-template <bool kMap64>
+// ---- K1': rotation warp, 128 x 16 output pixels per block.
+// (1) The tile's source footprint (static bounding box from the init-time tile table) is staged in
+//     shared memory with coalesced 16-byte loads and EXPANDED from packed BGR to one 32-bit word per
+//     pixel (PRMT), so that a bilinear tap is a single conflict-free LDS.32 instead of three byte loads.
+// (2) During the gather a warp covers 32 consecutive output pixels (lane = pixel): its four tap loads
+//     fall into a ~35-word window of one or two staged rows.  B and R are interpolated together in one
+//     packed 16|16-bit multiply for the horizontal pass (values <= 255*32 fit 16 bits).
+// (3) Results are transposed through shared memory and leave as 16-byte vectors of planar int16.
+template <bool kMap64, bool kGain>
 __global__ void __launch_bounds__(256) warp_tile_kernel(const PanoTables *__restrict__ T, const uint8_t *__restrict__ frames)
 {
-    __shared__ __align__(16) uint8_t sm[kWarpSmemRows * kWarpSmemRowBytes];
+    __shared__ __align__(16) uint32_t sm[kWarpSmemWords];
+    __shared__ __align__(16) int16_t so[3][kWarpTileH][kWarpTileW];
     const int ncam = T->num_cams;
     const int cam = blockIdx.z % ncam, slot = blockIdx.z / ncam;
     const CamTables &C = T->cam[cam];
@@ -633,66 +649,108 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(const PanoTables *__rest
     if (outside_window(T, 0, C.rx + blockIdx.x * kWarpTileW, C.rx + (blockIdx.x + 1) * kWarpTileW)) return;
     const int W = T->src_w, H = T->src_h, W3 = W * 3;
     const uint8_t *src = frames + ((size_t)slot * ncam + cam) * ((size_t)W3 * H);
-    const int4 td = __ldg(C.tiles + blockIdx.y * C.tiles_x + blockIdx.x);   // {xbyte0, y0, rows, chunks}
-    const int tid = threadIdx.y * 32 + threadIdx.x;
-    const int stride = td.w * 16;
-    if (td.z > 0) {
+    const int4 td = __ldg(C.tiles + blockIdx.y * C.tiles_x + blockIdx.x);   // {x0 (px, %16==0), y0, rows, 16-px groups}
+    const int lane = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * 32 + lane;
+    const int rw = td.w * 16;                   // staged words per row
+    const bool staged = td.z > 0;
+    const int Xt = blockIdx.x * kWarpTileW;
+    // all 8 map entries of this thread are requested up front (together with the staging loads):
+    // the kernel is otherwise bound by the latency of one dependent map load per pixel
+    uint32_t msx[8], msy[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int Y = blockIdx.y * kWarpTileH + ty + 8 * (k >> 2), X = Xt + 32 * (k & 3) + lane;
+        msx[k] = 0; msy[k] = 0;
+        if (Y < C.rh && X < C.rw) {
+            if (kMap64) {
+                const uint2 e = __ldg(C.map64 + (size_t)Y * C.map_pitch + X);
+                msx[k] = e.x; msy[k] = e.y;
+            } else {
+                msx[k] = __ldg(C.map32 + (size_t)Y * C.map_pitch + X);
+            }
+        }
+    }
+    if (staged) {
         const int total = td.z * td.w;
-        for (int i = tid; i < total; i += 256) {
-            const int r = i / td.w, c = i - r * td.w;
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)(td.y + r) * W3 + td.x) + c);
-            *reinterpret_cast<uint4 *>(sm + r * stride + c * 16) = v;
+        for (int g = tid; g < total; g += 256) {
+            const int r = g / td.w, q = g - r * td.w;
+            const uint4 *p = reinterpret_cast<const uint4 *>(src + (size_t)(td.y + r) * W3 + (td.x + 16 * q) * 3);
+            const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+            const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+            uint4 o[4];
+            uint32_t *ow = reinterpret_cast<uint32_t *>(o);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {       // 4 pixels from 3 words
+                ow[4 * k + 0] = w[3 * k];
+                ow[4 * k + 1] = __byte_perm(w[3 * k], w[3 * k + 1], 0x6543);
+                ow[4 * k + 2] = __byte_perm(w[3 * k + 1], w[3 * k + 2], 0x5432);
+                ow[4 * k + 3] = w[3 * k + 2] >> 8;
+            }
+            uint4 *d = reinterpret_cast<uint4 *>(sm + r * rw + 16 * q);
+            d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; d[3] = o[3];
         }
     }
     __syncthreads();
-    const int X = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int Y = blockIdx.y * 8 + threadIdx.y;
-    if (X >= C.rw || Y >= C.rh) return;
-    uint32_t sx[4], sy[4];
-    if (kMap64) {
-        const uint2 *m = C.map64 + (size_t)Y * C.map_pitch + X;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        const int row = ty + 8 * rr;
+        const int Y = blockIdx.y * kWarpTileH + row;
+        if (Y >= C.rh) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint2 e = __ldg(m + j);
-            sx[j] = e.x; sy[j] = e.y;
+            const int X = Xt + 32 * j + lane;
+            if (X >= C.rw) {                           // row padding: keep it defined
+                so[0][row][32 * j + lane] = 0; so[1][row][32 * j + lane] = 0; so[2][row][32 * j + lane] = 0;
+                continue;
+            }
+            uint32_t sx, sy;
+            if (kMap64) { sx = msx[rr * 4 + j]; sy = msy[rr * 4 + j]; }
+            else { sx = msx[rr * 4 + j] & 0xffffu; sy = msx[rr * 4 + j] >> 16; }
+            const int ix = sx >> 5, fx = sx & 31, iy = sy >> 5, fy = sy & 31;
+            uint32_t t00, t01, t10, t11;               // BGRx words of the four taps
+            if (staged) {
+                const uint32_t *p = sm + (iy - td.y) * rw + (ix - td.x);
+                const int dx = ix + 1 < W ? 1 : 0, dy = iy + 1 < H ? rw : 0;
+                t00 = p[0]; t01 = p[dx]; t10 = p[dy]; t11 = p[dy + dx];
+            } else {
+                const uint8_t *p = src + (size_t)iy * W3 + ix * 3;
+                const int dx = ix + 1 < W ? 3 : 0, dy = iy + 1 < H ? W3 : 0;
+                t00 = p[0] | (p[1] << 8) | (p[2] << 16);
+                t01 = p[dx] | (p[dx + 1] << 8) | (p[dx + 2] << 16);
+                t10 = p[dy] | (p[dy + 1] << 8) | (p[dy + 2] << 16);
+                t11 = p[dy + dx] | (p[dy + dx + 1] << 8) | (p[dy + dx + 2] << 16);
+            }
+            // horizontal pass: B|R packed as 16|16 bits, G alone; weights (32-fx, fx)
+            const uint32_t gx = 32 - fx;
+            const uint32_t br0 = gx * (t00 & 0x00ff00ffu) + fx * (t01 & 0x00ff00ffu);
+            const uint32_t br1 = gx * (t10 & 0x00ff00ffu) + fx * (t11 & 0x00ff00ffu);
+            const uint32_t g0 = gx * ((t00 >> 8) & 0xffu) + fx * ((t01 >> 8) & 0xffu);
+            const uint32_t g1 = gx * ((t10 >> 8) & 0xffu) + fx * ((t11 >> 8) & 0xffu);
+            // vertical pass + rounding: (sum w*p + 512) >> 10 with w = (32-fy | fy) * (32-fx | fx)
+            const uint32_t gy = 32 - fy;
+            int v[3];
+            v[0] = (int)((gy * (br0 & 0xffffu) + fy * (br1 & 0xffffu) + 512u) >> 10);
+            v[1] = (int)((gy * g0 + fy * g1 + 512u) >> 10);
+            v[2] = (int)((gy * (br0 >> 16) + fy * (br1 >> 16) + 512u) >> 10);
+            if (kGain) {
+                const float g = C.gain_mode == 1 ? __ldg(C.gain_map + (size_t)Y * C.map_pitch + X) : 1.f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[c] = apply_gain(v[c], C.gain_mode, g, C.gain_scalar);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) so[c][row][32 * j + lane] = (int16_t)v[c];
         }
-    } else {
-        const uint4 e = __ldg(reinterpret_cast<const uint4 *>(C.map32 + (size_t)Y * C.map_pitch + X));
-        sx[0] = e.x & 0xffffu; sy[0] = e.x >> 16;
-        sx[1] = e.y & 0xffffu; sy[1] = e.y >> 16;
-        sx[2] = e.z & 0xffffu; sy[2] = e.z >> 16;
-        sx[3] = e.w & 0xffffu; sy[3] = e.w >> 16;
     }
-    float g[4] = {1.f, 1.f, 1.f, 1.f};
-    if (C.gain_mode == 1) {
-        const float4 gv = __ldg(reinterpret_cast<const float4 *>(C.gain_map + (size_t)Y * C.map_pitch + X));
-        g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
-    }
-    short px[3][4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        int v[3];
-        if (td.z > 0) {
-            const int ix = sx[j] >> 5, fx = sx[j] & 31, iy = sy[j] >> 5, fy = sy[j] & 31;
-            const int ix1 = min(ix + 1, W - 1), iy1 = min(iy + 1, H - 1);
-            const uint8_t *r0 = sm + (iy - td.y) * stride - td.x, *r1 = sm + (iy1 - td.y) * stride - td.x;
-            const int w00 = (32 - fy) * (32 - fx), w01 = (32 - fy) * fx, w10 = fy * (32 - fx), w11 = fy * fx;
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-                v[c] = (w00 * r0[ix * 3 + c] + w01 * r0[ix1 * 3 + c] + w10 * r1[ix * 3 + c] + w11 * r1[ix1 * 3 + c] + 512) >> 10;
-        } else {
-            bilinear_bgr(src, W, H, sx[j], sy[j], v);
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) px[c][j] = (short)apply_gain(v[c], C.gain_mode, g[j], C.gain_scalar);
-    }
-    int16_t *dst = C.g[0] + (size_t)slot * C.g_slot[0] + (size_t)Y * C.g_pitch[0] + X;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        uint2 o;
-        o.x = (uint16_t)px[c][0] | ((uint32_t)(uint16_t)px[c][1] << 16);
-        o.y = (uint16_t)px[c][2] | ((uint32_t)(uint16_t)px[c][3] << 16);
-        *reinterpret_cast<uint2 *>(dst + (size_t)c * C.g_plane[0]) = o;
+    __syncthreads();
+    // 3 planes x 16 rows x 128 px x 2 B = 768 chunks of 16 bytes
+    int16_t *gbase = C.g[0] + (size_t)slot * C.g_slot[0];
+    const int gp = C.g_pitch[0];
+    for (int i = tid; i < 3 * kWarpTileH * (kWarpTileW / 8); i += 256) {
+        const int q = i & 15, r = (i >> 4) % kWarpTileH, c = i / (16 * kWarpTileH);
+        const int yy = blockIdx.y * kWarpTileH + r, xx = Xt + q * 8;
+        if (yy < C.rh && xx < gp)
+            *reinterpret_cast<uint4 *>(gbase + (size_t)c * C.g_plane[0] + yy * gp + xx) = *reinterpret_cast<const uint4 *>(&so[c][r][q * 8]);
     }
 }
 
@@ -802,8 +860,15 @@ void launch_warp(const PanoTables *dev, const PanoTables &host, const KernelChoi
             ty = max(ty, host.cam[i].tiles_y);
         }
         const dim3 block(32, 8), grid(tx, ty, host.num_cams * nslots);
-        if (host.cam[0].map64) warp_tile_kernel<true><<<grid, block, 0, stream>>>(dev, frames);
-        else warp_tile_kernel<false><<<grid, block, 0, stream>>>(dev, frames);
+        bool gain = false;
+        for (int i = 0; i < host.num_cams; ++i) gain = gain || host.cam[i].gain_mode != 0;
+        if (host.cam[0].map64) {
+            if (gain) warp_tile_kernel<true, true><<<grid, block, 0, stream>>>(dev, frames);
+            else warp_tile_kernel<true, false><<<grid, block, 0, stream>>>(dev, frames);
+        } else {
+            if (gain) warp_tile_kernel<false, true><<<grid, block, 0, stream>>>(dev, frames);
+            else warp_tile_kernel<false, false><<<grid, block, 0, stream>>>(dev, frames);
+        }
         return;
     }
     int maxw = 0, maxh = 0;

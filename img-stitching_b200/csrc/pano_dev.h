@@ -22,8 +22,8 @@ struct CamTables {
     const uint32_t *map32;
     const uint2 *map64;
     int map_pitch;
-    // per 128x8 output tile: source bounding box of the gather {x byte offset (16B aligned),
-    // first row, rows, 16-byte chunks per row}; rows == 0 -> tile gathers straight from global
+    // per 128x16 output tile: source bounding box of the gather {first column (multiple of 16),
+    // first row, rows, 16-pixel groups per row}; rows == 0 -> tile gathers straight from global
     const int4 *tiles;
     int tiles_x, tiles_y;
     // exposure gain: mode 0 off, 1 per-pixel float map (feed-rect layout, pitch = map_pitch),
@@ -67,8 +67,8 @@ struct PanoTables {
 };
 
 // launchers (kernels.cu) -- all asynchronous on `stream`
-constexpr int kWarpTileW = 128, kWarpTileH = 8;       // output pixels per warp-kernel block
-constexpr int kWarpSmemRows = 24, kWarpSmemRowBytes = 640;
+constexpr int kWarpTileW = 128, kWarpTileH = 16;      // output pixels per warp-kernel block
+constexpr int kWarpSmemWords = 7168;                  // staged source footprint, one 32-bit word per pixel (28 KB)
 
 struct KernelChoice {
     bool warp_tiled = false;                 // staged-gather warp kernel usable (row bytes % 16 == 0)
