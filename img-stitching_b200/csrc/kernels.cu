@@ -481,18 +481,41 @@ __device__ __forceinline__ void unpack8(const uint4 v, int o[8])
 // w_sum == 1.0f -> (short)(a / 1.00001f) == a - sign(a) for every 16-bit a (checked on the host).
 // Level 0 stages the three planes through shared memory so the interleaved 8-bit panorama
 // leaves in aligned 8-byte stores.
+// Everything the kernel needs about one level, pre-shifted and pre-offset on the host and passed BY
+// VALUE (kernel parameters live in the constant bank: uniform, latency-free reads instead of a
+// chain of dependent global loads through the table struct).
+struct C8Cam {
+    int x0, y0, fw, fh;              // camera rect at this level, dst coordinates
+    const int16_t *gf, *gc;          // g[l], g[l+1] (slot 0, plane 0)
+    int pf, pc;                      // pitches
+    unsigned plane_f, plane_c;       // plane strides
+    size_t slot_f, slot_c;           // slot strides
+    const void *w;                   // level-0 mask (u8) or float weights
+    int wp, use_mask;
+};
+struct C8Args {
+    C8Cam cam[kMaxCams];
+    const int16_t *outc;
+    int16_t *outf;
+    int poc, pof;
+    unsigned plane_oc, plane_of;
+    size_t slot_oc, slot_of;
+    const uint32_t *tile_cams;
+    int Wf, Hf, win_lo, win_hi, cut_x, cut_y, cut_w, cut_h, flags;
+};
+
 template <bool kLevel0, int TY>
-__global__ void __launch_bounds__(96 * TY, TY == 4 ? 2 : 3) collapse8_kernel(const PanoTables *__restrict__ T, int L,
+__global__ void __launch_bounds__(96 * TY, TY == 4 ? 2 : 3) collapse8_kernel(const __grid_constant__ C8Args A,
                                                                             uint8_t *__restrict__ pano)
 {
     __shared__ __align__(16) uint8_t tile[2 * TY][256 * 3];
     const int plane = threadIdx.z;
     const int X0 = (blockIdx.x * 32 + threadIdx.x) * 8, Y0 = (blockIdx.y * TY + threadIdx.y) * 2;
     const int slot = blockIdx.z;
-    const int Wf = T->pad_w >> L, Hf = T->pad_h >> L;
-    const bool in_window = !outside_window(T, L, blockIdx.x * 256, blockIdx.x * 256 + 256);
+    const int Wf = A.Wf, Hf = A.Hf;
+    const bool in_window = !((int)blockIdx.x * 256 + 256 <= A.win_lo || (int)blockIdx.x * 256 >= A.win_hi);
     // level 0 only produces panorama pixels: rows outside the cut rectangle are never needed
-    const bool in_cut = !kLevel0 || (Y0 + 1 >= T->cut_y && Y0 < T->cut_y + T->cut_h);
+    const bool in_cut = !kLevel0 || (Y0 + 1 >= A.cut_y && Y0 < A.cut_y + A.cut_h);
     const bool active = X0 < Wf && Y0 < Hf && in_window && in_cut;
     int res[16];
     float wsum[16];
@@ -504,31 +527,29 @@ __global__ void __launch_bounds__(96 * TY, TY == 4 ? 2 : 3) collapse8_kernel(con
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = 0;
         UpRaw raw_out;     // loads issued now, consumed after the camera loop
-        up_load(T->outp[L + 1] + (size_t)slot * T->out_slot[L + 1] + (size_t)plane * T->out_plane[L + 1],
-                T->out_pitch[L + 1], Wf >> 1, Hf >> 1, X0 >> 1, Y0 >> 1, raw_out);
-        uint32_t cams = __ldg(T->tile_cams[L] + ((blockIdx.y * 2 * TY) >> 3) * gridDim.x + blockIdx.x);
+        up_load(A.outc + slot * A.slot_oc + plane * A.plane_oc, A.poc, Wf >> 1, Hf >> 1, X0 >> 1, Y0 >> 1, raw_out);
+        uint32_t cams = __ldg(A.tile_cams + ((blockIdx.y * 2 * TY) >> 3) * gridDim.x + blockIdx.x);
         while (cams) {
             const int i = __ffs(cams) - 1;
             cams &= cams - 1;
-            const CamTables &C = T->cam[i];
-            const int x = X0 - (C.rx >> L), y = Y0 - (C.ry >> L);
-            const int fw = C.rw >> L, fh = C.rh >> L;
+            const C8Cam &C = A.cam[i];
+            const int x = X0 - C.x0, y = Y0 - C.y0;
+            const int fw = C.fw, fh = C.fh;
             if ((unsigned)x >= (unsigned)fw || (unsigned)y >= (unsigned)fh) continue;
             // the camera is listed for this tile: fetch its pyramid data unconditionally, together
             // with the weights, so that one memory round trip covers all of it
             UpRaw raw;
-            up_load(C.g[L + 1] + (size_t)slot * C.g_slot[L + 1] + (size_t)plane * C.g_plane[L + 1], C.g_pitch[L + 1],
-                    fw >> 1, fh >> 1, x >> 1, y >> 1, raw);
-            const int16_t *f = C.g[L] + (size_t)slot * C.g_slot[L] + (size_t)plane * C.g_plane[L] + y * C.g_pitch[L] + x;
-            const uint4 f0 = *reinterpret_cast<const uint4 *>(f), f1 = *reinterpret_cast<const uint4 *>(f + C.g_pitch[L]);
+            up_load(C.gc + slot * C.slot_c + plane * C.plane_c, C.pc, fw >> 1, fh >> 1, x >> 1, y >> 1, raw);
+            const int16_t *f = C.gf + slot * C.slot_f + plane * C.plane_f + y * C.pf + x;
+            const uint4 f0 = *reinterpret_cast<const uint4 *>(f), f1 = *reinterpret_cast<const uint4 *>(f + C.pf);
             float w[16];
             bool ones;
-            if (kLevel0 && !C.use_wt0) {
-                const uint8_t *mrow = C.mask0 + y * C.mask_pitch + x;
+            if (kLevel0 && C.use_mask) {
+                const uint8_t *mrow = static_cast<const uint8_t *>(C.w) + y * C.wp + x;
                 const uint2 a = *reinterpret_cast<const uint2 *>(mrow);
-                const uint2 b = *reinterpret_cast<const uint2 *>(mrow + C.mask_pitch);
+                const uint2 b = *reinterpret_cast<const uint2 *>(mrow + C.wp);
                 if ((a.x | a.y | b.x | b.y) == 0u) continue;
-                ones = (a.x & a.y & b.x & b.y) == 0xffffffffu && (T->unit_norm_exact & 2);   // 255 * (1/255.f) == 1.0f
+                ones = (a.x & a.y & b.x & b.y) == 0xffffffffu && (A.flags & 2);   // 255 * (1/255.f) == 1.0f
                 if (!ones) {
                     const uint32_t mw[4] = {a.x, a.y, b.x, b.y};
 #pragma unroll
@@ -536,10 +557,10 @@ __global__ void __launch_bounds__(96 * TY, TY == 4 ? 2 : 3) collapse8_kernel(con
                         w[j] = __fmul_rn((float)((mw[j >> 2] >> (8 * (j & 3))) & 0xffu), 1.f / 255.f);
                 }
             } else {
-                const float *wrow = C.wt[L] + y * C.wt_pitch[L] + x;
+                const float *wrow = static_cast<const float *>(C.w) + y * C.wp + x;
                 const float4 a0 = *reinterpret_cast<const float4 *>(wrow), a1 = *reinterpret_cast<const float4 *>(wrow + 4);
-                const float4 b0 = *reinterpret_cast<const float4 *>(wrow + C.wt_pitch[L]);
-                const float4 b1 = *reinterpret_cast<const float4 *>(wrow + C.wt_pitch[L] + 4);
+                const float4 b0 = *reinterpret_cast<const float4 *>(wrow + C.wp);
+                const float4 b1 = *reinterpret_cast<const float4 *>(wrow + C.wp + 4);
                 w[0] = a0.x; w[1] = a0.y; w[2] = a0.z; w[3] = a0.w; w[4] = a1.x; w[5] = a1.y; w[6] = a1.z; w[7] = a1.w;
                 w[8] = b0.x; w[9] = b0.y; w[10] = b0.z; w[11] = b0.w; w[12] = b1.x; w[13] = b1.y; w[14] = b1.z; w[15] = b1.w;
                 bool any = false;
@@ -573,7 +594,7 @@ __global__ void __launch_bounds__(96 * TY, TY == 4 ? 2 : 3) collapse8_kernel(con
         }
         int upo[16];
         up_compute(raw_out, upo);
-        if (n_soft == 0 && n_unit == 1 && (T->unit_norm_exact & 1)) {
+        if (n_soft == 0 && n_unit == 1 && (A.flags & 1)) {
             // exactly one camera, all weights 1.0f: dst_w == 1.0f and
             // (short)(a / (1.0f + 1e-5f)) == a - sign(a) for every |a| <= 32768 (host-verified)
             unit = true;
@@ -590,14 +611,14 @@ __global__ void __launch_bounds__(96 * TY, TY == 4 ? 2 : 3) collapse8_kernel(con
     }
     if (!kLevel0) {
         if (!active) return;
-        int16_t *o = T->outp[L] + (size_t)slot * T->out_slot[L] + (size_t)plane * T->out_plane[L] + Y0 * T->out_pitch[L] + X0;
+        int16_t *o = A.outf + slot * A.slot_of + plane * A.plane_of + Y0 * A.pof + X0;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int *v = res + 8 * r;
             uint4 q;
             q.x = (uint16_t)v[0] | ((uint32_t)v[1] << 16); q.y = (uint16_t)v[2] | ((uint32_t)v[3] << 16);
             q.z = (uint16_t)v[4] | ((uint32_t)v[5] << 16); q.w = (uint16_t)v[6] | ((uint32_t)v[7] << 16);
-            *reinterpret_cast<uint4 *>(o + r * T->out_pitch[L]) = q;
+            *reinterpret_cast<uint4 *>(o + r * A.pof) = q;
         }
         return;
     }
@@ -611,11 +632,11 @@ __global__ void __launch_bounds__(96 * TY, TY == 4 ? 2 : 3) collapse8_kernel(con
     if (!in_window) return;
     const int tid = (threadIdx.z * TY + threadIdx.y) * 32 + threadIdx.x;  // one 16-byte chunk of the tile each
     const int row = tid / 48, col = (tid % 48) * 16;
-    const int Y = blockIdx.y * 2 * TY + row - T->cut_y;
-    if ((unsigned)Y >= (unsigned)T->cut_h) return;
-    const int xbyte = (blockIdx.x * 256 - T->cut_x) * 3 + col;            // byte offset inside the output row
-    const int row_bytes = T->cut_w * 3;
-    uint8_t *orow = pano + ((size_t)slot * T->cut_h + Y) * (size_t)row_bytes;
+    const int Y = blockIdx.y * 2 * TY + row - A.cut_y;
+    if ((unsigned)Y >= (unsigned)A.cut_h) return;
+    const int xbyte = (blockIdx.x * 256 - A.cut_x) * 3 + col;            // byte offset inside the output row
+    const int row_bytes = A.cut_w * 3;
+    uint8_t *orow = pano + ((size_t)slot * A.cut_h + Y) * (size_t)row_bytes;
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
         const int b0 = xbyte + 8 * hh;
@@ -913,14 +934,35 @@ void launch_collapse(const PanoTables *dev, const PanoTables &host, const Kernel
     if (kc.collapse8[level]) {
         const int wf = host.pad_w >> level, hf = host.pad_h >> level;
         static const int ty = getenv("PANO_C8_TY") ? atoi(getenv("PANO_C8_TY")) : 4;
+        C8Args A{};
+        const int L = level;
+        for (int i = 0; i < host.num_cams; ++i) {
+            const CamTables &C = host.cam[i];
+            C8Cam &d = A.cam[i];
+            d.x0 = C.rx >> L; d.y0 = C.ry >> L; d.fw = C.rw >> L; d.fh = C.rh >> L;
+            d.gf = C.g[L]; d.gc = C.g[L + 1]; d.pf = C.g_pitch[L]; d.pc = C.g_pitch[L + 1];
+            d.plane_f = (unsigned)C.g_plane[L]; d.plane_c = (unsigned)C.g_plane[L + 1];
+            d.slot_f = C.g_slot[L]; d.slot_c = C.g_slot[L + 1];
+            d.use_mask = (L == 0 && !C.use_wt0) ? 1 : 0;
+            d.w = d.use_mask ? (const void *)C.mask0 : (const void *)C.wt[L];
+            d.wp = d.use_mask ? C.mask_pitch : C.wt_pitch[L];
+        }
+        A.outc = host.outp[L + 1]; A.outf = L > 0 ? host.outp[L] : nullptr;
+        A.poc = host.out_pitch[L + 1]; A.pof = L > 0 ? host.out_pitch[L] : 0;
+        A.plane_oc = (unsigned)host.out_plane[L + 1]; A.plane_of = L > 0 ? (unsigned)host.out_plane[L] : 0;
+        A.slot_oc = host.out_slot[L + 1]; A.slot_of = L > 0 ? host.out_slot[L] : 0;
+        A.tile_cams = host.tile_cams[L];
+        A.Wf = wf; A.Hf = hf; A.win_lo = host.win_lo[L]; A.win_hi = host.win_hi[L];
+        A.cut_x = host.cut_x; A.cut_y = host.cut_y; A.cut_w = host.cut_w; A.cut_h = host.cut_h;
+        A.flags = host.unit_norm_exact;
         if (ty == 4) {
             const dim3 block(32, 4, 3), grid((wf + 255) / 256, (hf + 7) / 8, nslots);
-            if (level == 0) collapse8_kernel<true, 4><<<grid, block, 0, stream>>>(dev, level, pano);
-            else collapse8_kernel<false, 4><<<grid, block, 0, stream>>>(dev, level, pano);
+            if (level == 0) collapse8_kernel<true, 4><<<grid, block, 0, stream>>>(A, pano);
+            else collapse8_kernel<false, 4><<<grid, block, 0, stream>>>(A, pano);
         } else {
             const dim3 block(32, 2, 3), grid((wf + 255) / 256, (hf + 3) / 4, nslots);
-            if (level == 0) collapse8_kernel<true, 2><<<grid, block, 0, stream>>>(dev, level, pano);
-            else collapse8_kernel<false, 2><<<grid, block, 0, stream>>>(dev, level, pano);
+            if (level == 0) collapse8_kernel<true, 2><<<grid, block, 0, stream>>>(A, pano);
+            else collapse8_kernel<false, 2><<<grid, block, 0, stream>>>(A, pano);
         }
         return;
     }
