@@ -159,11 +159,11 @@ def synth_numpy(seed):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="frame-sets per GPU per step")
-    ap.add_argument("--max-batch", type=int, default=4, help="frame-sets per launch wave")
+    ap.add_argument("--max-batch", type=int, default=8, help="frame-sets per launch wave")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -220,8 +220,16 @@ def main():
     launches_per_step = st.last_launch_count()
     torch.cuda.synchronize()
     barrier()
+    # clocks / throttle reasons are sampled under the same load: the sampler runs while the step loop
+    # keeps the GPU busy (a pre-roll of identical steps, then the K timed steps, then a post-roll so
+    # that at least a few 150 ms nvidia-smi samples land inside the loaded interval)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    t_pre = time.perf_counter()
+    while time.perf_counter() - t_pre < 0.4:
+        step()
+        torch.cuda.synchronize()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record(stream)
@@ -231,6 +239,10 @@ def main():
     torch.cuda.synchronize()
     barrier()
     ms = e0.elapsed_time(e1)
+    t_post = time.perf_counter()
+    while time.perf_counter() - t_post < 0.4:
+        step()
+        torch.cuda.synchronize()
     clocks = sampler.summary()
 
     # ---- per-kernel device time (CUDA events on the launching stream) for the roofline ----

@@ -28,7 +28,7 @@ struct ProfEntry {
     double bytes;
 };
 
-constexpr int kPipeDepth = 3;
+constexpr int kPipeDepth = 4;
 
 }  // namespace
 
@@ -63,8 +63,8 @@ struct pano_ctx {
     std::vector<std::vector<void *>> cam_wt;      // per camera per level
 
     // staging for host entry points
-    uint8_t *stage_in[kPipeDepth] = {nullptr, nullptr, nullptr};
-    uint8_t *stage_out[kPipeDepth] = {nullptr, nullptr, nullptr};
+    uint8_t *stage_in[kPipeDepth] = {};
+    uint8_t *stage_out[kPipeDepth] = {};
     cudaStream_t s_h2d = nullptr, s_compute = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_in[kPipeDepth]{}, ev_done[kPipeDepth]{}, ev_out[kPipeDepth]{};
 
@@ -792,7 +792,9 @@ int pano_process_batch(pano_handle h, const uint8_t *frames_host, uint8_t *out_h
     if (!h || !frames_host || !out_host || batch < 1) return fail(h, "pano_process_batch: bad argument");
     CK(h, cudaSetDevice(h->device));
     if (ensureStaging(h) || syncTables(h)) return PANO_ERR;
-    const int S = h->cfg.max_batch;
+    // small chunks keep the H2D / compute / D2H pipeline full (fill + drain cost one chunk each);
+    // the kernels have ample headroom over PCIe, so short waves do not hurt here
+    const int S = std::min(h->cfg.max_batch, 2);
     h->last_launches = 0;
     const bool prof = h->profiling;
     h->profiling = false;
