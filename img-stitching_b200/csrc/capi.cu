@@ -18,6 +18,12 @@
 
 using namespace pano;
 
+// internal front-end entry points (frontend.cu)
+int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img, uint8_t *out, size_t o_img, int batch,
+                      cudaStream_t st);
+int pano_frontend_launches(pano_frontend_handle h);
+void pano_frontend_sizes(pano_frontend_handle h, int *in_wh, int *out_wh);
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -54,6 +60,11 @@ struct pano_ctx {
     PanoTables *dev = nullptr;
     KernelChoice kc;
     bool tables_dirty = true;
+    // optional nvCam front end per camera (pano_attach_frontend): inputs become 8UC4 camera frames
+    pano_frontend_handle front[kMaxCams] = {};
+    bool has_front = false;
+    size_t in_frame_bytes = 0;                    // bytes of one input frame as the caller passes it
+    uint8_t *front_out = nullptr;                 // [max_batch][n][H][W][3] stitcher inputs produced by the front end
     int strip_x0 = 0, strip_x1 = 0;               // own dst columns (level 0, padded coords); full width = no split
     // [level][cam][tile] -> camera has a non-zero weight inside the 256x8 dst tile
     std::vector<std::vector<std::vector<uint8_t>>> tile_flags;
@@ -74,7 +85,7 @@ struct pano_ctx {
     int last_launches = 0;
 
     size_t frame_bytes() const { return (size_t)cfg.src_width * cfg.src_height * 3; }
-    size_t set_bytes() const { return frame_bytes() * n; }
+    size_t set_bytes() const { return (has_front ? in_frame_bytes : frame_bytes()) * n; }   // caller-side frame-set
     size_t out_bytes() const { return (size_t)host.cut_w * host.cut_h * 3; }
 };
 
@@ -325,8 +336,34 @@ int runPhase(pano_ctx *h, int p, const uint8_t *frames_dev, uint8_t *out_dev, in
     return PANO_OK;
 }
 
+int runFrontEnds(pano_ctx *h, const uint8_t *&frames_dev, int slots, cudaStream_t st)
+{
+    if (!h->has_front) return PANO_OK;
+    Launch L{h, st};
+    bool same = true;
+    for (int i = 1; i < h->n; ++i) same = same && h->front[i] == h->front[0];
+    L.begin("front_end", (double)slots * h->n * (h->in_frame_bytes + h->frame_bytes()));
+    if (same) {
+        if (pano_frontend_run(h->front[0], frames_dev, h->in_frame_bytes, h->front_out, h->frame_bytes(), slots * h->n, st))
+            return fail(h, "front end: %s", pano_frontend_last_error(h->front[0]));
+        h->last_launches += pano_frontend_launches(h->front[0]) - 1;
+    } else {
+        for (int i = 0; i < h->n; ++i) {
+            if (pano_frontend_run(h->front[i], frames_dev + i * h->in_frame_bytes, h->in_frame_bytes * h->n,
+                                  h->front_out + i * h->frame_bytes(), h->frame_bytes() * h->n, slots, st))
+                return fail(h, "front end: %s", pano_frontend_last_error(h->front[i]));
+            h->last_launches += pano_frontend_launches(h->front[i]);
+        }
+        h->last_launches -= 1;
+    }
+    L.end();
+    frames_dev = h->front_out;
+    return PANO_OK;
+}
+
 int runWave(pano_ctx *h, const uint8_t *frames_dev, uint8_t *out_dev, int slots, cudaStream_t st)
 {
+    if (runFrontEnds(h, frames_dev, slots, st)) return PANO_ERR;
     const int np = phaseCount(h);
     for (int p = 0; p < np; ++p)
         if (runPhase(h, p, frames_dev, out_dev, slots, st)) return PANO_ERR;
@@ -749,6 +786,34 @@ int pano_set_gain_scalar(pano_handle h, int cam, double gain)
     return PANO_OK;
 }
 
+int pano_attach_frontend(pano_handle h, int cam, pano_frontend_handle f)
+{
+    if (!h || cam < -1 || cam >= h->n) return fail(h, "pano_attach_frontend: bad argument");
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());
+    if (!f) {
+        for (int i = 0; i < h->n; ++i) h->front[i] = nullptr;
+        h->has_front = false;
+        return PANO_OK;
+    }
+    int in_wh[2], out_wh[2];
+    pano_frontend_sizes(f, in_wh, out_wh);
+    if (out_wh[0] != h->cfg.src_width || out_wh[1] != h->cfg.src_height)
+        return fail(h, "pano_attach_frontend: front end delivers %dx%d, stitcher expects %dx%d", out_wh[0], out_wh[1],
+                    h->cfg.src_width, h->cfg.src_height);
+    const size_t in_bytes = (size_t)in_wh[0] * in_wh[1] * 4;
+    if (h->has_front && in_bytes != h->in_frame_bytes) return fail(h, "pano_attach_frontend: all cameras must share one frame size");
+    for (int i = 0; i < h->n; ++i)
+        if (cam < 0 || cam == i) h->front[i] = f;
+    for (int i = 0; i < h->n; ++i)
+        if (!h->front[i]) h->front[i] = f;      // every camera needs one once the input format changes
+    if (h->stage_in[0]) return fail(h, "pano_attach_frontend: attach before the first host-side process call");
+    h->in_frame_bytes = in_bytes;
+    h->has_front = true;
+    if (!h->front_out && devAlloc(h, &h->front_out, h->frame_bytes() * h->n * h->cfg.max_batch, false)) return PANO_ERR;
+    return PANO_OK;
+}
+
 int pano_process_device(pano_handle h, const uint8_t *frames_dev, uint8_t *out_dev, int batch, void *stream)
 {
     if (!h || !frames_dev || !out_dev || batch < 1) return fail(h, "pano_process_device: bad argument");
@@ -770,12 +835,18 @@ int pano_process(pano_handle h, const uint8_t *const *frames, const int *strides
     if (!h || !frames || !out) return fail(h, "pano_process: bad argument");
     CK(h, cudaSetDevice(h->device));
     if (ensureStaging(h) || syncTables(h)) return PANO_ERR;
-    const int W3 = h->cfg.src_width * 3, H = h->cfg.src_height;
+    int W3 = h->cfg.src_width * 3, H = h->cfg.src_height;
+    size_t fbytes = h->frame_bytes();
+    if (h->has_front) {
+        int in_wh[2], out_wh[2];
+        pano_frontend_sizes(h->front[0], in_wh, out_wh);
+        W3 = in_wh[0] * 4; H = in_wh[1]; fbytes = h->in_frame_bytes;
+    }
     if (out_stride < h->host.cut_w * 3) return fail(h, "pano_process: out_stride too small");
     for (int i = 0; i < h->n; ++i) {
         const int st = strides ? strides[i] : W3;
         if (!frames[i] || st < W3) return fail(h, "pano_process: bad frame %d", i);
-        CK(h, cudaMemcpy2DAsync(h->stage_in[0] + (size_t)i * h->frame_bytes(), W3, frames[i], st, W3, H,
+        CK(h, cudaMemcpy2DAsync(h->stage_in[0] + (size_t)i * fbytes, W3, frames[i], st, W3, H,
                                 cudaMemcpyHostToDevice, h->s_compute));
     }
     h->last_launches = 0;

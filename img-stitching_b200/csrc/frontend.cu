@@ -246,15 +246,18 @@ int pano_frontend_get_maps(pano_frontend_handle h, float *mapx, float *mapy)
     return PANO_OK;
 }
 
-int pano_frontend_process_device(pano_frontend_handle h, const uint8_t *argb, uint8_t *out, int batch, void *stream)
+}  // extern "C"
+
+// Internal entry (also used by capi.cu when a front end is attached to a stitcher handle):
+// images may be strided (in_img / o_img bytes between consecutive images).
+int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img, uint8_t *out, size_t o_img, int batch,
+                      cudaStream_t st)
 {
-    if (!h || !argb || !out || batch < 1) return ffail(h, "pano_frontend_process_device: bad argument");
+    if (!h || !argb || !out || batch < 1) return ffail(h, "pano_frontend_run: bad argument");
     FCK(h, cudaSetDevice(h->cfg.device));
-    cudaStream_t st = (cudaStream_t)stream;
     const pano_frontend_config &c = h->cfg;
     const int S = c.max_batch, uw = c.undist_width, uh = c.undist_height;
-    const size_t in_img = (size_t)c.cam_src_width * c.cam_src_height * 4;
-    const size_t u_img = (size_t)uw * uh * 3, o_img = (size_t)c.out_width * c.out_height * 3;
+    const size_t u_img = (size_t)uw * uh * 3;
     const dim3 blk(32, 8);
     h->launches = 0;
     for (int b0 = 0; b0 < batch; b0 += S) {
@@ -274,7 +277,7 @@ int pano_frontend_process_device(pano_frontend_handle h, const uint8_t *argb, ui
             const int *rc = c.rect;
             const bool last2 = !h->use_r_mid && !h->use_r_out;
             uint8_t *d2 = target(last2, h->buf_b);
-            const size_t d2_img = (size_t)rc[2] * rc[3] * 3;
+            const size_t d2_img = last2 ? o_img : (size_t)rc[2] * rc[3] * 3;
             if (cur_c == 4)
                 cubic_kernel<4><<<grid2(rc[2], rc[3], blk, nb), blk, 0, st>>>(cur, cur_img, cw, chh, cw * 4, h->dmap, uw, h->dtab,
                                                                               rc[0], rc[1], rc[2], rc[3], d2, d2_img);
@@ -286,20 +289,23 @@ int pano_frontend_process_device(pano_frontend_handle h, const uint8_t *argb, ui
             // stage 3: resize the crop back to the undistort size (:917)
             if (h->use_r_mid) {
                 uint8_t *d3 = target(!h->use_r_out, h->buf_c);
-                resize_kernel<3><<<grid2(uw, uh, blk, nb), blk, 0, st>>>(cur, cur_img, cw * 3, d3, u_img, uw * 3, h->r_mid);
+                const size_t d3_img = h->use_r_out ? u_img : o_img;
+                resize_kernel<3><<<grid2(uw, uh, blk, nb), blk, 0, st>>>(cur, cur_img, cw * 3, d3, d3_img, uw * 3, h->r_mid);
                 ++h->launches;
-                cur = d3; cw = uw; chh = uh; cur_img = u_img;
+                cur = d3; cw = uw; chh = uh; cur_img = d3_img;
             }
         } else {
             uint8_t *d1 = target(!h->use_r_out, h->buf_a);
+            const size_t d1_img = h->use_r_out ? u_img : o_img;
             if (h->use_r_in) {
-                resize_kernel<4><<<grid2(uw, uh, blk, nb), blk, 0, st>>>(cur, cur_img, cw * 4, d1, u_img, uw * 3, h->r_in);
+                resize_kernel<4><<<grid2(uw, uh, blk, nb), blk, 0, st>>>(cur, cur_img, cw * 4, d1, d1_img, uw * 3, h->r_in);
             } else {
-                const size_t npx = (size_t)uw * uh * nb;
-                drop_alpha_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(cur, d1, npx);
+                const size_t npx = (size_t)uw * uh;
+                for (int k = 0; k < nb; ++k)
+                    drop_alpha_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(cur + k * cur_img, d1 + k * d1_img, npx);
             }
             ++h->launches;
-            cur = d1; cur_c = 3; cw = uw; chh = uh; cur_img = u_img;
+            cur = d1; cur_c = 3; cw = uw; chh = uh; cur_img = d1_img;
         }
         // stage 4: getFrame(.., src=false) resize to the stitcher input (:1094)
         if (h->use_r_out) {
@@ -310,6 +316,23 @@ int pano_frontend_process_device(pano_frontend_handle h, const uint8_t *argb, ui
     }
     FCK(h, cudaGetLastError());
     return PANO_OK;
+}
+
+int pano_frontend_launches(pano_frontend_handle h) { return h ? h->launches : 0; }
+void pano_frontend_sizes(pano_frontend_handle h, int *in_wh, int *out_wh)
+{
+    in_wh[0] = h->cfg.cam_src_width; in_wh[1] = h->cfg.cam_src_height;
+    out_wh[0] = h->cfg.out_width; out_wh[1] = h->cfg.out_height;
+}
+
+extern "C" {
+
+int pano_frontend_process_device(pano_frontend_handle h, const uint8_t *argb, uint8_t *out, int batch, void *stream)
+{
+    if (!h) return PANO_ERR;
+    const pano_frontend_config &c = h->cfg;
+    return pano_frontend_run(h, argb, (size_t)c.cam_src_width * c.cam_src_height * 4, out,
+                             (size_t)c.out_width * c.out_height * 3, batch, (cudaStream_t)stream);
 }
 
 int pano_frontend_process(pano_frontend_handle h, const uint8_t *argb_host, int stride, uint8_t *out_host, int out_stride)

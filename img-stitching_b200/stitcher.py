@@ -215,9 +215,11 @@ class ocvStitcher:
         if len(imgs) != c.num_images:
             raise capi.PanoError("expected %d images" % c.num_images)
         frames = [np.ascontiguousarray(im, np.uint8) for im in imgs]
+        front = getattr(self, "_front", None)
+        want = (c.height, c.width, 3) if front is None else (front.cfg.camSrcHeight, front.cfg.camSrcWidth, 4)
         for f in frames:
-            if f.shape != (c.height, c.width, 3):
-                raise capi.PanoError("frame must be %dx%dx3" % (c.height, c.width))
+            if f.shape != want:
+                raise capi.PanoError("frame must be %dx%dx%d" % want)
         ow, oh = self.out_size
         if ret is None:
             ret = np.empty((oh, ow, 3), np.uint8)
@@ -279,6 +281,11 @@ class ocvStitcher:
             else:
                 g = np.ascontiguousarray(g, np.float32)
                 capi.check(self._lib.pano_set_gain_map(self._h, i, capi.ptr(g), g.shape[1], g.shape[0]), self._h)
+
+    def attach_frontend(self, front, cam=-1):
+        """Chain an nvCamFrontEnd: process*() then take 8UC4 camera frames (src/master.cpp:300-318)."""
+        capi.check(self._lib.pano_attach_frontend(self._h, cam, front._h if front is not None else None), self._h)
+        self._front = front
 
     def enable_profile(self, on=True):
         capi.check(self._lib.pano_profile_enable(self._h, int(on)), self._h)

@@ -188,6 +188,13 @@ int pano_host_undistort_maps(const double *K, const double *D, const double *new
 int pano_host_cubic_table(int16_t *tab);
 int pano_host_resize_axis(int ssize, int dsize, int clamp_frac, int *ofs, int16_t *a0, int16_t *a1);
 
+/* Chain a front end in front of a stitcher handle (cam = -1: every camera): from then on
+ * pano_process / pano_process_device / pano_process_batch take the 8UC4 camera frames
+ * ([batch][num_images][cam_src_height][cam_src_width][4]) and run nvCam's pixel pipeline on the
+ * device first -- the loop of src/master.cpp:300-318 (getFrame x N, then process) as one call.
+ * f == NULL detaches.  Attach before the first host-memory process call. */
+int pano_attach_frontend(pano_handle h, int cam, pano_frontend_handle f);
+
 /* library / build identification: returns e.g. "panob200 sm_100a" */
 const char *pano_version(void);
 

@@ -277,6 +277,49 @@ def test_config4_full_size_8cam_4k_cylindrical_7_bands():
     assert np.array_equal(st.process(imgs), got)               # idempotent
 
 
+def test_config2_front_end_chained_into_process():
+    """BASELINE config 2 at half scale: 8UC4 camera frames -> cubic undistort -> crop -> resize ->
+    spherical warp -> 4-band blend, as ONE call (pano_attach_frontend), vs the oracle's sequential
+    undistort -> warp interpolation order."""
+    import torch
+    cam = calib.CAM_LIJING_390_FOV60_1920
+    s = 0.5
+    K = np.array(cam["K"], np.float64).reshape(3, 3).copy()
+    K[0, 0] *= s; K[0, 2] *= s; K[1, 1] *= s; K[1, 2] *= s
+    newK = np.array([[1627.5076 * s, 0, 943.1681 * s], [0, 1622.9720 * s, 571.5369 * s], [0, 0, 1]])
+    rect = [34, 52, 891, 444]
+    CamConfig = panob200.pkg.nvcam.CamConfig
+    fe = panob200.nvCamFrontEnd(CamConfig(camSrcWidth=960, camSrcHeight=540, undistoredWidth=960, undistoredHeight=540,
+                                          outPutWidth=960, outPutHeight=540, K=K.reshape(-1), distorParams=cam["distorParams"],
+                                          rect=rect, newK=newK, max_batch=8))
+    mx, my = fe.maps()
+    Ks, Rs, scale = calib.rig("2222", 960)
+    t = compose.build_tables(Ks, Rs, scale, (960, 540), "spherical")
+    t.blend_masks = util.soft_masks(t)
+    st = panob200.ocvStitcher(SC(width=960, height=540, num_images=4, Ks=Ks, Rs=Rs, warped_image_scale=scale,
+                                 blender="multiband", num_bands=4, max_batch=2))
+    assert st.initTables(t.blend_masks) == 0, st.last_error
+    st.attach_frontend(fe)
+    sets = [[util.synth_frame(540, 960, 900 + 10 * b + i, channels=4) for i in range(4)] for b in range(3)]
+    want = []
+    for frames in sets:
+        bgr = [compose.front_end(f, (960, 540), mx, my, rect, (960, 540)) for f in frames]
+        want.append(compose.process(t, bgr, "multiband", 4))
+    assert_equal("config2 host call", st.process(sets[0]), want[0])
+    dev = torch.from_numpy(np.stack([np.stack(f) for f in sets])).cuda()
+    ow, oh = st.out_size
+    out = torch.empty((3, oh, ow, 3), dtype=torch.uint8, device="cuda")
+    st.process_device(dev, out)
+    torch.cuda.synchronize()
+    for b in range(3):
+        assert_equal("config2 device batch %d" % b, out[b].cpu().numpy(), want[b])
+    host_in = torch.from_numpy(np.stack([np.stack(f) for f in sets])).pin_memory()
+    host_out = torch.empty((3, oh, ow, 3), dtype=torch.uint8).pin_memory()
+    st.process_batch(host_in, host_out)
+    for b in range(3):
+        assert_equal("config2 host batch %d" % b, host_out[b].numpy(), want[b])
+
+
 # ------------------------------------------------------------------ column-strip split (config 4)
 
 def _strip_setup(nranks, mode, W=960, H=540, nb=5, ncam=8):
