@@ -31,7 +31,32 @@ METRIC = "panoramas_per_sec"
 UNIT = "panoramas/s"
 W, H, NCAM, NBANDS = 1920, 1080, 4, 5
 CUT = [0, 64, 5336, 896]
-WORKLOAD = "config1: 4x1920x1080 BGR -> spherical warp + 5-band MultiBandBlender -> cut 5336x896 (imx390 rig, 2222 calibration x4)"
+WORKLOADS = {
+    "config1": "config1: 4x1920x1080 BGR -> spherical warp + 5-band MultiBandBlender -> cut 5336x896 (imx390 rig, 2222 calibration x4)",
+    "config2": "config2: 4x1920x1080 BGRA camera frames -> imx390 undistort (INTER_CUBIC) + crop [69,103,1782,889] + resize -> "
+               "spherical warp + 5-band MultiBandBlender -> cut 5336x896",
+}
+WORKLOAD = WORKLOADS["config1"]
+NEWK_FALLBACK = [[1627.5076, 0, 943.1681], [0, 1622.9720, 571.5369], [0, 0, 1]]   # SURVEY A10 (used when cv2 is absent)
+
+
+def camera_entry():
+    from golden import calib
+    return calib.CAM_LIJING_390_FOV60_1920
+
+
+def make_front_end(device, max_batch):
+    """nvCam front end of config 2 (cfg/cameras.yaml:80-88 entry, 1920x1080 in/out)."""
+    import panob200
+    cam = camera_entry()
+    newK = None
+    try:
+        import cv2  # noqa: F401  (prepareUndistorMap's getOptimalNewCameraMatrix: one-time host init)
+    except ImportError:
+        newK = NEWK_FALLBACK
+    cfg = panob200.pkg.nvcam.CamConfig(K=cam["K"], distorParams=cam["distorParams"], rect=cam["rect"], newK=newK,
+                                       device=device, max_batch=max_batch)
+    return panob200.nvCamFrontEnd(cfg)
 
 
 def calibration():
@@ -106,16 +131,27 @@ def cpu_reference_setup(frames0):
         return "c_port", t
 
 
-def cpu_reference_time(kind, t, frame_sets, repeats):
-    """Times the reference's per-frame path (ocvStitcher::process restated call for call) on the
-    host cores.  -> (panoramas/s, cores used, description)."""
+def cpu_reference_time(kind, t, frame_sets, repeats, front=False):
+    """Times the reference's per-frame path (ocvStitcher::process restated call for call; with
+    front=True preceded by nvCam's resize/undistort/crop/resize per camera) on the host cores.
+    -> (panoramas/s, cores used, description)."""
     n = 0
     if kind == "cv2":
         from oracle import cv2_reference as ref
-        ref.process(t, frame_sets[0], "multiband", NBANDS, cut=CUT)          # warm-up
+        fe = None
+        if front:
+            cam = camera_entry()
+            _, mx, my = ref.undistort_tables(cam["K"], cam["distorParams"], (W, H))
+            fe = lambda a: ref.front_end(a, (W, H), mx, my, cam["rect"], (W, H))     # noqa: E731
+
+        def one(fs):
+            if fe is not None:
+                fs = [fe(np.dstack([f, np.full(f.shape[:2], 255, np.uint8)])) if f.shape[2] == 3 else fe(f) for f in fs]
+            return ref.process(t, fs, "multiband", NBANDS, cut=CUT)   # 'faithful': maps rebuilt per call (:1171)
+        one(frame_sets[0])          # warm-up
         t0 = time.perf_counter()
         for r in range(repeats):
-            ref.process(t, frame_sets[r % len(frame_sets)], "multiband", NBANDS, cut=CUT)   # 'faithful': maps rebuilt per call (:1171)
+            one(frame_sets[r % len(frame_sets)])
             n += 1
         dt = time.perf_counter() - t0
         return n / dt, os.cpu_count() or 1, ("%d panoramas, cv2 %s cv::detail classes driven by the restated ocvStitcher::process "
@@ -137,14 +173,15 @@ def run_reference(args, rank, world):
     per_step = 2
     sets = [[np.ascontiguousarray(f) for f in synth_numpy(1000 + s)] for s in range(2)]
     kind, t = cpu_reference_setup(sets[0])
-    cpu_reference_time(kind, t, sets, max(1, args.warmup))
+    front = args.workload == "config2"
+    cpu_reference_time(kind, t, sets, max(1, args.warmup), front)
     t0 = time.perf_counter()
-    v, cores, desc = cpu_reference_time(kind, t, sets, per_step * args.steps)
+    v, cores, desc = cpu_reference_time(kind, t, sets, per_step * args.steps, front)
     dt = time.perf_counter() - t0
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/s16 fixed-point + f32 weights", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frame_sets_per_step": per_step},
+            "config": {"workload": WORKLOADS[args.workload], "frame_sets_per_step": per_step},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -163,9 +200,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="frame-sets per GPU per step")
-    ap.add_argument("--max-batch", type=int, default=8, help="frame-sets per launch wave")
+    ap.add_argument("--max-batch", type=int, default=16, help="frame-sets per launch wave")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -192,7 +230,15 @@ def main():
     Ks, Rs, scale = calibration()
     B = args.batch
     frames = synth_batch_torch(B, 1234 + rank, dev)
-    set0 = [frames[0, i].cpu().numpy() for i in range(NCAM)]
+    front = None
+    if args.workload == "config2":
+        # camera frames are 8UC4 (the VIC's ARGB output, include/nvcam.hpp:889-893): BGR + alpha 255
+        frames = torch.cat([frames, torch.full(frames.shape[:-1] + (1,), 255, dtype=torch.uint8, device=dev)], dim=-1).contiguous()
+        front = make_front_end(local_rank, args.max_batch * NCAM)
+    if front is None:
+        set0 = [frames[0, i].cpu().numpy() for i in range(NCAM)]
+    else:   # the stitcher calibrates on what the front end delivers
+        set0 = [front.getFrame(frames[0, i].cpu().numpy()) for i in range(NCAM)]
     cfg = panob200.StitcherConfig(width=W, height=H, num_images=NCAM, Ks=Ks, Rs=Rs, warped_image_scale=scale,
                                   blender="multiband", num_bands=NBANDS, cut=CUT, device=local_rank,
                                   max_batch=args.max_batch, initMode=2)
@@ -204,6 +250,8 @@ def main():
         rc, masks_how = st.initTables(), "warped all-255 masks (cv2 absent)"
     if rc != 0:
         raise SystemExit("stitcher init failed: " + st.last_error)
+    if front is not None:
+        st.attach_frontend(front)
     ow, oh = st.out_size
     out = torch.empty((B, oh, ow, 3), dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
@@ -301,13 +349,13 @@ def main():
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             sets = [[frames[b, i].cpu().numpy() for i in range(NCAM)] for b in range(2)]
-            kind, t = cpu_reference_setup(sets[0])
-            v, cores, desc = cpu_reference_time(kind, t, sets, 24 if kind == "cv2" else 4)
+            kind, t = cpu_reference_setup([f[:, :, :3] for f in sets[0]] if front is None else set0)
+            v, cores, desc = cpu_reference_time(kind, t, sets, 24 if kind == "cv2" else 4, front is not None)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8/s16 fixed-point + f32 weights", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "frame_sets_per_gpu_per_step": B, "frame_sets_per_wave": args.max_batch,
+                "config": {"workload": WORKLOADS[args.workload], "frame_sets_per_gpu_per_step": B, "frame_sets_per_wave": args.max_batch,
                            "masks": masks_how, "l2": "inputs (1.6 GB/step) larger than L2; no flush"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_in.numel()),
                         "d2h_bytes_per_step": int(host_out.numel()), "steps": e2e_steps, "matches_device_path": same},

@@ -23,6 +23,7 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
                       cudaStream_t st);
 int pano_frontend_launches(pano_frontend_handle h);
 void pano_frontend_sizes(pano_frontend_handle h, int *in_wh, int *out_wh);
+bool pano_frontend_set_prof(pano_frontend_handle h, cudaEvent_t *ev, double *cubic_bytes, double *resize_bytes);
 
 namespace {
 
@@ -32,6 +33,7 @@ struct ProfEntry {
     const char *name;
     cudaEvent_t e0, e1;
     double bytes;
+    bool shared_e0 = false;     // e0 belongs to the previous entry (do not destroy twice)
 };
 
 constexpr int kPipeDepth = 4;
@@ -225,7 +227,7 @@ struct Launch {
     void begin(const char *name, double bytes)
     {
         if (!h->profiling) return;
-        ProfEntry pe;
+        ProfEntry pe{};
         pe.name = name; pe.bytes = bytes;
         cudaEventCreate(&pe.e0); cudaEventCreate(&pe.e1);
         cudaEventRecord(pe.e0, st);
@@ -241,7 +243,7 @@ struct Launch {
 
 void clearProf(pano_ctx *h)
 {
-    for (auto &p : h->prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+    for (auto &p : h->prof) { if (!p.shared_e0) cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
     h->prof.clear();
 }
 
@@ -342,6 +344,26 @@ int runFrontEnds(pano_ctx *h, const uint8_t *&frames_dev, int slots, cudaStream_
     Launch L{h, st};
     bool same = true;
     for (int i = 1; i < h->n; ++i) same = same && h->front[i] == h->front[0];
+    if (same && h->profiling) {
+        // per-kernel timing of the fast path (cubic undistort / bilinear resize)
+        cudaEvent_t ev[3];
+        double cb = 0, rb = 0;
+        for (auto &e : ev) cudaEventCreate(&e);
+        if (pano_frontend_set_prof(h->front[0], ev, &cb, &rb)) {
+            const int rc = pano_frontend_run(h->front[0], frames_dev, h->in_frame_bytes, h->front_out, h->frame_bytes(), slots * h->n, st);
+            pano_frontend_set_prof(h->front[0], nullptr, nullptr, nullptr);
+            if (rc) return fail(h, "front end: %s", pano_frontend_last_error(h->front[0]));
+            ProfEntry a{"fe_cubic_undistort", ev[0], ev[1], cb * slots * h->n};
+            h->prof.push_back(a);
+            ProfEntry b{"fe_resize", ev[1], ev[2], rb * slots * h->n, true};   // shares the middle event
+            h->prof.push_back(b);
+            h->last_launches += pano_frontend_launches(h->front[0]);
+            frames_dev = h->front_out;
+            return PANO_OK;
+        }
+        pano_frontend_set_prof(h->front[0], nullptr, nullptr, nullptr);
+        for (auto &e : ev) cudaEventDestroy(e);
+    }
     L.begin("front_end", (double)slots * h->n * (h->in_frame_bytes + h->frame_bytes()));
     if (same) {
         if (pano_frontend_run(h->front[0], frames_dev, h->in_frame_bytes, h->front_out, h->frame_bytes(), slots * h->n, st))

@@ -29,6 +29,14 @@ struct ResizeTab {
 
 __device__ __forceinline__ int sat_u8(int v) { return max(0, min(255, v)); }
 
+// d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1  (signed 16-bit weights x unsigned 8-bit pixels)
+__device__ __forceinline__ int dp2a_su(int a, unsigned b, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 // cv::resize INTER_LINEAR u8: one thread = one output pixel (3 channels out, CIN in)
 template <int CIN>
 __global__ void __launch_bounds__(256) resize_kernel(const uint8_t *__restrict__ src, size_t src_img, int sstride,
@@ -96,6 +104,142 @@ __global__ void __launch_bounds__(256) cubic_kernel(const uint8_t *__restrict__ 
     for (int c = 0; c < 3; ++c) d[c] = (uint8_t)sat_u8((acc[c] + 16384) >> 15);
 }
 
+
+// ---------------------------------------------------------------- fast path (8UC4 camera frames)
+// The camera frame already has one 32-bit word per pixel, so every tap is one aligned word load
+// and a warp's 32 consecutive output pixels read a compact, coalesced window.  The cropped
+// undistorted image is kept in the same word-per-pixel form (an internal buffer), which makes the
+// bilinear resize that follows a 4-word gather as well.  Map entries / table offsets of all the
+// pixels a thread owns are requested before any of them is used (the kernels are otherwise bound
+// by one dependent load per pixel).
+
+// cv::remap INTER_CUBIC over the crop rect; src: 8UC4 words, dst: words (B | G<<8 | R<<16).
+// Map entry, packed form (sources up to 2043 pixels per side): (tx+4) | (ty+4) << 11 | fx << 22 | fy << 27
+// where (tx, ty) is the first of the 4x4 taps, clamped to [-4, size] (beyond that every tap is
+// outside the image and contributes 0 either way).
+template <bool kPacked>
+__global__ void __launch_bounds__(256) cubic4_kernel(const uint32_t *__restrict__ src, size_t src_img_words, int sw, int sh,
+                                                     const void *__restrict__ map_, int map_w, const uint4 *__restrict__ tab,
+                                                     int rx, int ry, int rw, int rh, uint32_t *__restrict__ dst,
+                                                     size_t dst_img_words)
+{
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (y >= rh) return;
+    const int xb = blockIdx.x * 128 + threadIdx.x;
+    const uint32_t *s = src + (size_t)blockIdx.z * src_img_words;
+    uint32_t *d = dst + (size_t)blockIdx.z * dst_img_words + (size_t)y * rw;
+    int2 m[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int x = xb + 32 * j;
+        m[j] = make_int2(0, 0);
+        if (x < rw) {
+            const size_t mi = (size_t)(y + ry) * map_w + (x + rx);
+            if (kPacked) m[j].x = (int)__ldg(static_cast<const uint32_t *>(map_) + mi);
+            else m[j] = __ldg(static_cast<const int2 *>(map_) + mi);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int x = xb + 32 * j;
+        if (x >= rw) continue;
+        int ix, iy, fidx;
+        if (kPacked) {
+            const uint32_t e = (uint32_t)m[j].x;
+            ix = (int)(e & 2047u) - 4; iy = (int)((e >> 11) & 2047u) - 4;
+            fidx = (int)(((e >> 27) << 5) | ((e >> 22) & 31u));
+        } else {
+            ix = (m[j].x >> 5) - 1; iy = (m[j].y >> 5) - 1;
+            fidx = ((m[j].y & 31) << 5) | (m[j].x & 31);
+        }
+        const uint4 *wp = tab + (fidx << 1);     // 16 shorts = 2 x uint4
+        const uint4 wa = __ldg(wp), wb = __ldg(wp + 1);
+        const uint32_t wpk[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        uint32_t t[16];
+        if (ix >= 0 && iy >= 0 && ix + 3 < sw && iy + 3 < sh) {
+            const uint32_t *p = s + (size_t)iy * sw + ix;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) t[4 * r + q] = __ldg(p + r * sw + q);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int px = ix + q, py = iy + r;
+                    t[4 * r + q] = ((unsigned)px < (unsigned)sw && (unsigned)py < (unsigned)sh) ? __ldg(s + (size_t)py * sw + px) : 0u;
+                }
+        }
+        // two taps per IDP.2A: the table already stores neighbouring weights as packed int16 pairs;
+        // PRMT pairs up the same channel of two neighbouring pixels
+        int a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            a0 = dp2a_su((int)wpk[k], __byte_perm(t[2 * k], t[2 * k + 1], 0x0040), a0);
+            a1 = dp2a_su((int)wpk[k], __byte_perm(t[2 * k], t[2 * k + 1], 0x0051), a1);
+            a2 = dp2a_su((int)wpk[k], __byte_perm(t[2 * k], t[2 * k + 1], 0x0062), a2);
+        }
+        d[x] = (uint32_t)sat_u8((a0 + 16384) >> 15) | ((uint32_t)sat_u8((a1 + 16384) >> 15) << 8) |
+               ((uint32_t)sat_u8((a2 + 16384) >> 15) << 16);
+    }
+}
+
+// cv::resize INTER_LINEAR from a word-per-pixel source to packed BGR bytes.  One warp row-chunk =
+// 32 consecutive output pixels = 96 bytes, assembled in shared memory and stored as 24 words.
+__global__ void __launch_bounds__(256) resize4_kernel(const uint32_t *__restrict__ src, size_t src_img_words, int sstride_words,
+                                                      uint8_t *__restrict__ dst, size_t dst_img, int dstride, ResizeTab t)
+{
+    __shared__ __align__(16) uint8_t sm[8][4][96];
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int lane = threadIdx.x;
+    const bool rowok = y < t.dh;
+    const uint32_t *s = src + (size_t)blockIdx.z * src_img_words;
+    const int yo = rowok ? t.yofs[y] : 0;
+    const int sy0 = min(max(yo, 0), t.sh - 1), sy1 = min(max(yo + 1, 0), t.sh - 1);
+    const short2 ay = rowok ? t.ya[y] : make_short2(0, 0);
+    const uint32_t *r0 = s + (size_t)sy0 * sstride_words, *r1 = s + (size_t)sy1 * sstride_words;
+    int xo[4];
+    short2 ax[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int x = blockIdx.x * 128 + 32 * j + lane;
+        xo[j] = (rowok && x < t.dw) ? t.xofs[x] : 0;
+        ax[j] = (rowok && x < t.dw) ? t.xa[x] : make_short2(0, 0);
+    }
+    uint32_t p[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int x1 = min(xo[j] + 1, t.sw - 1);
+        p[j][0] = __ldg(r0 + xo[j]); p[j][1] = __ldg(r0 + x1); p[j][2] = __ldg(r1 + xo[j]); p[j][3] = __ldg(r1 + x1);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int axp = (int)(((uint32_t)(uint16_t)ax[j].y << 16) | (uint16_t)ax[j].x);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const uint32_t sel = 0x0040u + 0x11u * c;                 // byte c of both taps
+            const int t0 = dp2a_su(axp, __byte_perm(p[j][0], p[j][1], sel), 0);
+            const int t1 = dp2a_su(axp, __byte_perm(p[j][2], p[j][3], sel), 0);
+            sm[threadIdx.y][j][lane * 3 + c] = (uint8_t)sat_u8((((ay.x * (t0 >> 4)) >> 16) + ((ay.y * (t1 >> 4)) >> 16) + 2) >> 2);
+        }
+    }
+    __syncwarp();
+    if (!rowok) return;
+    uint8_t *drow = dst + (size_t)blockIdx.z * dst_img + (size_t)y * dstride;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int x0 = blockIdx.x * 128 + 32 * j;
+        if (x0 >= t.dw) break;
+        uint8_t *o = drow + (size_t)x0 * 3;
+        if (x0 + 32 <= t.dw && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
+            if (lane < 24) reinterpret_cast<uint32_t *>(o)[lane] = reinterpret_cast<const uint32_t *>(sm[threadIdx.y][j])[lane];
+        } else {
+            for (int b = lane; b < 3 * min(32, t.dw - x0); b += 32) o[b] = sm[threadIdx.y][j][b];
+        }
+    }
+}
+
 thread_local std::string g_front_error;
 
 }  // namespace
@@ -110,6 +254,10 @@ struct pano_frontend_ctx {
     ResizeTab r_in, r_mid, r_out;       // cam->undist, rect->undist, undist->out
     bool use_r_in = false, use_r_mid = false, use_r_out = false;
     uint8_t *buf_a = nullptr, *buf_b = nullptr, *buf_c = nullptr;  // intermediates, max_batch deep
+    uint32_t *buf_w = nullptr;                                     // cropped undistorted image, one word per pixel (fast path)
+    uint32_t *dmap32 = nullptr;                                    // packed map entries (fast path, sources <= 2043 px)
+    bool fast4 = false;
+    cudaEvent_t *prof_ev = nullptr;                                // 3 events (before cubic, between, after resize) when profiling
     uint8_t *stage_in = nullptr, *stage_out = nullptr;
     int launches = 0;
 };
@@ -224,6 +372,23 @@ int pano_frontend_create(const pano_frontend_config *cfg, pano_frontend_handle *
     if (h->use_r_out && makeResize(h, h->r_out, uw, uh, cfg->out_width, cfg->out_height)) return bail();
     const size_t ubytes = (size_t)uw * uh * 3 * S;
     if (falloc(h, &h->buf_a, ubytes) || falloc(h, &h->buf_b, ubytes) || falloc(h, &h->buf_c, ubytes)) return bail();
+    // fast path: undistort straight from the 8UC4 camera frame, then one resize to the output size
+    h->fast4 = cfg->undistort && !h->use_r_in && h->use_r_mid && !h->use_r_out;
+    if (h->fast4 && falloc(h, &h->buf_w, (size_t)cfg->rect[2] * cfg->rect[3] * S)) return bail();
+    if (h->fast4 && cfg->cam_src_width + 4 <= 2047 && cfg->cam_src_height + 4 <= 2047) {
+        std::vector<uint32_t> pm(h->mapx.size());
+        for (size_t i = 0; i < pm.size(); ++i) {
+            const FixedCoord fc = toFixed(h->mapx[i], h->mapy[i]);
+            const int tx = std::max(-4, std::min(cfg->cam_src_width, fc.ix - 1));
+            const int ty = std::max(-4, std::min(cfg->cam_src_height, fc.iy - 1));
+            pm[i] = (uint32_t)(tx + 4) | ((uint32_t)(ty + 4) << 11) | ((uint32_t)fc.fx << 22) | ((uint32_t)fc.fy << 27);
+        }
+        if (falloc(h, &h->dmap32, pm.size())) return bail();
+        if (cudaMemcpy(h->dmap32, pm.data(), pm.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+            h->err = "front-end packed map upload failed";
+            return bail();
+        }
+    }
     *out = h;
     return PANO_OK;
 }
@@ -267,6 +432,24 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
         // stage 1: camera frame -> undist-sized 3-channel "tmp" (:903-904 / :924-927)
         const uint8_t *cur = src; int cur_c = 4; int cw = c.cam_src_width, chh = c.cam_src_height; size_t cur_img = in_img;
         auto target = [&](bool last, uint8_t *scratch) { return last ? final_dst : scratch; };
+        if (h->fast4 && (in_img & 3) == 0) {
+            const int *rc = c.rect;
+            const size_t w_img = (size_t)rc[2] * rc[3];
+            const dim3 cg((rc[2] + 127) / 128, (rc[3] + 7) / 8, nb);
+            if (h->prof_ev) cudaEventRecord(h->prof_ev[0], st);
+            if (h->dmap32)
+                cubic4_kernel<true><<<cg, blk, 0, st>>>(reinterpret_cast<const uint32_t *>(src), in_img / 4, cw, chh, h->dmap32, uw,
+                                                        reinterpret_cast<const uint4 *>(h->dtab), rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
+            else
+                cubic4_kernel<false><<<cg, blk, 0, st>>>(reinterpret_cast<const uint32_t *>(src), in_img / 4, cw, chh, h->dmap, uw,
+                                                         reinterpret_cast<const uint4 *>(h->dtab), rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
+            if (h->prof_ev) cudaEventRecord(h->prof_ev[1], st);
+            resize4_kernel<<<dim3((uw + 127) / 128, (uh + 7) / 8, nb), blk, 0, st>>>(h->buf_w, w_img, rc[2], final_dst, o_img,
+                                                                                     uw * 3, h->r_mid);
+            if (h->prof_ev) cudaEventRecord(h->prof_ev[2], st);
+            h->launches += 2;
+            continue;
+        }
         if (c.undistort) {
             if (h->use_r_in) {
                 resize_kernel<4><<<grid2(uw, uh, blk, nb), blk, 0, st>>>(cur, cur_img, cw * 4, h->buf_a, u_img, uw * 3, h->r_in);
@@ -319,6 +502,17 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
 }
 
 int pano_frontend_launches(pano_frontend_handle h) { return h ? h->launches : 0; }
+// fast path only, one chunk per call: record events around the two kernels; returns their algorithmic bytes per image
+bool pano_frontend_set_prof(pano_frontend_handle h, cudaEvent_t *ev, double *cubic_bytes, double *resize_bytes)
+{
+    h->prof_ev = ev;
+    if (!h->fast4) return false;
+    const pano_frontend_config &c = h->cfg;
+    const double rect_px = (double)c.rect[2] * c.rect[3];
+    if (cubic_bytes) *cubic_bytes = (double)c.cam_src_width * c.cam_src_height * 4 + rect_px * (h->dmap32 ? 4 : 8) + rect_px * 4;
+    if (resize_bytes) *resize_bytes = rect_px * 4 + (double)c.out_width * c.out_height * 3;
+    return true;
+}
 void pano_frontend_sizes(pano_frontend_handle h, int *in_wh, int *out_wh)
 {
     in_wh[0] = h->cfg.cam_src_width; in_wh[1] = h->cfg.cam_src_height;
