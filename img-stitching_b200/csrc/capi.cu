@@ -567,8 +567,10 @@ int pano_create(const pano_config *cfg, pano_handle *out)
                             if (h->map64) { sx = m64[(size_t)Y * C.map_pitch + X].x; sy = m64[(size_t)Y * C.map_pitch + X].y; }
                             else { sx = m32[(size_t)Y * C.map_pitch + X] & 0xffffu; sy = m32[(size_t)Y * C.map_pitch + X] >> 16; }
                             const int ix = sx >> 5, iy = sy >> 5;
-                            x0 = std::min(x0, ix); x1 = std::max(x1, std::min(ix + 1, W - 1));
-                            y0 = std::min(y0, iy); y1 = std::max(y1, std::min(iy + 1, H - 1));
+                            // taps (ix+1, iy+1) may lie one past the frame (weight 0 there); the kernel's
+                            // staging loop clamps the source address, the box keeps the unclamped extent
+                            x0 = std::min(x0, ix); x1 = std::max(x1, ix + 1);
+                            y0 = std::min(y0, iy); y1 = std::max(y1, iy + 1);
                         }
                     const int px0 = x0 / 16 * 16, groups = (x1 - px0) / 16 + 1;
                     const int rows = y1 - y0 + 1;

@@ -653,16 +653,19 @@ __global__ void __launch_bounds__(96 * TY, TY == 4 ? 2 : 3) collapse8_kernel(con
 // ---- K1': rotation warp, 128 x 16 output pixels per block.
 // (1) The tile's source footprint (static bounding box from the init-time tile table) is staged in
 //     shared memory with coalesced 16-byte loads and EXPANDED from packed BGR to one 32-bit word per
-//     pixel (PRMT), so that a bilinear tap is a single conflict-free LDS.32 instead of three byte loads.
+//     pixel (PRMT), so that a bilinear tap is a single conflict-free LDS.32 instead of three byte
+//     loads.  The box includes the (ix+1, iy+1) taps even where they fall one past the frame (their
+//     weight is 0 there by construction of the folded map); staging clamps the SOURCE address
+//     instead, so the gather needs no border logic at all.
 // (2) During the gather a warp covers 32 consecutive output pixels (lane = pixel): its four tap loads
 //     fall into a ~35-word window of one or two staged rows.  B and R are interpolated together in one
 //     packed 16|16-bit multiply for the horizontal pass (values <= 255*32 fit 16 bits).
-// (3) Results are transposed through shared memory and leave as 16-byte vectors of planar int16.
+// (3) All 8 map entries of a thread are requested before the staging loop, so their latency overlaps
+//     the staging loads; planar int16 results are stored straight from registers (64-byte runs).
 template <bool kMap64, bool kGain>
 __global__ void __launch_bounds__(256) warp_tile_kernel(const PanoTables *__restrict__ T, const uint8_t *__restrict__ frames)
 {
     __shared__ __align__(16) uint32_t sm[kWarpSmemWords];
-    __shared__ __align__(16) int16_t so[3][kWarpTileH][kWarpTileW];
     const int ncam = T->num_cams;
     const int cam = blockIdx.z % ncam, slot = blockIdx.z / ncam;
     const CamTables &C = T->cam[cam];
@@ -675,20 +678,24 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(const PanoTables *__rest
     const int tid = ty * 32 + lane;
     const int rw = td.w * 16;                   // staged words per row
     const bool staged = td.z > 0;
-    const int Xt = blockIdx.x * kWarpTileW;
-    // all 8 map entries of this thread are requested up front (together with the staging loads):
-    // the kernel is otherwise bound by the latency of one dependent map load per pixel
+    const int Xt = blockIdx.x * kWarpTileW + lane;
+    const int Y0 = blockIdx.y * kWarpTileH + ty;
+    const int mp = C.map_pitch, crw = C.rw, crh = C.rh;
     uint32_t msx[8], msy[8];
+    {
+        const uint32_t *m32 = C.map32 + Y0 * mp + Xt;
+        const uint2 *m64 = C.map64 + Y0 * mp + Xt;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int Y = blockIdx.y * kWarpTileH + ty + 8 * (k >> 2), X = Xt + 32 * (k & 3) + lane;
-        msx[k] = 0; msy[k] = 0;
-        if (Y < C.rh && X < C.rw) {
-            if (kMap64) {
-                const uint2 e = __ldg(C.map64 + (size_t)Y * C.map_pitch + X);
-                msx[k] = e.x; msy[k] = e.y;
-            } else {
-                msx[k] = __ldg(C.map32 + (size_t)Y * C.map_pitch + X);
+        for (int k = 0; k < 8; ++k) {
+            const int off = 8 * (k >> 2) * mp + 32 * (k & 3);
+            msx[k] = 0; msy[k] = 0;
+            if (Y0 + 8 * (k >> 2) < crh && Xt + 32 * (k & 3) < crw) {
+                if (kMap64) {
+                    const uint2 e = __ldg(m64 + off);
+                    msx[k] = e.x; msy[k] = e.y;
+                } else {
+                    msx[k] = __ldg(m32 + off);
+                }
             }
         }
     }
@@ -696,7 +703,8 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(const PanoTables *__rest
         const int total = td.z * td.w;
         for (int g = tid; g < total; g += 256) {
             const int r = g / td.w, q = g - r * td.w;
-            const uint4 *p = reinterpret_cast<const uint4 *>(src + (size_t)(td.y + r) * W3 + (td.x + 16 * q) * 3);
+            const int sy = min(td.y + r, H - 1), sx = min(td.x + 16 * q, W - 16);     // taps one past the frame have weight 0
+            const uint4 *p = reinterpret_cast<const uint4 *>(src + (size_t)sy * W3 + sx * 3);
             const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
             const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
             uint4 o[4];
@@ -713,65 +721,50 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(const PanoTables *__rest
         }
     }
     __syncthreads();
+    const uint32_t *smb = sm - td.y * rw - td.x;
+    int16_t *gout = C.g[0] + (size_t)slot * C.g_slot[0] + Y0 * C.g_pitch[0] + Xt;
+    const unsigned gplane = (unsigned)C.g_plane[0];
+    const int gp8 = 8 * C.g_pitch[0];
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-        const int row = ty + 8 * rr;
-        const int Y = blockIdx.y * kWarpTileH + row;
-        if (Y >= C.rh) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int X = Xt + 32 * j + lane;
-            if (X >= C.rw) {                           // row padding: keep it defined
-                so[0][row][32 * j + lane] = 0; so[1][row][32 * j + lane] = 0; so[2][row][32 * j + lane] = 0;
-                continue;
-            }
-            uint32_t sx, sy;
-            if (kMap64) { sx = msx[rr * 4 + j]; sy = msy[rr * 4 + j]; }
-            else { sx = msx[rr * 4 + j] & 0xffffu; sy = msx[rr * 4 + j] >> 16; }
-            const int ix = sx >> 5, fx = sx & 31, iy = sy >> 5, fy = sy & 31;
-            uint32_t t00, t01, t10, t11;               // BGRx words of the four taps
-            if (staged) {
-                const uint32_t *p = sm + (iy - td.y) * rw + (ix - td.x);
-                const int dx = ix + 1 < W ? 1 : 0, dy = iy + 1 < H ? rw : 0;
-                t00 = p[0]; t01 = p[dx]; t10 = p[dy]; t11 = p[dy + dx];
-            } else {
-                const uint8_t *p = src + (size_t)iy * W3 + ix * 3;
-                const int dx = ix + 1 < W ? 3 : 0, dy = iy + 1 < H ? W3 : 0;
-                t00 = p[0] | (p[1] << 8) | (p[2] << 16);
-                t01 = p[dx] | (p[dx + 1] << 8) | (p[dx + 2] << 16);
-                t10 = p[dy] | (p[dy + 1] << 8) | (p[dy + 2] << 16);
-                t11 = p[dy + dx] | (p[dy + dx + 1] << 8) | (p[dy + dx + 2] << 16);
-            }
-            // horizontal pass: B|R packed as 16|16 bits, G alone; weights (32-fx, fx)
-            const uint32_t gx = 32 - fx;
-            const uint32_t br0 = gx * (t00 & 0x00ff00ffu) + fx * (t01 & 0x00ff00ffu);
-            const uint32_t br1 = gx * (t10 & 0x00ff00ffu) + fx * (t11 & 0x00ff00ffu);
-            const uint32_t g0 = gx * ((t00 >> 8) & 0xffu) + fx * ((t01 >> 8) & 0xffu);
-            const uint32_t g1 = gx * ((t10 >> 8) & 0xffu) + fx * ((t11 >> 8) & 0xffu);
-            // vertical pass + rounding: (sum w*p + 512) >> 10 with w = (32-fy | fy) * (32-fx | fx)
-            const uint32_t gy = 32 - fy;
-            int v[3];
-            v[0] = (int)((gy * (br0 & 0xffffu) + fy * (br1 & 0xffffu) + 512u) >> 10);
-            v[1] = (int)((gy * g0 + fy * g1 + 512u) >> 10);
-            v[2] = (int)((gy * (br0 >> 16) + fy * (br1 >> 16) + 512u) >> 10);
-            if (kGain) {
-                const float g = C.gain_mode == 1 ? __ldg(C.gain_map + (size_t)Y * C.map_pitch + X) : 1.f;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) v[c] = apply_gain(v[c], C.gain_mode, g, C.gain_scalar);
-            }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) so[c][row][32 * j + lane] = (int16_t)v[c];
+    for (int k = 0; k < 8; ++k) {
+        if (Y0 + 8 * (k >> 2) >= crh || Xt + 32 * (k & 3) >= crw) continue;
+        uint32_t sx, sy;
+        if (kMap64) { sx = msx[k]; sy = msy[k]; }
+        else { sx = msx[k] & 0xffffu; sy = msx[k] >> 16; }
+        const int ix = sx >> 5, fx = sx & 31, iy = sy >> 5, fy = sy & 31;
+        uint32_t t00, t01, t10, t11;               // BGRx words of the four taps
+        if (staged) {
+            const uint32_t *p = smb + iy * rw + ix;
+            t00 = p[0]; t01 = p[1]; t10 = p[rw]; t11 = p[rw + 1];
+        } else {
+            const uint8_t *p = src + (size_t)iy * W3 + ix * 3;
+            const int dx = ix + 1 < W ? 3 : 0, dy = iy + 1 < H ? W3 : 0;
+            t00 = p[0] | (p[1] << 8) | (p[2] << 16);
+            t01 = p[dx] | (p[dx + 1] << 8) | (p[dx + 2] << 16);
+            t10 = p[dy] | (p[dy + 1] << 8) | (p[dy + 2] << 16);
+            t11 = p[dy + dx] | (p[dy + dx + 1] << 8) | (p[dy + dx + 2] << 16);
         }
-    }
-    __syncthreads();
-    // 3 planes x 16 rows x 128 px x 2 B = 768 chunks of 16 bytes
-    int16_t *gbase = C.g[0] + (size_t)slot * C.g_slot[0];
-    const int gp = C.g_pitch[0];
-    for (int i = tid; i < 3 * kWarpTileH * (kWarpTileW / 8); i += 256) {
-        const int q = i & 15, r = (i >> 4) % kWarpTileH, c = i / (16 * kWarpTileH);
-        const int yy = blockIdx.y * kWarpTileH + r, xx = Xt + q * 8;
-        if (yy < C.rh && xx < gp)
-            *reinterpret_cast<uint4 *>(gbase + (size_t)c * C.g_plane[0] + yy * gp + xx) = *reinterpret_cast<const uint4 *>(&so[c][r][q * 8]);
+        // horizontal pass: B|R packed as 16|16 bits, G alone; weights (32-fx, fx)
+        const uint32_t gx = 32 - fx;
+        const uint32_t br0 = gx * (t00 & 0x00ff00ffu) + fx * (t01 & 0x00ff00ffu);
+        const uint32_t br1 = gx * (t10 & 0x00ff00ffu) + fx * (t11 & 0x00ff00ffu);
+        const uint32_t g0 = gx * ((t00 >> 8) & 0xffu) + fx * ((t01 >> 8) & 0xffu);
+        const uint32_t g1 = gx * ((t10 >> 8) & 0xffu) + fx * ((t11 >> 8) & 0xffu);
+        // vertical pass + rounding: (sum w*p + 512) >> 10 with w = (32-fy | fy) * (32-fx | fx)
+        const uint32_t gy = 32 - fy;
+        int v[3];
+        v[0] = (int)((gy * (br0 & 0xffffu) + fy * (br1 & 0xffffu) + 512u) >> 10);
+        v[1] = (int)((gy * g0 + fy * g1 + 512u) >> 10);
+        v[2] = (int)((gy * (br0 >> 16) + fy * (br1 >> 16) + 512u) >> 10);
+        if (kGain) {
+            const float g = C.gain_mode == 1 ? __ldg(C.gain_map + (Y0 + 8 * (k >> 2)) * mp + Xt + 32 * (k & 3)) : 1.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] = apply_gain(v[c], C.gain_mode, g, C.gain_scalar);
+        }
+        int16_t *o = gout + (k >> 2) * gp8 + 32 * (k & 3);
+        o[0] = (int16_t)v[0];
+        o[gplane] = (int16_t)v[1];
+        o[2 * gplane] = (int16_t)v[2];
     }
 }
 
