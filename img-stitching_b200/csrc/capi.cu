@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -68,9 +69,10 @@ struct pano_ctx {
     size_t in_frame_bytes = 0;                    // bytes of one input frame as the caller passes it
     uint8_t *front_out = nullptr;                 // [max_batch][n][H][W][3] stitcher inputs produced by the front end
     int strip_x0 = 0, strip_x1 = 0;               // own dst columns (level 0, padded coords); full width = no split
-    // [level][cam][tile] -> camera has a non-zero weight inside the 256x8 dst tile
-    std::vector<std::vector<std::vector<uint8_t>>> tile_flags;
-    std::vector<uint32_t *> d_tile_cams;
+    // walker tiles (kWalkTileW x kWalkTileH): [level][cam][tile] -> any non-zero weight / count of weights == 1
+    std::vector<std::vector<std::vector<uint8_t>>> walk_nz;
+    std::vector<std::vector<std::vector<int>>> walk_ones;
+    std::vector<uint32_t *> d_walk_list, d_gen_list;
     std::vector<void *> owned;                    // device allocations to free
     std::vector<void *> cam_mask0, cam_gain;      // per camera, re-uploadable
     std::vector<std::vector<void *>> cam_wt;      // per camera per level
@@ -139,37 +141,71 @@ int upload2d(pano_ctx *h, T *dst, int dpitch, const T *src, int spitch, int w, i
     return PANO_OK;
 }
 
-inline int tilesX(const pano_ctx *h, int l) { return ((h->pad_w >> l) + 255) / 256; }
-inline int tilesY(const pano_ctx *h, int l) { return ((h->pad_h >> l) + 7) / 8; }
+inline int walkTilesX(const pano_ctx *h, int l) { return ((h->pad_w >> l) + kWalkTileW - 1) / kWalkTileW; }
+inline int walkTilesY(const pano_ctx *h, int l) { return ((h->pad_h >> l) + kWalkTileH - 1) / kWalkTileH; }
 
 // record which 256x8 dst tiles of level l see a non-zero weight of camera `cam`
+// per walker tile of level l: does camera `cam` have any non-zero weight there, and how many of its weights
+// are exactly one (`one` = the value that means weight 1.0f: 255 for the 8-bit level-0 mask)
 template <typename T>
-void markTiles(pano_ctx *h, int cam, int l, const T *data, int w, int hh, int pitch)
+void markTiles(pano_ctx *h, int cam, int l, const T *data, int w, int hh, int pitch, T one)
 {
-    if (h->tile_flags.empty()) return;
+    if (h->walk_nz.empty()) return;
     const CamTables &C = h->host.cam[cam];
-    const int ox = C.rx >> l, oy = C.ry >> l, tx = tilesX(h, l);
-    std::vector<uint8_t> &f = h->tile_flags[l][cam];
-    std::fill(f.begin(), f.end(), 0);
+    const int ox = C.rx >> l, oy = C.ry >> l, wtx = walkTilesX(h, l);
+    std::vector<uint8_t> &nz = h->walk_nz[l][cam];
+    std::vector<int> &ones = h->walk_ones[l][cam];
+    std::fill(nz.begin(), nz.end(), 0);
+    std::fill(ones.begin(), ones.end(), 0);
     for (int y = 0; y < hh; ++y) {
         const T *row = data + (size_t)y * pitch;
-        const int tyi = (oy + y) / 8;
-        for (int x = 0; x < w; ++x)
-            if (row[x] != (T)0) f[(size_t)tyi * tx + (ox + x) / 256] = 1;
+        const int wty = (oy + y) / kWalkTileH;
+        for (int x = 0; x < w; ++x) {
+            if (row[x] == (T)0) continue;
+            const size_t wt = (size_t)wty * wtx + (ox + x) / kWalkTileW;
+            nz[wt] = 1;
+            if (row[x] == one) ++ones[wt];
+        }
     }
 }
 
-int uploadTileCams(pano_ctx *h)
+// Collapse work lists (PanoTables::walk_list / gen_list) from the per-camera tile statistics.
+int uploadTileLists(pano_ctx *h)
 {
-    if (h->tile_flags.empty()) return PANO_OK;
-    for (int l = 0; l <= h->nb; ++l) {
-        if (!h->d_tile_cams[l]) continue;
-        const size_t cnt = (size_t)tilesX(h, l) * tilesY(h, l);
-        std::vector<uint32_t> m(cnt, 0u);
-        for (int c = 0; c < h->n; ++c)
-            for (size_t t = 0; t < cnt; ++t)
-                if (h->tile_flags[l][c][t]) m[t] |= 1u << c;
-        CK(h, cudaMemcpy(h->d_tile_cams[l], m.data(), cnt * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (h->walk_nz.empty()) return PANO_OK;
+    static const bool no_walk = getenv("PANO_NO_WALK") != nullptr;      // A/B switch: everything through collapse8_kernel
+    PanoTables &T = h->host;
+    for (int l = 0; l < h->nb; ++l) {
+        T.walk_list[l] = nullptr; T.gen_list[l] = nullptr; T.walk_n[l] = 0; T.gen_n[l] = 0;
+        if (!h->kc.collapse8[l]) continue;
+        const bool walk_ok = (T.unit_norm_exact & 1) && !no_walk;
+        const int wf = h->pad_w >> l, hf = h->pad_h >> l, wtx = walkTilesX(h, l), wty = walkTilesY(h, l);
+        std::vector<uint32_t> walk, gen;
+        size_t n_unit = 0, n_empty = 0;
+        for (int ty = 0; ty < wty; ++ty) {
+            if (l == 0 && (ty * kWalkTileH >= T.cut_y + T.cut_h || (ty + 1) * kWalkTileH <= T.cut_y)) continue;
+            for (int tx = 0; tx < wtx; ++tx) {
+                const size_t t = (size_t)ty * wtx + tx;
+                const int npx = (std::min(wf, (tx + 1) * kWalkTileW) - tx * kWalkTileW) *
+                                (std::min(hf, (ty + 1) * kWalkTileH) - ty * kWalkTileH);
+                uint32_t mask = 0;
+                int ncam = 0, cam = -1;
+                for (int c = 0; c < h->n; ++c)
+                    if (h->walk_nz[l][c][t]) { ++ncam; cam = c; mask |= 1u << c; }
+                const uint32_t pos = (uint32_t)tx | ((uint32_t)ty << 12);
+                if (walk_ok && ncam == 0) { walk.push_back(pos | ((uint32_t)kWalkEmpty << 24)); ++n_empty; }
+                else if (walk_ok && ncam == 1 && h->walk_ones[l][cam][t] == npx &&
+                         (l > 0 || T.cam[cam].use_wt0 || (T.unit_norm_exact & 2))) { walk.push_back(pos | ((uint32_t)(1 + cam) << 24)); ++n_unit; }
+                else gen.push_back(pos | (mask << 24));
+            }
+        }
+        if (!walk.empty()) CK(h, cudaMemcpy(h->d_walk_list[l], walk.data(), walk.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        if (!gen.empty()) CK(h, cudaMemcpy(h->d_gen_list[l], gen.data(), gen.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        T.walk_list[l] = h->d_walk_list[l]; T.walk_n[l] = (int)walk.size();
+        T.gen_list[l] = h->d_gen_list[l]; T.gen_n[l] = (int)gen.size();
+        if (getenv("PANO_DEBUG"))
+            fprintf(stderr, "[panob200] level %d: %dx%d tiles of %dx%d: unit-weight %zu, empty %zu, generic %zu\n", l, wtx, wty,
+                    kWalkTileW, kWalkTileH, n_unit, n_empty, gen.size());
     }
     return PANO_OK;
 }
@@ -194,7 +230,7 @@ int buildWeights(pano_ctx *h, int cam)
         std::memcpy(&m0[(size_t)(y + fr.top) * W + fr.left], &m[(size_t)y * img.w], img.w);
     if (upload2d(h, (uint8_t *)h->cam_mask0[cam], C.mask_pitch, m0.data(), W, W, H)) return PANO_ERR;
     C.use_wt0 = 0;
-    markTiles(h, cam, 0, m0.data(), W, H, W);
+    markTiles(h, cam, 0, m0.data(), W, H, W, (uint8_t)255);
     if (h->blender != PANO_BLEND_MULTIBAND) return PANO_OK;
     // float weight pyramid (MultiBandBlender::feed: convertTo(CV_32F, 1/255) + pyrDown chain)
     std::vector<float> cur((size_t)W * H);
@@ -205,7 +241,7 @@ int buildWeights(pano_ctx *h, int cam)
         pyrDownF32(cur.data(), cw, ch, nxt.data());
         cw = (cw + 1) / 2; ch = (ch + 1) / 2;
         if (upload2d(h, (float *)h->cam_wt[cam][l], C.wt_pitch[l], nxt.data(), cw, cw, ch)) return PANO_ERR;
-        markTiles(h, cam, l, nxt.data(), cw, ch, cw);
+        markTiles(h, cam, l, nxt.data(), cw, ch, cw, 1.0f);
         cur.swap(nxt);
     }
     return PANO_OK;
@@ -214,7 +250,7 @@ int buildWeights(pano_ctx *h, int cam)
 int syncTables(pano_ctx *h)
 {
     if (!h->tables_dirty) return PANO_OK;
-    if (uploadTileCams(h)) return PANO_ERR;
+    if (uploadTileLists(h)) return PANO_ERR;
     CK(h, cudaMemcpy(h->dev, &h->host, sizeof(PanoTables), cudaMemcpyHostToDevice));
     h->tables_dirty = false;
     return PANO_OK;
@@ -332,7 +368,7 @@ int runPhase(pano_ctx *h, int p, const uint8_t *frames_dev, uint8_t *out_dev, in
     } else {
         const int l = 2 * nb - p;
         L.begin(kCol[l], collapseBytes(h, l, slots));
-        launch_collapse(h->dev, h->host, h->kc, l, out_dev, slots, st);
+        h->last_launches += launch_collapse(h->dev, h->host, h->kc, l, out_dev, slots, st) - 1;
         L.end();
     }
     return PANO_OK;
@@ -631,15 +667,14 @@ int pano_create(const pano_config *cfg, pano_handle *out)
         }
     }
     if (h->blender == PANO_BLEND_MULTIBAND) {
-        h->tile_flags.assign(h->nb + 1, std::vector<std::vector<uint8_t>>(n));
-        h->d_tile_cams.assign(h->nb + 1, nullptr);
+        h->walk_nz.assign(h->nb + 1, std::vector<std::vector<uint8_t>>(n));
+        h->walk_ones.assign(h->nb + 1, std::vector<std::vector<int>>(n));
+        h->d_walk_list.assign(h->nb + 1, nullptr);
+        h->d_gen_list.assign(h->nb + 1, nullptr);
         for (int l = 0; l <= h->nb; ++l) {
-            const size_t cnt = (size_t)tilesX(h, l) * tilesY(h, l);
-            for (int c = 0; c < n; ++c) h->tile_flags[l][c].assign(cnt, 0);
-            uint32_t *d = nullptr;
-            if (devAlloc(h, &d, cnt)) return bail(0);
-            h->d_tile_cams[l] = d;
-            T.tile_cams[l] = d;
+            const size_t wcnt = (size_t)walkTilesX(h, l) * walkTilesY(h, l);
+            for (int c = 0; c < n; ++c) { h->walk_nz[l][c].assign(wcnt, 0); h->walk_ones[l][c].assign(wcnt, 0); }
+            if (devAlloc(h, &h->d_walk_list[l], wcnt) || devAlloc(h, &h->d_gen_list[l], wcnt)) return bail(0);
         }
     }
     {
@@ -753,7 +788,7 @@ int pano_set_weight_level(pano_handle h, int cam, int level, const float *w, int
     CK(h, cudaDeviceSynchronize());
     if (upload2d(h, (float *)h->cam_wt[cam][level], C.wt_pitch[level], w, width, width, height)) return PANO_ERR;
     if (level == 0) C.use_wt0 = 1;
-    markTiles(h, cam, level, w, width, height, width);
+    markTiles(h, cam, level, w, width, height, width, 1.0f);
     h->tables_dirty = true;
     return PANO_OK;
 }

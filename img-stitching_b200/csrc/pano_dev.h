@@ -54,9 +54,15 @@ struct PanoTables {
     // column window (spatial strip split): blocks whose dst columns at level l fall entirely
     // outside [win_lo[l], win_hi[l]) are skipped.  Full range = no split.
     int win_lo[kMaxLevels], win_hi[kMaxLevels];
-    // per level: one u32 per 256 x 8 tile of the padded dst = bitmask of cameras that have any
-    // non-zero weight inside the tile (static; rebuilt whenever masks / weights change)
-    const uint32_t *tile_cams[kMaxLevels];
+    // Collapse work lists, per level, over kWalkTileW x kWalkTileH tiles of the padded dst (static; rebuilt whenever
+    // masks / weights change).  Entry = tx | ty << 12 | info << 24.
+    //   walk_list: tiles whose blend needs no weights -- info = 1 + cam (exactly that camera has weight there and
+    //              all of its weights are exactly 1.0f) or kWalkEmpty (no camera has weight) -> collapse_walk_kernel
+    //   gen_list:  every other tile that is needed -- info = bitmask of the cameras with any non-zero weight inside
+    //              the tile (the others contribute exactly nothing and are never touched) -> collapse8_kernel
+    // Level-0 tiles outside the cut rows are in neither list.
+    const uint32_t *walk_list[kMaxLevels], *gen_list[kMaxLevels];
+    int walk_n[kMaxLevels], gen_n[kMaxLevels];
     int unit_norm_exact;     // host verified (short)(a / (1.0f + 1e-5f)) == a - sign(a) for all int16 a
     // collapsed dst pyramid, levels 1..nb: [slot][3][h_l][out_pitch[l]]
     int16_t *outp[kMaxLevels];
@@ -70,6 +76,9 @@ struct PanoTables {
 constexpr int kWarpTileW = 128, kWarpTileH = 16;      // output pixels per warp-kernel block
 constexpr int kWarpSmemWords = 7168;                  // staged source footprint, one 32-bit word per pixel (28 KB)
 
+constexpr int kWalkTileW = 64, kWalkR = 4, kWalkTileH = 8 * kWalkR;   // walker tile: 4 bands x 2R fine rows
+constexpr int kWalkEmpty = 0xff;
+
 struct KernelChoice {
     bool warp_tiled = false;                 // staged-gather warp kernel usable (row bytes % 16 == 0)
     bool pyrdown8[kMaxLevels] = {};          // packed 8-wide pyrDown usable at this source level
@@ -81,8 +90,9 @@ void launch_warp(const PanoTables *dev, const PanoTables &host, const KernelChoi
 void launch_pyrdown(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, int level, int nslots,
                     cudaStream_t stream);
 void launch_coarsest(const PanoTables *dev, const PanoTables &host, uint8_t *pano, int nslots, cudaStream_t stream);
-void launch_collapse(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, int level, uint8_t *pano,
-                     int nslots, cudaStream_t stream);
+// returns the number of kernels launched
+int launch_collapse(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, int level, uint8_t *pano,
+                    int nslots, cudaStream_t stream);
 void launch_direct_blend(const PanoTables *dev, const PanoTables &host, int blender, const uint8_t *frames,
                          uint8_t *pano, int nslots, cudaStream_t stream);
 
