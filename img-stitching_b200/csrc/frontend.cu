@@ -255,78 +255,83 @@ __global__ void __launch_bounds__(256) resize4_kernel(const uint32_t *__restrict
 // broadcast with shuffles.  The vertical pass is two multiply-high + one shift per channel
 // ((a * h) >> 16 == umulhi(a << 16, h) for the non-negative bilinear coefficients).  Four lanes' pixels
 // (12 bytes) leave as three aligned words built with one shuffle + one byte permute per lane.
-constexpr int kResizeBand = 24;      // virtual source rows per block (<= 31: one lane per table entry)
+constexpr int kResizeBand = 24;      // virtual source rows per block
+constexpr int kResizeRows = 64;      // most output rows one band may produce (row coefficients live in shared memory)
 
+// requires: dw % 32 == 0, dst rows 4-byte aligned, <= kResizeRows output rows per band (checked at launch)
 __global__ void __launch_bounds__(128, 8) resize4_walk_kernel(const uint32_t *__restrict__ src, size_t src_img_words,
-                                                           int sstride_words, uint8_t *__restrict__ dst, size_t dst_img,
-                                                           int dstride, ResizeTab t)
+                                                              unsigned sstride_words, uint8_t *__restrict__ dst, size_t dst_img,
+                                                              unsigned dstride, ResizeTab t)
 {
-    const int lane = threadIdx.x;
-    const int xw = (blockIdx.x * blockDim.y + threadIdx.y) * 32;       // first column of this warp
-    if (xw >= t.dw) return;
-    const int x = xw + lane;
-    const bool xok = x < t.dw;
+    __shared__ int s_yb[kResizeBand + 1];
+    __shared__ uint32_t s_ay[kResizeRows];
+    const int lane = threadIdx.x, tid = threadIdx.y * 32 + lane;
     const int sh = t.sh;
     const int v0 = (int)blockIdx.y * kResizeBand - 1;                  // v runs over [-1, sh - 1]
     const int nv = min(kResizeBand, sh - v0);
-    // lane i: first output row of virtual source row v0 + i (i = nv: end of the band)
-    const int yb_lane = __ldg(t.ybeg + (v0 + 1) + min(lane, nv));
-    const int ybase = __shfl_sync(0xffffffffu, yb_lane, 0), yend_band = __shfl_sync(0xffffffffu, yb_lane, nv);
-    if (ybase >= yend_band) return;
-    const short2 ay_lane = __ldg(t.ya + min(ybase + lane, t.dh - 1));  // row coefficients of output row ybase + lane
-    const uint32_t ay_pack = ((uint32_t)(uint16_t)ay_lane.y << 16) | (uint16_t)ay_lane.x;
-
-    const uint32_t *s = src + (size_t)blockIdx.z * src_img_words;
-    uint8_t *d = dst + (size_t)blockIdx.z * dst_img + (size_t)xw * 3;
-    const int xo = xok ? __ldg(t.xofs + x) : 0, x1 = min(xo + 1, t.sw - 1);
-    const short2 ax = xok ? __ldg(t.xa + x) : make_short2(0, 0);
+    const int ybase = __ldg(t.ybeg + v0 + 1);
+    if (tid <= nv) s_yb[tid] = __ldg(t.ybeg + v0 + 1 + tid);           // first output row of virtual row v0 + tid
+    if (tid >= 64) {
+        const short2 q = __ldg(t.ya + min(ybase + tid - 64, t.dh - 1));
+        s_ay[tid - 64] = ((uint32_t)(uint16_t)q.y << 16) | (uint16_t)q.x;
+    }
+    __syncthreads();
+    const int xw = (blockIdx.x * blockDim.y + threadIdx.y) * 32;       // first column of this warp
+    if (xw >= t.dw) return;
+    const int x = xw + lane;
+    const unsigned xo = __ldg(t.xofs + x), x1 = min(xo + 1u, (unsigned)t.sw - 1u);
+    const short2 ax = __ldg(t.xa + x);
     const int axp = (int)(((uint32_t)(uint16_t)ax.y << 16) | (uint16_t)ax.x);
-    const bool words = xw + 32 <= t.dw;                               // whole warp inside the row: word stores
+    const uint32_t *s0 = src + (size_t)blockIdx.z * src_img_words + xo;
+    const uint32_t *s1 = src + (size_t)blockIdx.z * src_img_words + x1;
     const int j = lane & 3;
     const uint32_t sel = j == 0 ? 0x4210u : (j == 1 ? 0x5421u : 0x6542u);
-    const int wofs = (lane >> 2) * 3 + j;
+    // lanes 4k..4k+2 store the three words of pixels 4k..4k+3; lane 4k+3 stores nothing
+    uint8_t *olane = dst + (size_t)blockIdx.z * dst_img + (size_t)ybase * dstride + (size_t)xw * 3 + ((lane >> 2) * 3 + j) * 4;
+    const uint32_t *ayp = s_ay;
 
-    auto fetch = [&](int v, uint32_t &a, uint32_t &b) {
-        const uint32_t *r = s + (size_t)min(max(v, 0), sh - 1) * sstride_words;
-        a = __ldg(r + xo); b = __ldg(r + x1);
-    };
-    auto hcalc = [&](uint32_t a, uint32_t b, uint32_t h[3]) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) h[c] = (uint32_t)dp2a_su(axp, __byte_perm(a, b, 0x0040u + 0x11u * c), 0) >> 4;
-    };
-    uint32_t hA[3], hB[3], n1a, n1b, n2a, n2b;
+#define RS_FETCH(v, A, B)                                                        \
+    {                                                                            \
+        const unsigned r_ = (unsigned)min(max((v), 0), sh - 1) * sstride_words;  \
+        A = __ldg(s0 + r_); B = __ldg(s1 + r_);                                  \
+    }
+#define RS_HCALC(A, B, H0, H1, H2)                                               \
+    H0 = (uint32_t)dp2a_su(axp, __byte_perm(A, B, 0x0040u), 0) >> 4;             \
+    H1 = (uint32_t)dp2a_su(axp, __byte_perm(A, B, 0x0051u), 0) >> 4;             \
+    H2 = (uint32_t)dp2a_su(axp, __byte_perm(A, B, 0x0062u), 0) >> 4;
+    // one step: emit the output rows that blend (A, B) = rows (v, v + 1), then row v + 2 replaces A (it is the
+    // next step's B) and the prefetch slot is refilled with row v + 4
+#define RS_STEP(i, A0, A1, A2, B0, B1, B2, PA, PB)                               \
+    {                                                                            \
+        for (int n_ = s_yb[(i) + 1] - s_yb[(i)]; n_ > 0; --n_) {                 \
+            const uint32_t w_ = *ayp++;                                          \
+            const uint32_t a0_ = w_ << 16, a1_ = w_ & 0xffff0000u;               \
+            const uint32_t c0_ = (__umulhi(a0_, A0) + __umulhi(a1_, B0) + 2u) >> 2;   \
+            const uint32_t c1_ = (__umulhi(a0_, A1) + __umulhi(a1_, B1) + 2u) >> 2;   \
+            const uint32_t c2_ = (__umulhi(a0_, A2) + __umulhi(a1_, B2) + 2u) >> 2;   \
+            const uint32_t px_ = c0_ | (c1_ << 8) | (c2_ << 16);                 \
+            const uint32_t nx_ = __shfl_down_sync(0xffffffffu, px_, 1);          \
+            if (j < 3) *reinterpret_cast<uint32_t *>(olane) = __byte_perm(px_, nx_, sel); \
+            olane += dstride;                                                    \
+        }                                                                        \
+        RS_HCALC(PA, PB, A0, A1, A2)                                             \
+        RS_FETCH(v0 + (i) + 4, PA, PB)                                           \
+    }
+
+    uint32_t g0, g1, g2, h0, h1, h2, p0a, p0b, p1a, p1b;
     {
         uint32_t a, b, c, e;
-        fetch(v0, a, b); fetch(v0 + 1, c, e);
-        fetch(v0 + 2, n1a, n1b); fetch(v0 + 3, n2a, n2b);
-        hcalc(a, b, hA); hcalc(c, e, hB);
+        RS_FETCH(v0, a, b) RS_FETCH(v0 + 1, c, e)
+        RS_FETCH(v0 + 2, p0a, p0b) RS_FETCH(v0 + 3, p1a, p1b)
+        RS_HCALC(a, b, g0, g1, g2) RS_HCALC(c, e, h0, h1, h2)
     }
-    int y = ybase;
-    for (int i = 0; i < nv; ++i) {
-        const int yend = __shfl_sync(0xffffffffu, yb_lane, i + 1);
-        uint32_t n3a, n3b;
-        fetch(v0 + i + 4, n3a, n3b);                                   // two steps ahead of its use
-        for (; y < yend; ++y) {                                        // 0..2 output rows blend (v, v + 1); warp-uniform
-            const int k = y - ybase;
-            uint32_t ayp;
-            if (k < 32) ayp = __shfl_sync(0xffffffffu, ay_pack, k);
-            else { const short2 q = __ldg(t.ya + y); ayp = ((uint32_t)(uint16_t)q.y << 16) | (uint16_t)q.x; }
-            const uint32_t a0 = ayp << 16, a1 = ayp & 0xffff0000u;
-            uint32_t px = 0;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) px |= ((__umulhi(a0, hA[c]) + __umulhi(a1, hB[c]) + 2u) >> 2) << (8 * c);
-            uint8_t *orow = d + (size_t)y * dstride;
-            if (words && (reinterpret_cast<uintptr_t>(orow) & 3) == 0) {
-                const uint32_t nx = __shfl_down_sync(0xffffffffu, px, 1);
-                if (j < 3) reinterpret_cast<uint32_t *>(orow)[wofs] = __byte_perm(px, nx, sel);
-            } else if (xok) {
-                orow[lane * 3] = (uint8_t)px; orow[lane * 3 + 1] = (uint8_t)(px >> 8); orow[lane * 3 + 2] = (uint8_t)(px >> 16);
-            }
-        }
-        hA[0] = hB[0]; hA[1] = hB[1]; hA[2] = hB[2];
-        hcalc(n1a, n1b, hB);
-        n1a = n2a; n1b = n2b; n2a = n3a; n2b = n3b;
+    for (int i = 0; i < nv; i += 2) {
+        RS_STEP(i, g0, g1, g2, h0, h1, h2, p0a, p0b)
+        if (i + 1 < nv) RS_STEP(i + 1, h0, h1, h2, g0, g1, g2, p1a, p1b)
     }
+#undef RS_STEP
+#undef RS_HCALC
+#undef RS_FETCH
 }
 
 thread_local std::string g_front_error;
@@ -406,7 +411,9 @@ int makeResize(pano_frontend_ctx *h, ResizeTab &t, int sw, int sh, int dw, int d
     }
     if (falloc(h, &t.ybeg, yb.size())) return PANO_ERR;
     FCK(h, cudaMemcpy(t.ybeg, yb.data(), yb.size() * sizeof(int), cudaMemcpyHostToDevice));
-    t.walk = mono && nonneg && dh >= sh;
+    bool fits = true;                                   // every band's output rows fit the kernel's coefficient table
+    for (int v = -1; v <= sh - 1; v += kResizeBand) fits = fits && yb[std::min(v + kResizeBand, sh) + 1] - yb[v + 1] <= kResizeRows;
+    t.walk = mono && nonneg && fits && dh >= sh && dw % 32 == 0;
     return PANO_OK;
 }
 
@@ -547,7 +554,7 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
                                                          reinterpret_cast<const uint4 *>(h->dtab), rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
             if (h->prof_ev) cudaEventRecord(h->prof_ev[1], st);
             static const bool no_walk = getenv("PANO_NO_RESIZE_WALK") != nullptr;
-            if (h->r_mid.walk && !no_walk)
+            if (h->r_mid.walk && !no_walk && (reinterpret_cast<uintptr_t>(final_dst) & 3) == 0 && (o_img & 3) == 0 && ((uw * 3) & 3) == 0)
                 resize4_walk_kernel<<<dim3((uw + 127) / 128, (rc[3] + 1 + kResizeBand - 1) / kResizeBand, nb), dim3(32, 4), 0, st>>>(
                     h->buf_w, w_img, rc[2], final_dst, o_img, uw * 3, h->r_mid);
             else
