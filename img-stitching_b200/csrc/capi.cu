@@ -611,7 +611,7 @@ int pano_create(const pano_config *cfg, pano_handle *out)
                     const int px0 = x0 / 16 * 16, groups = (x1 - px0) / 16 + 1;
                     const int rows = y1 - y0 + 1;
                     int4 d = make_int4(0, 0, 0, 0);
-                    if (W % 16 == 0 && rows * groups * 16 <= kWarpSmemWords) d = make_int4(px0, y0, rows, groups);
+                    if (W % 16 == 0 && groups <= 16 && rows * ((groups * 16 + 31) & ~31) <= kWarpSmemWords) d = make_int4(px0, y0, rows, groups);
                     tl[(size_t)ty * C.tiles_x + tx] = d;
                 }
             int4 *dt = nullptr;

@@ -120,11 +120,11 @@ __global__ void __launch_bounds__(256) cubic_kernel(const uint8_t *__restrict__ 
 // Map entry, packed form (sources up to 2043 pixels per side): (tx+4) | (ty+4) << 11 | fx << 22 | fy << 27
 // where (tx, ty) is the first of the 4x4 taps, clamped to [-4, size] (beyond that every tap is
 // outside the image and contributes 0 either way).
-template <bool kPacked>
+template <bool kPacked, bool kTexW>
 __global__ void __launch_bounds__(256) cubic4_kernel(const uint32_t *__restrict__ src, size_t src_img_words, int sw, int sh,
                                                      const void *__restrict__ map_, int map_w, const uint4 *__restrict__ tab,
-                                                     int rx, int ry, int rw, int rh, uint32_t *__restrict__ dst,
-                                                     size_t dst_img_words)
+                                                     cudaTextureObject_t wtex, int rx, int ry, int rw, int rh,
+                                                     uint32_t *__restrict__ dst, size_t dst_img_words)
 {
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (y >= rh) return;
@@ -155,8 +155,14 @@ __global__ void __launch_bounds__(256) cubic4_kernel(const uint32_t *__restrict_
             ix = (m[j].x >> 5) - 1; iy = (m[j].y >> 5) - 1;
             fidx = ((m[j].y & 31) << 5) | (m[j].x & 31);
         }
-        const uint4 *wp = tab + (fidx << 1);     // 16 shorts = 2 x uint4
-        const uint4 wa = __ldg(wp), wb = __ldg(wp + 1);
+        uint4 wa, wb;                            // 16 shorts = 2 x uint4
+        if (kTexW) {
+            // the weights travel through the texture pipe of L1TEX, the taps through the LSU pipe
+            wa = tex1Dfetch<uint4>(wtex, fidx << 1); wb = tex1Dfetch<uint4>(wtex, (fidx << 1) + 1);
+        } else {
+            const uint4 *wp = tab + (fidx << 1);
+            wa = __ldg(wp); wb = __ldg(wp + 1);
+        }
         const uint32_t wpk[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
         uint32_t t[16];
         if (ix >= 0 && iy >= 0 && ix + 3 < sw && iy + 3 < sh) {
@@ -345,6 +351,7 @@ struct pano_frontend_ctx {
     std::vector<void *> owned;
     int2 *dmap = nullptr;
     short *dtab = nullptr;
+    cudaTextureObject_t wtex = 0;                                  // dtab as a linear uint4 texture
     ResizeTab r_in, r_mid, r_out;       // cam->undist, rect->undist, undist->out
     bool use_r_in = false, use_r_mid = false, use_r_out = false;
     uint8_t *buf_a = nullptr, *buf_b = nullptr, *buf_c = nullptr;  // intermediates, max_batch deep
@@ -469,6 +476,16 @@ int pano_frontend_create(const pano_frontend_config *cfg, pano_frontend_handle *
             h->err = "front-end table upload failed";
             return bail();
         }
+        {
+            cudaResourceDesc rd{};
+            rd.resType = cudaResourceTypeLinear;
+            rd.res.linear.devPtr = h->dtab;
+            rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
+            rd.res.linear.sizeInBytes = tab.size() * sizeof(short);
+            cudaTextureDesc td{};
+            td.readMode = cudaReadModeElementType;
+            if (cudaCreateTextureObject(&h->wtex, &rd, &td, nullptr) != cudaSuccess) { h->err = "weight texture creation failed"; return bail(); }
+        }
         h->use_r_in = !(cfg->cam_src_width == uw && cfg->cam_src_height == uh);
         h->use_r_mid = !(rc[2] == uw && rc[3] == uh);
         if (h->use_r_in && makeResize(h, h->r_in, cfg->cam_src_width, cfg->cam_src_height, uw, uh)) return bail();
@@ -507,6 +524,7 @@ int pano_frontend_destroy(pano_frontend_handle h)
     if (!h) return PANO_OK;
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
+    if (h->wtex) cudaDestroyTextureObject(h->wtex);
     for (void *p : h->owned) cudaFree(p);
     delete h;
     return PANO_OK;
@@ -546,12 +564,15 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
             const size_t w_img = (size_t)rc[2] * rc[3];
             const dim3 cg((rc[2] + 127) / 128, (rc[3] + 7) / 8, nb);
             if (h->prof_ev) cudaEventRecord(h->prof_ev[0], st);
-            if (h->dmap32)
-                cubic4_kernel<true><<<cg, blk, 0, st>>>(reinterpret_cast<const uint32_t *>(src), in_img / 4, cw, chh, h->dmap32, uw,
-                                                        reinterpret_cast<const uint4 *>(h->dtab), rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
+            static const bool tex_w = getenv("PANO_CUBIC_TEX") != nullptr;
+            const uint32_t *src4 = reinterpret_cast<const uint32_t *>(src);
+            const uint4 *tab4 = reinterpret_cast<const uint4 *>(h->dtab);
+            if (h->dmap32 && tex_w)
+                cubic4_kernel<true, true><<<cg, blk, 0, st>>>(src4, in_img / 4, cw, chh, h->dmap32, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
+            else if (h->dmap32)
+                cubic4_kernel<true, false><<<cg, blk, 0, st>>>(src4, in_img / 4, cw, chh, h->dmap32, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
             else
-                cubic4_kernel<false><<<cg, blk, 0, st>>>(reinterpret_cast<const uint32_t *>(src), in_img / 4, cw, chh, h->dmap, uw,
-                                                         reinterpret_cast<const uint4 *>(h->dtab), rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
+                cubic4_kernel<false, false><<<cg, blk, 0, st>>>(src4, in_img / 4, cw, chh, h->dmap, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
             if (h->prof_ev) cudaEventRecord(h->prof_ev[1], st);
             static const bool no_walk = getenv("PANO_NO_RESIZE_WALK") != nullptr;
             if (h->r_mid.walk && !no_walk && (reinterpret_cast<uintptr_t>(final_dst) & 3) == 0 && (o_img & 3) == 0 && ((uw * 3) & 3) == 0)

@@ -837,86 +837,54 @@ __global__ void __launch_bounds__(96) collapse_walk_kernel(const __grid_constant
 // ---- K1': rotation warp, 128 x 16 output pixels per block.
 // (1) The tile's source footprint (static bounding box from the init-time tile table) is staged in
 //     shared memory with coalesced 16-byte loads and EXPANDED from packed BGR to one 32-bit word per
-//     pixel (PRMT), so that a bilinear tap is a single conflict-free LDS.32 instead of three byte
-//     loads.  The box includes the (ix+1, iy+1) taps even where they fall one past the frame (their
-//     weight is 0 there by construction of the folded map); staging clamps the SOURCE address
-//     instead, so the gather needs no border logic at all.
-// (2) During the gather a warp covers 32 consecutive output pixels (lane = pixel): its four tap loads
-//     fall into a ~35-word window of one or two staged rows.  B and R are interpolated together in one
-//     packed 16|16-bit multiply for the horizontal pass (values <= 255*32 fit 16 bits).
-// (3) All 8 map entries of a thread are requested before the staging loop, so their latency overlaps
-//     the staging loads; planar int16 results are stored straight from registers (64-byte runs).
-__device__ __forceinline__ void st_global_s16(int16_t *p, int v)
+//     pixel (PRMT), so that a bilinear tap is a single LDS.32 instead of three byte loads.  The box
+//     includes the (ix+1, iy+1) taps even where they fall one past the frame (their weight is 0 there by
+//     construction of the folded map); staging clamps the SOURCE address instead, so the gather needs no
+//     border logic at all.  The staged row pitch is a multiple of 32 words: a tap's bank then depends on
+//     its column only, so a warp's taps stay conflict-free across source-row changes.  The four 16-byte
+//     chunks a lane produces are stored in a lane-dependent order (slot k holds chunk (k + q/2) & 3), which
+//     makes every quarter-warp hit eight distinct bank groups.
+// (2) During the gather a warp covers 32 consecutive output pixels (lane = pixel).  The two weights of a
+//     source row are one packed 16|16-bit word (each product <= 1024), so a row of one channel is a single
+//     IDP.2A on the byte pair that PRMT lifts out of the two tap words; B and G share one PRMT.
+// (3) Everything static about the launch arrives as a __grid_constant__ struct (no dependent global loads
+//     in the prologue); all 8 map entries of a thread are requested before the staging loop; the planar
+//     int16 results go out through six precomputed row pointers with immediate offsets.
+struct WarpCam {
+    const uint32_t *map32;
+    const uint2 *map64;
+    const int4 *tiles;
+    const float *gain_map;
+    int16_t *g0;
+    double gain_scalar;
+    size_t g_slot;
+    int map_pitch, tiles_x, tiles_y, rx, rw, rh, g_pitch, gain_mode;
+    unsigned g_plane;
+};
+struct WarpArgs {
+    WarpCam cam[kMaxCams];
+    int ncam, W, H, win_lo, win_hi;
+};
+
+template <int kOff>
+__device__ __forceinline__ void st_s16(int16_t *p, int v)
 {
-    asm volatile("st.global.b16 [%0], %1;" ::"l"(p), "h"((short)v) : "memory");
+    asm volatile("st.global.b16 [%0+%1], %2;" ::"l"(p), "n"(kOff), "h"((short)v) : "memory");
 }
 
-template <bool kMap64, bool kGain>
-__global__ void __launch_bounds__(256) warp_tile_kernel(const PanoTables *__restrict__ T, const uint8_t *__restrict__ frames)
+template <bool kMap64, bool kGain, bool kFull>
+__device__ __forceinline__ void warp_gather(const WarpCam &C, const uint32_t *__restrict__ sm, const uint8_t *__restrict__ src,
+                                            bool staged, int rw, int sbase, int W, int H, const uint32_t (&msx)[8],
+                                            const uint32_t (&msy)[8], int Xt, int Y0, int slot)
 {
-    __shared__ __align__(16) uint32_t sm[kWarpSmemWords];
-    const int ncam = T->num_cams;
-    const int cam = blockIdx.z % ncam, slot = blockIdx.z / ncam;
-    const CamTables &C = T->cam[cam];
-    if ((int)blockIdx.x >= C.tiles_x || (int)blockIdx.y >= C.tiles_y) return;
-    if (outside_window(T, 0, C.rx + blockIdx.x * kWarpTileW, C.rx + (blockIdx.x + 1) * kWarpTileW)) return;
-    const int W = T->src_w, H = T->src_h, W3 = W * 3;
-    const uint8_t *src = frames + ((size_t)slot * ncam + cam) * ((size_t)W3 * H);
-    const int4 td = __ldg(C.tiles + blockIdx.y * C.tiles_x + blockIdx.x);   // {x0 (px, %16==0), y0, rows, 16-px groups}
-    const int lane = threadIdx.x, ty = threadIdx.y;
-    const int tid = ty * 32 + lane;
-    const int rw = td.w * 16;                   // staged words per row
-    const bool staged = td.z > 0;
-    const int Xt = blockIdx.x * kWarpTileW + lane;
-    const int Y0 = blockIdx.y * kWarpTileH + ty;
-    const int mp = C.map_pitch, crw = C.rw, crh = C.rh;
-    uint32_t msx[8], msy[8];
-    {
-        const uint32_t *m32 = C.map32 + Y0 * mp + Xt;
-        const uint2 *m64 = C.map64 + Y0 * mp + Xt;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int off = 8 * (k >> 2) * mp + 32 * (k & 3);
-            msx[k] = 0; msy[k] = 0;
-            if (Y0 + 8 * (k >> 2) < crh && Xt + 32 * (k & 3) < crw) {
-                if (kMap64) {
-                    const uint2 e = __ldg(m64 + off);
-                    msx[k] = e.x; msy[k] = e.y;
-                } else {
-                    msx[k] = __ldg(m32 + off);
-                }
-            }
-        }
-    }
-    if (staged) {
-        const int total = td.z * td.w;
-        for (int g = tid; g < total; g += 256) {
-            const int r = g / td.w, q = g - r * td.w;
-            const int sy = min(td.y + r, H - 1), sx = min(td.x + 16 * q, W - 16);     // taps one past the frame have weight 0
-            const uint4 *p = reinterpret_cast<const uint4 *>(src + (size_t)sy * W3 + sx * 3);
-            const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-            const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-            uint4 o[4];
-            uint32_t *ow = reinterpret_cast<uint32_t *>(o);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {       // 4 pixels from 3 words
-                ow[4 * k + 0] = w[3 * k];
-                ow[4 * k + 1] = __byte_perm(w[3 * k], w[3 * k + 1], 0x6543);
-                ow[4 * k + 2] = __byte_perm(w[3 * k + 1], w[3 * k + 2], 0x5432);
-                ow[4 * k + 3] = w[3 * k + 2] >> 8;
-            }
-            uint4 *d = reinterpret_cast<uint4 *>(sm + r * rw + 16 * q);
-            d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; d[3] = o[3];
-        }
-    }
-    __syncthreads();
-    const uint32_t *smb = sm - td.y * rw - td.x;
-    int16_t *gout = C.g[0] + (size_t)slot * C.g_slot[0] + Y0 * C.g_pitch[0] + Xt;
-    const unsigned gplane = (unsigned)C.g_plane[0];
-    const int gp8 = 8 * C.g_pitch[0];
+    const int W3 = W * 3;
+    const int pitch = C.g_pitch, crw = C.rw, crh = C.rh, mp = C.map_pitch;
+    int16_t *o00 = C.g0 + slot * C.g_slot + Y0 * pitch + Xt;
+    int16_t *o01 = o00 + C.g_plane, *o02 = o01 + C.g_plane;
+    int16_t *o10 = o00 + 8 * pitch, *o11 = o10 + C.g_plane, *o12 = o11 + C.g_plane;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        if (Y0 + 8 * (k >> 2) >= crh || Xt + 32 * (k & 3) >= crw) continue;
+        if (!kFull && (Y0 + 8 * (k >> 2) >= crh || Xt + 32 * (k & 3) >= crw)) continue;
         uint32_t sx, sy;
         if (kMap64) { sx = msx[k]; sy = msy[k]; }
         else { sx = msx[k] & 0xffffu; sy = msx[k] >> 16; }
@@ -924,8 +892,8 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(const PanoTables *__rest
         const uint32_t fx = sx & 31, fy = sy & 31;
         uint32_t t00, t01, t10, t11;               // BGRx words of the four taps
         if (staged) {
-            const uint32_t *p = smb + iy * rw + ix;
-            t00 = p[0]; t01 = p[1]; t10 = p[rw]; t11 = p[rw + 1];
+            const int idx = iy * rw + (ix + sbase);
+            t00 = sm[idx]; t01 = sm[idx + 1]; t10 = sm[idx + rw]; t11 = sm[idx + rw + 1];
         } else {
             const uint8_t *p = src + (size_t)iy * W3 + ix * 3;
             const int dx = ix + 1 < W ? 3 : 0, dy = iy + 1 < H ? W3 : 0;
@@ -934,9 +902,7 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(const PanoTables *__rest
             t10 = p[dy] | (p[dy + 1] << 8) | (p[dy + 2] << 16);
             t11 = p[dy + dx] | (p[dy + dx + 1] << 8) | (p[dy + dx + 2] << 16);
         }
-        // (sum_4 w*p + 512) >> 10 with w = (32-fy | fy) x (32-fx | fx): the two weights of a row are one packed
-        // 16|16-bit word (each product <= 1024), so a row of one channel is a single IDP.2A on the byte pair
-        // (c(x), c(x+1)) that PRMT lifts out of the two tap words; B and G share one PRMT (lo / hi halves).
+        // (sum_4 w*p + 512) >> 10 with w = (32-fy | fy) x (32-fx | fx)
         const uint32_t wxp = fx * 0xffffu + 32u;                              // (32 - fx) | fx << 16
         const uint32_t wt = (32u - fy) * wxp, wb = fy * wxp;
         const uint32_t bg0 = __byte_perm(t00, t01, 0x5140), r0 = __byte_perm(t00, t01, 0x0062);   // b0 b1 g0 g1 | r0 r1
@@ -950,11 +916,99 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(const PanoTables *__rest
 #pragma unroll
             for (int c = 0; c < 3; ++c) v[c] = apply_gain(v[c], C.gain_mode, g, C.gain_scalar);
         }
-        int16_t *o = gout + (k >> 2) * gp8 + 32 * (k & 3);
-        st_global_s16(o, v[0]);
-        st_global_s16(o + gplane, v[1]);
-        st_global_s16(o + 2 * gplane, v[2]);
+        // 32 samples = 64 bytes per column group: immediate offsets on the six row pointers
+        if (k < 4) {
+            if ((k & 3) == 0) { st_s16<0>(o00, v[0]); st_s16<0>(o01, v[1]); st_s16<0>(o02, v[2]); }
+            if ((k & 3) == 1) { st_s16<64>(o00, v[0]); st_s16<64>(o01, v[1]); st_s16<64>(o02, v[2]); }
+            if ((k & 3) == 2) { st_s16<128>(o00, v[0]); st_s16<128>(o01, v[1]); st_s16<128>(o02, v[2]); }
+            if ((k & 3) == 3) { st_s16<192>(o00, v[0]); st_s16<192>(o01, v[1]); st_s16<192>(o02, v[2]); }
+        } else {
+            if ((k & 3) == 0) { st_s16<0>(o10, v[0]); st_s16<0>(o11, v[1]); st_s16<0>(o12, v[2]); }
+            if ((k & 3) == 1) { st_s16<64>(o10, v[0]); st_s16<64>(o11, v[1]); st_s16<64>(o12, v[2]); }
+            if ((k & 3) == 2) { st_s16<128>(o10, v[0]); st_s16<128>(o11, v[1]); st_s16<128>(o12, v[2]); }
+            if ((k & 3) == 3) { st_s16<192>(o10, v[0]); st_s16<192>(o11, v[1]); st_s16<192>(o12, v[2]); }
+        }
     }
+}
+
+template <bool kMap64, bool kGain>
+__global__ void __launch_bounds__(256) warp_tile_kernel(const __grid_constant__ WarpArgs A, const uint8_t *__restrict__ frames)
+{
+    __shared__ __align__(16) uint32_t sm[kWarpSmemWords];
+    const int ncam = A.ncam;
+    const int cam = blockIdx.z % ncam, slot = blockIdx.z / ncam;
+    const WarpCam &C = A.cam[cam];
+    const int bx = blockIdx.x, by = blockIdx.y;
+    if (bx >= C.tiles_x || by >= C.tiles_y) return;
+    if (C.rx + bx * kWarpTileW + kWarpTileW <= A.win_lo || C.rx + bx * kWarpTileW >= A.win_hi) return;   // strip split
+    const int W = A.W, H = A.H, W3 = W * 3;
+    const uint8_t *src = frames + ((size_t)slot * ncam + cam) * ((size_t)W3 * H);
+    const int4 td = __ldg(C.tiles + by * C.tiles_x + bx);   // {x0 (px, %16==0), y0, rows, 16-px groups}
+    const int lane = threadIdx.x, ty = threadIdx.y;
+    const int rw = (td.w * 16 + 31) & ~31;                   // staged words per row
+    const bool staged = td.z > 0;
+    const int Xt = bx * kWarpTileW + lane;
+    const int Y0 = by * kWarpTileH + ty;
+    const int mp = C.map_pitch, crw = C.rw, crh = C.rh;
+    const bool full = bx * kWarpTileW + kWarpTileW <= crw && by * kWarpTileH + kWarpTileH <= crh;
+    uint32_t msx[8], msy[8];
+    {
+        const uint32_t *m32 = C.map32 + Y0 * mp + Xt;
+        const uint2 *m64 = C.map64 + Y0 * mp + Xt;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int off = 8 * (k >> 2) * mp + 32 * (k & 3);
+            msx[k] = 0; msy[k] = 0;
+            if (full || (Y0 + 8 * (k >> 2) < crh && Xt + 32 * (k & 3) < crw)) {
+                if (kMap64) {
+                    const uint2 e = __ldg(m64 + off);
+                    msx[k] = e.x; msy[k] = e.y;
+                } else {
+                    msx[k] = __ldg(m32 + off);
+                }
+            }
+        }
+    }
+    if (staged) {
+        // half a warp per source row: lane & 15 = 16-pixel group, two rows per warp and step
+        const int q = lane & 15;
+        if (q < td.w) {
+            const int rot = (q >> 1) & 3;
+            const uint8_t *scol = src + min(td.x + 16 * q, W - 16) * 3;      // taps one past the frame have weight 0
+            uint32_t *dcol = sm + 16 * q;
+#pragma unroll 2
+            for (int r = 2 * ty + (lane >> 4); r < td.z; r += 16) {
+                const uint4 *p = reinterpret_cast<const uint4 *>(scol + (size_t)min(td.y + r, H - 1) * W3);
+                const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+                uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+                // rotate by 3 * rot words: slot k then holds chunk (k + rot) & 3 (4 pixels from 3 words)
+                if (rot & 1) {
+                    const uint32_t t0 = w[0], t1 = w[1], t2 = w[2];
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) w[i] = w[i + 3];
+                    w[9] = t0; w[10] = t1; w[11] = t2;
+                }
+                if (rot & 2) {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) { const uint32_t t = w[i]; w[i] = w[i + 6]; w[i + 6] = t; }
+                }
+                uint32_t *d = dcol + r * rw;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint4 o;
+                    o.x = w[3 * k];
+                    o.y = __byte_perm(w[3 * k], w[3 * k + 1], 0x6543);
+                    o.z = __byte_perm(w[3 * k + 1], w[3 * k + 2], 0x5432);
+                    o.w = w[3 * k + 2] >> 8;
+                    *reinterpret_cast<uint4 *>(d + (((k + rot) & 3) << 2)) = o;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int sbase = -(td.y * rw + td.x);
+    if (full) warp_gather<kMap64, kGain, true>(C, sm, src, staged, rw, sbase, W, H, msx, msy, Xt, Y0, slot);
+    else warp_gather<kMap64, kGain, false>(C, sm, src, staged, rw, sbase, W, H, msx, msy, Xt, Y0, slot);
 }
 
 // ------------------------------------------------------------------ K4: single-pass blenders
@@ -1058,19 +1112,27 @@ void launch_warp(const PanoTables *dev, const PanoTables &host, const KernelChoi
 {
     if (kc.warp_tiled) {
         int tx = 0, ty = 0;
-        for (int i = 0; i < host.num_cams; ++i) {
-            tx = max(tx, host.cam[i].tiles_x);
-            ty = max(ty, host.cam[i].tiles_y);
-        }
-        const dim3 block(32, 8), grid(tx, ty, host.num_cams * nslots);
         bool gain = false;
-        for (int i = 0; i < host.num_cams; ++i) gain = gain || host.cam[i].gain_mode != 0;
+        WarpArgs A{};
+        for (int i = 0; i < host.num_cams; ++i) {
+            const CamTables &C = host.cam[i];
+            tx = max(tx, C.tiles_x);
+            ty = max(ty, C.tiles_y);
+            gain = gain || C.gain_mode != 0;
+            WarpCam &d = A.cam[i];
+            d.map32 = C.map32; d.map64 = C.map64; d.tiles = C.tiles; d.gain_map = C.gain_map; d.g0 = C.g[0];
+            d.gain_scalar = C.gain_scalar; d.g_slot = C.g_slot[0];
+            d.map_pitch = C.map_pitch; d.tiles_x = C.tiles_x; d.tiles_y = C.tiles_y; d.rx = C.rx; d.rw = C.rw; d.rh = C.rh;
+            d.g_pitch = C.g_pitch[0]; d.gain_mode = C.gain_mode; d.g_plane = (unsigned)C.g_plane[0];
+        }
+        A.ncam = host.num_cams; A.W = host.src_w; A.H = host.src_h; A.win_lo = host.win_lo[0]; A.win_hi = host.win_hi[0];
+        const dim3 block(32, 8), grid(tx, ty, host.num_cams * nslots);
         if (host.cam[0].map64) {
-            if (gain) warp_tile_kernel<true, true><<<grid, block, 0, stream>>>(dev, frames);
-            else warp_tile_kernel<true, false><<<grid, block, 0, stream>>>(dev, frames);
+            if (gain) warp_tile_kernel<true, true><<<grid, block, 0, stream>>>(A, frames);
+            else warp_tile_kernel<true, false><<<grid, block, 0, stream>>>(A, frames);
         } else {
-            if (gain) warp_tile_kernel<false, true><<<grid, block, 0, stream>>>(dev, frames);
-            else warp_tile_kernel<false, false><<<grid, block, 0, stream>>>(dev, frames);
+            if (gain) warp_tile_kernel<false, true><<<grid, block, 0, stream>>>(A, frames);
+            else warp_tile_kernel<false, false><<<grid, block, 0, stream>>>(A, frames);
         }
         return;
     }
