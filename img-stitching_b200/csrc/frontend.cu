@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -194,6 +195,74 @@ __global__ void __launch_bounds__(256) cubic4_kernel(const uint32_t *__restrict_
     }
 }
 
+// Tiled form of the same remap: a block owns a 64 x 16 tile of the crop rect (thread = 2 x 2 pixels, 32 columns /
+// 8 rows apart).
+//  * The tile's source footprint (static bounding box of all its 4x4 tap windows, from the init-time tile
+//    table) is staged in shared memory with coalesced 16-byte loads; positions outside the camera frame are
+//    staged as 0 (BORDER_CONSTANT), so the gather has no border logic.  The staged row pitch is a multiple
+//    of 32 words: a tap's bank depends on its column only, and the 32 consecutive pixels of a warp read
+//    (nearly) consecutive columns -> each of the 16 taps is one conflict-free LDS.32 (one wavefront instead
+//    of the two a global load spanning two cache lines costs).
+//  * The 32-byte weight entry of every pixel comes through the TEXTURE pipe of L1TEX (two 16-byte fetches of
+//    a linear texture over the 1024-entry table), which runs beside the LSU pipe that serves the taps.
+//  * Rounding is folded into the accumulator start value; saturate + pack is two cvt.pack instructions.
+constexpr int kCubTileW = 64, kCubTileH = 16, kCubSmemWords = 3072;    // 12 KB
+
+__global__ void __launch_bounds__(256) cubic5_kernel(const uint32_t *__restrict__ src, size_t src_img_words, int sw, int sh,
+                                                     const uint32_t *__restrict__ map, int map_w, cudaTextureObject_t wtex,
+                                                     const int4 *__restrict__ tiles, int rx, int ry, int rw, int rh,
+                                                     uint32_t *__restrict__ dst, size_t dst_img_words)
+{
+    __shared__ __align__(16) uint32_t sm[kCubSmemWords];
+    const int lane = threadIdx.x, wy = threadIdx.y, tid = wy * 32 + lane;
+    const int4 td = __ldg(tiles + blockIdx.y * gridDim.x + blockIdx.x);   // {x0 (%4 == 0), y0, rows | chunks per row << 16, 2^16 / chunks}
+    const int rows = td.z & 0xffff, W4 = td.z >> 16;
+    const int P = (W4 * 4 + 31) & ~31;                                  // staged row pitch, words
+    const int y = blockIdx.y * kCubTileH + wy, xb = blockIdx.x * kCubTileW + lane;
+    const uint32_t *s = src + (size_t)blockIdx.z * src_img_words;
+    uint32_t m[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int xx = xb + 32 * (j & 1), yy = y + 8 * (j >> 1);
+        m[j] = (xx < rw && yy < rh) ? __ldg(map + (size_t)(yy + ry) * map_w + rx + xx) : 0u;
+    }
+    for (int c = tid; c < rows * W4; c += 256) {
+        const int r = (c * td.w) >> 16, q = c - r * W4;
+        const int sy = td.y + r, sx = td.x + 4 * q;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if ((unsigned)sy < (unsigned)sh && (unsigned)sx < (unsigned)sw) v = __ldg(reinterpret_cast<const uint4 *>(s + (size_t)sy * sw + sx));
+        *reinterpret_cast<uint4 *>(sm + r * P + 4 * q) = v;
+    }
+    __syncthreads();
+    uint32_t *d = dst + (size_t)blockIdx.z * dst_img_words + (size_t)y * rw + xb;
+    const int sbase = -((td.y + 4) * P + td.x + 4);                     // the map stores tx + 4, ty + 4
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (xb + 32 * (j & 1) >= rw || y + 8 * (j >> 1) >= rh) continue;
+        const uint32_t e = m[j];
+        const int fidx = (int)(e >> 22);                                // (fy << 5) | fx
+        const uint4 wa = tex1Dfetch<uint4>(wtex, fidx << 1), wb = tex1Dfetch<uint4>(wtex, (fidx << 1) + 1);
+        const uint32_t wpk[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        const uint32_t *p = sm + (int)((e >> 11) & 2047u) * P + (int)(e & 2047u) + sbase;
+        uint32_t t[16];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) t[4 * r + q] = p[r * P + q];
+        int a0 = 16384, a1 = 16384, a2 = 16384;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            a0 = dp2a_su((int)wpk[k], __byte_perm(t[2 * k], t[2 * k + 1], 0x0040), a0);
+            a1 = dp2a_su((int)wpk[k], __byte_perm(t[2 * k], t[2 * k + 1], 0x0051), a1);
+            a2 = dp2a_su((int)wpk[k], __byte_perm(t[2 * k], t[2 * k + 1], 0x0062), a2);
+        }
+        uint32_t hi, px;
+        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, 0;" : "=r"(hi) : "r"(0), "r"(a2 >> 15));
+        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(px) : "r"(a1 >> 15), "r"(a0 >> 15), "r"(hi));
+        d[32 * (j & 1) + (size_t)(8 * (j >> 1)) * rw] = px;
+    }
+}
+
 // cv::resize INTER_LINEAR from a word-per-pixel source to packed BGR bytes.  One warp row-chunk =
 // 32 consecutive output pixels = 96 bytes, assembled in shared memory and stored as 24 words.
 __global__ void __launch_bounds__(256) resize4_kernel(const uint32_t *__restrict__ src, size_t src_img_words, int sstride_words,
@@ -358,6 +427,8 @@ struct pano_frontend_ctx {
     uint32_t *buf_w = nullptr;                                     // cropped undistorted image, one word per pixel (fast path)
     uint32_t *dmap32 = nullptr;                                    // packed map entries (fast path, sources <= 2043 px)
     bool fast4 = false;
+    int4 *cub_tiles = nullptr;                                     // per 128x8 tile of the crop rect: staged footprint (cubic5_kernel)
+    int cub_tx = 0, cub_ty = 0;
     cudaEvent_t *prof_ev = nullptr;                                // 3 events (before cubic, between, after resize) when profiling
     uint8_t *stage_in = nullptr, *stage_out = nullptr;
     int launches = 0;
@@ -514,6 +585,35 @@ int pano_frontend_create(const pano_frontend_config *cfg, pano_frontend_handle *
             h->err = "front-end packed map upload failed";
             return bail();
         }
+        // source footprint of every 128x8 output tile (cubic5_kernel); all tiles must fit its staging buffer
+        const int *rc = cfg->rect;
+        const int tx = (rc[2] + kCubTileW - 1) / kCubTileW, ty = (rc[3] + kCubTileH - 1) / kCubTileH;
+        std::vector<int4> tl((size_t)tx * ty);
+        bool fits = cfg->cam_src_width % 4 == 0;
+        for (int by = 0; by < ty && fits; ++by)
+            for (int bx = 0; bx < tx && fits; ++bx) {
+                int x0 = INT32_MAX, x1 = INT32_MIN, y0 = INT32_MAX, y1 = INT32_MIN;
+                for (int y = by * kCubTileH; y < std::min(rc[3], (by + 1) * kCubTileH); ++y)
+                    for (int x = bx * kCubTileW; x < std::min(rc[2], (bx + 1) * kCubTileW); ++x) {
+                        const uint32_t e = pm[(size_t)(y + rc[1]) * uw + (x + rc[0])];
+                        const int ix = (int)(e & 2047u) - 4, iy = (int)((e >> 11) & 2047u) - 4;
+                        x0 = std::min(x0, ix); x1 = std::max(x1, ix + 3);
+                        y0 = std::min(y0, iy); y1 = std::max(y1, iy + 3);
+                    }
+                const int ax0 = (x0 >= 0 ? x0 / 4 : -((-x0 + 3) / 4)) * 4;           // floor to a multiple of 4
+                const int w4 = (x1 - ax0) / 4 + 1, rows = y1 - y0 + 1;
+                fits = w4 <= 64 && rows * ((w4 * 4 + 31) & ~31) <= kCubSmemWords && rows * w4 < 1024;
+                tl[(size_t)by * tx + bx] = make_int4(ax0, y0, rows | (w4 << 16), (65536 + w4 - 1) / w4);
+            }
+        if (getenv("PANO_DEBUG")) fprintf(stderr, "[panob200] cubic tiles %dx%d of %dx%d: %s\n", tx, ty, kCubTileW, kCubTileH, fits ? "staged" : "footprint too large -> untiled kernel");
+        if (fits) {
+            if (falloc(h, &h->cub_tiles, tl.size())) return bail();
+            if (cudaMemcpy(h->cub_tiles, tl.data(), tl.size() * sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess) {
+                h->err = "front-end tile table upload failed";
+                return bail();
+            }
+            h->cub_tx = tx; h->cub_ty = ty;
+        }
     }
     *out = h;
     return PANO_OK;
@@ -567,7 +667,11 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
             static const bool tex_w = getenv("PANO_CUBIC_TEX") != nullptr;
             const uint32_t *src4 = reinterpret_cast<const uint32_t *>(src);
             const uint4 *tab4 = reinterpret_cast<const uint4 *>(h->dtab);
-            if (h->dmap32 && tex_w)
+            static const bool no_tiled = getenv("PANO_CUBIC_UNTILED") != nullptr;
+            if (h->cub_tiles && h->wtex && !no_tiled)
+                cubic5_kernel<<<dim3(h->cub_tx, h->cub_ty, nb), blk, 0, st>>>(src4, in_img / 4, cw, chh, h->dmap32, uw, h->wtex, h->cub_tiles,
+                                                                             rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
+            else if (h->dmap32 && tex_w)
                 cubic4_kernel<true, true><<<cg, blk, 0, st>>>(src4, in_img / 4, cw, chh, h->dmap32, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
             else if (h->dmap32)
                 cubic4_kernel<true, false><<<cg, blk, 0, st>>>(src4, in_img / 4, cw, chh, h->dmap32, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);

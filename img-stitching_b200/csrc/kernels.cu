@@ -932,7 +932,7 @@ __device__ __forceinline__ void warp_gather(const WarpCam &C, const uint32_t *__
 }
 
 template <bool kMap64, bool kGain>
-__global__ void __launch_bounds__(256) warp_tile_kernel(const __grid_constant__ WarpArgs A, const uint8_t *__restrict__ frames)
+__global__ void __launch_bounds__(256, 5) warp_tile_kernel(const __grid_constant__ WarpArgs A, const uint8_t *__restrict__ frames)
 {
     __shared__ __align__(16) uint32_t sm[kWarpSmemWords];
     const int ncam = A.ncam;
