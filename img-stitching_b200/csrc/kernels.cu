@@ -421,6 +421,120 @@ __global__ void __launch_bounds__(256) pyrdown8_kernel(const PanoTables *__restr
     }
 }
 
+// ---- K2'': pyrDown as a column walker.  A lane owns 8 output columns and walks DOWN a band of kDownBand
+// output rows.  Every source row is loaded and horizontally filtered exactly once (pyrdown8_kernel above
+// does it 3.5 times per output row): a filtered odd row 2k+1 adds 4x to the two output rows k, k+1 that are
+// in flight, a filtered even row 2k+2 completes row k (weight 1), adds 6x to row k+1 and opens row k+2 --
+// two accumulator sets whose roles swap every step, so nothing is ever copied.  The 16 samples a lane
+// filters come in two 16-byte loads; the two halo pairs come from the neighbouring lanes by shuffle (the
+// edge lanes load theirs), which halves the cache wavefronts of a row.
+constexpr int kDownBand = 8;
+
+struct DownRaw { uint4 a, b; int l, r; };      // loads in flight (nothing here depends on their arrival)
+struct DownRow { int q[10]; };
+
+__device__ __forceinline__ void down_fetch(const int16_t *__restrict__ row, int lane, bool lo_edge, DownRaw &d)
+{
+    d.a = *reinterpret_cast<const uint4 *>(row);
+    d.b = *reinterpret_cast<const uint4 *>(row + 8);
+    d.l = 0; d.r = 0;
+    if (lane == 0 && !lo_edge) d.l = *reinterpret_cast<const int *>(row - 2);
+    if (lane == 31) d.r = *reinterpret_cast<const int *>(row + 16);            // rows carry >= 24 samples of padding
+}
+
+__device__ __forceinline__ void down_finish(const DownRaw &w, int lane, bool lo_edge, int edge, DownRow &d)
+{
+    d.q[1] = w.a.x; d.q[2] = w.a.y; d.q[3] = w.a.z; d.q[4] = w.a.w; d.q[5] = w.b.x; d.q[6] = w.b.y; d.q[7] = w.b.z; d.q[8] = w.b.w;
+    const int left = __shfl_up_sync(0xffffffffu, (int)w.b.w, 1), right = __shfl_down_sync(0xffffffffu, (int)w.a.x, 1);
+    d.q[0] = lo_edge ? (int)__byte_perm(d.q[2], d.q[1], 0x7610) : (lane == 0 ? w.l : left);   // (v[-2], v[-1]) := (v[2], v[1])
+    d.q[9] = lane == 31 ? w.r : right;
+    if (edge <= 9) {
+#pragma unroll
+        for (int k = 1; k <= 9; ++k)
+            if (k == edge) d.q[k] = d.q[k - 1];                               // v[sw] := v[sw-2]
+    }
+}
+
+__device__ __forceinline__ void down_hfilter(const DownRow &d, int h[8])
+{
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        h[j] = __dp2a_lo(d.q[j], COEF(1, 4), __dp2a_lo(d.q[j + 1], COEF(6, 4), __dp2a_lo(d.q[j + 2], COEF(1, 0), 0)));
+}
+
+__global__ void __launch_bounds__(128) pyrdown8_walk_kernel(const PanoTables *__restrict__ T, int level, int band)
+{
+    const int ncam = T->num_cams;
+    int z = blockIdx.z;
+    const int plane = z % 3; z /= 3;
+    const int cam = z % ncam, slot = z / ncam;
+    const CamTables &C = T->cam[cam];
+    const int sw = C.rw >> level, sh = C.rh >> level;
+    const int dw = sw >> 1, dh = sh >> 1;
+    const int lane = threadIdx.x;
+    const int oxw = blockIdx.x * 256;                                        // first output column of this warp
+    const int oy0 = (blockIdx.y * blockDim.y + threadIdx.y) * band;
+    if (oxw >= dw || oy0 >= dh) return;
+    {
+        const int c0 = (C.rx >> (level + 1)) + oxw;
+        if (outside_window(T, level + 1, c0, c0 + 256)) return;
+    }
+    const int ox = oxw + lane * 8;
+    const bool live = ox < dw;
+    const int oxl = live ? ox : ((dw - 1) >> 3) << 3;                         // idle lanes still load + shuffle (in range)
+    const int sp = C.g_pitch[level], dp = C.g_pitch[level + 1];
+    const int16_t *src = C.g[level] + (size_t)slot * C.g_slot[level] + (size_t)plane * C.g_plane[level] + 2 * oxl;
+    int16_t *dst = C.g[level + 1] + (size_t)slot * C.g_slot[level + 1] + (size_t)plane * C.g_plane[level + 1] + ox;
+    const bool lo_edge = oxl == 0;
+    const int edge = dw - oxl + 1;            // local index of the pair that starts at column sw (reflect-101)
+    const int nrows = min(band, dh - oy0);
+
+    int accA[8], accB[8];                     // output rows k and k + 1 (128 = rounding, folded in when a row is opened)
+    DownRaw r0, r1;
+    {
+        DownRaw a, b, c;
+        down_fetch(src + reflect101(2 * oy0 - 2, sh) * sp, lane, lo_edge, a);
+        down_fetch(src + reflect101(2 * oy0 - 1, sh) * sp, lane, lo_edge, b);
+        down_fetch(src + 2 * oy0 * sp, lane, lo_edge, c);
+        down_fetch(src + reflect101(2 * oy0 + 1, sh) * sp, lane, lo_edge, r0);
+        down_fetch(src + reflect101(2 * oy0 + 2, sh) * sp, lane, lo_edge, r1);
+        DownRow qa, qb, qc;
+        down_finish(a, lane, lo_edge, edge, qa); down_finish(b, lane, lo_edge, edge, qb); down_finish(c, lane, lo_edge, edge, qc);
+        int ha[8], hb[8], hc[8];
+        down_hfilter(qa, ha); down_hfilter(qb, hb); down_hfilter(qc, hc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { accA[j] = ha[j] + 4 * hb[j] + 6 * hc[j] + 128; accB[j] = hc[j] + 128; }
+    }
+    // one step: rows 2k+1 (odd) and 2k+2 (even) finish output row k (in A), advance k+1 (in B) and open k+2 (in A)
+#define DOWN_STEP(i, A, B)                                                                       \
+    {                                                                                            \
+        DownRow co, ce;                                                                          \
+        down_finish(r0, lane, lo_edge, edge, co); down_finish(r1, lane, lo_edge, edge, ce);      \
+        if ((i) + 1 < nrows) {                                                                   \
+            down_fetch(src + reflect101(2 * (oy0 + (i)) + 3, sh) * sp, lane, lo_edge, r0);        \
+            down_fetch(src + reflect101(2 * (oy0 + (i)) + 4, sh) * sp, lane, lo_edge, r1);        \
+        }                                                                                        \
+        int ho[8], he[8];                                                                        \
+        down_hfilter(co, ho); down_hfilter(ce, he);                                              \
+        uint32_t o[4];                                                                           \
+        _Pragma("unroll") for (int j = 0; j < 8; j += 2) {                                       \
+            const int v0 = (A[j] + 4 * ho[j] + he[j]) >> 8, v1 = (A[j + 1] + 4 * ho[j + 1] + he[j + 1]) >> 8; \
+            o[j >> 1] = __byte_perm(v0, v1, 0x5410);                                             \
+        }                                                                                        \
+        _Pragma("unroll") for (int j = 0; j < 8; ++j) { B[j] += 4 * ho[j] + 6 * he[j]; A[j] = he[j] + 128; } \
+        if (live) {                                                                              \
+            int16_t *d = dst + (oy0 + (i)) * dp;                                                 \
+            if (ox + 8 <= dw) *reinterpret_cast<uint4 *>(d) = make_uint4(o[0], o[1], o[2], o[3]); \
+            else for (int j = 0; j < 8 && ox + j < dw; ++j) d[j] = (short)(o[j >> 1] >> (16 * (j & 1))); \
+        }                                                                                        \
+    }
+    for (int i = 0; i < nrows; i += 2) {
+        DOWN_STEP(i, accA, accB)
+        if (i + 1 < nrows) DOWN_STEP(i + 1, accB, accA)
+    }
+#undef DOWN_STEP
+}
+
 // ---- pyrUp of coarse columns k0..k0+3, rows m-1..m+1 -> the 8 x 2 fine block (rows 2m, 2m+1).
 // Split into an explicit LOAD step (12 words, issued early so several independent loads are in
 // flight) and a COMPUTE step.  k0 % 4 == 0, cw % 4 == 0.
@@ -1157,6 +1271,13 @@ void launch_pyrdown(const PanoTables *dev, const PanoTables &host, const KernelC
     }
     const dim3 block(32, 8);
     if (kc.pyrdown8[level]) {
+        static const bool no_walk = getenv("PANO_NO_DOWN_WALK") != nullptr;
+        if (!no_walk) {
+            static const int band = getenv("PANO_DOWN_BAND") ? atoi(getenv("PANO_DOWN_BAND")) : kDownBand;
+            const dim3 wb(32, 4), wg((maxw + 255) / 256, (maxh + 4 * band - 1) / (4 * band), host.num_cams * nslots * 3);
+            pyrdown8_walk_kernel<<<wg, wb, 0, stream>>>(dev, level, band);
+            return;
+        }
         const dim3 grid8 = grid2d((maxw + 7) / 8, (maxh + 1) / 2, block, host.num_cams * nslots * 3);
         pyrdown8_kernel<<<grid8, block, 0, stream>>>(dev, level);
         return;
