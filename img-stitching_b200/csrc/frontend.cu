@@ -364,11 +364,13 @@ __global__ void __launch_bounds__(128, 8) resize4_walk_kernel(const uint32_t *__
     // lanes 4k..4k+2 store the three words of pixels 4k..4k+3; lane 4k+3 stores nothing
     uint8_t *olane = dst + (size_t)blockIdx.z * dst_img + (size_t)ybase * dstride + (size_t)xw * 3 + ((lane >> 2) * 3 + j) * 4;
     const uint32_t *ayp = s_ay;
+    const unsigned sstride_bytes = sstride_words * 4u;
 
 #define RS_FETCH(v, A, B)                                                        \
     {                                                                            \
-        const unsigned r_ = (unsigned)min(max((v), 0), sh - 1) * sstride_words;  \
-        A = __ldg(s0 + r_); B = __ldg(s1 + r_);                                  \
+        const size_t rb_ = (size_t)((unsigned)min(max((v), 0), sh - 1) * sstride_bytes);  \
+        A = __ldg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s0) + rb_)); \
+        B = __ldg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s1) + rb_)); \
     }
 #define RS_HCALC(A, B, H0, H1, H2)                                               \
     H0 = (uint32_t)dp2a_su(axp, __byte_perm(A, B, 0x0040u), 0) >> 4;             \
@@ -378,13 +380,13 @@ __global__ void __launch_bounds__(128, 8) resize4_walk_kernel(const uint32_t *__
     // next step's B) and the prefetch slot is refilled with row v + 4
 #define RS_STEP(i, A0, A1, A2, B0, B1, B2, PA, PB)                               \
     {                                                                            \
-        for (int n_ = s_yb[(i) + 1] - s_yb[(i)]; n_ > 0; --n_) {                 \
+        _Pragma("unroll 1") for (int n_ = s_yb[(i) + 1] - s_yb[(i)]; n_ > 0; --n_) { \
             const uint32_t w_ = *ayp++;                                          \
             const uint32_t a0_ = w_ << 16, a1_ = w_ & 0xffff0000u;               \
-            const uint32_t c0_ = (__umulhi(a0_, A0) + __umulhi(a1_, B0) + 2u) >> 2;   \
-            const uint32_t c1_ = (__umulhi(a0_, A1) + __umulhi(a1_, B1) + 2u) >> 2;   \
-            const uint32_t c2_ = (__umulhi(a0_, A2) + __umulhi(a1_, B2) + 2u) >> 2;   \
-            const uint32_t px_ = c0_ | (c1_ << 8) | (c2_ << 16);                 \
+            const uint32_t c0_ = (__umulhi(a0_, A0) + 2u + __umulhi(a1_, B0)) >> 2;   \
+            const uint32_t c1_ = (__umulhi(a0_, A1) + 2u + __umulhi(a1_, B1)) >> 2;   \
+            const uint32_t c2_ = (__umulhi(a0_, A2) + 2u + __umulhi(a1_, B2)) >> 2;   \
+            const uint32_t px_ = __byte_perm(__byte_perm(c0_, c1_, 0x0040), c2_, 0x0410); \
             const uint32_t nx_ = __shfl_down_sync(0xffffffffu, px_, 1);          \
             if (j < 3) *reinterpret_cast<uint32_t *>(olane) = __byte_perm(px_, nx_, sel); \
             olane += dstride;                                                    \
