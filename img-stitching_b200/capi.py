@@ -89,6 +89,7 @@ _SIGS = {
     "pano_frontend_process_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "pano_frontend_process": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "pano_attach_frontend": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "pano_set_frontend_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "pano_host_warp_roi": (C.c_int, [C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "pano_host_build_maps": (C.c_int, [C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "pano_host_blend_geometry": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,

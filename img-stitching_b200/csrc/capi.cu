@@ -25,6 +25,7 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
 int pano_frontend_launches(pano_frontend_handle h);
 void pano_frontend_sizes(pano_frontend_handle h, int *in_wh, int *out_wh);
 bool pano_frontend_set_prof(pano_frontend_handle h, cudaEvent_t *ev, double *cubic_bytes, double *resize_bytes);
+void pano_frontend_backmap(pano_frontend_handle h, double *xs, double *ys, size_t count);
 
 namespace {
 
@@ -66,6 +67,10 @@ struct pano_ctx {
     // optional nvCam front end per camera (pano_attach_frontend): inputs become 8UC4 camera frames
     pano_frontend_handle front[kMaxCams] = {};
     bool has_front = false;
+    // fused front-end mode (pano_set_frontend_mode): the whole nvCam pipeline is folded into the warp's remap table
+    // and the gather reads the 8UC4 camera frames directly -- NOT bit-exact with the sequential path
+    bool fused = false;
+    std::vector<std::vector<float>> fxmap, fymap;  // composed float maps (rois[cam] large) while fused
     size_t in_frame_bytes = 0;                    // bytes of one input frame as the caller passes it
     uint8_t *front_out = nullptr;                 // [max_batch][n][H][W][3] stitcher inputs produced by the front end
     int strip_x0 = 0, strip_x1 = 0;               // own dst columns (level 0, padded coords); full width = no split
@@ -89,6 +94,7 @@ struct pano_ctx {
     int last_launches = 0;
 
     size_t frame_bytes() const { return (size_t)cfg.src_width * cfg.src_height * 3; }
+    size_t gather_frame_bytes() const { return fused ? in_frame_bytes : frame_bytes(); }   // frame the warp gathers from
     size_t set_bytes() const { return (has_front ? in_frame_bytes : frame_bytes()) * n; }   // caller-side frame-set
     size_t out_bytes() const { return (size_t)host.cut_w * host.cut_h * 3; }
 };
@@ -210,6 +216,87 @@ int uploadTileLists(pano_ctx *h)
     return PANO_OK;
 }
 
+template <typename T>
+void devFree(pano_ctx *h, T *p)
+{
+    if (!p) return;
+    auto it = std::find(h->owned.begin(), h->owned.end(), (void *)p);
+    if (it != h->owned.end()) h->owned.erase(it);
+    cudaFree((void *)p);
+}
+
+// Device remap table of camera `cam` from float backward maps xm/ym (rois[cam] large) into a W x H source: the
+// folded fixed-point table over the feed rect and the per-tile source footprints of the staged gather.  Re-callable
+// (the fused front-end mode swaps the maps); the previous tables are released.
+int buildCamMap(pano_ctx *h, int cam, const float *xm, const float *ym, int W, int H)
+{
+    CamTables &C = h->host.cam[cam];
+    const FeedRect &fr = h->feed[cam];
+    const Rect &img = h->rois[cam];
+    const bool map64 = (32 * (W - 1) + 31 > 65535) || (32 * (H - 1) + 31 > 65535);
+    C.rx = fr.rect.x; C.ry = fr.rect.y; C.rw = fr.rect.w; C.rh = fr.rect.h;
+    C.map_pitch = roundUp(C.rw, 64);
+    // folded map over the feed rect: copyMakeBorder(BORDER_REFLECT) of the warped image is a
+    // re-read of the warp at the mirrored coordinate
+    std::vector<uint32_t> m32;
+    std::vector<uint2> m64;
+    if (map64) m64.assign((size_t)C.map_pitch * C.rh, make_uint2(0, 0));
+    else m32.assign((size_t)C.map_pitch * C.rh, 0u);
+    for (int Y = 0; Y < C.rh; ++Y) {
+        const int y = reflectIdx(Y - fr.top, img.h);
+        for (int X = 0; X < C.rw; ++X) {
+            const int x = reflectIdx(X - fr.left, img.w);
+            const FixedCoord fc = toFixed(xm[(size_t)y * img.w + x], ym[(size_t)y * img.w + x]);
+            const uint32_t sx = foldReflect(fc.ix, fc.fx, W), sy = foldReflect(fc.iy, fc.fy, H);
+            if (map64) m64[(size_t)Y * C.map_pitch + X] = make_uint2(sx, sy);
+            else m32[(size_t)Y * C.map_pitch + X] = sx | (sy << 16);
+        }
+    }
+    devFree(h, C.map32); devFree(h, C.map64); devFree(h, C.tiles);
+    C.map32 = nullptr; C.map64 = nullptr; C.tiles = nullptr;
+    if (map64) {
+        uint2 *d = nullptr;
+        if (devAlloc(h, &d, m64.size(), false)) return PANO_ERR;
+        if (cudaMemcpy(d, m64.data(), m64.size() * sizeof(uint2), cudaMemcpyHostToDevice) != cudaSuccess) return fail(h, "map upload failed");
+        C.map64 = d;
+    } else {
+        uint32_t *d = nullptr;
+        if (devAlloc(h, &d, m32.size(), false)) return PANO_ERR;
+        if (cudaMemcpy(d, m32.data(), m32.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) return fail(h, "map upload failed");
+        C.map32 = d;
+    }
+    // source footprint of every 128x16 output tile (staged-gather warp kernel)
+    C.tiles_x = (C.rw + kWarpTileW - 1) / kWarpTileW;
+    C.tiles_y = (C.rh + kWarpTileH - 1) / kWarpTileH;
+    std::vector<int4> tl((size_t)C.tiles_x * C.tiles_y);
+    for (int ty = 0; ty < C.tiles_y; ++ty)
+        for (int tx = 0; tx < C.tiles_x; ++tx) {
+            int x0 = INT32_MAX, x1 = -1, y0 = INT32_MAX, y1 = -1;
+            const int xe = std::min(C.rw, (tx + 1) * kWarpTileW);
+            for (int Y = ty * kWarpTileH; Y < std::min(C.rh, (ty + 1) * kWarpTileH); ++Y)
+                for (int X = tx * kWarpTileW; X < xe; ++X) {
+                    uint32_t sx, sy;
+                    if (map64) { sx = m64[(size_t)Y * C.map_pitch + X].x; sy = m64[(size_t)Y * C.map_pitch + X].y; }
+                    else { sx = m32[(size_t)Y * C.map_pitch + X] & 0xffffu; sy = m32[(size_t)Y * C.map_pitch + X] >> 16; }
+                    const int ix = sx >> 5, iy = sy >> 5;
+                    // taps (ix+1, iy+1) may lie one past the frame (weight 0 there); the kernel's
+                    // staging loop clamps the source address, the box keeps the unclamped extent
+                    x0 = std::min(x0, ix); x1 = std::max(x1, ix + 1);
+                    y0 = std::min(y0, iy); y1 = std::max(y1, iy + 1);
+                }
+            const int px0 = x0 / 16 * 16, groups = (x1 - px0) / 16 + 1;
+            const int rows = y1 - y0 + 1;
+            int4 d = make_int4(0, 0, 0, 0);
+            if (W % 16 == 0 && groups <= 16 && rows * ((groups * 16 + 31) & ~31) <= kWarpSmemWords) d = make_int4(px0, y0, rows, groups);
+            tl[(size_t)ty * C.tiles_x + tx] = d;
+        }
+    int4 *dt = nullptr;
+    if (devAlloc(h, &dt, tl.size(), false)) return PANO_ERR;
+    if (cudaMemcpy(dt, tl.data(), tl.size() * sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess) return fail(h, "tile table upload failed");
+    C.tiles = dt;
+    return PANO_OK;
+}
+
 int buildWeights(pano_ctx *h, int cam)
 {
     CamTables &C = h->host.cam[cam];
@@ -289,7 +376,7 @@ double warpBytes(const pano_ctx *h, int slots)
     double b = 0;
     for (int i = 0; i < h->n; ++i) {
         const CamTables &C = h->host.cam[i];
-        b += (double)C.rw * C.rh * ((h->map64 ? 8 : 4) + 6 + (C.gain_mode == 1 ? 4 : 0)) + (double)h->frame_bytes();
+        b += (double)C.rw * C.rh * ((h->map64 ? 8 : 4) + 6 + (C.gain_mode == 1 ? 4 : 0)) + (double)h->gather_frame_bytes();
     }
     return b * slots;
 }
@@ -376,7 +463,7 @@ int runPhase(pano_ctx *h, int p, const uint8_t *frames_dev, uint8_t *out_dev, in
 
 int runFrontEnds(pano_ctx *h, const uint8_t *&frames_dev, int slots, cudaStream_t st)
 {
-    if (!h->has_front) return PANO_OK;
+    if (!h->has_front || h->fused) return PANO_OK;
     Launch L{h, st};
     bool same = true;
     for (int i = 1; i < h->n; ++i) same = same && h->front[i] == h->front[0];
@@ -521,7 +608,7 @@ int pano_create(const pano_config *cfg, pano_handle *out)
 
     // ---- blender geometry ----
     PanoTables &T = h->host;
-    T.num_cams = n; T.src_w = W; T.src_h = H;
+    T.num_cams = n; T.src_w = W; T.src_h = H; T.src_px = 3;
     T.roi_w = h->dst_roi.w; T.roi_h = h->dst_roi.h;
     h->feed.resize(n);
     if (h->blender == PANO_BLEND_MULTIBAND) {
@@ -559,66 +646,7 @@ int pano_create(const pano_config *cfg, pano_handle *out)
         const FeedRect &fr = h->feed[i];
         const Rect &img = h->rois[i];
         C.rx = fr.rect.x; C.ry = fr.rect.y; C.rw = fr.rect.w; C.rh = fr.rect.h;
-        C.map_pitch = roundUp(C.rw, 64);
-        // folded map over the feed rect: copyMakeBorder(BORDER_REFLECT) of the warped image is a
-        // re-read of the warp at the mirrored coordinate
-        std::vector<uint32_t> m32;
-        std::vector<uint2> m64;
-        if (h->map64) m64.assign((size_t)C.map_pitch * C.rh, make_uint2(0, 0));
-        else m32.assign((size_t)C.map_pitch * C.rh, 0u);
-        for (int Y = 0; Y < C.rh; ++Y) {
-            const int y = reflectIdx(Y - fr.top, img.h);
-            for (int X = 0; X < C.rw; ++X) {
-                const int x = reflectIdx(X - fr.left, img.w);
-                const FixedCoord fc = toFixed(h->xmap[i][(size_t)y * img.w + x], h->ymap[i][(size_t)y * img.w + x]);
-                const uint32_t sx = foldReflect(fc.ix, fc.fx, W), sy = foldReflect(fc.iy, fc.fy, H);
-                if (h->map64) m64[(size_t)Y * C.map_pitch + X] = make_uint2(sx, sy);
-                else m32[(size_t)Y * C.map_pitch + X] = sx | (sy << 16);
-            }
-        }
-        if (h->map64) {
-            uint2 *d = nullptr;
-            if (devAlloc(h, &d, m64.size(), false)) return bail(0);
-            if (cudaMemcpy(d, m64.data(), m64.size() * sizeof(uint2), cudaMemcpyHostToDevice) != cudaSuccess) { h->err = "map upload failed"; return bail(0); }
-            C.map64 = d; C.map32 = nullptr;
-        } else {
-            uint32_t *d = nullptr;
-            if (devAlloc(h, &d, m32.size(), false)) return bail(0);
-            if (cudaMemcpy(d, m32.data(), m32.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) { h->err = "map upload failed"; return bail(0); }
-            C.map32 = d; C.map64 = nullptr;
-        }
-        // source footprint of every 128x16 output tile (staged-gather warp kernel)
-        C.tiles_x = (C.rw + kWarpTileW - 1) / kWarpTileW;
-        C.tiles_y = (C.rh + kWarpTileH - 1) / kWarpTileH;
-        {
-            std::vector<int4> tl((size_t)C.tiles_x * C.tiles_y);
-            const int W3 = W * 3;
-            for (int ty = 0; ty < C.tiles_y; ++ty)
-                for (int tx = 0; tx < C.tiles_x; ++tx) {
-                    int x0 = INT32_MAX, x1 = -1, y0 = INT32_MAX, y1 = -1;
-                    const int xe = std::min(C.rw, (tx + 1) * kWarpTileW);
-                    for (int Y = ty * kWarpTileH; Y < std::min(C.rh, (ty + 1) * kWarpTileH); ++Y)
-                        for (int X = tx * kWarpTileW; X < xe; ++X) {
-                            uint32_t sx, sy;
-                            if (h->map64) { sx = m64[(size_t)Y * C.map_pitch + X].x; sy = m64[(size_t)Y * C.map_pitch + X].y; }
-                            else { sx = m32[(size_t)Y * C.map_pitch + X] & 0xffffu; sy = m32[(size_t)Y * C.map_pitch + X] >> 16; }
-                            const int ix = sx >> 5, iy = sy >> 5;
-                            // taps (ix+1, iy+1) may lie one past the frame (weight 0 there); the kernel's
-                            // staging loop clamps the source address, the box keeps the unclamped extent
-                            x0 = std::min(x0, ix); x1 = std::max(x1, ix + 1);
-                            y0 = std::min(y0, iy); y1 = std::max(y1, iy + 1);
-                        }
-                    const int px0 = x0 / 16 * 16, groups = (x1 - px0) / 16 + 1;
-                    const int rows = y1 - y0 + 1;
-                    int4 d = make_int4(0, 0, 0, 0);
-                    if (W % 16 == 0 && groups <= 16 && rows * ((groups * 16 + 31) & ~31) <= kWarpSmemWords) d = make_int4(px0, y0, rows, groups);
-                    tl[(size_t)ty * C.tiles_x + tx] = d;
-                }
-            int4 *dt = nullptr;
-            if (devAlloc(h, &dt, tl.size(), false)) return bail(0);
-            if (cudaMemcpy(dt, tl.data(), tl.size() * sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess) { h->err = "tile table upload failed"; return bail(0); }
-            C.tiles = dt;
-        }
+        if (buildCamMap(h, i, h->xmap[i].data(), h->ymap[i].data(), W, H)) return bail(0);
         C.gain_mode = 0; C.gain_map = nullptr; C.gain_scalar = 1.0;
         // weights
         C.mask_pitch = roundUp(C.rw, 64);
@@ -746,17 +774,19 @@ int pano_get_blend_geometry(pano_handle h, int *num_bands, int *padded_wh, int *
 int pano_get_warp_maps(pano_handle h, int cam, float *xmap, float *ymap)
 {
     if (!h || cam < 0 || cam >= h->n) return fail(h, "bad camera index");
-    if (xmap) std::memcpy(xmap, h->xmap[cam].data(), h->xmap[cam].size() * sizeof(float));
-    if (ymap) std::memcpy(ymap, h->ymap[cam].data(), h->ymap[cam].size() * sizeof(float));
+    const std::vector<float> &xm = h->fused ? h->fxmap[cam] : h->xmap[cam], &ym = h->fused ? h->fymap[cam] : h->ymap[cam];
+    if (xmap) std::memcpy(xmap, xm.data(), xm.size() * sizeof(float));
+    if (ymap) std::memcpy(ymap, ym.data(), ym.size() * sizeof(float));
     return PANO_OK;
 }
 
 int pano_get_fixed_maps(pano_handle h, int cam, int16_t *ixy, uint16_t *frac)
 {
     if (!h || cam < 0 || cam >= h->n) return fail(h, "bad camera index");
-    const size_t cnt = h->xmap[cam].size();
+    const std::vector<float> &xm = h->fused ? h->fxmap[cam] : h->xmap[cam], &ym = h->fused ? h->fymap[cam] : h->ymap[cam];
+    const size_t cnt = xm.size();
     for (size_t p = 0; p < cnt; ++p) {
-        const FixedCoord fc = toFixed(h->xmap[cam][p], h->ymap[cam][p]);
+        const FixedCoord fc = toFixed(xm[p], ym[p]);
         if (ixy) { ixy[2 * p] = (int16_t)fc.ix; ixy[2 * p + 1] = (int16_t)fc.iy; }
         if (frac) frac[p] = (uint16_t)(fc.fy * 32 + fc.fx);
     }
@@ -851,10 +881,12 @@ int pano_attach_frontend(pano_handle h, int cam, pano_frontend_handle f)
     CK(h, cudaSetDevice(h->device));
     CK(h, cudaDeviceSynchronize());
     if (!f) {
+        if (h->fused && pano_set_frontend_mode(h, PANO_FRONTEND_SEQUENTIAL)) return PANO_ERR;
         for (int i = 0; i < h->n; ++i) h->front[i] = nullptr;
         h->has_front = false;
         return PANO_OK;
     }
+    if (h->fused) return fail(h, "pano_attach_frontend: switch back to PANO_FRONTEND_SEQUENTIAL before re-attaching");
     int in_wh[2], out_wh[2];
     pano_frontend_sizes(f, in_wh, out_wh);
     if (out_wh[0] != h->cfg.src_width || out_wh[1] != h->cfg.src_height)
@@ -870,6 +902,62 @@ int pano_attach_frontend(pano_handle h, int cam, pano_frontend_handle f)
     h->in_frame_bytes = in_bytes;
     h->has_front = true;
     if (!h->front_out && devAlloc(h, &h->front_out, h->frame_bytes() * h->n * h->cfg.max_batch, false)) return PANO_ERR;
+    return PANO_OK;
+}
+
+int pano_set_frontend_mode(pano_handle h, int mode)
+{
+    if (!h || (mode != PANO_FRONTEND_SEQUENTIAL && mode != PANO_FRONTEND_FUSED)) return fail(h, "pano_set_frontend_mode: bad argument");
+    if (mode == PANO_FRONTEND_FUSED && !h->has_front) return fail(h, "pano_set_frontend_mode: attach a front end first");
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());
+    if ((mode == PANO_FRONTEND_FUSED) == h->fused) return PANO_OK;
+    const int n = h->n;
+    int W = h->cfg.src_width, H = h->cfg.src_height;
+    if (mode == PANO_FRONTEND_FUSED) {
+        int in_wh[2], out_wh[2];
+        pano_frontend_sizes(h->front[0], in_wh, out_wh);
+        for (int i = 1; i < n; ++i) {
+            int iw[2], ow[2];
+            pano_frontend_sizes(h->front[i], iw, ow);
+            if (iw[0] != in_wh[0] || iw[1] != in_wh[1]) return fail(h, "pano_set_frontend_mode: all cameras must share one frame size");
+        }
+        const int sw = out_wh[0], sh = out_wh[1];       // stitcher input = front-end output
+        W = in_wh[0]; H = in_wh[1];
+        h->fxmap.assign(n, {}); h->fymap.assign(n, {});
+        // BORDER_REFLECT of the rotation warp, continuous form: mirror about -0.5 and n - 0.5 (pixel-centre
+        // coordinates), then clamp to the pixel centres
+        auto foldc = [](double c, int nn) {
+            if (!(std::fabs(c) < 1e9)) return 0.0;
+            double t = std::fmod(c + 0.5, 2.0 * nn);
+            if (t < 0) t += 2.0 * nn;
+            if (t >= nn) t = 2.0 * nn - t;
+            return std::min((double)(nn - 1), std::max(0.0, t - 0.5));
+        };
+        for (int i = 0; i < n; ++i) {
+            const size_t cnt = h->xmap[i].size();
+            std::vector<double> xs(cnt), ys(cnt);
+            for (size_t p = 0; p < cnt; ++p) { xs[p] = foldc(h->xmap[i][p], sw); ys[p] = foldc(h->ymap[i][p], sh); }
+            pano_frontend_backmap(h->front[i], xs.data(), ys.data(), cnt);
+            h->fxmap[i].resize(cnt); h->fymap[i].resize(cnt);
+            for (size_t p = 0; p < cnt; ++p) {
+                // the sequential path reads 0 outside the camera frame (cv::remap BORDER_CONSTANT); here the edge is
+                // replicated -- only reachable when the crop rect keeps pixels whose undistort map leaves the frame
+                h->fxmap[i][p] = (float)std::min((double)(W - 1), std::max(0.0, xs[p]));
+                h->fymap[i][p] = (float)std::min((double)(H - 1), std::max(0.0, ys[p]));
+            }
+        }
+    }
+    h->fused = (mode == PANO_FRONTEND_FUSED);
+    for (int i = 0; i < n; ++i) {
+        const float *xm = h->fused ? h->fxmap[i].data() : h->xmap[i].data(), *ym = h->fused ? h->fymap[i].data() : h->ymap[i].data();
+        if (buildCamMap(h, i, xm, ym, W, H)) return PANO_ERR;
+    }
+    if (!h->fused) { h->fxmap.clear(); h->fymap.clear(); }
+    h->host.src_w = W; h->host.src_h = H; h->host.src_px = h->fused ? 4 : 3;
+    h->map64 = (32 * (W - 1) + 31 > 65535) || (32 * (H - 1) + 31 > 65535);
+    h->kc.warp_tiled = (W % 16 == 0);
+    h->tables_dirty = true;
     return PANO_OK;
 }
 

@@ -742,6 +742,38 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
     return PANO_OK;
 }
 
+// The whole pixel pipeline as ONE coordinate map, walked backwards: position (x, y) in the front end's output image
+// -> position in the 8UC4 camera frame (pixel-centre coordinates, double precision).  Host only; consumed by the
+// fused single-gather variant of the compose (pano_set_frontend_mode).  Each cv::resize stage inverts to
+// (d + 0.5) * (1 / (dsize / ssize)) - 0.5 clamped to the source (what its index/weight tables encode); the undistort
+// stage is the float map itself, bilinearly interpolated between its integer nodes.
+void pano_frontend_backmap(pano_frontend_handle h, double *xs, double *ys, size_t count)
+{
+    const pano_frontend_config &c = h->cfg;
+    const int uw = c.undist_width, uh = c.undist_height;
+    auto inv = [](double d, int ssize, int dsize) {
+        const double s = 1.0 / ((double)dsize / ssize);
+        return std::min((double)(ssize - 1), std::max(0.0, (d + 0.5) * s - 0.5));
+    };
+    for (size_t k = 0; k < count; ++k) {
+        double x = xs[k], y = ys[k];
+        if (h->use_r_out) { x = inv(x, uw, c.out_width); y = inv(y, uh, c.out_height); }
+        if (c.undistort) {
+            if (h->use_r_mid) { x = inv(x, c.rect[2], uw); y = inv(y, c.rect[3], uh); }
+            x += c.rect[0]; y += c.rect[1];
+            x = std::min((double)(uw - 1), std::max(0.0, x));
+            y = std::min((double)(uh - 1), std::max(0.0, y));
+            const int x0 = std::min(uw - 2, (int)x), y0 = std::min(uh - 2, (int)y);
+            const double fx = x - x0, fy = y - y0;
+            const float *mx = h->mapx.data() + (size_t)y0 * uw + x0, *my = h->mapy.data() + (size_t)y0 * uw + x0;
+            x = (1 - fy) * ((1 - fx) * mx[0] + fx * mx[1]) + fy * ((1 - fx) * mx[uw] + fx * mx[uw + 1]);
+            y = (1 - fy) * ((1 - fx) * my[0] + fx * my[1]) + fy * ((1 - fx) * my[uw] + fx * my[uw + 1]);
+        }
+        if (h->use_r_in) { x = inv(x, c.cam_src_width, uw); y = inv(y, c.cam_src_height, uh); }
+        xs[k] = x; ys[k] = y;
+    }
+}
+
 int pano_frontend_launches(pano_frontend_handle h) { return h ? h->launches : 0; }
 // fast path only, one chunk per call: record events around the two kernels; returns their algorithmic bytes per image
 bool pano_frontend_set_prof(pano_frontend_handle h, cudaEvent_t *ev, double *cubic_bytes, double *resize_bytes)

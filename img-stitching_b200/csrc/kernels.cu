@@ -49,16 +49,16 @@ __device__ __forceinline__ bool outside_window(const PanoTables *__restrict__ T,
 // + copyMakeBorder(BORDER_REFLECT) of MultiBandBlender::feed, in one gather.
 // One thread = 4 consecutive pixels of one row of one camera's feed rect.
 __device__ __forceinline__ void bilinear_bgr(const uint8_t *__restrict__ src, int W, int H, uint32_t sx, uint32_t sy,
-                                             int out[3])
+                                             int out[3], int px = 3)
 {
-    const int ix = sx >> 5, fx = sx & 31, iy = sy >> 5, fy = sy & 31;
-    const int ix1 = min(ix + 1, W - 1), iy1 = min(iy + 1, H - 1);
-    const uint8_t *r0 = src + ((size_t)iy * W) * 3, *r1 = src + ((size_t)iy1 * W) * 3;
+    const int fx = sx & 31, iy = sy >> 5, fy = sy & 31;
+    const int ix1 = min((int)(sx >> 5) + 1, W - 1) * px, iy1 = min(iy + 1, H - 1), ix = (int)(sx >> 5) * px;
+    const uint8_t *r0 = src + ((size_t)iy * W) * px, *r1 = src + ((size_t)iy1 * W) * px;
     const int w00 = (32 - fy) * (32 - fx), w01 = (32 - fy) * fx, w10 = fy * (32 - fx), w11 = fy * fx;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const int s = w00 * __ldg(r0 + ix * 3 + c) + w01 * __ldg(r0 + ix1 * 3 + c) +
-                      w10 * __ldg(r1 + ix * 3 + c) + w11 * __ldg(r1 + ix1 * 3 + c);
+        const int s = w00 * __ldg(r0 + ix + c) + w01 * __ldg(r0 + ix1 + c) +
+                      w10 * __ldg(r1 + ix + c) + w11 * __ldg(r1 + ix1 + c);
         out[c] = (s + 512) >> 10;  // == (sum(w*32*p) + 16384) >> 15
     }
 }
@@ -80,8 +80,8 @@ __global__ void __launch_bounds__(256) warp_kernel(const PanoTables *__restrict_
     const int Y = blockIdx.y * blockDim.y + threadIdx.y;
     if (X >= C.rw || Y >= C.rh) return;
     if (outside_window(T, 0, C.rx + blockIdx.x * blockDim.x * 4, C.rx + (blockIdx.x + 1) * blockDim.x * 4)) return;
-    const int W = T->src_w, H = T->src_h;
-    const uint8_t *src = frames + ((size_t)slot * ncam + cam) * ((size_t)W * H * 3);
+    const int W = T->src_w, H = T->src_h, spx = T->src_px;
+    const uint8_t *src = frames + ((size_t)slot * ncam + cam) * ((size_t)W * H * spx);
     uint32_t sx[4], sy[4];
     if (kMap64) {
         const uint2 *m = C.map64 + (size_t)Y * C.map_pitch + X;
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) warp_kernel(const PanoTables *__restrict_
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         int v[3];
-        bilinear_bgr(src, W, H, sx[j], sy[j], v);
+        bilinear_bgr(src, W, H, sx[j], sy[j], v, spx);
 #pragma unroll
         for (int c = 0; c < 3; ++c) px[c][j] = (short)apply_gain(v[c], C.gain_mode, g[j], C.gain_scalar);
     }
@@ -986,12 +986,12 @@ __device__ __forceinline__ void st_s16(int16_t *p, int v)
     asm volatile("st.global.b16 [%0+%1], %2;" ::"l"(p), "n"(kOff), "h"((short)v) : "memory");
 }
 
-template <bool kMap64, bool kGain, bool kFull>
+template <bool kMap64, bool kGain, bool kFull, int kPx>
 __device__ __forceinline__ void warp_gather(const WarpCam &C, const uint32_t *__restrict__ sm, const uint8_t *__restrict__ src,
                                             bool staged, int rw, int sbase, int W, int H, const uint32_t (&msx)[8],
                                             const uint32_t (&msy)[8], int Xt, int Y0, int slot)
 {
-    const int W3 = W * 3;
+    const int W3 = W * kPx;
     const int pitch = C.g_pitch, crw = C.rw, crh = C.rh, mp = C.map_pitch;
     int16_t *o00 = C.g0 + slot * C.g_slot + Y0 * pitch + Xt;
     int16_t *o01 = o00 + C.g_plane, *o02 = o01 + C.g_plane;
@@ -1009,8 +1009,8 @@ __device__ __forceinline__ void warp_gather(const WarpCam &C, const uint32_t *__
             const int idx = iy * rw + (ix + sbase);
             t00 = sm[idx]; t01 = sm[idx + 1]; t10 = sm[idx + rw]; t11 = sm[idx + rw + 1];
         } else {
-            const uint8_t *p = src + (size_t)iy * W3 + ix * 3;
-            const int dx = ix + 1 < W ? 3 : 0, dy = iy + 1 < H ? W3 : 0;
+            const uint8_t *p = src + (size_t)iy * W3 + ix * kPx;
+            const int dx = ix + 1 < W ? kPx : 0, dy = iy + 1 < H ? W3 : 0;
             t00 = p[0] | (p[1] << 8) | (p[2] << 16);
             t01 = p[dx] | (p[dx + 1] << 8) | (p[dx + 2] << 16);
             t10 = p[dy] | (p[dy + 1] << 8) | (p[dy + 2] << 16);
@@ -1045,7 +1045,7 @@ __device__ __forceinline__ void warp_gather(const WarpCam &C, const uint32_t *__
     }
 }
 
-template <bool kMap64, bool kGain>
+template <bool kMap64, bool kGain, bool kSrc4>
 __global__ void __launch_bounds__(256, 5) warp_tile_kernel(const __grid_constant__ WarpArgs A, const uint8_t *__restrict__ frames)
 {
     __shared__ __align__(16) uint32_t sm[kWarpSmemWords];
@@ -1055,7 +1055,8 @@ __global__ void __launch_bounds__(256, 5) warp_tile_kernel(const __grid_constant
     const int bx = blockIdx.x, by = blockIdx.y;
     if (bx >= C.tiles_x || by >= C.tiles_y) return;
     if (C.rx + bx * kWarpTileW + kWarpTileW <= A.win_lo || C.rx + bx * kWarpTileW >= A.win_hi) return;   // strip split
-    const int W = A.W, H = A.H, W3 = W * 3;
+    constexpr int kPx = kSrc4 ? 4 : 3;
+    const int W = A.W, H = A.H, W3 = W * kPx;
     const uint8_t *src = frames + ((size_t)slot * ncam + cam) * ((size_t)W3 * H);
     const int4 td = __ldg(C.tiles + by * C.tiles_x + bx);   // {x0 (px, %16==0), y0, rows, 16-px groups}
     const int lane = threadIdx.x, ty = threadIdx.y;
@@ -1083,7 +1084,17 @@ __global__ void __launch_bounds__(256, 5) warp_tile_kernel(const __grid_constant
             }
         }
     }
-    if (staged) {
+    if (staged && kSrc4) {
+        // word-per-pixel source (8UC4 camera frames, fused front end): the staged layout IS the source layout --
+        // one warp per source row, one lane per 16-byte chunk, conflict-free 16-byte stores
+        const int nchunk = 4 * td.w, cmax = W / 4 - 1, c0 = td.x >> 2;
+#pragma unroll 2
+        for (int r = ty; r < td.z; r += 8) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(src + (size_t)min(td.y + r, H - 1) * W3);
+            for (int c = lane; c < nchunk; c += 32)
+                *reinterpret_cast<uint4 *>(sm + r * rw + 4 * c) = __ldg(p + min(c0 + c, cmax));
+        }
+    } else if (staged) {
         // half a warp per source row: lane & 15 = 16-pixel group, two rows per warp and step
         const int q = lane & 15;
         if (q < td.w) {
@@ -1121,8 +1132,8 @@ __global__ void __launch_bounds__(256, 5) warp_tile_kernel(const __grid_constant
     }
     __syncthreads();
     const int sbase = -(td.y * rw + td.x);
-    if (full) warp_gather<kMap64, kGain, true>(C, sm, src, staged, rw, sbase, W, H, msx, msy, Xt, Y0, slot);
-    else warp_gather<kMap64, kGain, false>(C, sm, src, staged, rw, sbase, W, H, msx, msy, Xt, Y0, slot);
+    if (full) warp_gather<kMap64, kGain, true, kPx>(C, sm, src, staged, rw, sbase, W, H, msx, msy, Xt, Y0, slot);
+    else warp_gather<kMap64, kGain, false, kPx>(C, sm, src, staged, rw, sbase, W, H, msx, msy, Xt, Y0, slot);
 }
 
 // ------------------------------------------------------------------ K4: single-pass blenders
@@ -1154,9 +1165,9 @@ __global__ void __launch_bounds__(256) direct_blend_kernel(const PanoTables *__r
             const uint32_t e = __ldg(C.map32 + (size_t)y * C.map_pitch + x);
             sx = e & 0xffffu; sy = e >> 16;
         }
-        const uint8_t *src = frames + ((size_t)slot * ncam + i) * ((size_t)W * H * 3);
+        const uint8_t *src = frames + ((size_t)slot * ncam + i) * ((size_t)W * H * T->src_px);
         int v[3];
-        bilinear_bgr(src, W, H, sx, sy, v);
+        bilinear_bgr(src, W, H, sx, sy, v, T->src_px);
         const float g = C.gain_mode == 1 ? __ldg(C.gain_map + (size_t)y * C.map_pitch + x) : 1.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) v[c] = apply_gain(v[c], C.gain_mode, g, C.gain_scalar);
@@ -1241,12 +1252,16 @@ void launch_warp(const PanoTables *dev, const PanoTables &host, const KernelChoi
         }
         A.ncam = host.num_cams; A.W = host.src_w; A.H = host.src_h; A.win_lo = host.win_lo[0]; A.win_hi = host.win_hi[0];
         const dim3 block(32, 8), grid(tx, ty, host.num_cams * nslots);
-        if (host.cam[0].map64) {
-            if (gain) warp_tile_kernel<true, true><<<grid, block, 0, stream>>>(A, frames);
-            else warp_tile_kernel<true, false><<<grid, block, 0, stream>>>(A, frames);
-        } else {
-            if (gain) warp_tile_kernel<false, true><<<grid, block, 0, stream>>>(A, frames);
-            else warp_tile_kernel<false, false><<<grid, block, 0, stream>>>(A, frames);
+        const int variant = (host.cam[0].map64 ? 4 : 0) | (gain ? 2 : 0) | (host.src_px == 4 ? 1 : 0);
+        switch (variant) {
+        case 0: warp_tile_kernel<false, false, false><<<grid, block, 0, stream>>>(A, frames); break;
+        case 1: warp_tile_kernel<false, false, true><<<grid, block, 0, stream>>>(A, frames); break;
+        case 2: warp_tile_kernel<false, true, false><<<grid, block, 0, stream>>>(A, frames); break;
+        case 3: warp_tile_kernel<false, true, true><<<grid, block, 0, stream>>>(A, frames); break;
+        case 4: warp_tile_kernel<true, false, false><<<grid, block, 0, stream>>>(A, frames); break;
+        case 5: warp_tile_kernel<true, false, true><<<grid, block, 0, stream>>>(A, frames); break;
+        case 6: warp_tile_kernel<true, true, false><<<grid, block, 0, stream>>>(A, frames); break;
+        default: warp_tile_kernel<true, true, true><<<grid, block, 0, stream>>>(A, frames); break;
         }
         return;
     }

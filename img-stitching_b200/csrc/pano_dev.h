@@ -47,6 +47,7 @@ struct CamTables {
 struct PanoTables {
     int num_cams;
     int src_w, src_h;
+    int src_px;              // bytes per source pixel: 3 = interleaved BGR; 4 = 8UC4 camera frames (fused front end)
     int nb;                  // effective band count (levels 0..nb)
     int pad_w, pad_h;        // padded dst size (level 0)
     int roi_w, roi_h;        // unpadded dst roi size

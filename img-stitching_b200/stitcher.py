@@ -287,6 +287,12 @@ class ocvStitcher:
         capi.check(self._lib.pano_attach_frontend(self._h, cam, front._h if front is not None else None), self._h)
         self._front = front
 
+    def set_frontend_mode(self, fused: bool):
+        """False: the reference's sequential undistort -> crop -> resize -> warp order (bit-exact, default).
+        True: one composed remap table per camera, a single bilinear gather from the 8UC4 camera frame
+        (PANO_FRONTEND_FUSED; not bit-exact -- reported separately with its own PSNR)."""
+        capi.check(self._lib.pano_set_frontend_mode(self._h, 1 if fused else 0), self._h)
+
     def enable_profile(self, on=True):
         capi.check(self._lib.pano_profile_enable(self._h, int(on)), self._h)
 

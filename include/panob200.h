@@ -195,6 +195,18 @@ int pano_host_resize_axis(int ssize, int dsize, int clamp_frac, int *ofs, int16_
  * f == NULL detaches.  Attach before the first host-memory process call. */
 int pano_attach_frontend(pano_handle h, int cam, pano_frontend_handle f);
 
+/* How an attached front end is evaluated.
+ * PANO_FRONTEND_SEQUENTIAL (default, the parity mode): the reference's own order -- undistort (INTER_CUBIC) ->
+ *   crop -> resize -> rotation warp, every stage rounding to 8 bits like nvCam::read_frame + ocvStitcher::process
+ *   (include/nvcam.hpp:898-929, include/ocvstitcher.hpp:1171); bit-exact with the OpenCV CPU path.
+ * PANO_FRONTEND_FUSED: the coordinate maps of all stages are composed on the host into ONE remap table per camera and
+ *   the warp gathers bilinearly straight from the 8UC4 camera frame -- a single-gather variant that is NOT bit-exact
+ *   (one interpolation instead of three); report it separately with its own PSNR.  pano_get_warp_maps /
+ *   pano_get_fixed_maps then return the composed maps (into the camera frame).  Re-callable; needs a front end. */
+#define PANO_FRONTEND_SEQUENTIAL 0
+#define PANO_FRONTEND_FUSED 1
+int pano_set_frontend_mode(pano_handle h, int mode);
+
 /* library / build identification: returns e.g. "panob200 sm_100a" */
 const char *pano_version(void);
 

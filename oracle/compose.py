@@ -79,3 +79,38 @@ def front_end(argb, undist_size, mapx, mapy, rect, out_size, undistort=True):
     else:
         ret = orc.resize_bilinear_u8(np.ascontiguousarray(argb[:, :, :3]), undist_size)
     return orc.resize_bilinear_u8(ret, out_size)
+
+
+def fused_front_end_maps(xm, ym, out_size, undist_size, mapx, mapy, rect, cam_size, undistort=True):
+    """Composed backward map of the single-gather ("fused map") variant: rotation-warp map (into the
+    stitcher input, `out_size`) -> inverse of every front_end() stage -> position in the camera frame.
+    The reference has no such variant (it always resamples sequentially); this restates the
+    definition given in include/panob200.h (PANO_FRONTEND_FUSED) in float64 numpy so the tests can
+    check the library's composed maps independently.  Returns float64 (x, y)."""
+    def foldc(c, n):      # BORDER_REFLECT of the warp in continuous form, clamped to the pixel centres
+        t = np.mod(c + 0.5, 2.0 * n)
+        t = np.where(t >= n, 2.0 * n - t, t)
+        return np.clip(t - 0.5, 0.0, n - 1.0)
+
+    def inv(d, ssize, dsize):   # cv::resize INTER_LINEAR source coordinate, clamped like its tables
+        return np.clip((d + 0.5) * (1.0 / (dsize / ssize)) - 0.5, 0.0, ssize - 1.0)
+
+    x = foldc(np.asarray(xm, np.float64), out_size[0])
+    y = foldc(np.asarray(ym, np.float64), out_size[1])
+    uw, uh = undist_size
+    if tuple(out_size) != (uw, uh):
+        x, y = inv(x, uw, out_size[0]), inv(y, uh, out_size[1])
+    if undistort:
+        if (rect[2], rect[3]) != (uw, uh):
+            x, y = inv(x, rect[2], uw), inv(y, rect[3], uh)
+        x = np.clip(x + rect[0], 0.0, uw - 1.0)
+        y = np.clip(y + rect[1], 0.0, uh - 1.0)
+        x0 = np.minimum(uw - 2, x.astype(np.int64)); y0 = np.minimum(uh - 2, y.astype(np.int64))
+        fx, fy = x - x0, y - y0
+        def lerp(m):
+            m = np.asarray(m, np.float64)
+            return (1 - fy) * ((1 - fx) * m[y0, x0] + fx * m[y0, x0 + 1]) + fy * ((1 - fx) * m[y0 + 1, x0] + fx * m[y0 + 1, x0 + 1])
+        x, y = lerp(mapx), lerp(mapy)
+    if tuple(cam_size) != (uw, uh):
+        x, y = inv(x, cam_size[0], uw), inv(y, cam_size[1], uh)
+    return np.clip(x, 0.0, cam_size[0] - 1.0), np.clip(y, 0.0, cam_size[1] - 1.0)

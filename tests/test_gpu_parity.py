@@ -320,6 +320,55 @@ def test_config2_front_end_chained_into_process():
         assert_equal("config2 host batch %d" % b, host_out[b].numpy(), want[b])
 
 
+def test_config2_fused_single_gather_variant():
+    """The single-gather ("fused map") variant of config 2 (pano_set_frontend_mode): the library's composed maps
+    match an independent float64 restatement, the compose on those maps is bit-exact with the oracle gathering
+    from the raw camera frame, its PSNR against the sequential (parity) result is reported and bounded, and
+    switching back restores the bit-exact sequential path."""
+    import copy
+    cam = calib.CAM_LIJING_390_FOV60_1920
+    s = 0.5
+    K = np.array(cam["K"], np.float64).reshape(3, 3).copy()
+    K[0, 0] *= s; K[0, 2] *= s; K[1, 1] *= s; K[1, 2] *= s
+    newK = np.array([[1627.5076 * s, 0, 943.1681 * s], [0, 1622.9720 * s, 571.5369 * s], [0, 0, 1]])
+    rect = [34, 52, 891, 444]
+    CamConfig = panob200.pkg.nvcam.CamConfig
+    fe = panob200.nvCamFrontEnd(CamConfig(camSrcWidth=960, camSrcHeight=540, undistoredWidth=960, undistoredHeight=540,
+                                          outPutWidth=960, outPutHeight=540, K=K.reshape(-1), distorParams=cam["distorParams"],
+                                          rect=rect, newK=newK, max_batch=4))
+    mx, my = fe.maps()
+    Ks, Rs, scale = calib.rig("2222", 960)
+    t = compose.build_tables(Ks, Rs, scale, (960, 540), "spherical")
+    t.blend_masks = util.soft_masks(t)
+    frames = [util.synth_frame(540, 960, 950 + i, channels=4) for i in range(4)]
+    raw_bgr = [np.ascontiguousarray(f[:, :, :3]) for f in frames]
+    seq_bgr = [compose.front_end(f, (960, 540), mx, my, rect, (960, 540)) for f in frames]
+    for blender, nb in (("multiband", 4), ("feather", 0)):
+        st = panob200.ocvStitcher(SC(width=960, height=540, num_images=4, Ks=Ks, Rs=Rs, warped_image_scale=scale,
+                                     blender=blender, num_bands=nb, sharpness=0.05, max_batch=2))
+        assert st.initTables(t.blend_masks) == 0, st.last_error
+        fw = [panob200.capi.host_feather_weight(m, 0.05) for m in t.blend_masks] if blender == "feather" else None
+        st.attach_frontend(fe)
+        want_seq = compose.process(t, seq_bgr, blender, nb, feather_weights=fw)
+        assert_equal("sequential " + blender, st.process(frames), want_seq)
+        st.set_frontend_mode(True)
+        tf = copy.copy(t)
+        tf.maps = []
+        for i in range(4):
+            fx, fy = st.warp_maps(i)
+            wx, wy = compose.fused_front_end_maps(t.maps[i][0], t.maps[i][1], (960, 540), (960, 540), mx, my, rect, (960, 540))
+            assert np.abs(fx - wx).max() < 1e-3 and np.abs(fy - wy).max() < 1e-3, "composed map of camera %d" % i
+            tf.maps.append((fx, fy))
+        got = st.process(frames)
+        assert_equal("fused " + blender, got, compose.process(tf, raw_bgr, blender, nb, feather_weights=fw))
+        p = util.psnr(got, want_seq)
+        print("fused single-gather vs sequential (%s): %s" % (blender, util.report("fused", got, want_seq)))
+        assert p > 30.0
+        st.set_frontend_mode(False)
+        assert_equal("sequential again " + blender, st.process(frames), want_seq)
+        st.close()
+
+
 # ------------------------------------------------------------------ column-strip split (config 4)
 
 def _strip_setup(nranks, mode, W=960, H=540, nb=5, ncam=8):
