@@ -40,6 +40,13 @@ __device__ __forceinline__ int dp2a_su(int a, unsigned b, int c)
     asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+// d = c + a.lo16 * b.byte2 + a.hi16 * b.byte3: one PRMT (b0 b1 g0 g1) feeds the B and the G accumulator
+__device__ __forceinline__ int dp2a_su_hi(int a, unsigned b, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 
 // cv::resize INTER_LINEAR u8: one thread = one output pixel (3 channels out, CIN in)
 template <int CIN>
@@ -186,8 +193,9 @@ __global__ void __launch_bounds__(256) cubic4_kernel(const uint32_t *__restrict_
         int a0 = 0, a1 = 0, a2 = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            a0 = dp2a_su((int)wpk[k], __byte_perm(t[2 * k], t[2 * k + 1], 0x0040), a0);
-            a1 = dp2a_su((int)wpk[k], __byte_perm(t[2 * k], t[2 * k + 1], 0x0051), a1);
+            const uint32_t bg = __byte_perm(t[2 * k], t[2 * k + 1], 0x5140);
+            a0 = dp2a_su((int)wpk[k], bg, a0);
+            a1 = dp2a_su_hi((int)wpk[k], bg, a1);
             a2 = dp2a_su((int)wpk[k], __byte_perm(t[2 * k], t[2 * k + 1], 0x0062), a2);
         }
         d[x] = (uint32_t)sat_u8((a0 + 16384) >> 15) | ((uint32_t)sat_u8((a1 + 16384) >> 15) << 8) |
@@ -252,8 +260,9 @@ __global__ void __launch_bounds__(256) cubic5_kernel(const uint32_t *__restrict_
         int a0 = 16384, a1 = 16384, a2 = 16384;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            a0 = dp2a_su((int)wpk[k], __byte_perm(t[2 * k], t[2 * k + 1], 0x0040), a0);
-            a1 = dp2a_su((int)wpk[k], __byte_perm(t[2 * k], t[2 * k + 1], 0x0051), a1);
+            const uint32_t bg = __byte_perm(t[2 * k], t[2 * k + 1], 0x5140);
+            a0 = dp2a_su((int)wpk[k], bg, a0);
+            a1 = dp2a_su_hi((int)wpk[k], bg, a1);
             a2 = dp2a_su((int)wpk[k], __byte_perm(t[2 * k], t[2 * k + 1], 0x0062), a2);
         }
         uint32_t hi, px;
@@ -373,8 +382,8 @@ __global__ void __launch_bounds__(128, 8) resize4_walk_kernel(const uint32_t *__
         B = __ldg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s1) + rb_)); \
     }
 #define RS_HCALC(A, B, H0, H1, H2)                                               \
-    H0 = (uint32_t)dp2a_su(axp, __byte_perm(A, B, 0x0040u), 0) >> 4;             \
-    H1 = (uint32_t)dp2a_su(axp, __byte_perm(A, B, 0x0051u), 0) >> 4;             \
+    H0 = (uint32_t)dp2a_su(axp, __byte_perm(A, B, 0x5140u), 0) >> 4;             \
+    H1 = (uint32_t)dp2a_su_hi(axp, __byte_perm(A, B, 0x5140u), 0) >> 4;          \
     H2 = (uint32_t)dp2a_su(axp, __byte_perm(A, B, 0x0062u), 0) >> 4;
     // one step: emit the output rows that blend (A, B) = rows (v, v + 1), then row v + 2 replaces A (it is the
     // next step's B) and the prefetch slot is refilled with row v + 4
