@@ -67,6 +67,7 @@ _SIGS = {
     "pano_get_fixed_maps": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "pano_set_mask": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "pano_set_weight_level": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]),
+    "pano_get_weight_level": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "pano_set_feather_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "pano_set_gain_map": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "pano_set_gain_scalar": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),

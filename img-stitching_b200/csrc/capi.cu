@@ -78,6 +78,8 @@ struct pano_ctx {
     std::vector<std::vector<std::vector<uint8_t>>> walk_nz;
     std::vector<std::vector<std::vector<int>>> walk_ones;
     std::vector<uint32_t *> d_walk_list, d_gen_list;
+    uint8_t *d_stat_nz = nullptr;                 // walker-tile statistics of one camera, all levels (device build of the weights)
+    int *d_stat_ones = nullptr;
     std::vector<void *> owned;                    // device allocations to free
     std::vector<void *> cam_mask0, cam_gain;      // per camera, re-uploadable
     std::vector<std::vector<void *>> cam_wt;      // per camera per level
@@ -310,8 +312,51 @@ int buildWeights(pano_ctx *h, int cam)
         C.use_wt0 = 1;
         return PANO_OK;
     }
-    // level 0: padded 8-bit mask, zero outside the image (copyMakeBorder CONSTANT)
     const int W = fr.rect.w, H = fr.rect.h;
+    static const bool host_weights = getenv("PANO_HOST_WEIGHTS") != nullptr;    // A/B switch: the host builder below
+    if (!host_weights) {
+        // device build: upload the mask into the zeroed feed rect (copyMakeBorder CONSTANT), then the float pyrDown
+        // chain and the walker-tile statistics run as kernels; only the few-KB statistics come back
+        uint8_t *m0d = (uint8_t *)h->cam_mask0[cam];
+        CK(h, cudaMemsetAsync(m0d, 0, (size_t)C.mask_pitch * H, nullptr));
+        CK(h, cudaMemcpy2DAsync(m0d + (size_t)fr.top * C.mask_pitch + fr.left, C.mask_pitch, m.data(), img.w, img.w, img.h,
+                                cudaMemcpyHostToDevice, nullptr));
+        C.use_wt0 = 0;
+        const bool mb = h->blender == PANO_BLEND_MULTIBAND;
+        const int levels = mb ? h->nb : 0;
+        size_t off = 0;
+        std::vector<size_t> offs(levels + 1);
+        for (int l = 0; l <= levels && mb; ++l) {
+            const int lw = W >> l, lh = H >> l;
+            if (l > 0)
+                launch_weight_pyrdown(l == 1 ? (const void *)m0d : (const void *)h->cam_wt[cam][l - 1], l == 1,
+                                      l == 1 ? C.mask_pitch : C.wt_pitch[l - 1], W >> (l - 1), H >> (l - 1),
+                                      (float *)h->cam_wt[cam][l], C.wt_pitch[l], nullptr);
+            offs[l] = off;
+            const int wtx = walkTilesX(h, l), wty = walkTilesY(h, l);
+            launch_tile_stats(l == 0 ? (const void *)m0d : (const void *)h->cam_wt[cam][l], l == 0,
+                              l == 0 ? C.mask_pitch : C.wt_pitch[l], lw, lh, C.rx >> l, C.ry >> l, wtx, wty,
+                              h->d_stat_nz + off, h->d_stat_ones + off, nullptr);
+            off += (size_t)wtx * wty;
+        }
+        if (mb) {
+            std::vector<uint8_t> nz(off);
+            std::vector<int> ones(off);
+            CK(h, cudaMemcpyAsync(nz.data(), h->d_stat_nz, off, cudaMemcpyDeviceToHost, nullptr));
+            CK(h, cudaMemcpyAsync(ones.data(), h->d_stat_ones, off * sizeof(int), cudaMemcpyDeviceToHost, nullptr));
+            CK(h, cudaStreamSynchronize(nullptr));
+            for (int l = 0; l <= levels; ++l) {
+                const size_t cnt = h->walk_nz[l][cam].size();
+                std::copy(nz.begin() + offs[l], nz.begin() + offs[l] + cnt, h->walk_nz[l][cam].begin());
+                std::copy(ones.begin() + offs[l], ones.begin() + offs[l] + cnt, h->walk_ones[l][cam].begin());
+            }
+        } else {
+            CK(h, cudaStreamSynchronize(nullptr));
+        }
+        CK(h, cudaGetLastError());
+        return PANO_OK;
+    }
+    // level 0: padded 8-bit mask, zero outside the image (copyMakeBorder CONSTANT)
     std::vector<uint8_t> m0((size_t)W * H, 0);
     for (int y = 0; y < img.h; ++y)
         std::memcpy(&m0[(size_t)(y + fr.top) * W + fr.left], &m[(size_t)y * img.w], img.w);
@@ -704,6 +749,9 @@ int pano_create(const pano_config *cfg, pano_handle *out)
             for (int c = 0; c < n; ++c) { h->walk_nz[l][c].assign(wcnt, 0); h->walk_ones[l][c].assign(wcnt, 0); }
             if (devAlloc(h, &h->d_walk_list[l], wcnt) || devAlloc(h, &h->d_gen_list[l], wcnt)) return bail(0);
         }
+        size_t total = 0;
+        for (int l = 0; l <= h->nb; ++l) total += (size_t)walkTilesX(h, l) * walkTilesY(h, l);
+        if (devAlloc(h, &h->d_stat_nz, total) || devAlloc(h, &h->d_stat_ones, total)) return bail(0);
     }
     {
         // exactness of the two kernel shortcuts under this host's IEEE arithmetic (always true on
@@ -820,6 +868,26 @@ int pano_set_weight_level(pano_handle h, int cam, int level, const float *w, int
     if (level == 0) C.use_wt0 = 1;
     markTiles(h, cam, level, w, width, height, width, 1.0f);
     h->tables_dirty = true;
+    return PANO_OK;
+}
+
+int pano_get_weight_level(pano_handle h, int cam, int level, float *w)
+{
+    if (!h || cam < 0 || cam >= h->n || !w) return fail(h, "pano_get_weight_level: bad argument");
+    const int top = h->blender == PANO_BLEND_MULTIBAND ? h->nb : 0;
+    if (level < 0 || level > top) return fail(h, "pano_get_weight_level: bad level");
+    const CamTables &C = h->host.cam[cam];
+    const int lw = C.rw >> level, lh = C.rh >> level;
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());
+    if (level == 0 && !C.use_wt0) {
+        std::vector<uint8_t> m((size_t)lw * lh);
+        CK(h, cudaMemcpy2D(m.data(), lw, C.mask0, C.mask_pitch, lw, lh, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < m.size(); ++i) w[i] = (float)m[i] * (1.f / 255.f);
+        return PANO_OK;
+    }
+    CK(h, cudaMemcpy2D(w, (size_t)lw * sizeof(float), C.wt[level], (size_t)C.wt_pitch[level] * sizeof(float),
+                       (size_t)lw * sizeof(float), lh, cudaMemcpyDeviceToHost));
     return PANO_OK;
 }
 

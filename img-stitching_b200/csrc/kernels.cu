@@ -1228,6 +1228,68 @@ __global__ void __launch_bounds__(256) halo_copy_kernel(const PanoTables *__rest
     }
 }
 
+// ------------------------------------------------------------------ init-time tables on the device
+// MultiBandBlender::feed's weight pyramid -- convertTo(CV_32F, 1/255) + cv::pyrDown chain on CV_32F -- which the
+// reference recomputes for every frame although it only depends on the masks (ocvstitcher.hpp:1202).  Here it is
+// rebuilt whenever a mask changes (pano_set_mask: initSeam :1101, updateMask :1257).  The evaluation order is
+// exactly that of pano::pyrDownF32 (geometry.cpp) -- explicit round-to-nearest operations, no contraction -- so
+// the device and the host builder agree bit for bit.  One thread = one output weight.
+template <bool kFromMask>
+__global__ void __launch_bounds__(256) weight_pyrdown_kernel(const void *__restrict__ src, int spitch, int sw, int sh,
+                                                             float *__restrict__ dst, int dpitch)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int dw = (sw + 1) / 2, dh = (sh + 1) / 2;
+    if (x >= dw || y >= dh) return;
+    int cx[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) cx[k] = reflect101(2 * x - 2 + k, sw);
+    float hv[5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        const size_t row = (size_t)reflect101(2 * y - 2 + r, sh) * spitch;
+        float v[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            if (kFromMask) v[k] = __fmul_rn((float)__ldg(static_cast<const uint8_t *>(src) + row + cx[k]), 1.f / 255.f);
+            else v[k] = __ldg(static_cast<const float *>(src) + row + cx[k]);
+        }
+        hv[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v[2], 6.f), __fmul_rn(__fadd_rn(v[1], v[3]), 4.f)), v[0]), v[4]);
+    }
+    const float o = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(hv[2], 6.f), __fmul_rn(__fadd_rn(hv[1], hv[3]), 4.f)), hv[0]), hv[4]);
+    dst[(size_t)y * dpitch + x] = __fmul_rn(o, 1.f / 256.f);
+}
+
+// Per walker tile (kWalkTileW x kWalkTileH of the padded dst at this level) of one camera's weight level: is any
+// weight non-zero, and how many are exactly one (`one` = 255 for the 8-bit level-0 mask, 1.0f for float levels)?
+// The host turns these into the collapse work lists (PanoTables::walk_list / gen_list).  One block = one tile.
+template <typename T>
+__global__ void __launch_bounds__(256) tile_stats_kernel(const T *__restrict__ data, int pitch, int w, int h, int ox, int oy,
+                                                         T one, uint8_t *__restrict__ nz, int *__restrict__ ones)
+{
+    __shared__ int s_nz, s_ones;
+    if (threadIdx.x == 0) { s_nz = 0; s_ones = 0; }
+    __syncthreads();
+    const int x0 = blockIdx.x * kWalkTileW - ox, y0 = blockIdx.y * kWalkTileH - oy;      // tile origin in camera coordinates
+    int c_nz = 0, c_one = 0;
+    for (int i = threadIdx.x; i < kWalkTileW * kWalkTileH; i += blockDim.x) {
+        const int x = x0 + i % kWalkTileW, y = y0 + i / kWalkTileW;
+        if ((unsigned)x >= (unsigned)w || (unsigned)y >= (unsigned)h) continue;
+        const T v = data[(size_t)y * pitch + x];
+        c_nz += v != (T)0;
+        c_one += v == one;
+    }
+    c_nz = __reduce_add_sync(0xffffffffu, c_nz);
+    c_one = __reduce_add_sync(0xffffffffu, c_one);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_nz, c_nz); atomicAdd(&s_ones, c_one); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const size_t t = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+        nz[t] = s_nz != 0;
+        ones[t] = s_ones;
+    }
+}
+
 inline dim3 grid2d(int w, int h, dim3 block, int z) { return dim3((w + block.x - 1) / block.x, (h + block.y - 1) / block.y, z); }
 
 }  // namespace
@@ -1375,6 +1437,22 @@ void launch_halo_copy(const PanoTables *dev, const PanoTables &host, int kind, i
     const int rows = halo_rows(host, kind, level);
     const dim3 block(256), grid((rows + 255) / 256, 3 * (kind == 1 ? 1 : host.num_cams));
     halo_copy_kernel<<<grid, block, 0, stream>>>(dev, kind, level, col, ncols, buf, unpack ? 1 : 0, slot, rows);
+}
+
+void launch_weight_pyrdown(const void *src, bool from_mask, int spitch, int sw, int sh, float *dst, int dpitch,
+                           cudaStream_t stream)
+{
+    const dim3 block(32, 8), grid = grid2d((sw + 1) / 2, (sh + 1) / 2, block, 1);
+    if (from_mask) weight_pyrdown_kernel<true><<<grid, block, 0, stream>>>(src, spitch, sw, sh, dst, dpitch);
+    else weight_pyrdown_kernel<false><<<grid, block, 0, stream>>>(src, spitch, sw, sh, dst, dpitch);
+}
+
+void launch_tile_stats(const void *data, bool is_mask, int pitch, int w, int h, int ox, int oy, int tiles_x, int tiles_y,
+                       uint8_t *nz, int *ones, cudaStream_t stream)
+{
+    const dim3 grid(tiles_x, tiles_y);
+    if (is_mask) tile_stats_kernel<uint8_t><<<grid, 256, 0, stream>>>(static_cast<const uint8_t *>(data), pitch, w, h, ox, oy, (uint8_t)255, nz, ones);
+    else tile_stats_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float *>(data), pitch, w, h, ox, oy, 1.0f, nz, ones);
 }
 
 void launch_direct_blend(const PanoTables *dev, const PanoTables &host, int blender, const uint8_t *frames,

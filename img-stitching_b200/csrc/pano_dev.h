@@ -97,6 +97,14 @@ int launch_collapse(const PanoTables *dev, const PanoTables &host, const KernelC
 void launch_direct_blend(const PanoTables *dev, const PanoTables &host, int blender, const uint8_t *frames,
                          uint8_t *pano, int nslots, cudaStream_t stream);
 
+// init-time tables built on the device (mask refresh): one level of the float weight pyramid (cv::pyrDown on CV_32F,
+// same evaluation order as pano::pyrDownF32; from_mask: src is the 8-bit level-0 mask, weight = mask * (1/255.f)),
+// and the per-walker-tile statistics of one camera's weight level (any non-zero / count of exact ones)
+void launch_weight_pyrdown(const void *src, bool from_mask, int spitch, int sw, int sh, float *dst, int dpitch,
+                           cudaStream_t stream);
+void launch_tile_stats(const void *data, bool is_mask, int pitch, int w, int h, int ox, int oy, int tiles_x, int tiles_y,
+                       uint8_t *nz, int *ones, cudaStream_t stream);
+
 // strip-split halo columns: pack / unpack `ncols` dst columns starting at dst column `col`
 // (level `level`) of either every camera's g[level] (kind 0) or out[level] (kind 1) into / from a
 // dense buffer laid out [cam][plane][row][ncols] int16 (cameras that do not cover the column

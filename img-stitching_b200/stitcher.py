@@ -265,6 +265,17 @@ class ocvStitcher:
         capi.check(self._lib.pano_get_fixed_maps(self._h, cam, capi.ptr(ixy), capi.ptr(fr)), self._h)
         return ixy, fr
 
+    def weight_level(self, cam, level):
+        """The float weight level the compose uses (library-built on the device, or the caller's override)."""
+        if self.m_cfg.blender == "multiband":
+            _, _, rects = self.blend_geometry()
+            w, h = int(rects[cam][2]) >> level, int(rects[cam][3]) >> level
+        else:
+            w, h = self.m_sizes[cam]
+        out = np.empty((h, w), np.float32)
+        capi.check(self._lib.pano_get_weight_level(self._h, cam, level, capi.ptr(out)), self._h)
+        return out
+
     def blend_geometry(self):
         n = self.m_cfg.num_images
         nb = C.c_int(); pwh = (C.c_int * 2)(); fr = np.empty((n, 4), np.int32)

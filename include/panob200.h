@@ -87,6 +87,10 @@ int pano_set_mask(pano_handle h, int cam, const uint8_t *mask, int width, int he
  * (MultiBandBlender::feed builds it with cv::pyrDown on CV_32F, which is only ~1-ulp
  * reproducible outside OpenCV).  level in [0, num_bands]; size = feed rect >> level. */
 int pano_set_weight_level(pano_handle h, int cam, int level, const float *w, int width, int height);
+/* The weight level the compose currently uses for camera `cam` (feed rect >> level large, float32): the library's
+ * own pyramid (built on the device at every pano_set_mask) or the caller's override.  Multiband: level in
+ * [0, num_bands]; feather: level 0 = the feather weight map (sizes[cam] large). */
+int pano_get_weight_level(pano_handle h, int cam, int level, float *w);
 /* Optional: FeatherBlender weight map (distanceTransform-derived, static); sizes[cam] large.
  * Without it the library derives it from the mask. */
 int pano_set_feather_weight(pano_handle h, int cam, const float *w, int width, int height);

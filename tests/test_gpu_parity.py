@@ -158,6 +158,38 @@ def test_mask_update_at_runtime():
     assert not np.array_equal(want, want2)
 
 
+def test_device_built_weight_pyramid_equals_host_builder():
+    """pano_set_mask rebuilds the float weight pyramid and the collapse tile statistics ON THE DEVICE (the static part
+    of MultiBandBlender::feed, SURVEY 8f-1).  Every level must equal the host builder (pano_host_pyrdown_f32 chain on
+    mask * (1/255.f)) bit for bit, and stay within float rounding of cv2's own pyramid (golden fixture)."""
+    import time
+    g = load("cfg1_small")
+    Ks, Rs, scale = calib.rig("2222", 240)
+    st = make(Ks, Rs, scale, 240, 135, num_bands=5, cut=[int(v) for v in g["cut"]])
+    masks = [g["mask%d" % i] for i in range(4)]
+    assert st.initTables(masks) == 0, st.last_error
+    nb, _, rects = st.blend_geometry()
+    for i in range(4):
+        l0 = st.weight_level(i, 0)
+        x0, y0 = st.m_corners[i][0] - st.dst_roi[0], st.m_corners[i][1] - st.dst_roi[1]
+        pad = np.zeros(l0.shape, np.uint8)
+        ox, oy = x0 - rects[i][0], y0 - rects[i][1]
+        pad[oy:oy + masks[i].shape[0], ox:ox + masks[i].shape[1]] = masks[i]
+        cur = pad.astype(np.float32) * np.float32(1.0 / 255.0)
+        assert np.array_equal(l0, cur)
+        for l in range(1, nb + 1):
+            cur = panob200.capi.host_pyrdown_f32(cur)
+            got = st.weight_level(i, l)
+            assert got.shape == cur.shape and np.array_equal(got.view(np.uint32), cur.view(np.uint32)), "cam %d level %d" % (i, l)
+            assert np.abs(got - g["w%d_%d" % (i, l)]).max() < 1e-6            # cv2's SIMD pyrDown: ~1 ulp apart
+    t0 = time.perf_counter()
+    for i in range(4):
+        st.set_mask(i, masks[i])
+    print("pano_set_mask x4 (240x135 rig): %.2f ms" % (1e3 * (time.perf_counter() - t0)))
+    d = np.abs(st.process(util.synth_set(4, 135, 240, int(g["seed"]))).astype(int) - g["pano_multiband"].astype(int))
+    assert d.max() <= 1
+
+
 def test_batched_device_and_host_apis():
     import torch
     Ks, Rs, scale = calib.rig("2222", 240)
