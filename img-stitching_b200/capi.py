@@ -46,6 +46,11 @@ class pano_config(C.Structure):
                 ("cut", C.c_int * 4), ("device", C.c_int), ("max_batch", C.c_int)]
 
 
+class pano_ring_config(C.Structure):
+    _fields_ = [("up_width", C.c_int), ("up_height", C.c_int), ("down_width", C.c_int), ("down_height", C.c_int),
+                ("mode", C.c_int), ("finalcut", C.c_int), ("bar", C.c_int), ("device", C.c_int)]
+
+
 class pano_frontend_config(C.Structure):
     _fields_ = [("cam_src_width", C.c_int), ("cam_src_height", C.c_int),
                 ("undist_width", C.c_int), ("undist_height", C.c_int),
@@ -66,6 +71,8 @@ _SIGS = {
     "pano_get_warp_maps": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "pano_get_fixed_maps": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "pano_set_mask": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "pano_set_seam_mask": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "pano_get_mask": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "pano_set_weight_level": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "pano_get_weight_level": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "pano_set_feather_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),
@@ -91,6 +98,12 @@ _SIGS = {
     "pano_frontend_process": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "pano_attach_frontend": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "pano_set_frontend_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "pano_ring_create": (C.c_int, [C.POINTER(pano_ring_config), C.POINTER(C.c_void_p)]),
+    "pano_ring_destroy": (C.c_int, [C.c_void_p]),
+    "pano_ring_last_error": (C.c_char_p, [C.c_void_p]),
+    "pano_ring_out_size": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pano_ring_compose_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "pano_ring_compose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "pano_host_warp_roi": (C.c_int, [C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "pano_host_build_maps": (C.c_int, [C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "pano_host_blend_geometry": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
@@ -102,6 +115,7 @@ _SIGS = {
     "pano_host_undistort_maps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "pano_host_cubic_table": (C.c_int, [C.c_void_p]),
     "pano_host_resize_axis": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pano_host_linear_exact_axis": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
@@ -214,3 +228,9 @@ def host_resize_axis(ssize, dsize, clamp_frac):
     o = np.empty(dsize, np.int32); a0 = np.empty(dsize, np.int16); a1 = np.empty(dsize, np.int16)
     check(lib().pano_host_resize_axis(ssize, dsize, int(clamp_frac), ptr(o), ptr(a0), ptr(a1)))
     return o, a0, a1
+
+
+def host_linear_exact_axis(ssize, dsize):
+    ofs = np.empty(dsize, np.int32); c1 = np.empty(dsize, np.int32)
+    check(lib().pano_host_linear_exact_axis(ssize, dsize, ptr(ofs), ptr(c1)))
+    return ofs, c1

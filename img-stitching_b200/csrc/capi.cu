@@ -57,6 +57,9 @@ struct pano_ctx {
     std::vector<FeedRect> feed;
     std::vector<std::vector<float>> xmap, ymap;   // float maps (host, kept for inspection)
     std::vector<std::vector<uint8_t>> mask;       // current blend masks (sizes[cam])
+    std::vector<uint8_t *> cam_full;              // device: warped all-255 mask per camera (m_compensatorMaskWarped), tight
+    uint8_t *seam_tmp = nullptr;                  // device scratch of pano_set_seam_mask: low-res mask + result + axis tables
+    size_t seam_tmp_bytes = 0;
     bool map64 = false;
 
     // device tables
@@ -650,6 +653,11 @@ int pano_create(const pano_config *cfg, pano_handle *out)
         }
     }
     h->dst_roi = resultRoi(h->rois);
+    h->cam_full.assign(n, nullptr);
+    for (int i = 0; i < n; ++i) {
+        if (devAlloc(h, &h->cam_full[i], h->mask[i].size(), false)) return bail(0);
+        if (cudaMemcpy(h->cam_full[i], h->mask[i].data(), h->mask[i].size(), cudaMemcpyHostToDevice) != cudaSuccess) { h->err = "mask upload failed"; return bail(0); }
+    }
 
     // ---- blender geometry ----
     PanoTables &T = h->host;
@@ -852,6 +860,51 @@ int pano_set_mask(pano_handle h, int cam, const uint8_t *mask, int width, int he
     for (int y = 0; y < height; ++y) std::memcpy(&h->mask[cam][(size_t)y * width], mask + (size_t)y * stride, width);
     if (buildWeights(h, cam)) return PANO_ERR;
     h->tables_dirty = true;
+    return PANO_OK;
+}
+
+int pano_set_seam_mask(pano_handle h, int cam, const uint8_t *seam, int width, int height, int stride)
+{
+    if (!h || cam < 0 || cam >= h->n || !seam || width < 1 || height < 1 || stride < width)
+        return fail(h, "pano_set_seam_mask: bad argument");
+    const Rect &img = h->rois[cam];
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());  // tables may be in use by an in-flight wave
+    std::vector<int> xo, xc, yo, yc;
+    linearExactAxis(width, img.w, xo, xc);
+    linearExactAxis(height, img.h, yo, yc);
+    // scratch layout: [xo | xc | yo | yc] ints, low-res mask (tight), result (tight)
+    const size_t tab_bytes = (size_t)(2 * img.w + 2 * img.h) * sizeof(int);
+    const size_t low_bytes = ((size_t)width * height + 15) & ~(size_t)15, res_bytes = (size_t)img.w * img.h;
+    const size_t need = tab_bytes + low_bytes + res_bytes;
+    if (need > h->seam_tmp_bytes) {
+        devFree(h, h->seam_tmp);
+        h->seam_tmp = nullptr; h->seam_tmp_bytes = 0;
+        if (devAlloc(h, &h->seam_tmp, need, false)) return PANO_ERR;
+        h->seam_tmp_bytes = need;
+    }
+    int *d_xo = reinterpret_cast<int *>(h->seam_tmp), *d_xc = d_xo + img.w, *d_yo = d_xc + img.w, *d_yc = d_yo + img.h;
+    uint8_t *d_low = h->seam_tmp + tab_bytes, *d_res = d_low + low_bytes;
+    CK(h, cudaMemcpyAsync(d_xo, xo.data(), img.w * sizeof(int), cudaMemcpyHostToDevice, nullptr));
+    CK(h, cudaMemcpyAsync(d_xc, xc.data(), img.w * sizeof(int), cudaMemcpyHostToDevice, nullptr));
+    CK(h, cudaMemcpyAsync(d_yo, yo.data(), img.h * sizeof(int), cudaMemcpyHostToDevice, nullptr));
+    CK(h, cudaMemcpyAsync(d_yc, yc.data(), img.h * sizeof(int), cudaMemcpyHostToDevice, nullptr));
+    CK(h, cudaMemcpy2DAsync(d_low, width, seam, stride, width, height, cudaMemcpyHostToDevice, nullptr));
+    launch_seam_mask(d_low, width, height, width, d_xo, d_xc, d_yo, d_yc, h->cam_full[cam], d_res, img.w, img.h, nullptr);
+    CK(h, cudaMemcpyAsync(h->mask[cam].data(), d_res, res_bytes, cudaMemcpyDeviceToHost, nullptr));
+    CK(h, cudaStreamSynchronize(nullptr));
+    CK(h, cudaGetLastError());
+    if (buildWeights(h, cam)) return PANO_ERR;
+    h->tables_dirty = true;
+    return PANO_OK;
+}
+
+int pano_get_mask(pano_handle h, int cam, uint8_t *mask, int stride)
+{
+    if (!h || cam < 0 || cam >= h->n || !mask) return fail(h, "pano_get_mask: bad argument");
+    const Rect &img = h->rois[cam];
+    if (stride < img.w) return fail(h, "pano_get_mask: stride too small");
+    for (int y = 0; y < img.h; ++y) std::memcpy(mask + (size_t)y * stride, &h->mask[cam][(size_t)y * img.w], img.w);
     return PANO_OK;
 }
 

@@ -382,4 +382,25 @@ void resizeAxis(int ssize, int dsize, bool clamp_frac, std::vector<int> &ofs,
     }
 }
 
+// OpenCV resize.cpp, interpolationLinear<uchar>::getCoeffs: softdouble arithmetic == IEEE double operations;
+// ufixedpoint16(x) = cvRound(x * 256) (round half to even); outside the source range the edge sample is replicated.
+void linearExactAxis(int ssize, int dsize, std::vector<int> &ofs, std::vector<int> &c1)
+{
+    ofs.assign(dsize, 0); c1.assign(dsize, 0);
+    const double inv_scale = static_cast<double>(dsize) / ssize;
+    const double scale = 1.0 / inv_scale;
+    for (int d = 0; d < dsize; ++d) {
+        const double fval = scale * (d + 0.5) - 0.5;
+        const int ival = static_cast<int>(std::floor(fval));
+        if (ival >= 0 && ssize > 1) {
+            if (ival < ssize - 1) {
+                ofs[d] = ival;
+                c1[d] = static_cast<int>(std::nearbyint((fval - ival) * 256.0));
+            } else {
+                ofs[d] = ssize - 1;
+            }
+        }
+    }
+}
+
 }  // namespace pano

@@ -66,4 +66,8 @@ void cubicTable(int16_t *tab);
 void resizeAxis(int ssize, int dsize, bool clamp_frac, std::vector<int> &ofs,
                 std::vector<int16_t> &a0, std::vector<int16_t> &a1);
 
+// cv::resize INTER_LINEAR_EXACT coefficient table for one axis (8UC1 path: ufixedpoint16, 8 fractional bits):
+// sample d reads src[ofs[d]] * (256 - c1[d]) + src[min(ofs[d] + 1, ssize - 1)] * c1[d]
+void linearExactAxis(int ssize, int dsize, std::vector<int> &ofs, std::vector<int> &c1);
+
 }  // namespace pano

@@ -105,4 +105,14 @@ int pano_host_resize_axis(int ssize, int dsize, int clamp_frac, int *ofs, int16_
     return PANO_OK;
 }
 
+int pano_host_linear_exact_axis(int ssize, int dsize, int *ofs, int *c1)
+{
+    if (ssize < 1 || dsize < 1 || !ofs || !c1) return PANO_ERR;
+    std::vector<int> o, c;
+    linearExactAxis(ssize, dsize, o, c);
+    std::memcpy(ofs, o.data(), sizeof(int) * dsize);
+    std::memcpy(c1, c.data(), sizeof(int) * dsize);
+    return PANO_OK;
+}
+
 }  // extern "C"

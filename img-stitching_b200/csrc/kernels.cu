@@ -1260,6 +1260,37 @@ __global__ void __launch_bounds__(256) weight_pyrdown_kernel(const void *__restr
     dst[(size_t)y * dpitch + x] = __fmul_rn(o, 1.f / 256.f);
 }
 
+// Tail of initSeam / updateMask (ocvstitcher.hpp:1095-1101, 1251-1257) in one pass: the seam finder's low-resolution
+// mask -> cv::dilate (3x3, border ignored) -> cv::resize(INTER_LINEAR_EXACT) to the warped size (8.8 fixed-point
+// horizontal pass, 16.16 vertical pass, round half up) -> AND with the warped full mask.  The dilation is evaluated
+// on the fly at the four taps (the low-resolution mask is a few KB and lives in L1).  One thread = one mask byte.
+__global__ void __launch_bounds__(256) seam_mask_kernel(const uint8_t *__restrict__ seam, int sw, int sh, int spitch,
+                                                        const int *__restrict__ xo, const int *__restrict__ xc,
+                                                        const int *__restrict__ yo, const int *__restrict__ yc,
+                                                        const uint8_t *__restrict__ full, uint8_t *__restrict__ dst, int w, int h)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int x0 = xo[x], cx = xc[x], y0 = yo[y], cy = yc[y];
+    const int x1 = min(x0 + 1, sw - 1), y1 = min(y0 + 1, sh - 1);
+    auto dil = [&](int px, int py) {
+        int m = 0;
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = py + dy;
+            if ((unsigned)yy >= (unsigned)sh) continue;
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = px + dx;
+                if ((unsigned)xx < (unsigned)sw) m = max(m, (int)__ldg(seam + (size_t)yy * spitch + xx));
+            }
+        }
+        return m;
+    };
+    const unsigned h0 = dil(x0, y0) * (256 - cx) + dil(x1, y0) * cx;
+    const unsigned h1 = dil(x0, y1) * (256 - cx) + dil(x1, y1) * cx;
+    const unsigned v = (h0 * (256 - cy) + h1 * cy + 32768u) >> 16;
+    dst[(size_t)y * w + x] = (uint8_t)(v & full[(size_t)y * w + x]);
+}
+
 // Per walker tile (kWalkTileW x kWalkTileH of the padded dst at this level) of one camera's weight level: is any
 // weight non-zero, and how many are exactly one (`one` = 255 for the 8-bit level-0 mask, 1.0f for float levels)?
 // The host turns these into the collapse work lists (PanoTables::walk_list / gen_list).  One block = one tile.
@@ -1445,6 +1476,13 @@ void launch_weight_pyrdown(const void *src, bool from_mask, int spitch, int sw, 
     const dim3 block(32, 8), grid = grid2d((sw + 1) / 2, (sh + 1) / 2, block, 1);
     if (from_mask) weight_pyrdown_kernel<true><<<grid, block, 0, stream>>>(src, spitch, sw, sh, dst, dpitch);
     else weight_pyrdown_kernel<false><<<grid, block, 0, stream>>>(src, spitch, sw, sh, dst, dpitch);
+}
+
+void launch_seam_mask(const uint8_t *seam, int sw, int sh, int spitch, const int *xo, const int *xc, const int *yo, const int *yc,
+                      const uint8_t *full, uint8_t *dst, int w, int h, cudaStream_t stream)
+{
+    const dim3 block(32, 8);
+    seam_mask_kernel<<<grid2d(w, h, block, 1), block, 0, stream>>>(seam, sw, sh, spitch, xo, xc, yo, yc, full, dst, w, h);
 }
 
 void launch_tile_stats(const void *data, bool is_mask, int pitch, int w, int h, int ox, int oy, int tiles_x, int tiles_y,

@@ -102,6 +102,9 @@ void launch_direct_blend(const PanoTables *dev, const PanoTables &host, int blen
 // and the per-walker-tile statistics of one camera's weight level (any non-zero / count of exact ones)
 void launch_weight_pyrdown(const void *src, bool from_mask, int spitch, int sw, int sh, float *dst, int dpitch,
                            cudaStream_t stream);
+// m_blenderMask from the seam finder's low-resolution mask (dilate -> INTER_LINEAR_EXACT -> AND full mask), tight w x h
+void launch_seam_mask(const uint8_t *seam, int sw, int sh, int spitch, const int *xo, const int *xc, const int *yo, const int *yc,
+                      const uint8_t *full, uint8_t *dst, int w, int h, cudaStream_t stream);
 void launch_tile_stats(const void *data, bool is_mask, int pitch, int w, int h, int ox, int oy, int tiles_x, int tiles_y,
                        uint8_t *nz, int *ones, cudaStream_t stream);
 

@@ -161,7 +161,7 @@ class ocvStitcher:
         try:
             self._create_handle()
             masks = self._seam_masks(imgs)
-            self._upload_masks(masks)
+            self._upload_masks(masks, on_device=True)
             return RET_OK
         except capi.PanoError as e:
             self.last_error = str(e)
@@ -200,7 +200,7 @@ class ocvStitcher:
     def updateMask(self, imgs) -> int:
         """updateMask(), :1218-1261 -- explicit instead of every 200th process() call."""
         try:
-            self._upload_masks(self._seam_masks(imgs))
+            self._upload_masks(self._seam_masks(imgs), on_device=True)
             return RET_OK
         except capi.PanoError as e:
             self.last_error = str(e)
@@ -264,6 +264,18 @@ class ocvStitcher:
         ixy = np.empty((h, w, 2), np.int16); fr = np.empty((h, w), np.uint16)
         capi.check(self._lib.pano_get_fixed_maps(self._h, cam, capi.ptr(ixy), capi.ptr(fr)), self._h)
         return ixy, fr
+
+    def set_seam_mask(self, cam, seam_lowres):
+        """updateMask tail on the device: dilate -> INTER_LINEAR_EXACT up-scale -> AND with the warped full mask
+        (include/ocvstitcher.hpp:1251-1257), from the seam finder's low-resolution mask."""
+        m = np.ascontiguousarray(seam_lowres, np.uint8)
+        capi.check(self._lib.pano_set_seam_mask(self._h, cam, capi.ptr(m), m.shape[1], m.shape[0], m.strides[0]), self._h)
+
+    def get_mask(self, cam):
+        w, h = self.m_sizes[cam]
+        m = np.empty((h, w), np.uint8)
+        capi.check(self._lib.pano_get_mask(self._h, cam, capi.ptr(m), m.strides[0]), self._h)
+        return m
 
     def weight_level(self, cam, level):
         """The float weight level the compose uses (library-built on the device, or the caller's override)."""
@@ -402,20 +414,19 @@ class ocvStitcher:
             finder = cv2.detail_GraphCutSeamFinder("COST_COLOR")
             um = finder.find([a.astype(np.float32) for a in iw], corners, [cv2.UMat(m) for m in mw])
             mw = [m.get() for m in um]
+        # tail (:1095-1101, :1251-1257): dilate -> INTER_LINEAR_EXACT up-scale -> AND with the warped full mask runs on
+        # the device (pano_set_seam_mask, bit-exact with the cv2 calls); only the low-resolution masks are uploaded
         masks = []
         for i in range(n):
-            xm, ym = self.warp_maps(i)
-            full = cv2.remap(np.full((c.height, c.width), 255, np.uint8), xm, ym, cv2.INTER_NEAREST,
-                             borderMode=cv2.BORDER_CONSTANT)
-            dil = cv2.dilate(mw[i], None)
-            seam_mask = cv2.resize(dil, (full.shape[1], full.shape[0]), interpolation=cv2.INTER_LINEAR_EXACT)
-            masks.append(cv2.bitwise_and(seam_mask, full))
+            self.set_seam_mask(i, mw[i])
+            masks.append(self.get_mask(i))
         return masks
 
-    def _upload_masks(self, masks):
+    def _upload_masks(self, masks, on_device=False):
         self.m_blenderMask = [np.ascontiguousarray(m, np.uint8) for m in masks]
         for i, m in enumerate(self.m_blenderMask):
-            capi.check(self._lib.pano_set_mask(self._h, i, capi.ptr(m), m.shape[1], m.shape[0], m.strides[0]), self._h)
+            if not on_device:      # pano_set_seam_mask already installed them
+                capi.check(self._lib.pano_set_mask(self._h, i, capi.ptr(m), m.shape[1], m.shape[0], m.strides[0]), self._h)
         c = self.m_cfg
         if not c.exact_weights:
             return

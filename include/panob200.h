@@ -83,6 +83,14 @@ int pano_get_fixed_maps(pano_handle h, int cam, int16_t *ixy, uint16_t *frac);
 /* m_blenderMask[cam] (include/ocvstitcher.hpp:1101,1257).  Re-callable at run time: this is
  * how updateMask (:1218-1261) lands.  mask is sizes[cam] large, 8-bit, soft (0..255). */
 int pano_set_mask(pano_handle h, int cam, const uint8_t *mask, int width, int height, int stride);
+/* The tail of initSeam / updateMask on the device (include/ocvstitcher.hpp:1095-1101, 1251-1257), starting from the
+ * seam finder's LOW-RESOLUTION mask of camera `cam` (masks_warped[i] after seam_finder->find, any size):
+ *   cv::dilate(3x3) -> cv::resize(INTER_LINEAR_EXACT) to sizes[cam] -> AND with the warped full mask
+ *   (m_compensatorMaskWarped[cam]) = m_blenderMask[cam], then everything pano_set_mask does.
+ * Bit-exact with the OpenCV calls; uploads a few KB instead of the full-resolution mask. */
+int pano_set_seam_mask(pano_handle h, int cam, const uint8_t *seam, int width, int height, int stride);
+/* m_blenderMask[cam] as the handle currently holds it (sizes[cam] large) */
+int pano_get_mask(pano_handle h, int cam, uint8_t *mask, int stride);
 /* Optional: override the float weight pyramid level the library derives from the mask
  * (MultiBandBlender::feed builds it with cv::pyrDown on CV_32F, which is only ~1-ulp
  * reproducible outside OpenCV).  level in [0, num_bands]; size = feed rect >> level. */
@@ -191,6 +199,8 @@ int pano_host_undistort_maps(const double *K, const double *D, const double *new
 /* cv::remap's INTER_CUBIC 15-bit table (1024 x 16) and cv::resize's INTER_LINEAR axis tables */
 int pano_host_cubic_table(int16_t *tab);
 int pano_host_resize_axis(int ssize, int dsize, int clamp_frac, int *ofs, int16_t *a0, int16_t *a1);
+/* cv::resize's INTER_LINEAR_EXACT axis table (8.8 fixed point; pano_set_seam_mask): weight of src[ofs+1] is c1/256 */
+int pano_host_linear_exact_axis(int ssize, int dsize, int *ofs, int *c1);
 
 /* Chain a front end in front of a stitcher handle (cam = -1: every camera): from then on
  * pano_process / pano_process_device / pano_process_batch take the 8UC4 camera frames
@@ -198,6 +208,35 @@ int pano_host_resize_axis(int ssize, int dsize, int clamp_frac, int *ofs, int16_
  * device first -- the loop of src/master.cpp:300-318 (getFrame x N, then process) as one call.
  * f == NULL detaches.  Attach before the first host-memory process call. */
 int pano_attach_frontend(pano_handle h, int cam, pano_frontend_handle f);
+
+/* ---------------------------------------------------------------- two-ring epilogue (caller step after process)
+ * What the callers do with the upper- and lower-ring panoramas right after the two process calls:
+ * PANO_RING_RESIZE  src/master.cpp:321-326      cv::resize(up, up, down.size()) [INTER_LINEAR]; cv::vconcat(up, down, ret);
+ *                                               cv::rectangle(ret, Rect(0, ret.rows/2 - bar/2, ret.cols, bar), 0, -1)   (bar = 10)
+ * PANO_RING_CROP    src/panocamimpl.cpp:354-360 both cropped to Rect(0, finalcut, min width, min height - 2*finalcut);
+ *                                               cv::vconcat; cv::rectangle(ret, Rect(0, height - bar/2, width, bar), 0, -1) (bar = 4)
+ * One kernel writes the stacked frame (resize, copy and bar fused); bit-exact with the OpenCV calls. */
+#define PANO_RING_RESIZE 0
+#define PANO_RING_CROP 1
+typedef struct pano_ring_ctx *pano_ring_handle;
+typedef struct pano_ring_config {
+    int up_width, up_height;       /* stitcherOut[0] / `up` (8UC3) */
+    int down_width, down_height;   /* stitcherOut[1] / `down` */
+    int mode;                      /* PANO_RING_* */
+    int finalcut;                  /* PANO_RING_CROP only (panocamimpl's finalcut) */
+    int bar;                       /* separator rows */
+    int device;
+} pano_ring_config;
+int pano_ring_create(const pano_ring_config *cfg, pano_ring_handle *out);
+int pano_ring_destroy(pano_ring_handle h);
+const char *pano_ring_last_error(pano_ring_handle h);
+int pano_ring_out_size(pano_ring_handle h, int *wh);
+/* batch pairs in DEVICE memory: images `stride` bytes per row, consecutive images stride*height bytes apart; asynchronous */
+int pano_ring_compose_device(pano_ring_handle h, const uint8_t *up_dev, int up_stride, const uint8_t *down_dev, int down_stride,
+                             uint8_t *out_dev, int out_stride, int batch, void *stream);
+/* one pair in HOST memory; synchronous */
+int pano_ring_compose(pano_ring_handle h, const uint8_t *up_host, int up_stride, const uint8_t *down_host, int down_stride,
+                      uint8_t *out_host, int out_stride);
 
 /* How an attached front end is evaluated.
  * PANO_FRONTEND_SEQUENTIAL (default, the parity mode): the reference's own order -- undistort (INTER_CUBIC) ->

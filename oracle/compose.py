@@ -114,3 +114,78 @@ def fused_front_end_maps(xm, ym, out_size, undist_size, mapx, mapy, rect, cam_si
     if tuple(cam_size) != (uw, uh):
         x, y = inv(x, cam_size[0], uw), inv(y, cam_size[1], uh)
     return np.clip(x, 0.0, cam_size[0] - 1.0), np.clip(y, 0.0, cam_size[1] - 1.0)
+
+
+def ring_epilogue(up, down, mode="resize", finalcut=0, bar=None):
+    """Caller step after the two process calls: src/master.cpp:321-326 (mode 'resize': cv::resize(up, down.size()),
+    vconcat, rectangle(Rect(0, rows/2 - 5, cols, 10), 0, -1)) or src/panocamimpl.cpp:354-360 (mode 'crop': both
+    cropped to Rect(0, finalcut, min w, min h - 2*finalcut), vconcat, rectangle(Rect(0, height - 2, width, 4)))."""
+    up = np.ascontiguousarray(up, np.uint8); down = np.ascontiguousarray(down, np.uint8)
+    if mode == "resize":
+        bar = 10 if bar is None else bar
+        if up.shape != down.shape:
+            up = orc.resize_bilinear_u8(up, (down.shape[1], down.shape[0]))
+        ret = np.vstack([up, down])
+        y0 = ret.shape[0] // 2 - bar // 2
+    else:
+        bar = 4 if bar is None else bar
+        width = min(up.shape[1], down.shape[1])
+        height = min(up.shape[0], down.shape[0]) - 2 * finalcut
+        ret = np.vstack([up[finalcut:finalcut + height, :width], down[finalcut:finalcut + height, :width]])
+        y0 = height - bar // 2
+    ret = ret.copy()
+    ret[max(0, y0):max(0, min(ret.shape[0], y0 + bar))] = 0          # filled cv::rectangle covers exactly `bar` rows
+    return ret
+
+
+def dilate3x3_u8(m):
+    """cv::dilate(src, dst, Mat()) -- 3x3 rectangle, anchor at the centre, border pixels ignored
+    (include/ocvstitcher.hpp:1095, 1251)."""
+    m = np.asarray(m, np.uint8)
+    p = np.zeros((m.shape[0] + 2, m.shape[1] + 2), np.uint8)
+    p[1:-1, 1:-1] = m
+    out = np.zeros_like(m)
+    for dy in range(3):
+        for dx in range(3):
+            out = np.maximum(out, p[dy:dy + m.shape[0], dx:dx + m.shape[1]])
+    return out
+
+
+def linear_exact_axis(ssize, dsize):
+    """Offsets and 8.8 fixed-point coefficients of cv::resize(INTER_LINEAR_EXACT) along one axis
+    (OpenCV resize.cpp interpolationLinear::getCoeffs on softdouble == IEEE double, ufixedpoint16 = round(x * 256)).
+    Positions before the first / after the last source sample replicate the edge (coefficients 256, 0)."""
+    scale = 1.0 / (float(dsize) / float(ssize))
+    ofs = np.zeros(dsize, np.int32); c1 = np.zeros(dsize, np.int32)
+    for d in range(dsize):
+        fval = scale * (d + 0.5) - 0.5
+        ival = int(math.floor(fval))
+        if ival >= 0 and ssize > 1:
+            if ival < ssize - 1:
+                ofs[d] = ival
+                c1[d] = int(np.rint((fval - ival) * 256.0))
+            else:
+                ofs[d] = ssize - 1
+        # else: replicate sample 0
+    return ofs, c1
+
+
+def resize_linear_exact_u8(src, dsize):
+    """cv::resize(src, dst, dsize, 0, 0, INTER_LINEAR_EXACT) for 8UC1 (include/ocvstitcher.hpp:1096, 1253):
+    horizontal pass to 8.8 fixed point, vertical pass to 16.16, rounded half up."""
+    src = np.asarray(src, np.uint8)
+    dw, dh = dsize
+    xo, xc = linear_exact_axis(src.shape[1], dw)
+    yo, yc = linear_exact_axis(src.shape[0], dh)
+    x1 = np.minimum(xo + 1, src.shape[1] - 1); y1 = np.minimum(yo + 1, src.shape[0] - 1)
+    s = src.astype(np.int64)
+    hrow = s[:, xo] * (256 - xc)[None, :] + s[:, x1] * xc[None, :]                # 8.8, <= 65280
+    v = hrow[yo, :] * (256 - yc)[:, None] + hrow[y1, :] * yc[:, None]             # 16.16
+    return ((v + 32768) >> 16).astype(np.uint8)
+
+
+def seam_mask_tail(seam_lowres, full_mask):
+    """m_blenderMask[i] from the seam finder's low-resolution mask: dilate -> INTER_LINEAR_EXACT up-scale to the
+    warped size -> AND with the warped full mask (include/ocvstitcher.hpp:1095-1101, 1251-1257)."""
+    up = resize_linear_exact_u8(dilate3x3_u8(seam_lowres), (full_mask.shape[1], full_mask.shape[0]))
+    return up & np.asarray(full_mask, np.uint8)

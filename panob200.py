@@ -25,6 +25,7 @@ capi = pkg.capi
 ocvStitcher = pkg.ocvStitcher
 StitcherConfig = pkg.StitcherConfig
 nvCamFrontEnd = pkg.nvCamFrontEnd
+RingComposer = pkg.RingComposer
 sharding = pkg.sharding
 strips = pkg.strips
 PanoError = pkg.PanoError

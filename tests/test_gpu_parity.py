@@ -190,6 +190,43 @@ def test_device_built_weight_pyramid_equals_host_builder():
     assert d.max() <= 1
 
 
+def test_seam_mask_tail_on_device():
+    """pano_set_seam_mask = dilate -> INTER_LINEAR_EXACT -> AND with the warped full mask on the device, then the compose
+    with the resulting masks: mask bytes and panorama bit-exact with the oracle's restatement of the OpenCV calls."""
+    Ks, Rs, scale = calib.rig("2222", 480)
+    t, st, imgs, _ = oracle_case(Ks, Rs, scale, 480, 270, "spherical", "multiband", 4, seed=8)
+    rng = np.random.default_rng(12)
+    new = []
+    for i in range(4):
+        w, h = t.sizes[i]
+        low = np.zeros((max(1, h // 6), max(1, w // 6)), np.uint8)
+        lo, hi = sorted(rng.integers(0, low.shape[1], 2))
+        low[:, lo:hi + 1] = 255
+        low[rng.integers(0, low.shape[0]), :] = 0
+        st.set_seam_mask(i, low)
+        want = compose.seam_mask_tail(low, t.warped_masks[i])
+        assert_equal("seam mask %d" % i, st.get_mask(i), want)
+        new.append(want)
+    t.blend_masks = new
+    assert_equal("compose with device-built seam masks", st.process(imgs), compose.process(t, imgs, "multiband", 4))
+
+
+def test_calibration_flow_masks_equal_cv2_init_seam():
+    """ocvStitcher.calibration() (initMode 2: fixed parameters -> initSeam: GraphCut on low-res warps on the host, the
+    mask tail on the device) yields the masks of the reference call sequence replayed through cv2 (:975-1101)."""
+    pytest.importorskip("cv2")
+    from oracle import cv2_reference as ref
+    Ks, Rs, scale = calib.rig("2222", 480)
+    imgs = util.synth_set(4, 270, 480, 21)
+    t = ref.init_seam(imgs, Ks, Rs, scale, warp="spherical", seam="gc_color")
+    st = panob200.ocvStitcher(SC(width=480, height=270, num_images=4, Ks=Ks, Rs=Rs, warped_image_scale=scale,
+                                 blender="multiband", num_bands=4, initMode=2))
+    assert st.calibration(imgs) == 0, st.last_error
+    for i in range(4):
+        assert_equal("m_blenderMask[%d]" % i, st.get_mask(i), t.blend_masks[i])
+    assert_equal("panorama after calibration()", st.process(imgs), ref.process(t, imgs, "multiband", 4))
+
+
 def test_batched_device_and_host_apis():
     import torch
     Ks, Rs, scale = calib.rig("2222", 240)
@@ -486,3 +523,26 @@ def test_front_end_config2_shape_vs_oracle():
     torch.cuda.synchronize()
     for i in range(3):
         assert_equal("batch %d" % i, out[i].cpu().numpy(), want[i])
+
+
+# ------------------------------------------------------------------ two-ring epilogue
+
+@pytest.mark.parametrize("mode,up,down,fc", [("resize", (333, 57), (301, 64), 0), ("resize", (200, 40), (200, 40), 0),
+                                              ("resize", (5336, 896), (5000, 880), 0), ("crop", (333, 57), (301, 64), 3),
+                                              ("crop", (150, 33), (211, 30), 0)])
+def test_ring_epilogue_bit_exact(mode, up, down, fc):
+    """resize + vconcat + separator bar of src/master.cpp:321-326 / src/panocamimpl.cpp:354-360 as one kernel."""
+    import torch
+    rng = np.random.default_rng(31)
+    u = rng.integers(0, 256, (2, up[1], up[0], 3), np.uint8)
+    d = rng.integers(0, 256, (2, down[1], down[0], 3), np.uint8)
+    rc = panob200.RingComposer(up, down, mode, finalcut=fc)
+    want = [compose.ring_epilogue(u[b], d[b], mode, finalcut=fc) for b in range(2)]
+    assert rc.out_size == (want[0].shape[1], want[0].shape[0])
+    assert_equal("ring host", rc.compose(u[0], d[0]), want[0])
+    out = torch.empty((2,) + want[0].shape, dtype=torch.uint8, device="cuda")
+    rc.compose_device(torch.from_numpy(u).cuda(), torch.from_numpy(d).cuda(), out)
+    torch.cuda.synchronize()
+    for b in range(2):
+        assert_equal("ring device %d" % b, out[b].cpu().numpy(), want[b])
+    rc.close()

@@ -166,3 +166,13 @@ def test_float_pyrdown_and_feather_weight():
     want = cv2.distanceTransform(full, cv2.DIST_L1, 3)
     _, want = cv2.threshold(want * np.float32(0.05), 1.0, 1.0, cv2.THRESH_TRUNC)
     assert np.array_equal(capi.host_feather_weight(full, 0.05), want)
+
+
+def test_linear_exact_axis_matches_oracle_restatement():
+    """cv::resize(INTER_LINEAR_EXACT) axis tables of pano_set_seam_mask (updateMask tail) vs the oracle's restatement
+    (itself pinned live against cv2 in test_oracle_vs_cv2.py)."""
+    from oracle import compose
+    for ss, ds in ((171, 1690), (103, 1016), (5, 64), (100, 100), (64, 63), (1, 17), (200, 50), (7, 7)):
+        o, c = capi.host_linear_exact_axis(ss, ds)
+        wo, wc = compose.linear_exact_axis(ss, ds)
+        assert np.array_equal(o, wo) and np.array_equal(c, wc), (ss, ds)

@@ -159,3 +159,36 @@ def test_full_call_sequence_matches_cv2_reference():
     d = np.abs(got.astype(int) - want.astype(int))
     assert d.max() <= 1, util.report("compose", got, want)     # own float weight pyramid: <= 1 LSB
     eq(ref.process(t, imgs, "no", cut=cut), compose.process(ot, imgs, "no", cut=cut), "no-blend compose")
+
+
+def test_ring_epilogue_vs_cv2_calls():
+    """The two-ring caller step (src/master.cpp:321-326, src/panocamimpl.cpp:354-360) replayed with cv2."""
+    from oracle import compose
+    rng = np.random.default_rng(9)
+    for (uw, uh), (dw, dh) in (((333, 57), (301, 64)), ((200, 40), (200, 40)), ((150, 33), (211, 30))):
+        up = rng.integers(0, 256, (uh, uw, 3), np.uint8)
+        down = rng.integers(0, 256, (dh, dw, 3), np.uint8)
+        r = cv2.resize(up, (dw, dh))
+        ret = cv2.vconcat([r, down])
+        cv2.rectangle(ret, (0, ret.shape[0] // 2 - 5, ret.shape[1], 10), (0, 0, 0), -1)
+        eq(compose.ring_epilogue(up, down, "resize"), ret, "master.cpp epilogue %dx%d" % (uw, uh))
+        for fc in (0, 3):
+            width, height = min(uw, dw), min(uh, dh) - 2 * fc
+            ret = cv2.vconcat([np.ascontiguousarray(up[fc:fc + height, :width]), np.ascontiguousarray(down[fc:fc + height, :width])])
+            cv2.rectangle(ret, (0, height - 2, width, 4), (0, 0, 0), -1, 1, 0)
+            eq(compose.ring_epilogue(up, down, "crop", finalcut=fc), ret, "panocamimpl epilogue finalcut %d" % fc)
+
+
+def test_seam_mask_tail_vs_cv2_calls():
+    """dilate -> INTER_LINEAR_EXACT -> AND (include/ocvstitcher.hpp:1095-1101, 1251-1257) replayed with cv2."""
+    from oracle import compose
+    rng = np.random.default_rng(3)
+    for (sw, sh), (dw, dh) in (((171, 103), (1690, 1016)), ((40, 30), (97, 131)), ((5, 7), (64, 33)), ((100, 60), (100, 60)),
+                               ((64, 64), (63, 65)), ((1, 9), (17, 40)), ((33, 1), (90, 5)), ((200, 100), (50, 30))):
+        for binary in (True, False):
+            m = (rng.integers(0, 2, (sh, sw)) * 255).astype(np.uint8) if binary else rng.integers(0, 256, (sh, sw), np.uint8)
+            full = (rng.integers(0, 8, (dh, dw)) > 0).astype(np.uint8) * 255
+            eq(compose.dilate3x3_u8(m), cv2.dilate(m, None), "dilate")
+            eq(compose.resize_linear_exact_u8(m, (dw, dh)), cv2.resize(m, (dw, dh), interpolation=cv2.INTER_LINEAR_EXACT), "linear exact")
+            want = cv2.bitwise_and(cv2.resize(cv2.dilate(m, None), (dw, dh), interpolation=cv2.INTER_LINEAR_EXACT), full)
+            eq(compose.seam_mask_tail(m, full), want, "seam tail")
