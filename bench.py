@@ -35,6 +35,9 @@ WORKLOADS = {
     "config1": "config1: 4x1920x1080 BGR -> spherical warp + 5-band MultiBandBlender -> cut 5336x896 (imx390 rig, 2222 calibration x4)",
     "config2": "config2: 4x1920x1080 BGRA camera frames -> imx390 undistort (INTER_CUBIC) + crop [69,103,1782,889] + resize -> "
                "spherical warp + 5-band MultiBandBlender -> cut 5336x896",
+    # the YUYVCAM ingest (include/nvcam.hpp:880-886): frames cross PCIe as 8UC2, cvtColor(COLOR_YUV2BGRA_YUYV) runs on the device
+    "config2-yuyv": "config2 with 8UC2 YUYV 4:2:2 camera frames (2 B/px over PCIe): YUV2BGRA_YUYV + imx390 undistort (INTER_CUBIC) + crop "
+                    "[69,103,1782,889] + resize -> spherical warp + 5-band MultiBandBlender -> cut 5336x896",
     # NOT the parity path: the single-gather variant north_star asks to report separately, with its own PSNR
     "config2-fused": "config2 inputs, FUSED single-gather variant: undistort+crop+resize+warp maps composed into one table, one "
                      "bilinear gather from the BGRA frame -> 5-band MultiBandBlender -> cut 5336x896 (not bit-exact; see variant.psnr)",
@@ -48,7 +51,7 @@ def camera_entry():
     return calib.CAM_LIJING_390_FOV60_1920
 
 
-def make_front_end(device, max_batch):
+def make_front_end(device, max_batch, src_format="bgra"):
     """nvCam front end of config 2 (cfg/cameras.yaml:80-88 entry, 1920x1080 in/out)."""
     import panob200
     cam = camera_entry()
@@ -58,7 +61,7 @@ def make_front_end(device, max_batch):
     except ImportError:
         newK = NEWK_FALLBACK
     cfg = panob200.pkg.nvcam.CamConfig(K=cam["K"], distorParams=cam["distorParams"], rect=cam["rect"], newK=newK,
-                                       device=device, max_batch=max_batch)
+                                       device=device, max_batch=max_batch, srcFormat=src_format)
     return panob200.nvCamFrontEnd(cfg)
 
 
@@ -147,9 +150,14 @@ def cpu_reference_time(kind, t, frame_sets, repeats, front=False):
             _, mx, my = ref.undistort_tables(cam["K"], cam["distorParams"], (W, H))
             fe = lambda a: ref.front_end(a, (W, H), mx, my, cam["rect"], (W, H))     # noqa: E731
 
+        def to_bgra(f):
+            if f.shape[2] == 2:        # YUYVCAM ingest (include/nvcam.hpp:880-886)
+                return __import__("cv2").cvtColor(np.ascontiguousarray(f), __import__("cv2").COLOR_YUV2BGRA_YUYV)
+            return np.dstack([f, np.full(f.shape[:2], 255, np.uint8)]) if f.shape[2] == 3 else f
+
         def one(fs):
             if fe is not None:
-                fs = [fe(np.dstack([f, np.full(f.shape[:2], 255, np.uint8)])) if f.shape[2] == 3 else fe(f) for f in fs]
+                fs = [fe(to_bgra(f)) for f in fs]
             return ref.process(t, fs, "multiband", NBANDS, cut=CUT)   # 'faithful': maps rebuilt per call (:1171)
         one(frame_sets[0])          # warm-up
         t0 = time.perf_counter()
@@ -176,6 +184,12 @@ def run_reference(args, rank, world):
     per_step = 2
     sets = [[np.ascontiguousarray(f) for f in synth_numpy(1000 + s)] for s in range(2)]
     kind, t = cpu_reference_setup(sets[0])
+    if args.workload == "config2-yuyv":
+        def yuyv(f):
+            y = np.empty(f.shape[:2] + (2,), np.uint8)
+            y[:, :, 0] = f[:, :, 0]; y[:, 0::2, 1] = f[:, 0::2, 1]; y[:, 1::2, 1] = f[:, 0::2, 2]
+            return y
+        sets = [[yuyv(f) for f in s] for s in sets]
     front = args.workload.startswith("config2")
     cpu_reference_time(kind, t, sets, max(1, args.warmup), front)
     t0 = time.perf_counter()
@@ -236,8 +250,17 @@ def main():
     front = None
     if args.workload.startswith("config2"):
         # camera frames are 8UC4 (the VIC's ARGB output, include/nvcam.hpp:889-893): BGR + alpha 255
-        frames = torch.cat([frames, torch.full(frames.shape[:-1] + (1,), 255, dtype=torch.uint8, device=dev)], dim=-1).contiguous()
-        front = make_front_end(local_rank, args.max_batch * NCAM)
+        if args.workload == "config2-yuyv":
+            # valid YUYV bytes from the synthetic frames: Y = channel 0, U / V = channels 1 / 2 of the even pixel
+            yuyv = torch.empty(frames.shape[:-1] + (2,), dtype=torch.uint8, device=dev)
+            yuyv[..., 0] = frames[..., 0]
+            yuyv[..., 0::2, 1] = frames[..., 0::2, 1]
+            yuyv[..., 1::2, 1] = frames[..., 0::2, 2]
+            frames = yuyv.contiguous()
+            del yuyv
+        else:
+            frames = torch.cat([frames, torch.full(frames.shape[:-1] + (1,), 255, dtype=torch.uint8, device=dev)], dim=-1).contiguous()
+        front = make_front_end(local_rank, args.max_batch * NCAM, "yuyv" if args.workload == "config2-yuyv" else "bgra")
     if front is None:
         set0 = [frames[0, i].cpu().numpy() for i in range(NCAM)]
     else:   # the stitcher calibrates on what the front end delivers

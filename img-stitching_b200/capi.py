@@ -57,7 +57,7 @@ class pano_frontend_config(C.Structure):
                 ("out_width", C.c_int), ("out_height", C.c_int), ("undistort", C.c_int),
                 ("K", C.c_double * 9), ("D", C.c_double * 4), ("newK", C.c_double * 9),
                 ("rect", C.c_int * 4), ("mapx", C.POINTER(C.c_float)), ("mapy", C.POINTER(C.c_float)),
-                ("device", C.c_int), ("max_batch", C.c_int)]
+                ("device", C.c_int), ("max_batch", C.c_int), ("src_format", C.c_int)]
 
 
 # every symbol include/panob200.h declares (tests check the list against the header)

@@ -26,6 +26,8 @@ int pano_frontend_launches(pano_frontend_handle h);
 void pano_frontend_sizes(pano_frontend_handle h, int *in_wh, int *out_wh);
 bool pano_frontend_set_prof(pano_frontend_handle h, cudaEvent_t *ev, double *cubic_bytes, double *resize_bytes);
 void pano_frontend_backmap(pano_frontend_handle h, double *xs, double *ys, size_t count);
+int pano_frontend_in_px(pano_frontend_handle h);
+int pano_frontend_convert(pano_frontend_handle h, const uint8_t *yuyv, size_t in_img, uint8_t *dst, int count, cudaStream_t st);
 
 namespace {
 
@@ -75,6 +77,8 @@ struct pano_ctx {
     bool fused = false;
     std::vector<std::vector<float>> fxmap, fymap;  // composed float maps (rois[cam] large) while fused
     size_t in_frame_bytes = 0;                    // bytes of one input frame as the caller passes it
+    size_t in_frame_bytes4 = 0;                   // the same frame as 8UC4 (what the fused gather reads)
+    uint8_t *fused_in = nullptr;                  // fused mode + YUYV ingest: converted 8UC4 frames [max_batch][n]
     uint8_t *front_out = nullptr;                 // [max_batch][n][H][W][3] stitcher inputs produced by the front end
     int strip_x0 = 0, strip_x1 = 0;               // own dst columns (level 0, padded coords); full width = no split
     // walker tiles (kWalkTileW x kWalkTileH): [level][cam][tile] -> any non-zero weight / count of weights == 1
@@ -99,7 +103,7 @@ struct pano_ctx {
     int last_launches = 0;
 
     size_t frame_bytes() const { return (size_t)cfg.src_width * cfg.src_height * 3; }
-    size_t gather_frame_bytes() const { return fused ? in_frame_bytes : frame_bytes(); }   // frame the warp gathers from
+    size_t gather_frame_bytes() const { return fused ? in_frame_bytes4 : frame_bytes(); }   // frame the warp gathers from
     size_t set_bytes() const { return (has_front ? in_frame_bytes : frame_bytes()) * n; }   // caller-side frame-set
     size_t out_bytes() const { return (size_t)host.cut_w * host.cut_h * 3; }
 };
@@ -511,20 +515,37 @@ int runPhase(pano_ctx *h, int p, const uint8_t *frames_dev, uint8_t *out_dev, in
 
 int runFrontEnds(pano_ctx *h, const uint8_t *&frames_dev, int slots, cudaStream_t st)
 {
-    if (!h->has_front || h->fused) return PANO_OK;
+    if (!h->has_front) return PANO_OK;
     Launch L{h, st};
+    if (h->fused) {
+        // single-gather variant: the warp reads the camera frames itself; only a YUYV ingest still needs its conversion
+        if (h->in_frame_bytes4 == h->in_frame_bytes) return PANO_OK;
+        L.begin("fe_yuyv_to_bgra", (double)slots * h->n * (h->in_frame_bytes + h->in_frame_bytes4));
+        if (pano_frontend_convert(h->front[0], frames_dev, h->in_frame_bytes, h->fused_in, slots * h->n, st))
+            return fail(h, "front end: %s", pano_frontend_last_error(h->front[0]));
+        L.end();
+        frames_dev = h->fused_in;
+        return PANO_OK;
+    }
     bool same = true;
     for (int i = 1; i < h->n; ++i) same = same && h->front[i] == h->front[0];
     if (same && h->profiling) {
         // per-kernel timing of the fast path (cubic undistort / bilinear resize)
-        cudaEvent_t ev[3];
+        cudaEvent_t ev[4];
         double cb = 0, rb = 0;
         for (auto &e : ev) cudaEventCreate(&e);
+        const bool yuyv = h->in_frame_bytes4 != h->in_frame_bytes;
         if (pano_frontend_set_prof(h->front[0], ev, &cb, &rb)) {
             const int rc = pano_frontend_run(h->front[0], frames_dev, h->in_frame_bytes, h->front_out, h->frame_bytes(), slots * h->n, st);
             pano_frontend_set_prof(h->front[0], nullptr, nullptr, nullptr);
             if (rc) return fail(h, "front end: %s", pano_frontend_last_error(h->front[0]));
-            ProfEntry a{"fe_cubic_undistort", ev[0], ev[1], cb * slots * h->n};
+            if (yuyv) {
+                ProfEntry y{"fe_yuyv_to_bgra", ev[3], ev[0], (double)(h->in_frame_bytes + h->in_frame_bytes4) * slots * h->n};
+                h->prof.push_back(y);
+            } else {
+                cudaEventDestroy(ev[3]);
+            }
+            ProfEntry a{"fe_cubic_undistort", ev[0], ev[1], cb * slots * h->n, yuyv};
             h->prof.push_back(a);
             ProfEntry b{"fe_resize", ev[1], ev[2], rb * slots * h->n, true};   // shares the middle event
             h->prof.push_back(b);
@@ -1013,14 +1034,15 @@ int pano_attach_frontend(pano_handle h, int cam, pano_frontend_handle f)
     if (out_wh[0] != h->cfg.src_width || out_wh[1] != h->cfg.src_height)
         return fail(h, "pano_attach_frontend: front end delivers %dx%d, stitcher expects %dx%d", out_wh[0], out_wh[1],
                     h->cfg.src_width, h->cfg.src_height);
-    const size_t in_bytes = (size_t)in_wh[0] * in_wh[1] * 4;
-    if (h->has_front && in_bytes != h->in_frame_bytes) return fail(h, "pano_attach_frontend: all cameras must share one frame size");
+    const size_t in_bytes = (size_t)in_wh[0] * in_wh[1] * pano_frontend_in_px(f);
+    if (h->has_front && in_bytes != h->in_frame_bytes) return fail(h, "pano_attach_frontend: all cameras must share one frame size and format");
     for (int i = 0; i < h->n; ++i)
         if (cam < 0 || cam == i) h->front[i] = f;
     for (int i = 0; i < h->n; ++i)
         if (!h->front[i]) h->front[i] = f;      // every camera needs one once the input format changes
     if (h->stage_in[0]) return fail(h, "pano_attach_frontend: attach before the first host-side process call");
     h->in_frame_bytes = in_bytes;
+    h->in_frame_bytes4 = (size_t)in_wh[0] * in_wh[1] * 4;
     h->has_front = true;
     if (!h->front_out && devAlloc(h, &h->front_out, h->frame_bytes() * h->n * h->cfg.max_batch, false)) return PANO_ERR;
     return PANO_OK;
@@ -1045,6 +1067,9 @@ int pano_set_frontend_mode(pano_handle h, int mode)
         }
         const int sw = out_wh[0], sh = out_wh[1];       // stitcher input = front-end output
         W = in_wh[0]; H = in_wh[1];
+        if (h->in_frame_bytes4 != h->in_frame_bytes && !h->fused_in &&
+            devAlloc(h, &h->fused_in, h->in_frame_bytes4 * n * h->cfg.max_batch, false))
+            return PANO_ERR;
         h->fxmap.assign(n, {}); h->fymap.assign(n, {});
         // BORDER_REFLECT of the rotation warp, continuous form: mirror about -0.5 and n - 0.5 (pixel-centre
         // coordinates), then clamp to the pixel centres
@@ -1108,7 +1133,7 @@ int pano_process(pano_handle h, const uint8_t *const *frames, const int *strides
     if (h->has_front) {
         int in_wh[2], out_wh[2];
         pano_frontend_sizes(h->front[0], in_wh, out_wh);
-        W3 = in_wh[0] * 4; H = in_wh[1]; fbytes = h->in_frame_bytes;
+        W3 = in_wh[0] * pano_frontend_in_px(h->front[0]); H = in_wh[1]; fbytes = h->in_frame_bytes;
     }
     if (out_stride < h->host.cut_w * 3) return fail(h, "pano_process: out_stride too small");
     for (int i = 0; i < h->n; ++i) {

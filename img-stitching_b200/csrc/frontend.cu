@@ -81,6 +81,45 @@ __global__ void __launch_bounds__(256) drop_alpha_kernel(const uint8_t *__restri
     dst[3 * i] = p.x; dst[3 * i + 1] = p.y; dst[3 * i + 2] = p.z;
 }
 
+// cv::cvtColor(COLOR_YUV2BGRA_YUYV) (the YUYVCAM ingest, include/nvcam.hpp:880-886): ITU-R BT.601 in 20-bit fixed
+// point, alpha 255.  Streaming kernel: one thread = 16 bytes in (8 pixels: Y0 U Y1 V ...) -> two 16-byte stores.
+__device__ __forceinline__ uint32_t yuv_px(int y, int ruv, int guv, int buv)
+{
+    const int yy = max(0, y - 16) * 1220542;
+    uint32_t hi, px;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, 0;" : "=r"(hi) : "r"(255), "r"((yy + ruv) >> 20));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(px) : "r"((yy + guv) >> 20), "r"((yy + buv) >> 20), "r"(hi));
+    return px;
+}
+__device__ __forceinline__ uint2 yuyv_pair(uint32_t w)      // bytes Y0 U Y1 V -> two BGRA words
+{
+    const int u = (int)((w >> 8) & 255u) - 128, v = (int)(w >> 24) - 128;
+    const int ruv = (1 << 19) + 1673527 * v, guv = (1 << 19) - 852492 * v - 409993 * u, buv = (1 << 19) + 2116026 * u;
+    return make_uint2(yuv_px((int)(w & 255u), ruv, guv, buv), yuv_px((int)((w >> 16) & 255u), ruv, guv, buv));
+}
+__global__ void __launch_bounds__(256) yuyv_to_bgra_kernel(const uint4 *__restrict__ src, size_t src_img16, uint4 *__restrict__ dst,
+                                                           size_t dst_img16, size_t n16)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n16) return;
+    const uint4 s = __ldg(src + (size_t)blockIdx.y * src_img16 + i);
+    const uint2 a = yuyv_pair(s.x), b = yuyv_pair(s.y), c = yuyv_pair(s.z), d = yuyv_pair(s.w);
+    uint4 *o = dst + (size_t)blockIdx.y * dst_img16 + 2 * i;
+    o[0] = make_uint4(a.x, a.y, b.x, b.y);
+    o[1] = make_uint4(c.x, c.y, d.x, d.y);
+}
+// any size / alignment: one thread = one pixel pair
+__global__ void __launch_bounds__(256) yuyv_to_bgra_pair_kernel(const uint8_t *__restrict__ src, size_t src_img, uint8_t *__restrict__ dst,
+                                                                size_t dst_img, size_t npairs)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npairs) return;
+    const uint8_t *s = src + (size_t)blockIdx.y * src_img + 4 * i;
+    const uint2 p = yuyv_pair((uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[2] << 16) | ((uint32_t)s[3] << 24));
+    uint8_t *o = dst + (size_t)blockIdx.y * dst_img + 8 * i;
+    for (int k = 0; k < 4; ++k) { o[k] = (uint8_t)(p.x >> (8 * k)); o[4 + k] = (uint8_t)(p.y >> (8 * k)); }
+}
+
 // cv::remap INTER_CUBIC, BORDER_CONSTANT(0), restricted to the crop rect.
 // map: per undistorted pixel {sx, sy} = cvRound(32*map) with the integer part saturated to int16.
 template <int CIN>
@@ -440,7 +479,9 @@ struct pano_frontend_ctx {
     bool fast4 = false;
     int4 *cub_tiles = nullptr;                                     // per 128x8 tile of the crop rect: staged footprint (cubic5_kernel)
     int cub_tx = 0, cub_ty = 0;
-    cudaEvent_t *prof_ev = nullptr;                                // 3 events (before cubic, between, after resize) when profiling
+    cudaEvent_t *prof_ev = nullptr;                                // events when profiling: before cubic, between, after resize, [3] before the YUYV conversion
+    uint8_t *buf_argb = nullptr;                                   // YUYV ingest: converted 8UC4 frames, max_batch deep
+    int in_px() const { return cfg.src_format == PANO_SRC_YUYV ? 2 : 4; }
     uint8_t *stage_in = nullptr, *stage_out = nullptr;
     int launches = 0;
 };
@@ -522,6 +563,8 @@ int pano_frontend_create(const pano_frontend_config *cfg, pano_frontend_handle *
         cfg->out_width < 2 || cfg->out_height < 2)
         return ffail(nullptr, "bad sizes");
     int ndev = 0;
+    if (cfg->src_format != PANO_SRC_BGRA && cfg->src_format != PANO_SRC_YUYV) return ffail(nullptr, "bad src_format");
+    if (cfg->src_format == PANO_SRC_YUYV && (cfg->cam_src_width & 1)) return ffail(nullptr, "YUYV frames need an even width");
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return ffail(nullptr, "no CUDA device: this library has no CPU path");
     if (cfg->device < 0 || cfg->device >= ndev) return ffail(nullptr, "bad device ordinal");
     pano_frontend_ctx *h = new pano_frontend_ctx();
@@ -578,6 +621,7 @@ int pano_frontend_create(const pano_frontend_config *cfg, pano_frontend_handle *
     }
     h->use_r_out = !(cfg->out_width == uw && cfg->out_height == uh);
     if (h->use_r_out && makeResize(h, h->r_out, uw, uh, cfg->out_width, cfg->out_height)) return bail();
+    if (cfg->src_format == PANO_SRC_YUYV && falloc(h, &h->buf_argb, (size_t)cfg->cam_src_width * cfg->cam_src_height * 4 * S)) return bail();
     const size_t ubytes = (size_t)uw * uh * 3 * S;
     if (falloc(h, &h->buf_a, ubytes) || falloc(h, &h->buf_b, ubytes) || falloc(h, &h->buf_c, ubytes)) return bail();
     // fast path: undistort straight from the 8UC4 camera frame, then one resize to the output size
@@ -651,8 +695,24 @@ int pano_frontend_get_maps(pano_frontend_handle h, float *mapx, float *mapy)
 
 }  // extern "C"
 
+// YUYV ingest: `count` frames (in_img bytes apart) -> dense 8UC4 frames at dst
+int pano_frontend_convert(pano_frontend_handle h, const uint8_t *yuyv, size_t in_img, uint8_t *dst, int count, cudaStream_t st)
+{
+    const pano_frontend_config &c = h->cfg;
+    const size_t npx = (size_t)c.cam_src_width * c.cam_src_height, out_img = npx * 4;
+    if (npx % 8 == 0 && in_img % 16 == 0 && (reinterpret_cast<uintptr_t>(yuyv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0)
+        yuyv_to_bgra_kernel<<<dim3((unsigned)((npx / 8 + 255) / 256), count), 256, 0, st>>>(
+            reinterpret_cast<const uint4 *>(yuyv), in_img / 16, reinterpret_cast<uint4 *>(dst), out_img / 16, npx / 8);
+    else
+        yuyv_to_bgra_pair_kernel<<<dim3((unsigned)((npx / 2 + 255) / 256), count), 256, 0, st>>>(yuyv, in_img, dst, out_img, npx / 2);
+    FCK(h, cudaGetLastError());
+    return PANO_OK;
+}
+int pano_frontend_in_px(pano_frontend_handle h) { return h ? h->in_px() : 4; }
+
 // Internal entry (also used by capi.cu when a front end is attached to a stitcher handle):
 // images may be strided (in_img / o_img bytes between consecutive images).
+
 int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img, uint8_t *out, size_t o_img, int batch,
                       cudaStream_t st)
 {
@@ -667,10 +727,19 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
         const int nb = std::min(S, batch - b0);
         const uint8_t *src = argb + (size_t)b0 * in_img;
         uint8_t *final_dst = out + (size_t)b0 * o_img;
+        size_t img_stride = in_img;                     // bytes between consecutive 8UC4 frames at `src`
+        if (c.src_format == PANO_SRC_YUYV) {
+            // stage 0 (YUYVCAM builds, :880-886): cv::cvtColor(COLOR_YUV2BGRA_YUYV) into the 8UC4 frame m_argb
+            if (h->prof_ev) cudaEventRecord(h->prof_ev[3], st);
+            if (pano_frontend_convert(h, src, in_img, h->buf_argb, nb, st)) return PANO_ERR;
+            ++h->launches;
+            src = h->buf_argb;
+            img_stride = (size_t)c.cam_src_width * c.cam_src_height * 4;
+        }
         // stage 1: camera frame -> undist-sized 3-channel "tmp" (:903-904 / :924-927)
-        const uint8_t *cur = src; int cur_c = 4; int cw = c.cam_src_width, chh = c.cam_src_height; size_t cur_img = in_img;
+        const uint8_t *cur = src; int cur_c = 4; int cw = c.cam_src_width, chh = c.cam_src_height; size_t cur_img = img_stride;
         auto target = [&](bool last, uint8_t *scratch) { return last ? final_dst : scratch; };
-        if (h->fast4 && (in_img & 3) == 0) {
+        if (h->fast4 && (img_stride & 3) == 0) {
             const int *rc = c.rect;
             const size_t w_img = (size_t)rc[2] * rc[3];
             const dim3 cg((rc[2] + 127) / 128, (rc[3] + 7) / 8, nb);
@@ -680,14 +749,14 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
             const uint4 *tab4 = reinterpret_cast<const uint4 *>(h->dtab);
             static const bool no_tiled = getenv("PANO_CUBIC_UNTILED") != nullptr;
             if (h->cub_tiles && h->wtex && !no_tiled)
-                cubic5_kernel<<<dim3(h->cub_tx, h->cub_ty, nb), blk, 0, st>>>(src4, in_img / 4, cw, chh, h->dmap32, uw, h->wtex, h->cub_tiles,
+                cubic5_kernel<<<dim3(h->cub_tx, h->cub_ty, nb), blk, 0, st>>>(src4, img_stride / 4, cw, chh, h->dmap32, uw, h->wtex, h->cub_tiles,
                                                                              rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
             else if (h->dmap32 && tex_w)
-                cubic4_kernel<true, true><<<cg, blk, 0, st>>>(src4, in_img / 4, cw, chh, h->dmap32, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
+                cubic4_kernel<true, true><<<cg, blk, 0, st>>>(src4, img_stride / 4, cw, chh, h->dmap32, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
             else if (h->dmap32)
-                cubic4_kernel<true, false><<<cg, blk, 0, st>>>(src4, in_img / 4, cw, chh, h->dmap32, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
+                cubic4_kernel<true, false><<<cg, blk, 0, st>>>(src4, img_stride / 4, cw, chh, h->dmap32, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
             else
-                cubic4_kernel<false, false><<<cg, blk, 0, st>>>(src4, in_img / 4, cw, chh, h->dmap, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
+                cubic4_kernel<false, false><<<cg, blk, 0, st>>>(src4, img_stride / 4, cw, chh, h->dmap, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
             if (h->prof_ev) cudaEventRecord(h->prof_ev[1], st);
             static const bool no_walk = getenv("PANO_NO_RESIZE_WALK") != nullptr;
             if (h->r_mid.walk && !no_walk && (reinterpret_cast<uintptr_t>(final_dst) & 3) == 0 && (o_img & 3) == 0 && ((uw * 3) & 3) == 0)
@@ -807,7 +876,7 @@ int pano_frontend_process_device(pano_frontend_handle h, const uint8_t *argb, ui
 {
     if (!h) return PANO_ERR;
     const pano_frontend_config &c = h->cfg;
-    return pano_frontend_run(h, argb, (size_t)c.cam_src_width * c.cam_src_height * 4, out,
+    return pano_frontend_run(h, argb, (size_t)c.cam_src_width * c.cam_src_height * h->in_px(), out,
                              (size_t)c.out_width * c.out_height * 3, batch, (cudaStream_t)stream);
 }
 
@@ -816,7 +885,7 @@ int pano_frontend_process(pano_frontend_handle h, const uint8_t *argb_host, int 
     if (!h || !argb_host || !out_host) return ffail(h, "pano_frontend_process: bad argument");
     FCK(h, cudaSetDevice(h->cfg.device));
     const pano_frontend_config &c = h->cfg;
-    const size_t in_row = (size_t)c.cam_src_width * 4, out_row = (size_t)c.out_width * 3;
+    const size_t in_row = (size_t)c.cam_src_width * h->in_px(), out_row = (size_t)c.out_width * 3;
     if (stride < (int)in_row || out_stride < (int)out_row) return ffail(h, "stride too small");
     if (!h->stage_in) {
         if (falloc(h, &h->stage_in, in_row * c.cam_src_height) || falloc(h, &h->stage_out, out_row * c.out_height)) return PANO_ERR;

@@ -30,6 +30,8 @@ class CamConfig:
     newK: Optional[Sequence[float]] = None   # getOptimalNewCameraMatrix result; None -> computed via cv2
     device: int = 0
     max_batch: int = 1
+    srcFormat: str = "bgra"     # "bgra": the VIC's 8UC4 output (:889-893); "yuyv": 8UC2 as captured, converted on the
+                                # device like the YUYVCAM build's cv::cvtColor(COLOR_YUV2BGRA_YUYV) (:880-886)
 
 
 def match_camera_entry(cameras_yaml, vendor, sensor, fov, srcsz, undistorsz, sttype="default"):
@@ -75,6 +77,7 @@ class nvCamFrontEnd:
             self._keep = (mx, my)
             fc.mapx = mx.ctypes.data_as(C.POINTER(C.c_float)); fc.mapy = my.ctypes.data_as(C.POINTER(C.c_float))
         fc.device = cfg.device; fc.max_batch = cfg.max_batch
+        fc.src_format = 1 if cfg.srcFormat == "yuyv" else 0
         h = C.c_void_p()
         if self._lib.pano_frontend_create(C.byref(fc), C.byref(h)) != capi.PANO_OK:
             raise capi.PanoError(self._lib.pano_frontend_last_error(None).decode())
@@ -87,7 +90,7 @@ class nvCamFrontEnd:
         return mx, my
 
     def getFrame(self, argb: np.ndarray) -> np.ndarray:
-        """read_frame's pixel pipeline + getFrame(mat, src=false) for one 8UC4 host frame."""
+        """read_frame's pixel pipeline + getFrame(mat, src=false) for one 8UC4 (or 8UC2 YUYV) host frame."""
         argb = np.ascontiguousarray(argb, np.uint8)
         out = np.empty((self.cfg.outPutHeight, self.cfg.outPutWidth, 3), np.uint8)
         capi.check(self._lib.pano_frontend_process(self._h, capi.ptr(argb), argb.strides[0], capi.ptr(out), out.strides[0]),

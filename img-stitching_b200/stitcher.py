@@ -216,7 +216,8 @@ class ocvStitcher:
             raise capi.PanoError("expected %d images" % c.num_images)
         frames = [np.ascontiguousarray(im, np.uint8) for im in imgs]
         front = getattr(self, "_front", None)
-        want = (c.height, c.width, 3) if front is None else (front.cfg.camSrcHeight, front.cfg.camSrcWidth, 4)
+        want = (c.height, c.width, 3) if front is None else (front.cfg.camSrcHeight, front.cfg.camSrcWidth,
+                                                             2 if front.cfg.srcFormat == "yuyv" else 4)
         for f in frames:
             if f.shape != want:
                 raise capi.PanoError("frame must be %dx%dx%d" % want)

@@ -149,8 +149,12 @@ int pano_last_launch_count(pano_handle h);
  * nvCam::read_frame's pixel pipeline (include/nvcam.hpp:898-929): resize(8UC4) -> drop alpha
  * -> remap INTER_CUBIC over initUndistortRectifyMap maps -> crop rect -> resize, followed by
  * getFrame(.., src=false)'s resize to the stitcher input (:1092-1094). */
+#define PANO_SRC_BGRA 0   /* 8UC4: the VIC's ABGR32 output (NvBufferTransform, include/nvcam.hpp:889-893) */
+#define PANO_SRC_YUYV 1   /* 8UC2 YUYV 4:2:2 as captured: the YUYVCAM build converts it with cv::cvtColor(COLOR_YUV2BGRA_YUYV)
+                             (include/nvcam.hpp:880-886); here that conversion runs on the device, so the caller
+                             transfers 2 bytes per pixel instead of 4 */
 typedef struct pano_frontend_config {
-    int cam_src_width, cam_src_height;   /* stCamCfg::camSrcWidth/Height: 8UC4 input */
+    int cam_src_width, cam_src_height;   /* stCamCfg::camSrcWidth/Height: camera frame (8UC4, or 8UC2 with PANO_SRC_YUYV) */
     int undist_width, undist_height;     /* stCamCfg::undistoredWidth/Height */
     int out_width, out_height;           /* stCamCfg::outPutWidth/Height */
     int undistort;                       /* stCamCfg::undistor */
@@ -161,6 +165,7 @@ typedef struct pano_frontend_config {
     const float *mapx, *mapy;            /* optional: caller-supplied m_mapx/m_mapy (undist size) */
     int device;
     int max_batch;
+    int src_format;                      /* PANO_SRC_*; frames are [cam_src_height][cam_src_width][4 or 2] */
 } pano_frontend_config;
 
 int pano_frontend_create(const pano_frontend_config *cfg, pano_frontend_handle *out);
@@ -168,7 +173,7 @@ int pano_frontend_destroy(pano_frontend_handle h);
 const char *pano_frontend_last_error(pano_frontend_handle h);
 /* m_mapx / m_mapy as prepareUndistorMap builds them (include/nvcam.hpp:823-833) */
 int pano_frontend_get_maps(pano_frontend_handle h, float *mapx, float *mapy);
-/* frames: [batch][cam_src_height][cam_src_width][4] -> out [batch][out_height][out_width][3] */
+/* frames: [batch][cam_src_height][cam_src_width][4 (2 for YUYV)] -> out [batch][out_height][out_width][3] */
 int pano_frontend_process_device(pano_frontend_handle h, const uint8_t *argb_dev, uint8_t *out_dev,
                                  int batch, void *stream);
 int pano_frontend_process(pano_frontend_handle h, const uint8_t *argb_host, int stride,

@@ -189,3 +189,24 @@ def seam_mask_tail(seam_lowres, full_mask):
     warped size -> AND with the warped full mask (include/ocvstitcher.hpp:1095-1101, 1251-1257)."""
     up = resize_linear_exact_u8(dilate3x3_u8(seam_lowres), (full_mask.shape[1], full_mask.shape[0]))
     return up & np.asarray(full_mask, np.uint8)
+
+
+def yuyv_to_bgra(yuyv):
+    """cv::cvtColor(mtt, m_argb, cv::COLOR_YUV2BGRA_YUYV) of the YUYVCAM ingest (include/nvcam.hpp:880-886):
+    OpenCV's ITU-R BT.601 conversion in 20-bit fixed point (color_yuv: CY 1220542, CUB 2116026, CUG -409993,
+    CVG -852492, CVR 1673527), alpha 255.  yuyv: [H][W][2] uint8 (Y0 U | Y1 V per pixel pair)."""
+    yuyv = np.asarray(yuyv, np.uint8)
+    Y = yuyv[:, :, 0].astype(np.int64)
+    U = np.repeat(yuyv[:, 0::2, 1], 2, axis=1).astype(np.int64) - 128
+    V = np.repeat(yuyv[:, 1::2, 1], 2, axis=1).astype(np.int64) - 128
+    half = 1 << 19
+    ruv = half + 1673527 * V
+    guv = half - 852492 * V - 409993 * U
+    buv = half + 2116026 * U
+    y = np.maximum(0, Y - 16) * 1220542
+    out = np.empty(yuyv.shape[:2] + (4,), np.uint8)
+    out[..., 0] = np.clip((y + buv) >> 20, 0, 255)
+    out[..., 1] = np.clip((y + guv) >> 20, 0, 255)
+    out[..., 2] = np.clip((y + ruv) >> 20, 0, 255)
+    out[..., 3] = 255
+    return out

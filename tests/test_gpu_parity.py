@@ -546,3 +546,68 @@ def test_ring_epilogue_bit_exact(mode, up, down, fc):
     for b in range(2):
         assert_equal("ring device %d" % b, out[b].cpu().numpy(), want[b])
     rc.close()
+
+
+# ------------------------------------------------------------------ YUYV ingest
+
+def _yuyv_frame(h, w, seed):
+    """Valid 8UC2 YUYV bytes from a synthetic 3-channel frame: Y = channel 0, U / V = channels 1 / 2 of the even pixel."""
+    f = util.synth_frame(h, w, seed, channels=3)
+    y = np.empty((h, w, 2), np.uint8)
+    y[:, :, 0] = f[:, :, 0]
+    y[:, 0::2, 1] = f[:, 0::2, 1]
+    y[:, 1::2, 1] = f[:, 0::2, 2]
+    y[0, :6] = [[0, 0], [0, 0], [255, 255], [255, 255], [0, 255], [255, 0]]
+    return y
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_yuyv_ingest_chained_into_process(fused):
+    """8UC2 YUYV camera frames in (half the bytes of 8UC4): cvtColor(COLOR_YUV2BGRA_YUYV) + nvCam front end + compose as
+    one call, bit-exact with the oracle's sequential restatement (fused=True: the single-gather variant on the
+    converted frames, bit-exact with the oracle gathering through the library's composed maps)."""
+    import copy
+    import torch
+    cam = calib.CAM_LIJING_390_FOV60_1920
+    s = 0.5
+    K = np.array(cam["K"], np.float64).reshape(3, 3).copy()
+    K[0, 0] *= s; K[0, 2] *= s; K[1, 1] *= s; K[1, 2] *= s
+    newK = np.array([[1627.5076 * s, 0, 943.1681 * s], [0, 1622.9720 * s, 571.5369 * s], [0, 0, 1]])
+    rect = [34, 52, 891, 444]
+    CamConfig = panob200.pkg.nvcam.CamConfig
+    fe = panob200.nvCamFrontEnd(CamConfig(camSrcWidth=960, camSrcHeight=540, undistoredWidth=960, undistoredHeight=540,
+                                          outPutWidth=960, outPutHeight=540, K=K.reshape(-1), distorParams=cam["distorParams"],
+                                          rect=rect, newK=newK, max_batch=8, srcFormat="yuyv"))
+    mx, my = fe.maps()
+    sets = [[_yuyv_frame(540, 960, 1200 + 10 * b + i) for i in range(4)] for b in range(2)]
+    bgra = [[compose.yuyv_to_bgra(f) for f in fs] for fs in sets]
+    want_fe = compose.front_end(bgra[0][0], (960, 540), mx, my, rect, (960, 540))
+    assert_equal("yuyv front end alone", fe.getFrame(sets[0][0]), want_fe)
+    Ks, Rs, scale = calib.rig("2222", 960)
+    t = compose.build_tables(Ks, Rs, scale, (960, 540), "spherical")
+    t.blend_masks = util.soft_masks(t)
+    st = panob200.ocvStitcher(SC(width=960, height=540, num_images=4, Ks=Ks, Rs=Rs, warped_image_scale=scale,
+                                 blender="multiband", num_bands=4, max_batch=2))
+    assert st.initTables(t.blend_masks) == 0, st.last_error
+    st.attach_frontend(fe)
+    tt = t
+    if fused:
+        st.set_frontend_mode(True)
+        tt = copy.copy(t)
+        tt.maps = [st.warp_maps(i) for i in range(4)]
+    want = []
+    for fs in bgra:
+        src = [np.ascontiguousarray(f[:, :, :3]) for f in fs] if fused else [compose.front_end(f, (960, 540), mx, my, rect, (960, 540)) for f in fs]
+        want.append(compose.process(tt, src, "multiband", 4))
+    assert_equal("yuyv host call", st.process(sets[0]), want[0])
+    dev = torch.from_numpy(np.stack([np.stack(f) for f in sets])).cuda()
+    ow, oh = st.out_size
+    out = torch.empty((2, oh, ow, 3), dtype=torch.uint8, device="cuda")
+    st.process_device(dev, out)
+    torch.cuda.synchronize()
+    host_in = torch.from_numpy(np.stack([np.stack(f) for f in sets])).pin_memory()
+    host_out = torch.empty((2, oh, ow, 3), dtype=torch.uint8).pin_memory()
+    st.process_batch(host_in, host_out)
+    for b in range(2):
+        assert_equal("yuyv device batch %d" % b, out[b].cpu().numpy(), want[b])
+        assert_equal("yuyv host batch %d" % b, host_out[b].numpy(), want[b])

@@ -192,3 +192,16 @@ def test_seam_mask_tail_vs_cv2_calls():
             eq(compose.resize_linear_exact_u8(m, (dw, dh)), cv2.resize(m, (dw, dh), interpolation=cv2.INTER_LINEAR_EXACT), "linear exact")
             want = cv2.bitwise_and(cv2.resize(cv2.dilate(m, None), (dw, dh), interpolation=cv2.INTER_LINEAR_EXACT), full)
             eq(compose.seam_mask_tail(m, full), want, "seam tail")
+
+
+def test_yuyv_ingest_vs_cv2_cvtcolor():
+    """cv::cvtColor(COLOR_YUV2BGRA_YUYV) (include/nvcam.hpp:880-886): random frames plus a dense sweep of (Y, U, V)."""
+    from oracle import compose
+    rng = np.random.default_rng(0)
+    f = rng.integers(0, 256, (64, 96, 2), np.uint8)
+    eq(compose.yuyv_to_bgra(f), cv2.cvtColor(f, cv2.COLOR_YUV2BGRA_YUYV), "random yuyv")
+    yy, uu, vv = np.meshgrid(np.arange(256), np.arange(0, 256, 3), np.arange(0, 256, 5), indexing="ij")
+    n = yy.size
+    a = np.zeros((1, 2 * n, 2), np.uint8)
+    a[0, 0::2, 0] = yy.ravel(); a[0, 1::2, 0] = 255 - yy.ravel(); a[0, 0::2, 1] = uu.ravel(); a[0, 1::2, 1] = vv.ravel()
+    eq(compose.yuyv_to_bgra(a), cv2.cvtColor(a, cv2.COLOR_YUV2BGRA_YUYV), "yuv sweep")
