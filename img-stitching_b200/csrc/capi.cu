@@ -1158,7 +1158,8 @@ int pano_process_batch(pano_handle h, const uint8_t *frames_host, uint8_t *out_h
     if (ensureStaging(h) || syncTables(h)) return PANO_ERR;
     // small chunks keep the H2D / compute / D2H pipeline full (fill + drain cost one chunk each);
     // the kernels have ample headroom over PCIe, so short waves do not hurt here
-    const int S = std::min(h->cfg.max_batch, 2);
+    static const int chunk = getenv("PANO_HOST_CHUNK") ? std::max(1, atoi(getenv("PANO_HOST_CHUNK"))) : 2;   // tuning knob
+    const int S = std::min(h->cfg.max_batch, chunk);
     h->last_launches = 0;
     const bool prof = h->profiling;
     h->profiling = false;

@@ -9,5 +9,5 @@ CMD="python bench.py --steps 1 --warmup 3 --batch 16 --max-batch 16 --no-cpu-bas
 $CMD > gpurun_out/${TAG}_plain.json 2> gpurun_out/${TAG}_plain.err || { echo "plain run failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
 $CMD > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on \
-    -k regex:"collapse8|warp_tile|pyrdown8|cubic4|resize4" -s 24 -c 10 -o gpurun_out/${TAG}_full $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
+    -k regex:"collapse8|collapse_walk|warp_tile|pyrdown8|cubic5|resize4_walk" -s 34 -c 17 -o gpurun_out/${TAG}_full $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
 ls -la gpurun_out | tail -8
