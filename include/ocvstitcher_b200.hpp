@@ -15,6 +15,9 @@
 #define OCVSTITCHER_B200_HPP
 
 #include <cmath>
+#include <ctime>
+#include <fstream>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -112,6 +115,13 @@ public:
         return RET_OK;
     }
 
+    // chain a front end: process() then takes the camera frames themselves (getFrame x N + process, src/master.cpp:300-318)
+    int attachFrontEnd(pano_frontend_handle f)
+    {
+        if (!h_ || pano_attach_frontend(h_, -1, f) != PANO_OK) { err_ = h_ ? pano_last_error(h_) : "calibration() first"; return RET_ERR; }
+        return RET_OK;
+    }
+
     int outWidth() const { int wh[2] = {0, 0}; pano_get_geometry(h_, nullptr, nullptr, nullptr, wh); return wh[0]; }
     int outHeight() const { int wh[2] = {0, 0}; pano_get_geometry(h_, nullptr, nullptr, nullptr, wh); return wh[1]; }
     pano_handle handle() const { return h_; }
@@ -120,6 +130,149 @@ public:
 private:
     StitcherParams p_;
     pano_handle h_ = nullptr;
+    std::string err_;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Calibration-file persistence (include/ocvstitcher.hpp:452-562): cameraparaout_<id>.txt holds blocks of
+//   <%F-%H-%M-%S>:            one line containing ':'
+//   k00,...,k22,r00,...,r22,  one line of 18 floats per camera
+//   <warped_image_scale>
+// initCamParams reads the LAST block; saveCameraParams appends one.
+inline int loadCameraParams(const std::string &cfgPath, int id, int num_images, StitcherParams &p, std::string *err = nullptr)
+{
+    const std::string filename = cfgPath + "cameraparaout_" + std::to_string(id) + ".txt";
+    std::ifstream fin(filename);
+    auto fail = [&](const char *m) { if (err) *err = std::string(m) + " (" + filename + ")"; return RET_ERR; };
+    if (!fin.is_open()) return fail("can not open camerapara file, no preset parameters found");
+    std::vector<std::string> lines;
+    for (std::string l; std::getline(fin, l);) {
+        while (!l.empty() && (l.back() == '\r' || l.back() == ' ')) l.pop_back();
+        if (!l.empty()) lines.push_back(l);
+    }
+    int last = -1;
+    for (size_t i = 0; i < lines.size(); ++i)
+        if (lines[i].find(':') != std::string::npos) last = (int)i;
+    if (last < 0) return fail("no preset parameters found");
+    if ((int)lines.size() < last + 2 + num_images) return fail("camera preset parameter block incomplete");
+    p.K.assign(9 * num_images, 0.f); p.R.assign(9 * num_images, 0.f);
+    for (int i = 0; i < num_images; ++i) {
+        std::vector<float> v;
+        std::stringstream ss(lines[last + 1 + i]);
+        for (std::string tok; std::getline(ss, tok, ',');)
+            if (!tok.empty()) v.push_back(std::stof(tok));
+        if (v.size() != 18) return fail("camera preset parameter incorrect");                     // :497-501
+        for (int k = 0; k < 9; ++k) { p.K[9 * i + k] = v[k]; p.R[9 * i + k] = v[9 + k]; }
+    }
+    p.warped_image_scale = std::stof(lines[last + 1 + num_images]);
+    p.num_images = num_images;
+    return RET_OK;
+}
+
+inline int saveCameraParams(const std::string &cfgPath, int id, const StitcherParams &p)
+{
+    const std::string filename = cfgPath + "cameraparaout_" + std::to_string(id) + ".txt";
+    std::ofstream fout(filename, std::ofstream::out | std::ofstream::app);
+    if (!fout.is_open()) return RET_ERR;
+    const std::time_t tt = std::time(nullptr);
+    char stamp[64];
+    std::strftime(stamp, sizeof stamp, "%F-%H-%M-%S", std::localtime(&tt));
+    fout << stamp << ":\n";
+    for (int i = 0; i < p.num_images; ++i) {
+        for (int k = 0; k < 9; ++k) fout << p.K[9 * i + k] << ",";
+        for (int k = 0; k < 9; ++k) fout << p.R[9 * i + k] << ",";
+        fout << "\n";
+    }
+    fout << p.warped_image_scale << "\n";
+    return RET_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// nvCam's pixel pipeline (include/nvcam.hpp:898-929 + getFrame(mat, false) :1092-1094) behind the reference's
+// getFrame name; capture itself (V4L2 / NvBuffer) stays with the application, which hands the camera frame in.
+struct CamParams {               // stCamCfg (include/stitcherglobal.h:39-55) + the matched cameras.yaml entry
+    int camSrcWidth = 1920, camSrcHeight = 1080, undistoredWidth = 1920, undistoredHeight = 1080;
+    int outPutWidth = 1920, outPutHeight = 1080;
+    bool undistor = true;
+    double K[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, distorParams[4] = {0, 0, 0, 0};
+    double newK[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};   // getOptimalNewCameraMatrix(K, D, size, 1, size, 0)  (:831, host, OpenCV)
+    int rect[4] = {0, 0, 0, 0};
+    bool yuyv = false;           // 8UC2 YUYV frames (the YUYVCAM build, :880-886) instead of the VIC's 8UC4
+    int device = 0, max_batch = 1;
+};
+
+class nvCamFrontEnd {
+public:
+    nvCamFrontEnd() = default;
+    nvCamFrontEnd(const nvCamFrontEnd &) = delete;
+    nvCamFrontEnd &operator=(const nvCamFrontEnd &) = delete;
+    ~nvCamFrontEnd() { pano_frontend_destroy(h_); }
+    int init(const CamParams &c)
+    {
+        pano_frontend_config f{};
+        f.cam_src_width = c.camSrcWidth; f.cam_src_height = c.camSrcHeight;
+        f.undist_width = c.undistoredWidth; f.undist_height = c.undistoredHeight;
+        f.out_width = c.outPutWidth; f.out_height = c.outPutHeight;
+        f.undistort = c.undistor ? 1 : 0;
+        for (int k = 0; k < 9; ++k) { f.K[k] = c.K[k]; f.newK[k] = c.newK[k]; }
+        for (int k = 0; k < 4; ++k) { f.D[k] = c.distorParams[k]; f.rect[k] = c.rect[k]; }
+        f.device = c.device; f.max_batch = c.max_batch;
+        f.src_format = c.yuyv ? PANO_SRC_YUYV : PANO_SRC_BGRA;
+        pano_frontend_destroy(h_);
+        h_ = nullptr;
+        if (pano_frontend_create(&f, &h_) != PANO_OK) { err_ = pano_frontend_last_error(nullptr); return RET_ERR; }
+        return RET_OK;
+    }
+    // getFrame(frame, src=false): camera frame in (8UC4, or 8UC2 when yuyv), stitcher input (8UC3) out
+    int getFrame(const Image &camFrame, Image &out)
+    {
+        if (!h_) return RET_ERR;
+        if (pano_frontend_process(h_, camFrame.data, camFrame.step, out.data, out.step) != PANO_OK) {
+            err_ = pano_frontend_last_error(h_);
+            return RET_ERR;
+        }
+        return RET_OK;
+    }
+    pano_frontend_handle handle() const { return h_; }
+    const std::string &lastError() const { return err_; }
+
+private:
+    pano_frontend_handle h_ = nullptr;
+    std::string err_;
+};
+
+// The two-ring caller step after the two process calls (src/master.cpp:321-326; crop variant src/panocamimpl.cpp:354-360)
+class RingComposer {
+public:
+    RingComposer() = default;
+    RingComposer(const RingComposer &) = delete;
+    RingComposer &operator=(const RingComposer &) = delete;
+    ~RingComposer() { pano_ring_destroy(h_); }
+    int init(int upW, int upH, int downW, int downH, int mode = PANO_RING_RESIZE, int finalcut = 0, int bar = -1, int device = 0)
+    {
+        pano_ring_config c{};
+        c.up_width = upW; c.up_height = upH; c.down_width = downW; c.down_height = downH;
+        c.mode = mode; c.finalcut = finalcut; c.bar = bar >= 0 ? bar : (mode == PANO_RING_RESIZE ? 10 : 4); c.device = device;
+        pano_ring_destroy(h_);
+        h_ = nullptr;
+        if (pano_ring_create(&c, &h_) != PANO_OK) { err_ = pano_ring_last_error(nullptr); return RET_ERR; }
+        return RET_OK;
+    }
+    int outWidth() const { int wh[2] = {0, 0}; pano_ring_out_size(h_, wh); return wh[0]; }
+    int outHeight() const { int wh[2] = {0, 0}; pano_ring_out_size(h_, wh); return wh[1]; }
+    int compose(const Image &up, const Image &down, Image &ret)
+    {
+        if (!h_) return RET_ERR;
+        if (pano_ring_compose(h_, up.data, up.step, down.data, down.step, ret.data, ret.step) != PANO_OK) {
+            err_ = pano_ring_last_error(h_);
+            return RET_ERR;
+        }
+        return RET_OK;
+    }
+    const std::string &lastError() const { return err_; }
+
+private:
+    pano_ring_handle h_ = nullptr;
     std::string err_;
 };
 
