@@ -27,6 +27,7 @@ void pano_frontend_sizes(pano_frontend_handle h, int *in_wh, int *out_wh);
 bool pano_frontend_set_prof(pano_frontend_handle h, cudaEvent_t *ev, double *cubic_bytes, double *resize_bytes);
 void pano_frontend_backmap(pano_frontend_handle h, double *xs, double *ys, size_t count);
 int pano_frontend_in_px(pano_frontend_handle h);
+bool pano_frontend_is_mixed(pano_frontend_handle h);
 int pano_frontend_convert(pano_frontend_handle h, const uint8_t *yuyv, size_t in_img, uint8_t *dst, int count, cudaStream_t st);
 
 namespace {
@@ -545,10 +546,17 @@ int runFrontEnds(pano_ctx *h, const uint8_t *&frames_dev, int slots, cudaStream_
             } else {
                 cudaEventDestroy(ev[3]);
             }
-            ProfEntry a{"fe_cubic_undistort", ev[0], ev[1], cb * slots * h->n, yuyv};
-            h->prof.push_back(a);
-            ProfEntry b{"fe_resize", ev[1], ev[2], rb * slots * h->n, true};   // shares the middle event
-            h->prof.push_back(b);
+            if (pano_frontend_is_mixed(h->front[0])) {
+                // cubic + resize run as horizontally fused launches: one entry, both kernels' algorithmic bytes
+                ProfEntry a{"fe_undistort_resize", ev[0], ev[2], (cb + rb) * slots * h->n, yuyv};
+                h->prof.push_back(a);
+                cudaEventDestroy(ev[1]);
+            } else {
+                ProfEntry a{"fe_cubic_undistort", ev[0], ev[1], cb * slots * h->n, yuyv};
+                h->prof.push_back(a);
+                ProfEntry b{"fe_resize", ev[1], ev[2], rb * slots * h->n, true};   // shares the middle event
+                h->prof.push_back(b);
+            }
             h->last_launches += pano_frontend_launches(h->front[0]);
             frames_dev = h->front_out;
             return PANO_OK;

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -255,18 +256,27 @@ __global__ void __launch_bounds__(256) cubic4_kernel(const uint32_t *__restrict_
 //  * Rounding is folded into the accumulator start value; saturate + pack is two cvt.pack instructions.
 constexpr int kCubTileW = 64, kCubTileH = 16, kCubSmemWords = 3072;    // 12 KB
 
-__global__ void __launch_bounds__(256) cubic5_kernel(const uint32_t *__restrict__ src, size_t src_img_words, int sw, int sh,
-                                                     const uint32_t *__restrict__ map, int map_w, cudaTextureObject_t wtex,
-                                                     const int4 *__restrict__ tiles, int rx, int ry, int rw, int rh,
-                                                     uint32_t *__restrict__ dst, size_t dst_img_words)
+struct CubicArgs {
+    const uint32_t *src; size_t src_img_words; int sw, sh;
+    const uint32_t *map; int map_w; cudaTextureObject_t wtex; const int4 *tiles;
+    int rx, ry, rw, rh;
+    uint32_t *dst; size_t dst_img_words;
+    int tx, ty;                      // tiles per image row / column (logical grid = tx x ty x images)
+};
+
+// one 256-thread block = tile (bx, by) of image bz; sm = kCubSmemWords words of shared memory
+__device__ __forceinline__ void cubic5_body(const CubicArgs &A, uint32_t *__restrict__ sm, int bx, int by, int bz)
 {
-    __shared__ __align__(16) uint32_t sm[kCubSmemWords];
+    const uint32_t *__restrict__ src = A.src, *__restrict__ map = A.map;
+    const int sw = A.sw, sh = A.sh, map_w = A.map_w, rx = A.rx, ry = A.ry, rw = A.rw, rh = A.rh;
+    const cudaTextureObject_t wtex = A.wtex;
+    uint32_t *__restrict__ dst = A.dst;
     const int lane = threadIdx.x, wy = threadIdx.y, tid = wy * 32 + lane;
-    const int4 td = __ldg(tiles + blockIdx.y * gridDim.x + blockIdx.x);   // {x0 (%4 == 0), y0, rows | chunks per row << 16, 2^16 / chunks}
+    const int4 td = __ldg(A.tiles + by * A.tx + bx);   // {x0 (%4 == 0), y0, rows | chunks per row << 16, 2^16 / chunks}
     const int rows = td.z & 0xffff, W4 = td.z >> 16;
     const int P = (W4 * 4 + 31) & ~31;                                  // staged row pitch, words
-    const int y = blockIdx.y * kCubTileH + wy, xb = blockIdx.x * kCubTileW + lane;
-    const uint32_t *s = src + (size_t)blockIdx.z * src_img_words;
+    const int y = by * kCubTileH + wy, xb = bx * kCubTileW + lane;
+    const uint32_t *s = src + (size_t)bz * A.src_img_words;
     uint32_t m[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -281,7 +291,7 @@ __global__ void __launch_bounds__(256) cubic5_kernel(const uint32_t *__restrict_
         *reinterpret_cast<uint4 *>(sm + r * P + 4 * q) = v;
     }
     __syncthreads();
-    uint32_t *d = dst + (size_t)blockIdx.z * dst_img_words + (size_t)y * rw + xb;
+    uint32_t *d = dst + (size_t)bz * A.dst_img_words + (size_t)y * rw + xb;
     const int sbase = -((td.y + 4) * P + td.x + 4);                     // the map stores tx + 4, ty + 4
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -309,6 +319,12 @@ __global__ void __launch_bounds__(256) cubic5_kernel(const uint32_t *__restrict_
         asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(px) : "r"(a1 >> 15), "r"(a0 >> 15), "r"(hi));
         d[32 * (j & 1) + (size_t)(8 * (j >> 1)) * rw] = px;
     }
+}
+
+__global__ void __launch_bounds__(256) cubic5_kernel(const __grid_constant__ CubicArgs A)
+{
+    __shared__ __align__(16) uint32_t sm[kCubSmemWords];
+    cubic5_body(A, sm, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
 // cv::resize INTER_LINEAR from a word-per-pixel source to packed BGR bytes.  One warp row-chunk =
@@ -382,15 +398,30 @@ constexpr int kResizeBand = 24;      // virtual source rows per block
 constexpr int kResizeRows = 64;      // most output rows one band may produce (row coefficients live in shared memory)
 
 // requires: dw % 32 == 0, dst rows 4-byte aligned, <= kResizeRows output rows per band (checked at launch)
-__global__ void __launch_bounds__(128, 8) resize4_walk_kernel(const uint32_t *__restrict__ src, size_t src_img_words,
-                                                              unsigned sstride_words, uint8_t *__restrict__ dst, size_t dst_img,
-                                                              unsigned dstride, ResizeTab t)
+struct ResizeArgs {
+    const uint32_t *src; size_t src_img_words; unsigned sstride_words;
+    uint8_t *dst; size_t dst_img; unsigned dstride;
+    ResizeTab t;
+    int gx, gy;                      // logical grid of 128-thread blocks = gx x gy x images
+};
+constexpr int kResizeSmemWords = kResizeBand + 1 + kResizeRows;
+
+// one 128-thread block (4 warps: wy = 0..3) = column group bx, band by of image bz.  kBar = 0: the block is a whole
+// CUDA block (__syncthreads); kBar > 0: it is one of several 128-thread sub-blocks of a larger block and
+// synchronises on named barrier kBar (a compile-time id: a run-time id makes ptxas reserve all 16 barriers).
+template <int kBar>
+__device__ __forceinline__ void resize4_walk_body(const ResizeArgs &A, uint32_t *__restrict__ smem, int bx, int by, int bz, int wy)
 {
-    __shared__ int s_yb[kResizeBand + 1];
-    __shared__ uint32_t s_ay[kResizeRows];
-    const int lane = threadIdx.x, tid = threadIdx.y * 32 + lane;
+    const uint32_t *__restrict__ src = A.src;
+    uint8_t *__restrict__ dst = A.dst;
+    const size_t src_img_words = A.src_img_words, dst_img = A.dst_img;
+    const unsigned sstride_words = A.sstride_words, dstride = A.dstride;
+    const ResizeTab &t = A.t;
+    int *s_yb = reinterpret_cast<int *>(smem);
+    uint32_t *s_ay = smem + kResizeBand + 1;
+    const int lane = threadIdx.x, tid = wy * 32 + lane;
     const int sh = t.sh;
-    const int v0 = (int)blockIdx.y * kResizeBand - 1;                  // v runs over [-1, sh - 1]
+    const int v0 = by * kResizeBand - 1;                               // v runs over [-1, sh - 1]
     const int nv = min(kResizeBand, sh - v0);
     const int ybase = __ldg(t.ybeg + v0 + 1);
     if (tid <= nv) s_yb[tid] = __ldg(t.ybeg + v0 + 1 + tid);           // first output row of virtual row v0 + tid
@@ -398,19 +429,20 @@ __global__ void __launch_bounds__(128, 8) resize4_walk_kernel(const uint32_t *__
         const short2 q = __ldg(t.ya + min(ybase + tid - 64, t.dh - 1));
         s_ay[tid - 64] = ((uint32_t)(uint16_t)q.y << 16) | (uint16_t)q.x;
     }
-    __syncthreads();
-    const int xw = (blockIdx.x * blockDim.y + threadIdx.y) * 32;       // first column of this warp
+    if (kBar > 0) asm volatile("bar.sync %0, 128;" ::"n"(kBar) : "memory");
+    else __syncthreads();
+    const int xw = (bx * 4 + wy) * 32;                                  // first column of this warp
     if (xw >= t.dw) return;
     const int x = xw + lane;
     const unsigned xo = __ldg(t.xofs + x), x1 = min(xo + 1u, (unsigned)t.sw - 1u);
     const short2 ax = __ldg(t.xa + x);
     const int axp = (int)(((uint32_t)(uint16_t)ax.y << 16) | (uint16_t)ax.x);
-    const uint32_t *s0 = src + (size_t)blockIdx.z * src_img_words + xo;
-    const uint32_t *s1 = src + (size_t)blockIdx.z * src_img_words + x1;
+    const uint32_t *s0 = src + (size_t)bz * src_img_words + xo;
+    const uint32_t *s1 = src + (size_t)bz * src_img_words + x1;
     const int j = lane & 3;
     const uint32_t sel = j == 0 ? 0x4210u : (j == 1 ? 0x5421u : 0x6542u);
     // lanes 4k..4k+2 store the three words of pixels 4k..4k+3; lane 4k+3 stores nothing
-    uint8_t *olane = dst + (size_t)blockIdx.z * dst_img + (size_t)ybase * dstride + (size_t)xw * 3 + ((lane >> 2) * 3 + j) * 4;
+    uint8_t *olane = dst + (size_t)bz * dst_img + (size_t)ybase * dstride + (size_t)xw * 3 + ((lane >> 2) * 3 + j) * 4;
     const uint32_t *ayp = s_ay;
     const unsigned sstride_bytes = sstride_words * 4u;
 
@@ -459,6 +491,46 @@ __global__ void __launch_bounds__(128, 8) resize4_walk_kernel(const uint32_t *__
 #undef RS_FETCH
 }
 
+__global__ void __launch_bounds__(128, 8) resize4_walk_kernel(const __grid_constant__ ResizeArgs A)
+{
+    __shared__ uint32_t smem[kResizeSmemWords];
+    resize4_walk_body<0>(A, smem, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.y);
+}
+
+// EXPERIMENT (PANO_FE_MIXED=1; off by default): horizontal fusion of the two front-end kernels.  cubic5 saturates the
+// L1 data pipes (LSU 84 %, TEX 81 %) at 64 % issue utilisation; resize4_walk saturates the issue slots (76 %) at 34 % L1
+// utilisation, so ONE launch carrying cubic tiles of image chunk k and resize bands of chunk k-1, interleaved in
+// block-index order (nc cubic blocks, then nr blocks that each hold two 128-thread resize sub-blocks on named barriers),
+// keeps both kinds co-resident on every SM.  Bit-identical output (same device code), but MEASURED SLOWER: 0.976 ms per
+// wave against 0.85 ms back to back -- the mix is issue-bound at 74.5 % (ncu) and executes 21 % more instructions than
+// the two kernels apart, so the idle L1 / issue capacity it was meant to use does not exist in practice.
+struct MixArgs {
+    CubicArgs c; ResizeArgs r;
+    int c_imgs, r_imgs;              // images per role in this launch (0 = role absent)
+    int nc, nr;                      // interleave pattern
+};
+
+__global__ void __launch_bounds__(256, 6) undistort_resize_mixed_kernel(const __grid_constant__ MixArgs M)
+{
+    __shared__ __align__(16) uint32_t sm[kCubSmemWords];
+    static_assert(2 * kResizeSmemWords <= kCubSmemWords, "resize sub-blocks share the cubic staging buffer");
+    const int period = M.nc + M.nr;
+    const int g = blockIdx.x / period, k = blockIdx.x - g * period;
+    if (k < M.nc) {
+        const int ci = g * M.nc + k, per_img = M.c.tx * M.c.ty;
+        if (ci >= per_img * M.c_imgs) return;
+        const int bz = ci / per_img, rem = ci - bz * per_img;
+        cubic5_body(M.c, sm, rem % M.c.tx, rem / M.c.tx, bz);
+    } else {
+        const int sub = threadIdx.y >> 2;
+        const int ri = (g * M.nr + (k - M.nc)) * 2 + sub, per_img = M.r.gx * M.r.gy;
+        if (ri >= per_img * M.r_imgs) return;
+        const int bz = ri / per_img, rem = ri - bz * per_img;
+        if (sub == 0) resize4_walk_body<1>(M.r, sm, rem % M.r.gx, rem / M.r.gx, bz, threadIdx.y & 3);
+        else resize4_walk_body<2>(M.r, sm + kResizeSmemWords, rem % M.r.gx, rem / M.r.gx, bz, threadIdx.y & 3);
+    }
+}
+
 thread_local std::string g_front_error;
 
 }  // namespace
@@ -477,6 +549,7 @@ struct pano_frontend_ctx {
     uint32_t *buf_w = nullptr;                                     // cropped undistorted image, one word per pixel (fast path)
     uint32_t *dmap32 = nullptr;                                    // packed map entries (fast path, sources <= 2043 px)
     bool fast4 = false;
+    bool mixed = getenv("PANO_FE_MIXED") != nullptr;              // experiment: cubic + resize as horizontally fused launches (measured slower, off)
     int4 *cub_tiles = nullptr;                                     // per 128x8 tile of the crop rect: staged footprint (cubic5_kernel)
     int cub_tx = 0, cub_ty = 0;
     cudaEvent_t *prof_ev = nullptr;                                // events when profiling: before cubic, between, after resize, [3] before the YUYV conversion
@@ -743,14 +816,47 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
             const int *rc = c.rect;
             const size_t w_img = (size_t)rc[2] * rc[3];
             const dim3 cg((rc[2] + 127) / 128, (rc[3] + 7) / 8, nb);
-            if (h->prof_ev) cudaEventRecord(h->prof_ev[0], st);
             static const bool tex_w = getenv("PANO_CUBIC_TEX") != nullptr;
+            static const bool no_tiled = getenv("PANO_CUBIC_UNTILED") != nullptr;
+            static const bool no_walk = getenv("PANO_NO_RESIZE_WALK") != nullptr;
             const uint32_t *src4 = reinterpret_cast<const uint32_t *>(src);
             const uint4 *tab4 = reinterpret_cast<const uint4 *>(h->dtab);
-            static const bool no_tiled = getenv("PANO_CUBIC_UNTILED") != nullptr;
-            if (h->cub_tiles && h->wtex && !no_tiled)
-                cubic5_kernel<<<dim3(h->cub_tx, h->cub_ty, nb), blk, 0, st>>>(src4, img_stride / 4, cw, chh, h->dmap32, uw, h->wtex, h->cub_tiles,
-                                                                             rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
+            const bool tiled = h->cub_tiles && h->wtex && !no_tiled;
+            const bool walk = h->r_mid.walk && !no_walk && (reinterpret_cast<uintptr_t>(final_dst) & 3) == 0 && (o_img & 3) == 0 && ((uw * 3) & 3) == 0;
+            CubicArgs ca{src4, img_stride / 4, cw, chh, h->dmap32, uw, h->wtex, h->cub_tiles, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img,
+                         h->cub_tx, h->cub_ty};
+            ResizeArgs ra{h->buf_w, w_img, (unsigned)rc[2], final_dst, o_img, (unsigned)(uw * 3), h->r_mid,
+                          (uw + 127) / 128, (rc[3] + 1 + kResizeBand - 1) / kResizeBand};
+            if (tiled && walk && h->mixed) {
+                // horizontally fused launches: cubic(chunk k) + resize(chunk k - 1), k = 0 .. K
+                if (h->prof_ev) cudaEventRecord(h->prof_ev[0], st);
+                const int C = std::max(1, (nb + 3) / 4), K = (nb + C - 1) / C;
+                const int cper = ca.tx * ca.ty, rper = ra.gx * ra.gy;
+                const int nr_mix = 2, nc_mix = std::max(1, (int)std::lround(2.0 * nr_mix * cper / std::max(1, rper)));
+                for (int k = 0; k <= K; ++k) {
+                    MixArgs M{};
+                    M.c = ca; M.r = ra;
+                    M.c_imgs = k < K ? std::min(C, nb - k * C) : 0;
+                    M.r_imgs = k >= 1 ? std::min(C, nb - (k - 1) * C) : 0;
+                    M.c.src = src4 + (size_t)k * C * (img_stride / 4);
+                    M.c.dst = h->buf_w + (size_t)k * C * w_img;
+                    if (k >= 1) {
+                        M.r.src = h->buf_w + (size_t)(k - 1) * C * w_img;
+                        M.r.dst = final_dst + (size_t)(k - 1) * C * o_img;
+                    }
+                    M.nc = M.c_imgs ? (M.r_imgs ? nc_mix : 1) : 0;
+                    M.nr = M.r_imgs ? (M.c_imgs ? nr_mix : 1) : 0;
+                    const long long cb = (long long)cper * M.c_imgs, rb = ((long long)rper * M.r_imgs + 1) / 2;
+                    const long long groups = std::max(M.nc ? (cb + M.nc - 1) / M.nc : 0, M.nr ? (rb + M.nr - 1) / M.nr : 0);
+                    undistort_resize_mixed_kernel<<<(unsigned)(groups * (M.nc + M.nr)), blk, 0, st>>>(M);
+                }
+                if (h->prof_ev) { cudaEventRecord(h->prof_ev[1], st); cudaEventRecord(h->prof_ev[2], st); }
+                h->launches += K + 1;
+                continue;
+            }
+            if (h->prof_ev) cudaEventRecord(h->prof_ev[0], st);
+            if (tiled)
+                cubic5_kernel<<<dim3(h->cub_tx, h->cub_ty, nb), blk, 0, st>>>(ca);
             else if (h->dmap32 && tex_w)
                 cubic4_kernel<true, true><<<cg, blk, 0, st>>>(src4, img_stride / 4, cw, chh, h->dmap32, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
             else if (h->dmap32)
@@ -758,10 +864,8 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
             else
                 cubic4_kernel<false, false><<<cg, blk, 0, st>>>(src4, img_stride / 4, cw, chh, h->dmap, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
             if (h->prof_ev) cudaEventRecord(h->prof_ev[1], st);
-            static const bool no_walk = getenv("PANO_NO_RESIZE_WALK") != nullptr;
-            if (h->r_mid.walk && !no_walk && (reinterpret_cast<uintptr_t>(final_dst) & 3) == 0 && (o_img & 3) == 0 && ((uw * 3) & 3) == 0)
-                resize4_walk_kernel<<<dim3((uw + 127) / 128, (rc[3] + 1 + kResizeBand - 1) / kResizeBand, nb), dim3(32, 4), 0, st>>>(
-                    h->buf_w, w_img, rc[2], final_dst, o_img, uw * 3, h->r_mid);
+            if (walk)
+                resize4_walk_kernel<<<dim3(ra.gx, ra.gy, nb), dim3(32, 4), 0, st>>>(ra);
             else
                 resize4_kernel<<<dim3((uw + 127) / 128, (uh + 7) / 8, nb), blk, 0, st>>>(h->buf_w, w_img, rc[2], final_dst, o_img,
                                                                                          uw * 3, h->r_mid);
@@ -854,6 +958,11 @@ void pano_frontend_backmap(pano_frontend_handle h, double *xs, double *ys, size_
 
 int pano_frontend_launches(pano_frontend_handle h) { return h ? h->launches : 0; }
 // fast path only, one chunk per call: record events around the two kernels; returns their algorithmic bytes per image
+// true when the fast path runs cubic + resize as horizontally fused launches: the profile then has ONE entry for both
+bool pano_frontend_is_mixed(pano_frontend_handle h)
+{
+    return h && h->fast4 && h->mixed && h->cub_tiles && h->wtex && h->r_mid.walk && !getenv("PANO_CUBIC_UNTILED") && !getenv("PANO_NO_RESIZE_WALK");
+}
 bool pano_frontend_set_prof(pano_frontend_handle h, cudaEvent_t *ev, double *cubic_bytes, double *resize_bytes)
 {
     h->prof_ev = ev;
