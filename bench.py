@@ -230,6 +230,12 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner to fd 1) are pointed at
+    # stderr until the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import panob200
@@ -404,7 +410,11 @@ def main():
                 "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
         if variant is not None:
             line["variant"] = variant
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
