@@ -217,7 +217,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="frame-sets per GPU per step")
-    ap.add_argument("--max-batch", type=int, default=16, help="frame-sets per launch wave")
+    ap.add_argument("--max-batch", type=int, default=64, help="frame-sets per launch wave (workspace: 73 MB per slot)")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
@@ -387,7 +387,8 @@ def main():
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(dom)
+                per_set = json.load(open(tp)).get(dom)      # ncu DRAM bytes per frame-set
+                traffic = per_set * min(B, args.max_batch) if per_set is not None else None
             except Exception:
                 traffic = None
         roof = {"bound": "hbm", "kernel": dom, "achieved": d["bytes"] / d["ms"] / 1e6, "peak": peak, "peak_source": peak_src,
@@ -403,7 +404,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8/s16 fixed-point + f32 weights", "data": "synthetic",
-                "config": {"workload": WORKLOADS[args.workload], "frame_sets_per_gpu_per_step": B, "frame_sets_per_wave": args.max_batch,
+                "config": {"workload": WORKLOADS[args.workload], "frame_sets_per_gpu_per_step": B, "frame_sets_per_wave": min(B, args.max_batch),
                            "masks": masks_how, "l2": "inputs (1.6 GB/step) larger than L2; no flush"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_in.numel()),
                         "d2h_bytes_per_step": int(host_out.numel()), "steps": e2e_steps, "matches_device_path": same},
