@@ -273,6 +273,44 @@ def test_error_behaviour():
         st.process([np.zeros((100, 240, 3), np.uint8)] * 4)
 
 
+def test_error_behaviour_of_the_widened_entry_points():
+    """Every new entry point returns PANO_ERR with a message instead of crashing on bad input."""
+    import ctypes as C
+    capi = panob200.capi
+    lib = capi.lib()
+    Ks, Rs, scale = calib.rig("2222", 240)
+    st = make(Ks, Rs, scale, 240, 135, num_bands=3)
+    assert st.initTables() == 0
+    with pytest.raises(panob200.PanoError, match="attach a front end first"):
+        st.set_frontend_mode(True)                                   # fused mode needs a front end
+    st.set_frontend_mode(False)                                      # no-op without one
+    with pytest.raises(panob200.PanoError):
+        st.set_seam_mask(7, np.zeros((4, 4), np.uint8))              # bad camera index
+    assert lib.pano_set_seam_mask(st._h, 0, None, 4, 4, 4) == capi.PANO_ERR
+    assert lib.pano_get_weight_level(st._h, 0, 9, capi.ptr(np.zeros(4, np.float32))) == capi.PANO_ERR   # level > num_bands
+    assert lib.pano_get_mask(st._h, 0, capi.ptr(np.zeros(4, np.uint8)), 1) == capi.PANO_ERR              # stride < width
+    # front end: odd YUYV width, bad format; wrong frame size at attach
+    CamConfig = panob200.pkg.nvcam.CamConfig
+    with pytest.raises(panob200.PanoError, match="even width"):
+        panob200.nvCamFrontEnd(CamConfig(camSrcWidth=241, camSrcHeight=135, undistoredWidth=241, undistoredHeight=135,
+                                         outPutWidth=240, outPutHeight=135, undistor=False, srcFormat="yuyv"))
+    fe = panob200.nvCamFrontEnd(CamConfig(camSrcWidth=320, camSrcHeight=180, undistoredWidth=320, undistoredHeight=180,
+                                          outPutWidth=320, outPutHeight=180, undistor=False))
+    with pytest.raises(panob200.PanoError, match="delivers 320x180"):
+        st.attach_frontend(fe)
+    # ring epilogue
+    rc = capi.pano_ring_config()
+    rc.up_width, rc.up_height, rc.down_width, rc.down_height, rc.mode, rc.finalcut, rc.bar = 100, 20, 90, 24, 1, 10, 4
+    h = C.c_void_p()
+    assert lib.pano_ring_create(C.byref(rc), C.byref(h)) == capi.PANO_ERR and b"finalcut" in lib.pano_ring_last_error(None)
+    rc.mode = 5
+    assert lib.pano_ring_create(C.byref(rc), C.byref(h)) == capi.PANO_ERR
+    r = panob200.RingComposer((100, 20), (90, 24), "resize")
+    with pytest.raises(panob200.PanoError, match="stride"):
+        r._check(lib.pano_ring_compose(r._h, capi.ptr(np.zeros((20, 100, 3), np.uint8)), 10, capi.ptr(np.zeros((24, 90, 3), np.uint8)), 270,
+                                       capi.ptr(np.zeros((48, 90, 3), np.uint8)), 270))
+
+
 # ------------------------------------------------------------------ BASELINE full sizes
 
 def test_config1_full_size_vs_oracle_and_properties():
