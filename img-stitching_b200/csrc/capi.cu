@@ -92,6 +92,15 @@ struct pano_ctx {
     std::vector<void *> cam_mask0, cam_gain;      // per camera, re-uploadable
     std::vector<std::vector<void *>> cam_wt;      // per camera per level
 
+    // peer-memory halo exchange (pano_strip_p2p_*): own mailbox (flags + halo slots), the neighbours' mapped mailboxes
+    uint8_t *mailbox = nullptr;
+    size_t mailbox_bytes = 0;
+    std::vector<size_t> mail_off;                 // [phase][from-side][parity] -> byte offset of the slot
+    uint8_t *peer_mail[2] = {nullptr, nullptr};   // left / right neighbour's mailbox as addressable from this device
+    bool peer_ipc[2] = {false, false};            // mapped with cudaIpcOpenMemHandle (to be closed)
+    unsigned *p2p_counters = nullptr;             // block-completion counters of halo_push_kernel
+    uint32_t p2p_seq = 0;                         // frame sequence number
+
     // staging for host entry points
     uint8_t *stage_in[kPipeDepth] = {};
     uint8_t *stage_out[kPipeDepth] = {};
@@ -818,6 +827,8 @@ int pano_destroy(pano_handle h)
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     clearProf(h);
+    for (int s = 0; s < 2; ++s)
+        if (h->peer_mail[s] && h->peer_ipc[s]) cudaIpcCloseMemHandle(h->peer_mail[s]);
     for (void *p : h->owned) cudaFree(p);
     for (int i = 0; i < kPipeDepth; ++i) {
         if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
@@ -1259,6 +1270,161 @@ int pano_strip_halo_pack(pano_handle h, int phase, int side, void *buf_dev, void
 int pano_strip_halo_unpack(pano_handle h, int phase, int side, const void *buf_dev, void *stream)
 {
     return haloCopy(h, phase, side, const_cast<void *>(buf_dev), stream, true);
+}
+
+// ---- peer-memory halo exchange ----
+namespace {
+constexpr size_t kMailFlagBytes = 1024;          // flag words: [phase][from-side] uint32, phases <= 2 * kMaxLevels + 1
+
+int mailLayout(pano_ctx *h)
+{
+    if (!h->mail_off.empty()) return PANO_OK;
+    const int np = phaseCount(h);
+    h->mail_off.assign((size_t)np * 4, 0);
+    size_t off = kMailFlagBytes;
+    for (int p = 0; p < np; ++p) {
+        int kind, level, ncols;
+        if (!phaseHalo(h, p, kind, level, ncols)) continue;
+        const size_t bytes = (halo_elems(h->host, kind, level, ncols) * sizeof(int16_t) + 255) & ~(size_t)255;
+        for (int k = 0; k < 4; ++k) { h->mail_off[(size_t)p * 4 + k] = off; off += bytes; }
+    }
+    h->mailbox_bytes = off;
+    return PANO_OK;
+}
+inline uint8_t *mailSlot(pano_ctx *h, uint8_t *base, int phase, int from_side, int parity)
+{
+    return base + h->mail_off[(size_t)phase * 4 + from_side * 2 + parity];
+}
+inline uint32_t *mailFlag(uint8_t *base, int phase, int from_side) { return reinterpret_cast<uint32_t *>(base) + phase * 2 + from_side; }
+}  // namespace
+
+int pano_strip_p2p_create(pano_handle h, void *ipc_handle64, size_t *mailbox_bytes)
+{
+    if (!h) return PANO_ERR;
+    if (h->blender != PANO_BLEND_MULTIBAND) return fail(h, "pano_strip_p2p_create: only the multiband path exchanges halos");
+    CK(h, cudaSetDevice(h->device));
+    if (mailLayout(h)) return PANO_ERR;
+    if (!h->mailbox) {
+        if (devAlloc(h, &h->mailbox, h->mailbox_bytes, true)) return PANO_ERR;
+        if (devAlloc(h, &h->p2p_counters, 2, true)) return PANO_ERR;
+    }
+    if (ipc_handle64) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t hd;
+        CK(h, cudaIpcGetMemHandle(&hd, h->mailbox));
+        std::memcpy(ipc_handle64, &hd, sizeof hd);
+    }
+    if (mailbox_bytes) *mailbox_bytes = h->mailbox_bytes;
+    return PANO_OK;
+}
+
+static int p2pDisconnect(pano_ctx *h, int side)
+{
+    if (h->peer_mail[side] && h->peer_ipc[side]) cudaIpcCloseMemHandle(h->peer_mail[side]);
+    h->peer_mail[side] = nullptr; h->peer_ipc[side] = false;
+    return PANO_OK;
+}
+
+int pano_strip_p2p_connect(pano_handle h, int side, const void *ipc_handle64)
+{
+    if (!h || (side != 0 && side != 1)) return fail(h, "pano_strip_p2p_connect: bad argument");
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());
+    p2pDisconnect(h, side);
+    if (!ipc_handle64) return PANO_OK;
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, ipc_handle64, sizeof hd);
+    void *p = nullptr;
+    CK(h, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_mail[side] = (uint8_t *)p; h->peer_ipc[side] = true;
+    return PANO_OK;
+}
+
+int pano_strip_p2p_connect_local(pano_handle h, int side, pano_handle neighbour)
+{
+    if (!h || (side != 0 && side != 1)) return fail(h, "pano_strip_p2p_connect_local: bad argument");
+    CK(h, cudaSetDevice(h->device));
+    CK(h, cudaDeviceSynchronize());
+    p2pDisconnect(h, side);
+    if (!neighbour) return PANO_OK;
+    if (!neighbour->mailbox) return fail(h, "pano_strip_p2p_connect_local: the neighbour has no mailbox (pano_strip_p2p_create)");
+    if (neighbour->device != h->device) {
+        int can = 0;
+        CK(h, cudaDeviceCanAccessPeer(&can, h->device, neighbour->device));
+        if (!can) return fail(h, "pano_strip_p2p_connect_local: device %d cannot address device %d", h->device, neighbour->device);
+        const cudaError_t e = cudaDeviceEnablePeerAccess(neighbour->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(h, e);
+        (void)cudaGetLastError();
+    }
+    h->peer_mail[side] = neighbour->mailbox;
+    return PANO_OK;
+}
+
+int pano_strip_p2p_begin(pano_handle h)
+{
+    if (!h || !h->mailbox) return fail(h, "pano_strip_p2p_begin: no mailbox (pano_strip_p2p_create)");
+    ++h->p2p_seq;
+    return PANO_OK;
+}
+
+// side s of this rank <-> the neighbour sees this rank on ITS side 1 - s
+int pano_strip_p2p_push(pano_handle h, int phase, void *stream)
+{
+    int kind, level, ncols;
+    if (!h || !h->mailbox || !phaseHalo(h, phase, kind, level, ncols)) return fail(h, "pano_strip_p2p_push: bad argument / no halo after phase %d", phase);
+    if (!h->peer_mail[0] && !h->peer_mail[1]) return PANO_OK;
+    CK(h, cudaSetDevice(h->device));
+    if (syncTables(h)) return PANO_ERR;
+    const int lo = h->strip_x0 >> level, hi = h->strip_x1 >> level, par = h->p2p_seq & 1;
+    HaloSide s[2];
+    for (int side = 0; side < 2; ++side) {
+        uint8_t *pm = h->peer_mail[side];
+        s[side].col = side == 0 ? lo : hi - ncols;
+        s[side].buf = pm ? reinterpret_cast<int16_t *>(mailSlot(h, pm, phase, 1 - side, par)) : nullptr;
+        s[side].flag = pm ? mailFlag(pm, phase, 1 - side) : nullptr;
+    }
+    launch_halo_push(h->dev, h->host, kind, level, ncols, s[0], s[1], h->p2p_seq, h->p2p_counters, (cudaStream_t)stream);
+    ++h->last_launches;
+    CK(h, cudaGetLastError());
+    return PANO_OK;
+}
+
+int pano_strip_p2p_wait_unpack(pano_handle h, int phase, void *stream)
+{
+    int kind, level, ncols;
+    if (!h || !h->mailbox || !phaseHalo(h, phase, kind, level, ncols)) return fail(h, "pano_strip_p2p_wait_unpack: bad argument / no halo after phase %d", phase);
+    if (!h->peer_mail[0] && !h->peer_mail[1]) return PANO_OK;
+    CK(h, cudaSetDevice(h->device));
+    const int lo = h->strip_x0 >> level, hi = h->strip_x1 >> level, par = h->p2p_seq & 1;
+    HaloSide s[2];
+    for (int side = 0; side < 2; ++side) {
+        const bool has = h->peer_mail[side] != nullptr;
+        s[side].col = side == 0 ? lo - ncols : hi;
+        s[side].buf = has ? reinterpret_cast<int16_t *>(mailSlot(h, h->mailbox, phase, side, par)) : nullptr;
+        s[side].flag = has ? mailFlag(h->mailbox, phase, side) : nullptr;
+    }
+    launch_halo_wait_unpack(h->dev, h->host, kind, level, ncols, s[0], s[1], h->p2p_seq, (cudaStream_t)stream);
+    ++h->last_launches;
+    CK(h, cudaGetLastError());
+    return PANO_OK;
+}
+
+int pano_strip_run_p2p(pano_handle h, const uint8_t *frames_dev, uint8_t *pano_dev, void *stream)
+{
+    if (!h || !frames_dev || !pano_dev) return fail(h, "pano_strip_run_p2p: bad argument");
+    if (pano_strip_p2p_begin(h)) return PANO_ERR;
+    CK(h, cudaSetDevice(h->device));
+    if (syncTables(h)) return PANO_ERR;
+    h->last_launches = 0;
+    const int np = phaseCount(h);
+    for (int p = 0; p < np; ++p) {
+        if (runPhase(h, p, frames_dev, pano_dev, 1, (cudaStream_t)stream)) return PANO_ERR;
+        int kind, level, ncols;
+        if (!phaseHalo(h, p, kind, level, ncols)) continue;
+        if (pano_strip_p2p_push(h, p, stream) || pano_strip_p2p_wait_unpack(h, p, stream)) return PANO_ERR;
+    }
+    CK(h, cudaGetLastError());
+    return PANO_OK;
 }
 
 int pano_profile_enable(pano_handle h, int on)

@@ -1229,6 +1229,78 @@ __global__ void __launch_bounds__(256) halo_copy_kernel(const PanoTables *__rest
     }
 }
 
+// ---- halo exchange over PEER MEMORY (NVLink / NVSwitch), no library collective on the data path.
+// Every rank owns a mailbox in its own HBM that its neighbours can address (CUDA IPC mapping).  After a phase, ONE
+// launch packs this rank's edge columns for both neighbours and stores them straight into the neighbours' mailboxes
+// (P2P stores over NVLink); the last block of each side publishes the frame's sequence number in the neighbour's
+// flag word (system-scope fence + store).  Before the next phase ONE launch per rank waits for both flags
+// (system-scope acquire loads by one thread per block) and unpacks the received columns into the pyramid halos.
+// Layout of a mailbox slot: [cam][plane][row][ncols] int16, as halo_copy_kernel packs it.
+__device__ __forceinline__ int16_t *halo_elem(const PanoTables *__restrict__ T, int kind, int level, int cam, int plane, int r, int x, bool &ok)
+{
+    if (kind == 1) {
+        ok = r < (T->pad_h >> level) && x >= 0 && x < (T->pad_w >> level);
+        return T->outp[level] + (size_t)plane * T->out_plane[level] + (size_t)r * T->out_pitch[level] + x;
+    }
+    const CamTables &C = T->cam[cam];
+    const int xx = x - (C.rx >> level);
+    ok = r < (C.rh >> level) && xx >= 0 && xx < (C.rw >> level);
+    return C.g[level] + (size_t)plane * C.g_plane[level] + (size_t)r * C.g_pitch[level] + xx;
+}
+
+__global__ void __launch_bounds__(256) halo_push_kernel(const PanoTables *__restrict__ T, int kind, int level, int ncols, HaloSide s0,
+                                                        HaloSide s1, uint32_t seq, unsigned *__restrict__ counters, int rows_max)
+{
+    const int side = blockIdx.z;
+    const HaloSide S = side ? s1 : s0;
+    if (!S.buf) return;                                             // no neighbour on this side (block-uniform)
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int plane = blockIdx.y % 3, cam = blockIdx.y / 3;
+    if (r < rows_max) {
+        int16_t *b = S.buf + (((size_t)cam * 3 + plane) * rows_max + r) * ncols;
+        for (int c = 0; c < ncols; ++c) {
+            bool ok;
+            const int16_t *p = halo_elem(T, kind, level, cam, plane, r, S.col + c, ok);
+            b[c] = ok ? *p : (int16_t)0;                            // b may live in the neighbour's HBM
+        }
+    }
+    __threadfence_system();                                         // my stores are ordered before the flag below
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y;
+        if (atomicAdd(&counters[side], 1u) == total - 1) {          // last block of this side
+            counters[side] = 0;
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(S.flag), "r"(seq) : "memory");
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) halo_wait_unpack_kernel(const PanoTables *__restrict__ T, int kind, int level, int ncols,
+                                                               HaloSide s0, HaloSide s1, uint32_t seq, int rows_max)
+{
+    const int side = blockIdx.z;
+    const HaloSide S = side ? s1 : s0;
+    if (!S.buf) return;
+    if (threadIdx.x == 0) {
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(S.flag) : "memory");
+        } while ((int32_t)(v - seq) < 0);                            // sequence numbers only grow
+    }
+    __syncthreads();
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int plane = blockIdx.y % 3, cam = blockIdx.y / 3;
+    if (r >= rows_max) return;
+    const volatile int16_t *b = S.buf + (((size_t)cam * 3 + plane) * rows_max + r) * ncols;   // written by the neighbour: bypass L1
+    for (int c = 0; c < ncols; ++c) {
+        bool ok;
+        int16_t *p = halo_elem(T, kind, level, cam, plane, r, S.col + c, ok);
+        const int16_t v = b[c];
+        if (ok) *p = v;
+    }
+}
+
 // ------------------------------------------------------------------ init-time tables on the device
 // MultiBandBlender::feed's weight pyramid -- convertTo(CV_32F, 1/255) + cv::pyrDown chain on CV_32F -- which the
 // reference recomputes for every frame although it only depends on the masks (ocvstitcher.hpp:1202).  Here it is
@@ -1469,6 +1541,22 @@ void launch_halo_copy(const PanoTables *dev, const PanoTables &host, int kind, i
     const int rows = halo_rows(host, kind, level);
     const dim3 block(256), grid((rows + 255) / 256, 3 * (kind == 1 ? 1 : host.num_cams));
     halo_copy_kernel<<<grid, block, 0, stream>>>(dev, kind, level, col, ncols, buf, unpack ? 1 : 0, slot, rows);
+}
+
+void launch_halo_push(const PanoTables *dev, const PanoTables &host, int kind, int level, int ncols, const HaloSide &left,
+                      const HaloSide &right, uint32_t seq, unsigned *counters, cudaStream_t stream)
+{
+    const int rows = halo_rows(host, kind, level);
+    const dim3 block(256), grid((rows + 255) / 256, 3 * (kind == 1 ? 1 : host.num_cams), 2);
+    halo_push_kernel<<<grid, block, 0, stream>>>(dev, kind, level, ncols, left, right, seq, counters, rows);
+}
+
+void launch_halo_wait_unpack(const PanoTables *dev, const PanoTables &host, int kind, int level, int ncols, const HaloSide &left,
+                             const HaloSide &right, uint32_t seq, cudaStream_t stream)
+{
+    const int rows = halo_rows(host, kind, level);
+    const dim3 block(256), grid((rows + 255) / 256, 3 * (kind == 1 ? 1 : host.num_cams), 2);
+    halo_wait_unpack_kernel<<<grid, block, 0, stream>>>(dev, kind, level, ncols, left, right, seq, rows);
 }
 
 void launch_weight_pyrdown(const void *src, bool from_mask, int spitch, int sw, int sh, float *dst, int dpitch,

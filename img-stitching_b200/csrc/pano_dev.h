@@ -116,4 +116,14 @@ void launch_halo_copy(const PanoTables *dev, const PanoTables &host, int kind, i
                       int16_t *buf, bool unpack, int slot, cudaStream_t stream);
 size_t halo_elems(const PanoTables &host, int kind, int level, int ncols);
 
+// Peer-memory halo exchange (no collective library on the data path): one side of one exchange.
+//   push:        col = first of this rank's own edge columns, buf = slot in the NEIGHBOUR's mailbox, flag = word in the
+//                neighbour's flag array;  buf == nullptr: no neighbour on that side
+//   wait/unpack: col = first halo column to fill, buf / flag = this rank's own mailbox slot / flag word
+struct HaloSide { int col; int16_t *buf; uint32_t *flag; };
+void launch_halo_push(const PanoTables *dev, const PanoTables &host, int kind, int level, int ncols, const HaloSide &left,
+                      const HaloSide &right, uint32_t seq, unsigned *counters, cudaStream_t stream);
+void launch_halo_wait_unpack(const PanoTables *dev, const PanoTables &host, int kind, int level, int ncols, const HaloSide &left,
+                             const HaloSide &right, uint32_t seq, cudaStream_t stream);
+
 }  // namespace pano

@@ -5,6 +5,9 @@ Every rank holds the full static tables, owns the padded-dst columns given by
 phase that produces pyramid data a neighbour needs, the ranks exchange the edge columns:
 
 * `NcclExchange`   -- torch.distributed point-to-point (`batch_isend_irecv`, NCCL over NVLink);
+* peer memory       -- `p2p_setup_*` + `compose_p2p`: every rank's mailbox is mapped by its neighbours (CUDA IPC); a
+                      push kernel stores the edge columns straight into the neighbours' HBM over NVLink and raises a
+                      flag, a wait/unpack kernel consumes them -- no collective library, no host sync on the data path;
 * `LocalExchange`  -- all "ranks" are handles inside one process on one GPU (used to test the
                       decomposition bit-for-bit on a single device: ranks are stepped in lockstep,
                       no kernel ever waits on another);
@@ -117,6 +120,71 @@ def compose_local(ranks, frames, panos):
             if r.has_right:
                 allbufs[i][p]["rr"].copy_(allbufs[i + 1][p]["sl"])
                 r.unpack(p, 1, allbufs[i][p]["rr"], stream)
+
+
+# ------------------------------------------------------------------ peer-memory exchange (NVLink P2P stores + flags)
+
+def p2p_setup_distributed(rank_obj):
+    """One process per GPU (torch.distributed initialised): create the mailbox, ship its CUDA IPC handle to the
+    neighbours and map theirs.  Collective: every rank must call it."""
+    import torch.distributed as dist
+    r = rank_obj
+    hd = C.create_string_buffer(64)
+    capi.check(r.lib.pano_strip_p2p_create(r.h, hd, None), r.h)
+    handles = [None] * r.world
+    dist.all_gather_object(handles, bytes(hd.raw))
+    r._peer_handles = handles                      # keep the buffers alive
+    capi.check(r.lib.pano_strip_p2p_connect(r.h, 0, handles[r.rank - 1] if r.has_left else None), r.h)
+    capi.check(r.lib.pano_strip_p2p_connect(r.h, 1, handles[r.rank + 1] if r.has_right else None), r.h)
+    dist.barrier()
+
+
+def p2p_setup_local(ranks):
+    """All ranks are handles of ONE process (tests): neighbours are connected by pointer."""
+    for r in ranks:
+        capi.check(r.lib.pano_strip_p2p_create(r.h, None, None), r.h)
+    for i, r in enumerate(ranks):
+        capi.check(r.lib.pano_strip_p2p_connect_local(r.h, 0, ranks[i - 1].h if r.has_left else None), r.h)
+        capi.check(r.lib.pano_strip_p2p_connect_local(r.h, 1, ranks[i + 1].h if r.has_right else None), r.h)
+
+
+def compose_p2p(rank_obj, frames, pano, stream=None):
+    """One frame-set on this rank, halos through peer memory; asynchronous on `stream`."""
+    import torch
+    if stream is None:
+        stream = torch.cuda.current_stream(frames.device).cuda_stream
+    r = rank_obj
+    capi.check(r.lib.pano_strip_run_p2p(r.h, capi.ptr(frames), capi.ptr(pano), C.c_void_p(stream)), r.h)
+
+
+def compose_p2p_local(ranks, frames, panos, concurrent=False):
+    """All ranks inside one process on one GPU.  concurrent=False: lockstep on one stream (every push precedes the
+    matching wait, so no kernel ever spins).  concurrent=True: one stream per rank, each running its whole frame
+    (`pano_strip_run_p2p`) -- the wait kernels really spin on flags that kernels of other streams raise."""
+    import torch
+    if concurrent:
+        streams = getattr(compose_p2p_local, "_streams", None)
+        if streams is None or len(streams) < len(ranks):
+            streams = compose_p2p_local._streams = [torch.cuda.Stream(frames.device) for _ in ranks]
+        cur = torch.cuda.current_stream(frames.device)
+        for s, r, pano in zip(streams, ranks, panos):
+            s.wait_stream(cur)
+            compose_p2p(r, frames, pano, s.cuda_stream)
+        for s in streams[:len(ranks)]:
+            cur.wait_stream(s)
+        return
+    stream = torch.cuda.current_stream(frames.device).cuda_stream
+    for r in ranks:
+        capi.check(r.lib.pano_strip_p2p_begin(r.h), r.h)
+    for p in range(ranks[0].phases):
+        for r, pano in zip(ranks, panos):
+            r.run_phase(p, frames, pano, stream)
+        if not ranks[0].halo_bytes(p):
+            continue
+        for r in ranks:
+            capi.check(r.lib.pano_strip_p2p_push(r.h, p, C.c_void_p(stream)), r.h)
+        for r in ranks:
+            capi.check(r.lib.pano_strip_p2p_wait_unpack(r.h, p, C.c_void_p(stream)), r.h)
 
 
 def assemble(ranks, panos):

@@ -138,6 +138,26 @@ size_t pano_strip_halo_bytes(pano_handle h, int phase);
 int pano_strip_halo_pack(pano_handle h, int phase, int side, void *buf_dev, void *stream);
 int pano_strip_halo_unpack(pano_handle h, int phase, int side, const void *buf_dev, void *stream);
 
+/* ---- the same exchange over PEER MEMORY (NVLink / NVSwitch) instead of a collective library: every rank owns a
+ * mailbox in its HBM; after a phase ONE kernel packs the rank's edge columns and stores them straight into both
+ * neighbours' mailboxes (P2P stores), then publishes the frame's sequence number in the neighbour's flag word
+ * (system-scope release); before the next phase ONE kernel waits for both neighbours' flags (system-scope acquire) and
+ * unpacks.  No host synchronisation, no NCCL call on the data path; bit-identical to the undivided panorama.
+ *   create:        allocates the mailbox; ipc_handle64 (64 bytes, may be NULL) receives its cudaIpcMemHandle_t for the
+ *                  neighbours' processes (one process per GPU; ship it with any side channel, e.g. torch.distributed)
+ *   connect:       maps the neighbour's mailbox on `side` (0 = left, 1 = right); NULL = no neighbour on that side
+ *   connect_local: neighbour handle in the same process (tests; single-process multi-GPU)
+ *   run_p2p:       one frame-set: begin + every phase with push / wait_unpack in between; asynchronous on `stream`.
+ *                  All ranks must call it once per frame-set (a rank waits for its neighbours' columns on the device).
+ *   begin / push / wait_unpack: the same, phase by phase. */
+int pano_strip_p2p_create(pano_handle h, void *ipc_handle64, size_t *mailbox_bytes);
+int pano_strip_p2p_connect(pano_handle h, int side, const void *ipc_handle64);
+int pano_strip_p2p_connect_local(pano_handle h, int side, pano_handle neighbour);
+int pano_strip_p2p_begin(pano_handle h);
+int pano_strip_p2p_push(pano_handle h, int phase, void *stream);
+int pano_strip_p2p_wait_unpack(pano_handle h, int phase, void *stream);
+int pano_strip_run_p2p(pano_handle h, const uint8_t *frames_dev, uint8_t *pano_dev, void *stream);
+
 /* Per-kernel device time of the last pano_process_device call made while profiling was
  * enabled (CUDA events on the launching stream).  names: up to max entries. */
 int pano_profile_enable(pano_handle h, int on);

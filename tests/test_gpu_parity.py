@@ -520,6 +520,28 @@ def test_strip_split_equals_single_gpu(nranks, mode):
         assert not np.array_equal(panob200.strips.assemble(ranks, panos).cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("nranks,concurrent", [(2, False), (4, False), (8, False), (2, True), (4, True)])
+def test_strip_split_peer_memory_exchange(nranks, concurrent):
+    """Halo exchange through peer-memory mailboxes (push kernel stores into the neighbour's mailbox and raises a flag,
+    wait/unpack kernel consumes it).  Ranks are handles on one GPU: in lockstep on one stream, or concurrently on one
+    stream per rank, where the wait kernels really spin on flags raised by other streams.  Three consecutive frame-sets
+    (sequence numbers, slot parity) must each equal the undivided panorama byte for byte."""
+    import torch
+    t, imgs, want, frames, ranks, panos = _strip_setup(nranks, "exchange")
+    panob200.strips.p2p_setup_local(ranks)
+    ref_st = make(*calib.ring(8, 960, 540, 65.2, 40.0), 960, 540, "cylindrical", "multiband", 5)
+    assert ref_st.initTables(t.blend_masks) == 0, ref_st.last_error
+    variants = [frames, torch.flip(frames, dims=[2]).contiguous(), frames]
+    for k, fr in enumerate(variants):
+        for p_ in panos:
+            p_.fill_(77)
+        panob200.strips.compose_p2p_local(ranks, fr, panos, concurrent=concurrent)
+        torch.cuda.synchronize()
+        got = panob200.strips.assemble(ranks, panos).cpu().numpy()
+        ref = want if k != 1 else ref_st.process([f for f in fr.cpu().numpy()])
+        assert_equal("p2p strip split %d ranks, frame %d" % (nranks, k), got, ref)
+
+
 # ------------------------------------------------------------------ nvCam front end
 
 def test_front_end_golden_bit_exact():

@@ -1,12 +1,14 @@
 #!/usr/bin/env python
 """BASELINE config 4 across GPUs: ONE 8-camera 4K cylindrical 7-band panorama split into column
-strips, pyramid halos exchanged with NCCL point-to-point (torch.distributed batch_isend_irecv).
+strips; pyramid halos exchanged (a) with NCCL point-to-point (torch.distributed batch_isend_irecv), (b) through
+peer-memory mailboxes (P2P stores over NVLink + flags, no collective library on the data path), or (c) not at all
+(redundant halo).
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
       --master-port P tools/strip_split_nccl.py [--small] [--steps K]
 
 Checks on every rank that its own columns equal the undivided single-GPU result (computed locally
-with a second handle), then times `exchange` (NCCL halo) and `redundant` (recomputed halo) modes:
+with a second handle), then times `exchange` (NCCL halo), `p2p` (peer-memory halo) and `redundant` (recomputed halo):
 device time per panorama, max over ranks.  Prints one JSON line on rank 0."""
 import argparse
 import json
@@ -66,20 +68,25 @@ def main():
     single_ms = e0.elapsed_time(e1) / args.steps
 
     res = {}
-    for mode in ("exchange", "redundant"):
-        r = panob200.strips.StripRank(stitcher(), rank, world, mode)
+    for mode in ("exchange", "p2p", "redundant"):
+        r = panob200.strips.StripRank(stitcher(), rank, world, "exchange" if mode == "p2p" else mode)
         pano = torch.zeros((oh, ow, 3), dtype=torch.uint8, device=dev)
-        bufs = panob200.strips.compose_nccl(r, frames, pano)
+        if mode == "p2p":
+            panob200.strips.p2p_setup_distributed(r)
+            run = lambda bufs=None: panob200.strips.compose_p2p(r, frames, pano)      # noqa: E731
+        else:
+            run = lambda bufs=None: panob200.strips.compose_nccl(r, frames, pano, bufs)  # noqa: E731
+        bufs = run()
         torch.cuda.synchronize()
         c0, c1 = r.own_output_columns()
         ok = bool(torch.equal(pano[:, c0:c1], want[0][:, c0:c1]))
         for _ in range(args.warmup):
-            panob200.strips.compose_nccl(r, frames, pano, bufs)
+            run(bufs)
         torch.cuda.synchronize()
         dist.barrier()
         e0.record()
         for _ in range(args.steps):
-            panob200.strips.compose_nccl(r, frames, pano, bufs)
+            run(bufs)
         e1.record()
         torch.cuda.synchronize()
         dist.barrier()
