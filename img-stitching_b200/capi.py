@@ -90,9 +90,10 @@ _SIGS = {
     "pano_strip_p2p_create": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]),
     "pano_strip_p2p_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "pano_strip_p2p_connect_local": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
-    "pano_strip_p2p_begin": (C.c_int, [C.c_void_p]),
+    "pano_strip_p2p_begin": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pano_strip_p2p_push": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "pano_strip_p2p_wait_unpack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "pano_strip_p2p_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pano_strip_run_p2p": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pano_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "pano_profile_read": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

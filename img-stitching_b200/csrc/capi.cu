@@ -99,7 +99,11 @@ struct pano_ctx {
     uint8_t *peer_mail[2] = {nullptr, nullptr};   // left / right neighbour's mailbox as addressable from this device
     bool peer_ipc[2] = {false, false};            // mapped with cudaIpcOpenMemHandle (to be closed)
     unsigned *p2p_counters = nullptr;             // block-completion counters of halo_push_kernel
-    uint32_t p2p_seq = 0;                         // frame sequence number
+    int sm_count = 0;
+    uint32_t *p2p_seq = nullptr;                  // device: frame sequence number (bumped by the first kernel of a frame)
+    // one frame's launch sequence captured once and replayed (the exchange is launch-latency bound)
+    cudaGraphExec_t p2p_graph = nullptr;
+    const void *p2p_graph_frames = nullptr, *p2p_graph_pano = nullptr;
 
     // staging for host entry points
     uint8_t *stage_in[kPipeDepth] = {};
@@ -827,6 +831,7 @@ int pano_destroy(pano_handle h)
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     clearProf(h);
+    if (h->p2p_graph) cudaGraphExecDestroy(h->p2p_graph);
     for (int s = 0; s < 2; ++s)
         if (h->peer_mail[s] && h->peer_ipc[s]) cudaIpcCloseMemHandle(h->peer_mail[s]);
     for (void *p : h->owned) cudaFree(p);
@@ -1306,7 +1311,8 @@ int pano_strip_p2p_create(pano_handle h, void *ipc_handle64, size_t *mailbox_byt
     if (mailLayout(h)) return PANO_ERR;
     if (!h->mailbox) {
         if (devAlloc(h, &h->mailbox, h->mailbox_bytes, true)) return PANO_ERR;
-        if (devAlloc(h, &h->p2p_counters, 2, true)) return PANO_ERR;
+        if (devAlloc(h, &h->p2p_counters, 2, true) || devAlloc(h, &h->p2p_seq, 1, true)) return PANO_ERR;
+        CK(h, cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device));
     }
     if (ipc_handle64) {
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -1360,14 +1366,32 @@ int pano_strip_p2p_connect_local(pano_handle h, int side, pano_handle neighbour)
     return PANO_OK;
 }
 
-int pano_strip_p2p_begin(pano_handle h)
+int pano_strip_p2p_begin(pano_handle h, void *stream)
 {
     if (!h || !h->mailbox) return fail(h, "pano_strip_p2p_begin: no mailbox (pano_strip_p2p_create)");
-    ++h->p2p_seq;
+    CK(h, cudaSetDevice(h->device));
+    launch_p2p_begin(h->p2p_seq, (cudaStream_t)stream);
+    CK(h, cudaGetLastError());
     return PANO_OK;
 }
 
 // side s of this rank <-> the neighbour sees this rank on ITS side 1 - s
+static void p2pSides(pano_ctx *h, int phase, int level, int ncols, HaloSide push[2], HaloSide recv[2])
+{
+    const int lo = h->strip_x0 >> level, hi = h->strip_x1 >> level;
+    for (int side = 0; side < 2; ++side) {
+        uint8_t *pm = h->peer_mail[side];
+        push[side].col = side == 0 ? lo : hi - ncols;                // my own edge columns, for that neighbour
+        recv[side].col = side == 0 ? lo - ncols : hi;                // the neighbour's edge columns, into my halo
+        for (int par = 0; par < 2; ++par) {
+            push[side].buf[par] = pm ? reinterpret_cast<int16_t *>(mailSlot(h, pm, phase, 1 - side, par)) : nullptr;
+            recv[side].buf[par] = pm ? reinterpret_cast<int16_t *>(mailSlot(h, h->mailbox, phase, side, par)) : nullptr;
+        }
+        push[side].flag = pm ? mailFlag(pm, phase, 1 - side) : nullptr;
+        recv[side].flag = pm ? mailFlag(h->mailbox, phase, side) : nullptr;
+    }
+}
+
 int pano_strip_p2p_push(pano_handle h, int phase, void *stream)
 {
     int kind, level, ncols;
@@ -1375,15 +1399,9 @@ int pano_strip_p2p_push(pano_handle h, int phase, void *stream)
     if (!h->peer_mail[0] && !h->peer_mail[1]) return PANO_OK;
     CK(h, cudaSetDevice(h->device));
     if (syncTables(h)) return PANO_ERR;
-    const int lo = h->strip_x0 >> level, hi = h->strip_x1 >> level, par = h->p2p_seq & 1;
-    HaloSide s[2];
-    for (int side = 0; side < 2; ++side) {
-        uint8_t *pm = h->peer_mail[side];
-        s[side].col = side == 0 ? lo : hi - ncols;
-        s[side].buf = pm ? reinterpret_cast<int16_t *>(mailSlot(h, pm, phase, 1 - side, par)) : nullptr;
-        s[side].flag = pm ? mailFlag(pm, phase, 1 - side) : nullptr;
-    }
-    launch_halo_push(h->dev, h->host, kind, level, ncols, s[0], s[1], h->p2p_seq, h->p2p_counters, (cudaStream_t)stream);
+    HaloSide push[2], recv[2];
+    p2pSides(h, phase, level, ncols, push, recv);
+    launch_halo_push(h->dev, h->host, kind, level, ncols, push[0], push[1], h->p2p_seq, h->p2p_counters, (cudaStream_t)stream);
     ++h->last_launches;
     CK(h, cudaGetLastError());
     return PANO_OK;
@@ -1395,35 +1413,88 @@ int pano_strip_p2p_wait_unpack(pano_handle h, int phase, void *stream)
     if (!h || !h->mailbox || !phaseHalo(h, phase, kind, level, ncols)) return fail(h, "pano_strip_p2p_wait_unpack: bad argument / no halo after phase %d", phase);
     if (!h->peer_mail[0] && !h->peer_mail[1]) return PANO_OK;
     CK(h, cudaSetDevice(h->device));
-    const int lo = h->strip_x0 >> level, hi = h->strip_x1 >> level, par = h->p2p_seq & 1;
-    HaloSide s[2];
-    for (int side = 0; side < 2; ++side) {
-        const bool has = h->peer_mail[side] != nullptr;
-        s[side].col = side == 0 ? lo - ncols : hi;
-        s[side].buf = has ? reinterpret_cast<int16_t *>(mailSlot(h, h->mailbox, phase, side, par)) : nullptr;
-        s[side].flag = has ? mailFlag(h->mailbox, phase, side) : nullptr;
-    }
-    launch_halo_wait_unpack(h->dev, h->host, kind, level, ncols, s[0], s[1], h->p2p_seq, (cudaStream_t)stream);
+    HaloSide push[2], recv[2];
+    p2pSides(h, phase, level, ncols, push, recv);
+    launch_halo_wait_unpack(h->dev, h->host, kind, level, ncols, recv[0], recv[1], h->p2p_seq, (cudaStream_t)stream);
     ++h->last_launches;
     CK(h, cudaGetLastError());
     return PANO_OK;
 }
 
-int pano_strip_run_p2p(pano_handle h, const uint8_t *frames_dev, uint8_t *pano_dev, void *stream)
+static int p2pFrame(pano_handle h, const uint8_t *frames_dev, uint8_t *pano_dev, void *stream)
 {
-    if (!h || !frames_dev || !pano_dev) return fail(h, "pano_strip_run_p2p: bad argument");
-    if (pano_strip_p2p_begin(h)) return PANO_ERR;
-    CK(h, cudaSetDevice(h->device));
-    if (syncTables(h)) return PANO_ERR;
-    h->last_launches = 0;
+    if (pano_strip_p2p_begin(h, stream)) return PANO_ERR;
+    h->last_launches = 1;
     const int np = phaseCount(h);
     for (int p = 0; p < np; ++p) {
         if (runPhase(h, p, frames_dev, pano_dev, 1, (cudaStream_t)stream)) return PANO_ERR;
         int kind, level, ncols;
         if (!phaseHalo(h, p, kind, level, ncols)) continue;
+        if (!h->peer_mail[0] && !h->peer_mail[1]) continue;
+        // one launch per exchange while all its blocks are certainly co-resident (256-thread blocks, 8 fit an SM; 6 per
+        // SM are claimed, the rank's own stream is idle by then), otherwise push and wait/unpack as two launches
+        static const bool split = getenv("PANO_P2P_SPLIT") != nullptr;
+        HaloSide push[2], recv[2];
+        p2pSides(h, p, level, ncols, push, recv);
+        if (!split && launch_halo_exchange(h->dev, h->host, kind, level, ncols, push, recv, h->p2p_seq, h->p2p_counters,
+                                           h->sm_count * 6, (cudaStream_t)stream)) {
+            ++h->last_launches;
+            continue;
+        }
         if (pano_strip_p2p_push(h, p, stream) || pano_strip_p2p_wait_unpack(h, p, stream)) return PANO_ERR;
     }
-    CK(h, cudaGetLastError());
+    return PANO_OK;
+}
+
+static bool p2pUseGraph(pano_handle h, cudaStream_t st)
+{
+    static const bool no_graph = getenv("PANO_P2P_NO_GRAPH") != nullptr;
+    return !(no_graph || h->profiling || st == nullptr || st == cudaStreamLegacy);     // the legacy stream cannot be captured
+}
+
+// The frame's ~60 small launches are identical from frame to frame (the sequence number lives in device memory):
+// they are captured once per (frames, panorama) buffer pair and replayed as a graph.
+int pano_strip_p2p_prepare(pano_handle h, const uint8_t *frames_dev, uint8_t *pano_dev, void *stream)
+{
+    if (!h || !frames_dev || !pano_dev || !h->mailbox) return fail(h, "pano_strip_p2p_prepare: bad argument / no mailbox");
+    CK(h, cudaSetDevice(h->device));
+    if (h->tables_dirty && h->p2p_graph) { cudaGraphExecDestroy(h->p2p_graph); h->p2p_graph = nullptr; }
+    if (syncTables(h)) return PANO_ERR;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!p2pUseGraph(h, st)) return PANO_OK;
+    if (h->p2p_graph && (h->p2p_graph_frames != frames_dev || h->p2p_graph_pano != pano_dev)) {
+        cudaGraphExecDestroy(h->p2p_graph);
+        h->p2p_graph = nullptr;
+    }
+    if (!h->p2p_graph) {
+        cudaGraph_t g = nullptr;
+        CK(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int rc = p2pFrame(h, frames_dev, pano_dev, stream);
+        const cudaError_t e = cudaStreamEndCapture(st, &g);
+        if (rc || e != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            (void)cudaGetLastError();
+            return rc ? PANO_ERR : fail(h, "pano_strip_run_p2p: graph capture failed: %s", cudaGetErrorString(e));
+        }
+        const cudaError_t ei = cudaGraphInstantiate(&h->p2p_graph, g, 0);
+        cudaGraphDestroy(g);
+        if (ei != cudaSuccess) { h->p2p_graph = nullptr; return fail(h, "pano_strip_run_p2p: graph instantiation failed: %s", cudaGetErrorString(ei)); }
+        h->p2p_graph_frames = frames_dev; h->p2p_graph_pano = pano_dev;
+        CK(h, cudaGraphUpload(h->p2p_graph, st));
+    }
+    return PANO_OK;
+}
+
+int pano_strip_run_p2p(pano_handle h, const uint8_t *frames_dev, uint8_t *pano_dev, void *stream)
+{
+    if (pano_strip_p2p_prepare(h, frames_dev, pano_dev, stream)) return PANO_ERR;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!p2pUseGraph(h, st)) {
+        if (p2pFrame(h, frames_dev, pano_dev, stream)) return PANO_ERR;
+        CK(h, cudaGetLastError());
+        return PANO_OK;
+    }
+    CK(h, cudaGraphLaunch(h->p2p_graph, st));
     return PANO_OK;
 }
 

@@ -1248,16 +1248,20 @@ __device__ __forceinline__ int16_t *halo_elem(const PanoTables *__restrict__ T, 
     return C.g[level] + (size_t)plane * C.g_plane[level] + (size_t)r * C.g_pitch[level] + xx;
 }
 
+__global__ void p2p_begin_kernel(uint32_t *seq) { ++*seq; }
+
 __global__ void __launch_bounds__(256) halo_push_kernel(const PanoTables *__restrict__ T, int kind, int level, int ncols, HaloSide s0,
-                                                        HaloSide s1, uint32_t seq, unsigned *__restrict__ counters, int rows_max)
+                                                        HaloSide s1, const uint32_t *__restrict__ seq_ptr,
+                                                        unsigned *__restrict__ counters, int rows_max)
 {
     const int side = blockIdx.z;
     const HaloSide S = side ? s1 : s0;
-    if (!S.buf) return;                                             // no neighbour on this side (block-uniform)
+    if (!S.flag) return;                                            // no neighbour on this side (block-uniform)
+    const uint32_t seq = *seq_ptr;
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const int plane = blockIdx.y % 3, cam = blockIdx.y / 3;
     if (r < rows_max) {
-        int16_t *b = S.buf + (((size_t)cam * 3 + plane) * rows_max + r) * ncols;
+        int16_t *b = S.buf[seq & 1] + (((size_t)cam * 3 + plane) * rows_max + r) * ncols;
         for (int c = 0; c < ncols; ++c) {
             bool ok;
             const int16_t *p = halo_elem(T, kind, level, cam, plane, r, S.col + c, ok);
@@ -1277,11 +1281,12 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const PanoTables *__rest
 }
 
 __global__ void __launch_bounds__(256) halo_wait_unpack_kernel(const PanoTables *__restrict__ T, int kind, int level, int ncols,
-                                                               HaloSide s0, HaloSide s1, uint32_t seq, int rows_max)
+                                                               HaloSide s0, HaloSide s1, const uint32_t *__restrict__ seq_ptr, int rows_max)
 {
     const int side = blockIdx.z;
     const HaloSide S = side ? s1 : s0;
-    if (!S.buf) return;
+    if (!S.flag) return;
+    const uint32_t seq = *seq_ptr;
     if (threadIdx.x == 0) {
         uint32_t v;
         do {
@@ -1292,10 +1297,58 @@ __global__ void __launch_bounds__(256) halo_wait_unpack_kernel(const PanoTables 
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const int plane = blockIdx.y % 3, cam = blockIdx.y / 3;
     if (r >= rows_max) return;
-    const volatile int16_t *b = S.buf + (((size_t)cam * 3 + plane) * rows_max + r) * ncols;   // written by the neighbour: bypass L1
+    const volatile int16_t *b = S.buf[seq & 1] + (((size_t)cam * 3 + plane) * rows_max + r) * ncols;   // written by the neighbour: bypass L1
     for (int c = 0; c < ncols; ++c) {
         bool ok;
         int16_t *p = halo_elem(T, kind, level, cam, plane, r, S.col + c, ok);
+        const int16_t v = b[c];
+        if (ok) *p = v;
+    }
+}
+
+// push + wait/unpack of one exchange in ONE launch (one kernel boundary less on a latency-bound chain): every block
+// first stores its share of this rank's edge columns into the neighbour's mailbox, the last block of a side raises the
+// neighbour's flag, then the same blocks wait for this rank's own flag of that side and unpack.  All blocks must be
+// co-resident (a spinning block never yields its SM slot), which the launcher guarantees by grid size.
+__global__ void __launch_bounds__(256) halo_exchange_kernel(const PanoTables *__restrict__ T, int kind, int level, int ncols,
+                                                            HaloSide p0, HaloSide p1, HaloSide r0, HaloSide r1,
+                                                            const uint32_t *__restrict__ seq_ptr, unsigned *__restrict__ counters, int rows_max)
+{
+    const int side = blockIdx.z;
+    const HaloSide P = side ? p1 : p0, R = side ? r1 : r0;
+    if (!P.flag) return;                                            // no neighbour on this side (block-uniform)
+    const uint32_t seq = *seq_ptr;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int plane = blockIdx.y % 3, cam = blockIdx.y / 3;
+    const size_t slot_off = (((size_t)cam * 3 + plane) * rows_max + r) * ncols;
+    if (r < rows_max) {
+        int16_t *b = P.buf[seq & 1] + slot_off;
+        for (int c = 0; c < ncols; ++c) {
+            bool ok;
+            const int16_t *p = halo_elem(T, kind, level, cam, plane, r, P.col + c, ok);
+            b[c] = ok ? *p : (int16_t)0;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y;
+        if (atomicAdd(&counters[side], 1u) == total - 1) {
+            counters[side] = 0;
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.flag), "r"(seq) : "memory");
+        }
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(R.flag) : "memory");
+        } while ((int32_t)(v - seq) < 0);
+    }
+    __syncthreads();
+    if (r >= rows_max) return;
+    const volatile int16_t *b = R.buf[seq & 1] + slot_off;
+    for (int c = 0; c < ncols; ++c) {
+        bool ok;
+        int16_t *p = halo_elem(T, kind, level, cam, plane, r, R.col + c, ok);
         const int16_t v = b[c];
         if (ok) *p = v;
     }
@@ -1543,16 +1596,28 @@ void launch_halo_copy(const PanoTables *dev, const PanoTables &host, int kind, i
     halo_copy_kernel<<<grid, block, 0, stream>>>(dev, kind, level, col, ncols, buf, unpack ? 1 : 0, slot, rows);
 }
 
+void launch_p2p_begin(uint32_t *seq, cudaStream_t stream) { p2p_begin_kernel<<<1, 1, 0, stream>>>(seq); }
+
 void launch_halo_push(const PanoTables *dev, const PanoTables &host, int kind, int level, int ncols, const HaloSide &left,
-                      const HaloSide &right, uint32_t seq, unsigned *counters, cudaStream_t stream)
+                      const HaloSide &right, const uint32_t *seq, unsigned *counters, cudaStream_t stream)
 {
     const int rows = halo_rows(host, kind, level);
     const dim3 block(256), grid((rows + 255) / 256, 3 * (kind == 1 ? 1 : host.num_cams), 2);
     halo_push_kernel<<<grid, block, 0, stream>>>(dev, kind, level, ncols, left, right, seq, counters, rows);
 }
 
+bool launch_halo_exchange(const PanoTables *dev, const PanoTables &host, int kind, int level, int ncols, const HaloSide push[2],
+                          const HaloSide recv[2], const uint32_t *seq, unsigned *counters, int max_resident_blocks, cudaStream_t stream)
+{
+    const int rows = halo_rows(host, kind, level);
+    const dim3 block(256), grid((rows + 255) / 256, 3 * (kind == 1 ? 1 : host.num_cams), 2);
+    if ((long long)grid.x * grid.y * grid.z > max_resident_blocks) return false;     // would not be co-resident: use push + wait_unpack
+    halo_exchange_kernel<<<grid, block, 0, stream>>>(dev, kind, level, ncols, push[0], push[1], recv[0], recv[1], seq, counters, rows);
+    return true;
+}
+
 void launch_halo_wait_unpack(const PanoTables *dev, const PanoTables &host, int kind, int level, int ncols, const HaloSide &left,
-                             const HaloSide &right, uint32_t seq, cudaStream_t stream)
+                             const HaloSide &right, const uint32_t *seq, cudaStream_t stream)
 {
     const int rows = halo_rows(host, kind, level);
     const dim3 block(256), grid((rows + 255) / 256, 3 * (kind == 1 ? 1 : host.num_cams), 2);

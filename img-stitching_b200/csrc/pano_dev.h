@@ -120,10 +120,16 @@ size_t halo_elems(const PanoTables &host, int kind, int level, int ncols);
 //   push:        col = first of this rank's own edge columns, buf = slot in the NEIGHBOUR's mailbox, flag = word in the
 //                neighbour's flag array;  buf == nullptr: no neighbour on that side
 //   wait/unpack: col = first halo column to fill, buf / flag = this rank's own mailbox slot / flag word
-struct HaloSide { int col; int16_t *buf; uint32_t *flag; };
+// The frame's sequence number lives in DEVICE memory (*seq, bumped by launch_p2p_begin) and selects the slot parity
+// (buf[seq & 1]), so that a whole frame's launch sequence is identical from frame to frame and can be replayed as a CUDA graph.
+struct HaloSide { int col; int16_t *buf[2]; uint32_t *flag; };
+void launch_p2p_begin(uint32_t *seq, cudaStream_t stream);
 void launch_halo_push(const PanoTables *dev, const PanoTables &host, int kind, int level, int ncols, const HaloSide &left,
-                      const HaloSide &right, uint32_t seq, unsigned *counters, cudaStream_t stream);
+                      const HaloSide &right, const uint32_t *seq, unsigned *counters, cudaStream_t stream);
+// both halves in one launch; false (nothing launched) when the grid would exceed max_resident_blocks
+bool launch_halo_exchange(const PanoTables *dev, const PanoTables &host, int kind, int level, int ncols, const HaloSide push[2],
+                          const HaloSide recv[2], const uint32_t *seq, unsigned *counters, int max_resident_blocks, cudaStream_t stream);
 void launch_halo_wait_unpack(const PanoTables *dev, const PanoTables &host, int kind, int level, int ncols, const HaloSide &left,
-                             const HaloSide &right, uint32_t seq, cudaStream_t stream);
+                             const HaloSide &right, const uint32_t *seq, cudaStream_t stream);
 
 }  // namespace pano

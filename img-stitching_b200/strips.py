@@ -167,6 +167,10 @@ def compose_p2p_local(ranks, frames, panos, concurrent=False):
         if streams is None or len(streams) < len(ranks):
             streams = compose_p2p_local._streams = [torch.cuda.Stream(frames.device) for _ in ranks]
         cur = torch.cuda.current_stream(frames.device)
+        # build every rank's graph BEFORE anything spins: instantiating a graph may synchronise the device, which must
+        # not happen while another rank's wait kernel is waiting for this rank (one process = one context here)
+        for s, r, pano in zip(streams, ranks, panos):
+            capi.check(r.lib.pano_strip_p2p_prepare(r.h, capi.ptr(frames), capi.ptr(pano), C.c_void_p(s.cuda_stream)), r.h)
         for s, r, pano in zip(streams, ranks, panos):
             s.wait_stream(cur)
             compose_p2p(r, frames, pano, s.cuda_stream)
@@ -175,7 +179,7 @@ def compose_p2p_local(ranks, frames, panos, concurrent=False):
         return
     stream = torch.cuda.current_stream(frames.device).cuda_stream
     for r in ranks:
-        capi.check(r.lib.pano_strip_p2p_begin(r.h), r.h)
+        capi.check(r.lib.pano_strip_p2p_begin(r.h, C.c_void_p(stream)), r.h)
     for p in range(ranks[0].phases):
         for r, pano in zip(ranks, panos):
             r.run_phase(p, frames, pano, stream)

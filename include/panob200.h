@@ -149,13 +149,16 @@ int pano_strip_halo_unpack(pano_handle h, int phase, int side, const void *buf_d
  *   connect_local: neighbour handle in the same process (tests; single-process multi-GPU)
  *   run_p2p:       one frame-set: begin + every phase with push / wait_unpack in between; asynchronous on `stream`.
  *                  All ranks must call it once per frame-set (a rank waits for its neighbours' columns on the device).
+ *                  On a non-default stream the frame's launch sequence is captured once per (frames, panorama)
+ *                  buffer pair and replayed as a CUDA graph (the exchange is launch-latency bound).
  *   begin / push / wait_unpack: the same, phase by phase. */
 int pano_strip_p2p_create(pano_handle h, void *ipc_handle64, size_t *mailbox_bytes);
 int pano_strip_p2p_connect(pano_handle h, int side, const void *ipc_handle64);
 int pano_strip_p2p_connect_local(pano_handle h, int side, pano_handle neighbour);
-int pano_strip_p2p_begin(pano_handle h);
+int pano_strip_p2p_begin(pano_handle h, void *stream);
 int pano_strip_p2p_push(pano_handle h, int phase, void *stream);
 int pano_strip_p2p_wait_unpack(pano_handle h, int phase, void *stream);
+int pano_strip_p2p_prepare(pano_handle h, const uint8_t *frames_dev, uint8_t *pano_dev, void *stream);   /* builds the graph only */
 int pano_strip_run_p2p(pano_handle h, const uint8_t *frames_dev, uint8_t *pano_dev, void *stream);
 
 /* Per-kernel device time of the last pano_process_device call made while profiling was

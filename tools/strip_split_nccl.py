@@ -73,7 +73,12 @@ def main():
         pano = torch.zeros((oh, ow, 3), dtype=torch.uint8, device=dev)
         if mode == "p2p":
             panob200.strips.p2p_setup_distributed(r)
-            run = lambda bufs=None: panob200.strips.compose_p2p(r, frames, pano)      # noqa: E731
+            side = torch.cuda.Stream(dev)            # a capturable stream: the frame is replayed as a CUDA graph
+
+            def run(bufs=None):
+                side.wait_stream(torch.cuda.current_stream(dev))
+                panob200.strips.compose_p2p(r, frames, pano, side.cuda_stream)
+                torch.cuda.current_stream(dev).wait_stream(side)
         else:
             run = lambda bufs=None: panob200.strips.compose_nccl(r, frames, pano, bufs)  # noqa: E731
         bufs = run()
