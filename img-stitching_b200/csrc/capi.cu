@@ -480,6 +480,16 @@ double directBytes(const pano_ctx *h, int slots)
     return b * slots;
 }
 
+double blendG0Bytes(const pano_ctx *h, int slots)
+{
+    double b = (double)h->out_bytes();
+    for (int i = 0; i < h->n; ++i) {
+        const CamTables &C = h->host.cam[i];
+        b += (double)C.rw * C.rh * (6 + (h->blender == PANO_BLEND_FEATHER ? 4 : 1));
+    }
+    return b * slots;
+}
+
 // The kernel chain is a sequence of PHASES (one wave = all phases for up to max_batch frame-sets):
 //   multiband:  p in [0, nb): (p == 0: warp) + pyrDown level p     -> produces g[p+1]
 //               p == nb: coarsest level                            -> produces out[nb]
@@ -497,9 +507,21 @@ int runPhase(pano_ctx *h, int p, const uint8_t *frames_dev, uint8_t *out_dev, in
                                  "collapse_l5", "collapse_l6", "collapse_l7", "collapse_l8"};
     const int nb = h->nb;
     if (h->blender != PANO_BLEND_MULTIBAND) {
-        L.begin("direct_blend", directBytes(h, slots));
-        launch_direct_blend(h->dev, h->host, h->blender, frames_dev, out_dev, slots, st);
-        L.end();
+        static const bool force_direct = getenv("PANO_DIRECT_BLEND") != nullptr;
+        const bool windowed = h->strip_x0 != 0 || h->strip_x1 != h->pad_w;
+        if (h->kc.warp_tiled && !windowed && !force_direct) {
+            // two passes: staged tile gather into the warped images, then a streaming weight / accumulate / normalise pass
+            L.begin("warp", warpBytes(h, slots));
+            launch_warp(h->dev, h->host, h->kc, frames_dev, slots, st);
+            L.end();
+            L.begin("blend_warped", blendG0Bytes(h, slots));
+            launch_blend_g0(h->dev, h->host, h->blender, out_dev, slots, st);
+            L.end();
+        } else {
+            L.begin("direct_blend", directBytes(h, slots));
+            launch_direct_blend(h->dev, h->host, h->blender, frames_dev, out_dev, slots, st);
+            L.end();
+        }
     } else if (p < nb) {
         if (p == 0) {
             L.begin("warp", warpBytes(h, slots));
@@ -755,8 +777,8 @@ int pano_create(const pano_config *cfg, pano_handle *out)
             if (devAlloc(h, &w, (size_t)C.wt_pitch[l] * std::max(1, C.rh >> l))) return bail(0);
             h->cam_wt[i][l] = w; C.wt[l] = w;
         }
-        // pyramid workspace
-        if (h->blender == PANO_BLEND_MULTIBAND) {
+        // pyramid workspace (feather / no-blend: level 0 only = the warped images of the two-pass blend)
+        {
             for (int l = 0; l <= h->nb; ++l) {
                 const int lw = C.rw >> l, lh = C.rh >> l;
                 C.g_pitch[l] = roundUp(lw + 24, 64);   // packed kernels over-read up to 18 samples past a row

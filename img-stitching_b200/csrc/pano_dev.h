@@ -94,6 +94,8 @@ void launch_coarsest(const PanoTables *dev, const PanoTables &host, uint8_t *pan
 // returns the number of kernels launched
 int launch_collapse(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, int level, uint8_t *pano,
                     int nslots, cudaStream_t stream);
+// feather / no-blend as two passes: launch_warp (staged gather -> g[0]) + this streaming blend over the warped images
+void launch_blend_g0(const PanoTables *dev, const PanoTables &host, int blender, uint8_t *pano, int nslots, cudaStream_t stream);
 void launch_direct_blend(const PanoTables *dev, const PanoTables &host, int blender, const uint8_t *frames,
                          uint8_t *pano, int nslots, cudaStream_t stream);
 
