@@ -35,6 +35,9 @@ WORKLOADS = {
     "config1": "config1: 4x1920x1080 BGR -> spherical warp + 5-band MultiBandBlender -> cut 5336x896 (imx390 rig, 2222 calibration x4)",
     "config2": "config2: 4x1920x1080 BGRA camera frames -> imx390 undistort (INTER_CUBIC) + crop [69,103,1782,889] + resize -> "
                "spherical warp + 5-band MultiBandBlender -> cut 5336x896",
+    # BASELINE config 3 (a parity-test configuration; measured on request)
+    "config3": "config3: 4x1920x1080 BGR, imx424 rig (cfg/424camcfg/cameraparaout_1.txt x3) -> spherical warp -> BlocksGainCompensator "
+               "apply -> FeatherBlender(sharpness = 1/blend_width, strength 5) -> whole panorama 6383x1131",
     # the YUYVCAM ingest (include/nvcam.hpp:880-886): frames cross PCIe as 8UC2, cvtColor(COLOR_YUV2BGRA_YUYV) runs on the device
     "config2-yuyv": "config2 with 8UC2 YUYV 4:2:2 camera frames (2 B/px over PCIe): YUV2BGRA_YUYV + imx390 undistort (INTER_CUBIC) + crop "
                     "[69,103,1782,889] + resize -> spherical warp + 5-band MultiBandBlender -> cut 5336x896",
@@ -65,9 +68,15 @@ def make_front_end(device, max_batch, src_format="bgra"):
     return panob200.nvCamFrontEnd(cfg)
 
 
-def calibration():
+def calibration(workload="config1"):
     from golden import calib
-    return calib.rig("2222", W)
+    return calib.rig("424" if workload == "config3" else "2222", W)
+
+
+def config3_sharpness(dst_roi):
+    """FeatherBlender::setSharpness(1 / blend_width), blend_width = sqrt(dst area) * strength / 100 (src/stitching_detailed.cpp:865-869)."""
+    bw = np.float32(np.sqrt(np.float32(dst_roi[2] * dst_roi[3]))) * np.float32(5.0) / np.float32(100.0)
+    return float(np.float32(1.0) / bw)
 
 
 def peaks():
@@ -122,14 +131,14 @@ def synth_batch_torch(batch, seed, device):
     return up.clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().view(batch, NCAM, H, W, 3)
 
 
-def cpu_reference_setup(frames0):
+def cpu_reference_setup(frames0, workload="config1"):
     """Static tables of the reference init flow (initSeam) for the CPU arm; cv2 path if present."""
-    Ks, Rs, scale = calibration()
+    Ks, Rs, scale = calibration(workload)
     try:
         import cv2
         from oracle import cv2_reference as ref
         cv2.setNumThreads(os.cpu_count() or 1)
-        t = ref.init_seam(frames0, Ks, Rs, scale, warp="spherical", seam="gc_color")
+        t = ref.init_seam(frames0, Ks, Rs, scale, warp="spherical", seam="gc_color", want_gains=workload == "config3")
         return "cv2", t
     except ImportError:
         from oracle import compose
@@ -137,7 +146,7 @@ def cpu_reference_setup(frames0):
         return "c_port", t
 
 
-def cpu_reference_time(kind, t, frame_sets, repeats, front=False):
+def cpu_reference_time(kind, t, frame_sets, repeats, front=False, workload="config1"):
     """Times the reference's per-frame path (ocvStitcher::process restated call for call; with
     front=True preceded by nvCam's resize/undistort/crop/resize per camera) on the host cores.
     -> (panoramas/s, cores used, description)."""
@@ -158,6 +167,8 @@ def cpu_reference_time(kind, t, frame_sets, repeats, front=False):
         def one(fs):
             if fe is not None:
                 fs = [fe(to_bgra(f)) for f in fs]
+            if workload == "config3":    # warp -> compensator->apply -> FeatherBlender (src/stitching_detailed.cpp:829-871)
+                return ref.process(t, fs, "feather", sharpness=config3_sharpness(t.dst_roi), apply_gain=True)
             return ref.process(t, fs, "multiband", NBANDS, cut=CUT)   # 'faithful': maps rebuilt per call (:1171)
         one(frame_sets[0])          # warm-up
         t0 = time.perf_counter()
@@ -183,7 +194,7 @@ def run_reference(args, rank, world):
         return
     per_step = 2
     sets = [[np.ascontiguousarray(f) for f in synth_numpy(1000 + s)] for s in range(2)]
-    kind, t = cpu_reference_setup(sets[0])
+    kind, t = cpu_reference_setup(sets[0], args.workload)
     if args.workload == "config2-yuyv":
         def yuyv(f):
             y = np.empty(f.shape[:2] + (2,), np.uint8)
@@ -191,9 +202,9 @@ def run_reference(args, rank, world):
             return y
         sets = [[yuyv(f) for f in s] for s in sets]
     front = args.workload.startswith("config2")
-    cpu_reference_time(kind, t, sets, max(1, args.warmup), front)
+    cpu_reference_time(kind, t, sets, max(1, args.warmup), front, args.workload)
     t0 = time.perf_counter()
-    v, cores, desc = cpu_reference_time(kind, t, sets, per_step * args.steps, front)
+    v, cores, desc = cpu_reference_time(kind, t, sets, per_step * args.steps, front, args.workload)
     dt = time.perf_counter() - t0
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -250,7 +261,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- init (one-time, host): calibration -> initSeam -> tables uploaded once ----
-    Ks, Rs, scale = calibration()
+    Ks, Rs, scale = calibration(args.workload)
     B = args.batch
     frames = synth_batch_torch(B, 1234 + rank, dev)
     front = None
@@ -271,15 +282,27 @@ def main():
         set0 = [frames[0, i].cpu().numpy() for i in range(NCAM)]
     else:   # the stitcher calibrates on what the front end delivers
         set0 = [front.getFrame(frames[0, i].cpu().numpy()) for i in range(NCAM)]
-    cfg = panob200.StitcherConfig(width=W, height=H, num_images=NCAM, Ks=Ks, Rs=Rs, warped_image_scale=scale,
-                                  blender="multiband", num_bands=NBANDS, cut=CUT, device=local_rank,
-                                  max_batch=args.max_batch, initMode=2)
-    st = panob200.ocvStitcher(cfg)
     masks_how = "GraphCut seam masks (cv2, host init)"
-    try:
-        rc = st.calibration(set0)
-    except ImportError:
-        rc, masks_how = st.initTables(), "warped all-255 masks (cv2 absent)"
+    if args.workload == "config3":
+        # init like src/stitching_detailed.cpp: seam masks + block gains from frame-set 0 (host, cv2), uploaded once
+        from oracle import cv2_reference as ref
+        t3 = ref.init_seam(set0, Ks, Rs, scale, warp="spherical", seam="gc_color", want_gains=True)
+        sharp = config3_sharpness(t3.dst_roi)
+        cfg = panob200.StitcherConfig(width=W, height=H, num_images=NCAM, Ks=Ks, Rs=Rs, warped_image_scale=scale,
+                                      blender="feather", num_bands=0, sharpness=sharp, device=local_rank, max_batch=args.max_batch)
+        st = panob200.ocvStitcher(cfg)
+        rc = st.initTables(t3.blend_masks, None, ref.feather_weights(t3, sharp))
+        if rc == 0:
+            st.set_gain_maps(ref.full_res_gain_maps(t3))
+    else:
+        cfg = panob200.StitcherConfig(width=W, height=H, num_images=NCAM, Ks=Ks, Rs=Rs, warped_image_scale=scale,
+                                      blender="multiband", num_bands=NBANDS, cut=CUT, device=local_rank,
+                                      max_batch=args.max_batch, initMode=2)
+        st = panob200.ocvStitcher(cfg)
+        try:
+            rc = st.calibration(set0)
+        except ImportError:
+            rc, masks_how = st.initTables(), "warped all-255 masks (cv2 absent)"
     if rc != 0:
         raise SystemExit("stitcher init failed: " + st.last_error)
     if front is not None:
@@ -398,8 +421,8 @@ def main():
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             sets = [[frames[b, i].cpu().numpy() for i in range(NCAM)] for b in range(2)]
-            kind, t = cpu_reference_setup([f[:, :, :3] for f in sets[0]] if front is None else set0)
-            v, cores, desc = cpu_reference_time(kind, t, sets, 24 if kind == "cv2" else 4, front is not None)
+            kind, t = cpu_reference_setup([f[:, :, :3] for f in sets[0]] if front is None else set0, args.workload)
+            v, cores, desc = cpu_reference_time(kind, t, sets, 24 if kind == "cv2" else 4, front is not None, args.workload)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
