@@ -124,9 +124,40 @@ def primitive_hashes():
     print("primitives", len(h))
 
 
+def widened_case():
+    """cv2 outputs for the SURVEY 8(f) rows: YUYV ingest (include/nvcam.hpp:880-886), the updateMask tail
+    (include/ocvstitcher.hpp:1251-1257) and the two-ring epilogue (src/master.cpp:321-326, src/panocamimpl.cpp:354-360)."""
+    rng = np.random.default_rng(77)
+    d = {}
+    yuyv = rng.integers(0, 256, (36, 64, 2), np.uint8)
+    yuyv[0, :6] = [[0, 0], [0, 0], [255, 255], [255, 255], [0, 255], [255, 0]]
+    d["yuyv"] = yuyv
+    d["yuyv_bgra"] = cv2.cvtColor(yuyv, cv2.COLOR_YUV2BGRA_YUYV)
+    low = (rng.integers(0, 2, (23, 41)) * 255).astype(np.uint8)
+    full = ((rng.integers(0, 9, (131, 240)) > 0) * 255).astype(np.uint8)
+    d["seam_low"], d["seam_full"] = low, full
+    d["seam_mask"] = cv2.bitwise_and(cv2.resize(cv2.dilate(low, None), (240, 131), interpolation=cv2.INTER_LINEAR_EXACT), full)
+    up = rng.integers(0, 256, (57, 333, 3), np.uint8)
+    down = rng.integers(0, 256, (64, 301, 3), np.uint8)
+    d["ring_up"], d["ring_down"] = up, down
+    ret = cv2.vconcat([cv2.resize(up, (301, 64)), down])
+    cv2.rectangle(ret, (0, ret.shape[0] // 2 - 5, ret.shape[1], 10), (0, 0, 0), -1)
+    d["ring_resize"] = ret
+    fc, width, height = 3, 301, 57 - 6
+    ret = cv2.vconcat([np.ascontiguousarray(up[fc:fc + height, :width]), np.ascontiguousarray(down[fc:fc + height, :width])])
+    cv2.rectangle(ret, (0, height - 2, width, 4), (0, 0, 0), -1, 1, 0)
+    d["ring_crop"] = ret
+    np.savez_compressed(os.path.join(HERE, "widened_small.npz"), **d)
+    print("widened", {k: v.shape for k, v in d.items()})
+
+
 if __name__ == "__main__":
     cv2.setNumThreads(1)
+    if len(sys.argv) > 1 and sys.argv[1] == "widened":
+        widened_case()
+        sys.exit(0)
     compose_case("cfg1_small", "2222", 240, 135, "spherical", 5, seed=1)
     compose_case("cfg1_cyl_small", "2222", 240, 135, "cylindrical", 3, seed=2, extras=False)
     frontend_case()
     primitive_hashes()
+    widened_case()

@@ -671,3 +671,15 @@ def test_yuyv_ingest_chained_into_process(fused):
     for b in range(2):
         assert_equal("yuyv device batch %d" % b, out[b].cpu().numpy(), want[b])
         assert_equal("yuyv host batch %d" % b, host_out[b].numpy(), want[b])
+
+
+def test_ring_epilogue_against_cv2_fixture():
+    """The two-ring kernel against cv2's own resize + vconcat + rectangle output (tests/golden/widened_small.npz)."""
+    g = load("widened_small")
+    up, down = g["ring_up"], g["ring_down"]
+    rc = panob200.RingComposer((up.shape[1], up.shape[0]), (down.shape[1], down.shape[0]), "resize")
+    assert_equal("ring resize vs cv2", rc.compose(up, down), g["ring_resize"])
+    rc.close()
+    rc = panob200.RingComposer((up.shape[1], up.shape[0]), (down.shape[1], down.shape[0]), "crop", finalcut=3)
+    assert_equal("ring crop vs cv2", rc.compose(up, down), g["ring_crop"])
+    rc.close()

@@ -118,3 +118,13 @@ def test_front_end_bit_exact():
     b = util.synth_frame(540, 960, 78, channels=4)
     assert np.array_equal(compose.front_end(b, (480, 270), mx, my, rect, (360, 203)), g["out_down"])
     assert np.array_equal(compose.front_end(b, (480, 270), mx, my, rect, (360, 203), undistort=False), g["out_noud"])
+
+
+def test_widened_rows_against_cv2_fixture():
+    """SURVEY 8(f) restatements (YUYV ingest, updateMask tail, two-ring epilogue) vs cv2 outputs stored in
+    tests/golden/widened_small.npz -- the pin that holds without cv2."""
+    g = load("widened_small")
+    assert np.array_equal(compose.yuyv_to_bgra(g["yuyv"]), g["yuyv_bgra"])
+    assert np.array_equal(compose.seam_mask_tail(g["seam_low"], g["seam_full"]), g["seam_mask"])
+    assert np.array_equal(compose.ring_epilogue(g["ring_up"], g["ring_down"], "resize"), g["ring_resize"])
+    assert np.array_equal(compose.ring_epilogue(g["ring_up"], g["ring_down"], "crop", finalcut=3), g["ring_crop"])
