@@ -259,6 +259,31 @@ def test_batched_device_and_host_apis():
     assert_equal("strided", st.process(padded), want[0])
 
 
+def test_gain_map_rounding_edge_cases():
+    """BlocksGainCompensator::apply is sat_u8(cvRound(v * g)): gains that produce exact ties (x.5 -> even), overflow,
+    zero, negative, infinite and NaN products must round / saturate like the oracle (the warp kernel evaluates it
+    with mantissa arithmetic instead of I2F / F2I).  OpenCV quirk included: saturate_cast<uchar>(cvRound(x)) is 0, not
+    255, once x leaves the int range (cvtss2si returns INT_MIN) -- verified against cv2.multiply."""
+    Ks, Rs, scale = calib.rig("2222", 320)
+    special = np.array([0.5, 1.5, 2.5, 0.25, 0.75, 300.0, 0.0, -1.0, np.inf, np.nan, 1.0, 0.9999999, 1.0000001, 127.5 / 255.0,
+                        254.5 / 255.0, 3.0e38, 2.2e7, -3.0e38, 8421504.5, 1.0e9 / 255.0], np.float32)
+    for blender, nb in (("multiband", 3), ("feather", 0)):
+        t = compose.build_tables(Ks, Rs, scale, (320, 180), "spherical")
+        t.blend_masks = util.soft_masks(t)
+        gains = []
+        for i, (w, h) in enumerate(t.sizes):
+            yy, xx = np.mgrid[0:h, 0:w]
+            gains.append(special[(xx + 3 * yy + i) % len(special)].astype(np.float32))
+        imgs = util.synth_set(4, 180, 320, 55)
+        imgs[0][:16, :16] = np.arange(256, dtype=np.uint8).reshape(16, 16)[:, :, None]      # every 8-bit value
+        st = make(Ks, Rs, scale, 320, 180, "spherical", blender, nb, sharp=0.05)
+        assert st.initTables(t.blend_masks) == 0, st.last_error
+        st.set_gain_maps(gains)
+        t.gain_maps = gains
+        fw = [panob200.capi.host_feather_weight(m, 0.05) for m in t.blend_masks] if blender == "feather" else None
+        assert_equal("gain edge cases " + blender, st.process(imgs), compose.process(t, imgs, blender, nb, feather_weights=fw))
+
+
 def test_error_behaviour():
     Ks, Rs, scale = calib.rig("2222", 240)
     st = make(Ks, Rs, scale, 240, 135, num_bands=3, cut=[0, 0, 5000, 50])

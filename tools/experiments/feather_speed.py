@@ -11,13 +11,13 @@ from oracle import compose
 dev = torch.device("cuda", 0)
 B = 64
 frames = bench.synth_batch_torch(B, 99, dev)
-Ks, Rs, scale = bench.calibration()
+Ks, Rs, scale = bench.calibration(os.environ.get("WORKLOAD", "config1"))
 t = compose.build_tables(Ks, Rs, scale, (1920, 1080), "spherical")
 masks = util.soft_masks(t)
 res = {}
 for blender in ("feather", "no"):
     st = panob200.ocvStitcher(panob200.StitcherConfig(width=1920, height=1080, num_images=4, Ks=Ks, Rs=Rs, warped_image_scale=scale,
-                                                      blender=blender, num_bands=0, sharpness=0.02, cut=bench.CUT, max_batch=64))
+                                                      blender=blender, num_bands=0, sharpness=0.02, cut=bench.CUT if os.environ.get("WORKLOAD", "config1") != "config3" else None, max_batch=64))
     assert st.initTables(masks) == 0, st.last_error
     for gains in (False, True):
         if gains:
@@ -33,5 +33,7 @@ for blender in ("feather", "no"):
         for _ in range(10):
             st.process_device(frames, out)
         e1.record(); torch.cuda.synchronize()
-        res["%s%s" % (blender, "+gain" if gains else "")] = {"panoramas_per_s": B * 10 / (e0.elapsed_time(e1) / 1e3), "ms_per_64": e0.elapsed_time(e1) / 10}
+        st.enable_profile(True); st.process_device(frames, out); torch.cuda.synchronize()
+        prof = {p["name"]: round(p["ms"], 3) for p in st.read_profile()}; st.enable_profile(False)
+        res["%s%s" % (blender, "+gain" if gains else "")] = {"panoramas_per_s": B * 10 / (e0.elapsed_time(e1) / 1e3), "ms_per_64": e0.elapsed_time(e1) / 10, "kernels_ms": prof}
 print(json.dumps(res))
