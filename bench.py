@@ -49,11 +49,11 @@ WORKLOAD = WORKLOADS["config1"]
 # what ncu shows as the on-chip limiter of each hot kernel (profiles/r1p_ncu_summary.txt): the HBM
 # roofline is the denominator the task asks for, but none of the exact-arithmetic gathers is DRAM-limited
 LIMITERS = {
-    "fe_cubic_undistort": "L1 data pipes: LSU wavefronts 84 % + TEX 81 % (16 smem taps + 32-byte weight entry per pixel); DRAM 40 %",
-    "fe_resize": "issue slots 76 % (exact cv::resize fixed point, ~60 instructions per pixel); DRAM 41 %",
-    "warp": "L1 LSU wavefronts 80 % + issue 72 %; DRAM 57 %",
-    "pyrdown_l0": "DRAM 74 % at 28 % occupancy (94 registers)",
-    "collapse_l0": "issue slots 61 %; DRAM 58 %",
+    "fe_cubic_undistort": "L1 data pipes: LSU wavefronts 84 % + TEX 81 % (16 smem taps + 32-byte weight entry per pixel); DRAM traffic 24 % of the copy rate",
+    "fe_resize": "issue slots 76 % (exact cv::resize fixed point, ~60 instructions per pixel); DRAM traffic 40 % of the copy rate",
+    "warp": "L1 LSU wavefronts 80 % + issue 72 %; DRAM traffic 56 % of the copy rate",
+    "pyrdown_l0": "DRAM traffic 72 % of the copy rate at 28 % occupancy (94 registers)",
+    "collapse_l0": "issue slots 61 %; DRAM traffic 48 % of the copy rate",
     "fe_yuyv_to_bgra": "HBM (97 % of the measured copy rate)",
 }
 NEWK_FALLBACK = [[1627.5076, 0, 943.1681], [0, 1622.9720, 571.5369], [0, 0, 1]]   # SURVEY A10 (used when cv2 is absent)
