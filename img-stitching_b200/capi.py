@@ -95,6 +95,7 @@ _SIGS = {
     "pano_strip_p2p_wait_unpack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "pano_strip_p2p_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pano_strip_run_p2p": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pano_strip_p2p_check": (C.c_int, [C.c_void_p]),
     "pano_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "pano_profile_read": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pano_last_launch_count": (C.c_int, [C.c_void_p]),

@@ -21,13 +21,14 @@ using namespace pano;
 
 // internal front-end entry points (frontend.cu)
 int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img, uint8_t *out, size_t o_img, int batch,
-                      cudaStream_t st);
+                      cudaStream_t st, int out_px);
+bool pano_frontend_can_words(pano_frontend_handle h);
+int pano_frontend_max_batch(pano_frontend_handle h);
 int pano_frontend_launches(pano_frontend_handle h);
 void pano_frontend_sizes(pano_frontend_handle h, int *in_wh, int *out_wh);
-bool pano_frontend_set_prof(pano_frontend_handle h, cudaEvent_t *ev, double *cubic_bytes, double *resize_bytes);
+bool pano_frontend_set_prof(pano_frontend_handle h, cudaEvent_t *ev, double *cubic_bytes, double *resize_bytes, int out_px);
 void pano_frontend_backmap(pano_frontend_handle h, double *xs, double *ys, size_t count);
 int pano_frontend_in_px(pano_frontend_handle h);
-bool pano_frontend_is_mixed(pano_frontend_handle h);
 int pano_frontend_convert(pano_frontend_handle h, const uint8_t *yuyv, size_t in_img, uint8_t *dst, int count, cudaStream_t st);
 
 namespace {
@@ -80,7 +81,10 @@ struct pano_ctx {
     size_t in_frame_bytes = 0;                    // bytes of one input frame as the caller passes it
     size_t in_frame_bytes4 = 0;                   // the same frame as 8UC4 (what the fused gather reads)
     uint8_t *fused_in = nullptr;                  // fused mode + YUYV ingest: converted 8UC4 frames [max_batch][n]
-    uint8_t *front_out = nullptr;                 // [max_batch][n][H][W][3] stitcher inputs produced by the front end
+    uint8_t *front_out = nullptr;                 // [max_batch][n][H][W][3 or 4] stitcher inputs produced by the front end
+    bool front_px4 = false;                       // the front ends hand over one word per pixel (warp_tile_kernel<.., kSrc4> + TMA)
+    cudaGraphExec_t graph1 = nullptr;             // pano_process: the kernel chain of ONE frame-set (stage_in[0] -> stage_out[0])
+    int graph1_launches = 0;
     int strip_x0 = 0, strip_x1 = 0;               // own dst columns (level 0, padded coords); full width = no split
     // walker tiles (kWalkTileW x kWalkTileH): [level][cam][tile] -> any non-zero weight / count of weights == 1
     std::vector<std::vector<std::vector<uint8_t>>> walk_nz;
@@ -98,8 +102,8 @@ struct pano_ctx {
     std::vector<size_t> mail_off;                 // [phase][from-side][parity] -> byte offset of the slot
     uint8_t *peer_mail[2] = {nullptr, nullptr};   // left / right neighbour's mailbox as addressable from this device
     bool peer_ipc[2] = {false, false};            // mapped with cudaIpcOpenMemHandle (to be closed)
-    unsigned *p2p_counters = nullptr;             // block-completion counters of halo_push_kernel
-    int sm_count = 0;
+    unsigned *p2p_counters = nullptr;             // [0], [1] block-completion counters of the push kernels, [2] error flag (a spin ran out)
+    int p2p_resident = 0;                         // most halo_exchange_kernel blocks that are certainly co-resident (fused exchange)
     uint32_t *p2p_seq = nullptr;                  // device: frame sequence number (bumped by the first kernel of a frame)
     // one frame's launch sequence captured once and replayed (the exchange is launch-latency bound)
     cudaGraphExec_t p2p_graph = nullptr;
@@ -117,7 +121,9 @@ struct pano_ctx {
     int last_launches = 0;
 
     size_t frame_bytes() const { return (size_t)cfg.src_width * cfg.src_height * 3; }
-    size_t gather_frame_bytes() const { return fused ? in_frame_bytes4 : frame_bytes(); }   // frame the warp gathers from
+    size_t front_out_bytes() const { return (size_t)cfg.src_width * cfg.src_height * 4; }   // per frame, sized for the word hand-over
+    size_t front_frame_bytes() const { return (size_t)cfg.src_width * cfg.src_height * (front_px4 ? 4 : 3); }
+    size_t gather_frame_bytes() const { return fused ? in_frame_bytes4 : (has_front ? front_frame_bytes() : frame_bytes()); }   // frame the warp gathers from
     size_t set_bytes() const { return (has_front ? in_frame_bytes : frame_bytes()) * n; }   // caller-side frame-set
     size_t out_bytes() const { return (size_t)host.cut_w * host.cut_h * 3; }
 };
@@ -310,7 +316,9 @@ int buildCamMap(pano_ctx *h, int cam, const float *xm, const float *ym, int W, i
             const int px0 = x0 / 16 * 16, groups = (x1 - px0) / 16 + 1;
             const int rows = y1 - y0 + 1;
             int4 d = make_int4(0, 0, 0, 0);
-            if (W % 16 == 0 && groups <= 16 && rows * ((groups * 16 + 31) & ~31) <= kWarpSmemWords) d = make_int4(px0, y0, rows, groups);
+            // capacity as the TMA staging needs it (rows in boxes of 4, pitch >= 128 words); the LDG/STS loop needs less
+            if (W % 16 == 0 && groups <= 16 && ((rows + 3) & ~3) * std::max(128, (groups * 16 + 31) & ~31) <= kWarpSmemWords)
+                d = make_int4(px0, y0, rows, groups);
             tl[(size_t)ty * C.tiles_x + tx] = d;
         }
     int4 *dt = nullptr;
@@ -403,6 +411,8 @@ int buildWeights(pano_ctx *h, int cam)
 int syncTables(pano_ctx *h)
 {
     if (!h->tables_dirty) return PANO_OK;
+    // captured launch sequences bake table pointers, work-list sizes and grid shapes in: they die with the tables
+    if (h->graph1) { cudaGraphExecDestroy(h->graph1); h->graph1 = nullptr; }
     if (uploadTileLists(h)) return PANO_ERR;
     CK(h, cudaMemcpy(h->dev, &h->host, sizeof(PanoTables), cudaMemcpyHostToDevice));
     h->tables_dirty = false;
@@ -442,7 +452,7 @@ double warpBytes(const pano_ctx *h, int slots)
     double b = 0;
     for (int i = 0; i < h->n; ++i) {
         const CamTables &C = h->host.cam[i];
-        b += (double)C.rw * C.rh * ((h->map64 ? 8 : 4) + 6 + (C.gain_mode == 1 ? 4 : 0)) + (double)h->gather_frame_bytes();
+        b += (double)C.rw * C.rh * ((h->map64 ? 8 : 4) + 3 + (C.gain_mode == 1 ? 4 : 0)) + (double)h->gather_frame_bytes();
     }
     return b * slots;
 }
@@ -451,7 +461,7 @@ double pyrdownBytes(const pano_ctx *h, int l, int slots)
     double b = 0;
     for (int i = 0; i < h->n; ++i) {
         const CamTables &C = h->host.cam[i];
-        b += 6.0 * (C.rw >> l) * (C.rh >> l) + 6.0 * (C.rw >> (l + 1)) * (C.rh >> (l + 1));
+        b += 3.0 * (C.rw >> l) * (C.rh >> l) + 3.0 * (C.rw >> (l + 1)) * (C.rh >> (l + 1));
     }
     return b * slots;
 }
@@ -462,8 +472,8 @@ double collapseBytes(const pano_ctx *h, int l, int slots)
     for (int i = 0; i < h->n; ++i) {
         const CamTables &C = h->host.cam[i];
         const double px = (double)(C.rw >> l) * (C.rh >> l);
-        b += px * (6 + ((l == 0 && !C.use_wt0) ? 1 : 4));
-        if (l < nb) b += 6.0 * (C.rw >> (l + 1)) * (C.rh >> (l + 1));
+        b += px * (3 + ((l == 0 && !C.use_wt0) ? 1 : 4));
+        if (l < nb) b += 3.0 * (C.rw >> (l + 1)) * (C.rh >> (l + 1));
     }
     if (l < nb) b += 6.0 * (h->pad_w >> (l + 1)) * (h->pad_h >> (l + 1));
     if (l == 0) b += (double)h->out_bytes();
@@ -485,7 +495,7 @@ double blendG0Bytes(const pano_ctx *h, int slots)
     double b = (double)h->out_bytes();
     for (int i = 0; i < h->n; ++i) {
         const CamTables &C = h->host.cam[i];
-        b += (double)C.rw * C.rh * (6 + (h->blender == PANO_BLEND_FEATHER ? 4 : 1));
+        b += (double)C.rw * C.rh * (3 + (h->blender == PANO_BLEND_FEATHER ? 4 : 1));
     }
     return b * slots;
 }
@@ -565,15 +575,18 @@ int runFrontEnds(pano_ctx *h, const uint8_t *&frames_dev, int slots, cudaStream_
     }
     bool same = true;
     for (int i = 1; i < h->n; ++i) same = same && h->front[i] == h->front[0];
-    if (same && h->profiling) {
+    const int opx = h->front_px4 ? 4 : 3;
+    const size_t ofb = h->front_frame_bytes();
+    // per-kernel timing only when the front end runs the batch as ONE chunk (its events are re-recorded per chunk)
+    if (same && h->profiling && slots * h->n <= pano_frontend_max_batch(h->front[0])) {
         // per-kernel timing of the fast path (cubic undistort / bilinear resize)
         cudaEvent_t ev[4];
         double cb = 0, rb = 0;
         for (auto &e : ev) cudaEventCreate(&e);
         const bool yuyv = h->in_frame_bytes4 != h->in_frame_bytes;
-        if (pano_frontend_set_prof(h->front[0], ev, &cb, &rb)) {
-            const int rc = pano_frontend_run(h->front[0], frames_dev, h->in_frame_bytes, h->front_out, h->frame_bytes(), slots * h->n, st);
-            pano_frontend_set_prof(h->front[0], nullptr, nullptr, nullptr);
+        if (pano_frontend_set_prof(h->front[0], ev, &cb, &rb, opx)) {
+            const int rc = pano_frontend_run(h->front[0], frames_dev, h->in_frame_bytes, h->front_out, ofb, slots * h->n, st, opx);
+            pano_frontend_set_prof(h->front[0], nullptr, nullptr, nullptr, opx);
             if (rc) return fail(h, "front end: %s", pano_frontend_last_error(h->front[0]));
             if (yuyv) {
                 ProfEntry y{"fe_yuyv_to_bgra", ev[3], ev[0], (double)(h->in_frame_bytes + h->in_frame_bytes4) * slots * h->n};
@@ -581,12 +594,7 @@ int runFrontEnds(pano_ctx *h, const uint8_t *&frames_dev, int slots, cudaStream_
             } else {
                 cudaEventDestroy(ev[3]);
             }
-            if (pano_frontend_is_mixed(h->front[0])) {
-                // cubic + resize run as horizontally fused launches: one entry, both kernels' algorithmic bytes
-                ProfEntry a{"fe_undistort_resize", ev[0], ev[2], (cb + rb) * slots * h->n, yuyv};
-                h->prof.push_back(a);
-                cudaEventDestroy(ev[1]);
-            } else {
+            {
                 ProfEntry a{"fe_cubic_undistort", ev[0], ev[1], cb * slots * h->n, yuyv};
                 h->prof.push_back(a);
                 ProfEntry b{"fe_resize", ev[1], ev[2], rb * slots * h->n, true};   // shares the middle event
@@ -596,18 +604,18 @@ int runFrontEnds(pano_ctx *h, const uint8_t *&frames_dev, int slots, cudaStream_
             frames_dev = h->front_out;
             return PANO_OK;
         }
-        pano_frontend_set_prof(h->front[0], nullptr, nullptr, nullptr);
+        pano_frontend_set_prof(h->front[0], nullptr, nullptr, nullptr, opx);
         for (auto &e : ev) cudaEventDestroy(e);
     }
-    L.begin("front_end", (double)slots * h->n * (h->in_frame_bytes + h->frame_bytes()));
+    L.begin("front_end", (double)slots * h->n * (h->in_frame_bytes + ofb));
     if (same) {
-        if (pano_frontend_run(h->front[0], frames_dev, h->in_frame_bytes, h->front_out, h->frame_bytes(), slots * h->n, st))
+        if (pano_frontend_run(h->front[0], frames_dev, h->in_frame_bytes, h->front_out, ofb, slots * h->n, st, opx))
             return fail(h, "front end: %s", pano_frontend_last_error(h->front[0]));
         h->last_launches += pano_frontend_launches(h->front[0]) - 1;
     } else {
         for (int i = 0; i < h->n; ++i) {
             if (pano_frontend_run(h->front[i], frames_dev + i * h->in_frame_bytes, h->in_frame_bytes * h->n,
-                                  h->front_out + i * h->frame_bytes(), h->frame_bytes() * h->n, slots, st))
+                                  h->front_out + i * ofb, ofb * h->n, slots, st, opx))
                 return fail(h, "front end: %s", pano_frontend_last_error(h->front[i]));
             h->last_launches += pano_frontend_launches(h->front[i]);
         }
@@ -642,19 +650,35 @@ bool phaseHalo(const pano_ctx *h, int p, int &kind, int &level, int &ncols)
 
 int ensureStaging(pano_ctx *h)
 {
+    if (!h->s_h2d) {
+        for (int i = 0; i < kPipeDepth; ++i) {
+            CK(h, cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+            CK(h, cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+            CK(h, cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+        }
+        CK(h, cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+        CK(h, cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+        CK(h, cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    }
     if (h->stage_in[0]) return PANO_OK;
     const size_t S = h->cfg.max_batch;
     for (int i = 0; i < kPipeDepth; ++i) {
         if (devAlloc(h, &h->stage_in[i], h->set_bytes() * S, false)) return PANO_ERR;
         if (devAlloc(h, &h->stage_out[i], h->out_bytes() * S, false)) return PANO_ERR;
-        CK(h, cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
-        CK(h, cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
-        CK(h, cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
     }
-    CK(h, cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
-    CK(h, cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
-    CK(h, cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
     return PANO_OK;
+}
+
+// The staging buffers are sized from set_bytes(), which changes when a front end is attached or detached (8UC4 / YUYV
+// camera frames vs BGR stitcher inputs): release them so that the next host-side call re-creates them at the new size.
+// The device must be idle (callers synchronise first).
+void dropStaging(pano_ctx *h)
+{
+    for (int i = 0; i < kPipeDepth; ++i) {
+        devFree(h, h->stage_in[i]); devFree(h, h->stage_out[i]);
+        h->stage_in[i] = nullptr; h->stage_out[i] = nullptr;
+    }
+    if (h->graph1) { cudaGraphExecDestroy(h->graph1); h->graph1 = nullptr; }
 }
 
 }  // namespace
@@ -781,10 +805,10 @@ int pano_create(const pano_config *cfg, pano_handle *out)
         {
             for (int l = 0; l <= h->nb; ++l) {
                 const int lw = C.rw >> l, lh = C.rh >> l;
-                C.g_pitch[l] = roundUp(lw + 24, 64);   // packed kernels over-read up to 18 samples past a row
+                C.g_pitch[l] = roundUp(lw + 24, 128);  // 8-bit samples, 128-byte aligned rows; packed kernels over-read up to 20 bytes past a row
                 C.g_plane[l] = (size_t)C.g_pitch[l] * lh;
                 C.g_slot[l] = 3 * C.g_plane[l];
-                int16_t *g = nullptr;
+                uint8_t *g = nullptr;
                 if (devAlloc(h, &g, C.g_slot[l] * S)) return bail(0);
                 C.g[l] = g;
             }
@@ -854,6 +878,7 @@ int pano_destroy(pano_handle h)
     cudaDeviceSynchronize();
     clearProf(h);
     if (h->p2p_graph) cudaGraphExecDestroy(h->p2p_graph);
+    if (h->graph1) cudaGraphExecDestroy(h->graph1);
     for (int s = 0; s < 2; ++s)
         if (h->peer_mail[s] && h->peer_ipc[s]) cudaIpcCloseMemHandle(h->peer_mail[s]);
     for (void *p : h->owned) cudaFree(p);
@@ -1071,26 +1096,42 @@ int pano_attach_frontend(pano_handle h, int cam, pano_frontend_handle f)
     if (!f) {
         if (h->fused && pano_set_frontend_mode(h, PANO_FRONTEND_SEQUENTIAL)) return PANO_ERR;
         for (int i = 0; i < h->n; ++i) h->front[i] = nullptr;
+        if (h->has_front) dropStaging(h);         // the caller-side frame-set shrinks or grows: re-size on next use
         h->has_front = false;
+        h->front_px4 = false;
+        h->host.src_px = 3;
+        h->tables_dirty = true;
         return PANO_OK;
     }
     if (h->fused) return fail(h, "pano_attach_frontend: switch back to PANO_FRONTEND_SEQUENTIAL before re-attaching");
+    // every check comes before the handle is touched: a failing call leaves it exactly as it was
     int in_wh[2], out_wh[2];
     pano_frontend_sizes(f, in_wh, out_wh);
     if (out_wh[0] != h->cfg.src_width || out_wh[1] != h->cfg.src_height)
         return fail(h, "pano_attach_frontend: front end delivers %dx%d, stitcher expects %dx%d", out_wh[0], out_wh[1],
                     h->cfg.src_width, h->cfg.src_height);
     const size_t in_bytes = (size_t)in_wh[0] * in_wh[1] * pano_frontend_in_px(f);
-    if (h->has_front && in_bytes != h->in_frame_bytes) return fail(h, "pano_attach_frontend: all cameras must share one frame size and format");
+    if (h->has_front && in_bytes != h->in_frame_bytes) {
+        bool replaces_all = cam < 0;
+        if (!replaces_all) return fail(h, "pano_attach_frontend: all cameras must share one frame size and format");
+    }
+    if (!h->front_out && devAlloc(h, &h->front_out, h->front_out_bytes() * h->n * h->cfg.max_batch, false)) return PANO_ERR;
+    const size_t old_set = h->set_bytes();
     for (int i = 0; i < h->n; ++i)
         if (cam < 0 || cam == i) h->front[i] = f;
     for (int i = 0; i < h->n; ++i)
         if (!h->front[i]) h->front[i] = f;      // every camera needs one once the input format changes
-    if (h->stage_in[0]) return fail(h, "pano_attach_frontend: attach before the first host-side process call");
     h->in_frame_bytes = in_bytes;
     h->in_frame_bytes4 = (size_t)in_wh[0] * in_wh[1] * 4;
     h->has_front = true;
-    if (!h->front_out && devAlloc(h, &h->front_out, h->frame_bytes() * h->n * h->cfg.max_batch, false)) return PANO_ERR;
+    // hand-over layout: one word per pixel when every camera's front end can produce it (the warp then stages its
+    // source tiles by TMA), else packed BGR
+    h->front_px4 = h->kc.warp_tiled;
+    for (int i = 0; i < h->n; ++i) h->front_px4 = h->front_px4 && pano_frontend_can_words(h->front[i]);
+    h->host.src_px = h->front_px4 ? 4 : 3;
+    h->tables_dirty = true;
+    if (h->graph1) { cudaGraphExecDestroy(h->graph1); h->graph1 = nullptr; }
+    if (h->set_bytes() != old_set) dropStaging(h);
     return PANO_OK;
 }
 
@@ -1146,7 +1187,7 @@ int pano_set_frontend_mode(pano_handle h, int mode)
         if (buildCamMap(h, i, xm, ym, W, H)) return PANO_ERR;
     }
     if (!h->fused) { h->fxmap.clear(); h->fymap.clear(); }
-    h->host.src_w = W; h->host.src_h = H; h->host.src_px = h->fused ? 4 : 3;
+    h->host.src_w = W; h->host.src_h = H; h->host.src_px = (h->fused || h->front_px4) ? 4 : 3;
     h->map64 = (32 * (W - 1) + 31 > 65535) || (32 * (H - 1) + 31 > 65535);
     h->kc.warp_tiled = (W % 16 == 0);
     h->tables_dirty = true;
@@ -1188,9 +1229,33 @@ int pano_process(pano_handle h, const uint8_t *const *frames, const int *strides
         CK(h, cudaMemcpy2DAsync(h->stage_in[0] + (size_t)i * fbytes, W3, frames[i], st, W3, H,
                                 cudaMemcpyHostToDevice, h->s_compute));
     }
-    h->last_launches = 0;
     if (h->profiling) clearProf(h);
-    if (runWave(h, h->stage_in[0], h->stage_out[0], 1, h->s_compute)) return PANO_ERR;
+    // The drop-in call (one frame-set per process(), src/replay.cpp:284-292): the ~20 launches of the kernel chain are
+    // captured ONCE (they only touch the handle's own staging buffers and tables) and replayed as a CUDA graph.
+    static const bool no_graph = getenv("PANO_NO_GRAPH") != nullptr;
+    if (no_graph || h->profiling) {
+        h->last_launches = 0;
+        if (runWave(h, h->stage_in[0], h->stage_out[0], 1, h->s_compute)) return PANO_ERR;
+    } else {
+        if (!h->graph1) {
+            cudaGraph_t g = nullptr;
+            h->last_launches = 0;
+            CK(h, cudaStreamBeginCapture(h->s_compute, cudaStreamCaptureModeThreadLocal));
+            const int rc = runWave(h, h->stage_in[0], h->stage_out[0], 1, h->s_compute);
+            const cudaError_t e = cudaStreamEndCapture(h->s_compute, &g);
+            if (rc || e != cudaSuccess || !g) {
+                if (g) cudaGraphDestroy(g);
+                (void)cudaGetLastError();
+                return rc ? PANO_ERR : fail(h, "pano_process: graph capture failed: %s", cudaGetErrorString(e));
+            }
+            const cudaError_t ei = cudaGraphInstantiate(&h->graph1, g, 0);
+            cudaGraphDestroy(g);
+            if (ei != cudaSuccess) { h->graph1 = nullptr; return fail(h, "pano_process: graph instantiation failed: %s", cudaGetErrorString(ei)); }
+            h->graph1_launches = h->last_launches;
+        }
+        CK(h, cudaGraphLaunch(h->graph1, h->s_compute));
+        h->last_launches = h->graph1_launches;
+    }
     CK(h, cudaMemcpy2DAsync(out, out_stride, h->stage_out[0], (size_t)h->host.cut_w * 3, (size_t)h->host.cut_w * 3,
                             h->host.cut_h, cudaMemcpyDeviceToHost, h->s_compute));
     CK(h, cudaStreamSynchronize(h->s_compute));
@@ -1333,8 +1398,8 @@ int pano_strip_p2p_create(pano_handle h, void *ipc_handle64, size_t *mailbox_byt
     if (mailLayout(h)) return PANO_ERR;
     if (!h->mailbox) {
         if (devAlloc(h, &h->mailbox, h->mailbox_bytes, true)) return PANO_ERR;
-        if (devAlloc(h, &h->p2p_counters, 2, true) || devAlloc(h, &h->p2p_seq, 1, true)) return PANO_ERR;
-        CK(h, cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device));
+        if (devAlloc(h, &h->p2p_counters, 4, true) || devAlloc(h, &h->p2p_seq, 1, true)) return PANO_ERR;
+        h->p2p_resident = halo_exchange_resident_limit(h->device);
     }
     if (ipc_handle64) {
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -1348,6 +1413,8 @@ int pano_strip_p2p_create(pano_handle h, void *ipc_handle64, size_t *mailbox_byt
 
 static int p2pDisconnect(pano_ctx *h, int side)
 {
+    // the captured frame graph bakes the peer mailbox pointers in: it dies with the mapping
+    if (h->p2p_graph) { cudaGraphExecDestroy(h->p2p_graph); h->p2p_graph = nullptr; }
     if (h->peer_mail[side] && h->peer_ipc[side]) cudaIpcCloseMemHandle(h->peer_mail[side]);
     h->peer_mail[side] = nullptr; h->peer_ipc[side] = false;
     return PANO_OK;
@@ -1437,7 +1504,7 @@ int pano_strip_p2p_wait_unpack(pano_handle h, int phase, void *stream)
     CK(h, cudaSetDevice(h->device));
     HaloSide push[2], recv[2];
     p2pSides(h, phase, level, ncols, push, recv);
-    launch_halo_wait_unpack(h->dev, h->host, kind, level, ncols, recv[0], recv[1], h->p2p_seq, (cudaStream_t)stream);
+    launch_halo_wait_unpack(h->dev, h->host, kind, level, ncols, recv[0], recv[1], h->p2p_seq, h->p2p_counters, (cudaStream_t)stream);
     ++h->last_launches;
     CK(h, cudaGetLastError());
     return PANO_OK;
@@ -1453,13 +1520,14 @@ static int p2pFrame(pano_handle h, const uint8_t *frames_dev, uint8_t *pano_dev,
         int kind, level, ncols;
         if (!phaseHalo(h, p, kind, level, ncols)) continue;
         if (!h->peer_mail[0] && !h->peer_mail[1]) continue;
-        // one launch per exchange while all its blocks are certainly co-resident (256-thread blocks, 8 fit an SM; 6 per
-        // SM are claimed, the rank's own stream is idle by then), otherwise push and wait/unpack as two launches
+        // one launch per exchange while all its blocks are certainly co-resident (the runtime's occupancy figure for the
+        // kernel x SMs, minus a quarter as margin for other work on the device; every spin is bounded and raises the
+        // handle's error flag -- pano_strip_p2p_check), otherwise push and wait/unpack as two launches
         static const bool split = getenv("PANO_P2P_SPLIT") != nullptr;
         HaloSide push[2], recv[2];
         p2pSides(h, p, level, ncols, push, recv);
         if (!split && launch_halo_exchange(h->dev, h->host, kind, level, ncols, push, recv, h->p2p_seq, h->p2p_counters,
-                                           h->sm_count * 6, (cudaStream_t)stream)) {
+                                           h->p2p_resident, (cudaStream_t)stream)) {
             ++h->last_launches;
             continue;
         }
@@ -1517,6 +1585,19 @@ int pano_strip_run_p2p(pano_handle h, const uint8_t *frames_dev, uint8_t *pano_d
         return PANO_OK;
     }
     CK(h, cudaGraphLaunch(h->p2p_graph, st));
+    return PANO_OK;
+}
+
+int pano_strip_p2p_check(pano_handle h)
+{
+    if (!h || !h->p2p_counters) return fail(h, "pano_strip_p2p_check: no mailbox (pano_strip_p2p_create)");
+    CK(h, cudaSetDevice(h->device));
+    unsigned flag = 0;
+    CK(h, cudaMemcpy(&flag, h->p2p_counters + 2, sizeof flag, cudaMemcpyDeviceToHost));
+    if (flag) {
+        CK(h, cudaMemset(h->p2p_counters, 0, 4 * sizeof(unsigned)));
+        return fail(h, "pano_strip_p2p: a halo wait ran out of patience (a neighbour never published its columns)");
+    }
     return PANO_OK;
 }
 

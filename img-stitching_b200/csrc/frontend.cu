@@ -19,6 +19,7 @@
 
 #include "../../include/panob200.h"
 #include "geometry.hpp"
+#include "tma.h"
 
 using namespace pano;
 
@@ -255,9 +256,16 @@ __global__ void __launch_bounds__(256) cubic4_kernel(const uint32_t *__restrict_
 //  * The 32-byte weight entry of every pixel comes through the TEXTURE pipe of L1TEX (two 16-byte fetches of
 //    a linear texture over the 1024-entry table), which runs beside the LSU pipe that serves the taps.
 //  * Rounding is folded into the accumulator start value; saturate + pack is two cvt.pack instructions.
+//  * On the TMA path (default) the footprint is not staged by the threads at all: one elected thread issues a single
+//    cp.async.bulk.tensor box load (kCubBoxW x 24 or 32 words at the tile's source origin) that the copy engine lands
+//    in shared memory while the block fetches its map entries; out-of-bounds parts of the box are ZERO-FILLED by the
+//    hardware, which is exactly BORDER_CONSTANT(0).  The LDG/STS staging loop remains as the fallback for geometries
+//    whose footprints exceed the box.
 constexpr int kCubTileW = 64, kCubTileH = 16, kCubSmemWords = 3072;    // 12 KB
+constexpr int kCubBoxW = 96, kCubBoxH0 = 24, kCubBoxH1 = 32;           // TMA boxes (words x rows); 96 * 32 = kCubSmemWords
 
 struct CubicArgs {
+    CUtensorMap tm0, tm1;            // [images][sh][sw] words, boxes kCubBoxW x kCubBoxH0 / kCubBoxH1 (TMA path only)
     const uint32_t *src; size_t src_img_words; int sw, sh;
     const uint32_t *map; int map_w; cudaTextureObject_t wtex; const int4 *tiles;
     int rx, ry, rw, rh;
@@ -266,7 +274,8 @@ struct CubicArgs {
 };
 
 // one 256-thread block = tile (bx, by) of image bz; sm = kCubSmemWords words of shared memory
-__device__ __forceinline__ void cubic5_body(const CubicArgs &A, uint32_t *__restrict__ sm, int bx, int by, int bz)
+template <bool kTma>
+__device__ __forceinline__ void cubic5_body(const CubicArgs &A, uint32_t *__restrict__ sm, uint64_t *bar, int bx, int by, int bz)
 {
     const uint32_t *__restrict__ src = A.src, *__restrict__ map = A.map;
     const int sw = A.sw, sh = A.sh, map_w = A.map_w, rx = A.rx, ry = A.ry, rw = A.rw, rh = A.rh;
@@ -275,7 +284,13 @@ __device__ __forceinline__ void cubic5_body(const CubicArgs &A, uint32_t *__rest
     const int lane = threadIdx.x, wy = threadIdx.y, tid = wy * 32 + lane;
     const int4 td = __ldg(A.tiles + by * A.tx + bx);   // {x0 (%4 == 0), y0, rows | chunks per row << 16, 2^16 / chunks}
     const int rows = td.z & 0xffff, W4 = td.z >> 16;
-    const int P = (W4 * 4 + 31) & ~31;                                  // staged row pitch, words
+    const int P = kTma ? kCubBoxW : ((W4 * 4 + 31) & ~31);              // staged row pitch, words
+    if (kTma && tid == 0) {
+        mbar_init(bar, 1);
+        const bool small = rows <= kCubBoxH0;
+        mbar_expect_tx(bar, (unsigned)(kCubBoxW * (small ? kCubBoxH0 : kCubBoxH1) * 4));
+        tma_load_3d(sm, small ? &A.tm0 : &A.tm1, td.x, td.y, bz, bar);
+    }
     const int y = by * kCubTileH + wy, xb = bx * kCubTileW + lane;
     const uint32_t *s = src + (size_t)bz * A.src_img_words;
     uint32_t m[4];
@@ -284,14 +299,17 @@ __device__ __forceinline__ void cubic5_body(const CubicArgs &A, uint32_t *__rest
         const int xx = xb + 32 * (j & 1), yy = y + 8 * (j >> 1);
         m[j] = (xx < rw && yy < rh) ? __ldg(map + (size_t)(yy + ry) * map_w + rx + xx) : 0u;
     }
-    for (int c = tid; c < rows * W4; c += 256) {
-        const int r = (c * td.w) >> 16, q = c - r * W4;
-        const int sy = td.y + r, sx = td.x + 4 * q;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if ((unsigned)sy < (unsigned)sh && (unsigned)sx < (unsigned)sw) v = __ldg(reinterpret_cast<const uint4 *>(s + (size_t)sy * sw + sx));
-        *reinterpret_cast<uint4 *>(sm + r * P + 4 * q) = v;
+    if (!kTma) {
+        for (int c = tid; c < rows * W4; c += 256) {
+            const int r = (c * td.w) >> 16, q = c - r * W4;
+            const int sy = td.y + r, sx = td.x + 4 * q;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if ((unsigned)sy < (unsigned)sh && (unsigned)sx < (unsigned)sw) v = __ldg(reinterpret_cast<const uint4 *>(s + (size_t)sy * sw + sx));
+            *reinterpret_cast<uint4 *>(sm + r * P + 4 * q) = v;
+        }
     }
-    __syncthreads();
+    __syncthreads();                                                    // staging done / the mbarrier is initialised
+    if (kTma) mbar_wait(bar, 0);                                        // the box has landed
     uint32_t *d = dst + (size_t)bz * A.dst_img_words + (size_t)y * rw + xb;
     const int sbase = -((td.y + 4) * P + td.x + 4);                     // the map stores tx + 4, ty + 4
 #pragma unroll
@@ -322,10 +340,12 @@ __device__ __forceinline__ void cubic5_body(const CubicArgs &A, uint32_t *__rest
     }
 }
 
+template <bool kTma>
 __global__ void __launch_bounds__(256) cubic5_kernel(const __grid_constant__ CubicArgs A)
 {
-    __shared__ __align__(16) uint32_t sm[kCubSmemWords];
-    cubic5_body(A, sm, blockIdx.x, blockIdx.y, blockIdx.z);
+    __shared__ __align__(128) uint32_t sm[kCubSmemWords];
+    __shared__ __align__(8) uint64_t bar;
+    cubic5_body<kTma>(A, sm, &bar, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
 // cv::resize INTER_LINEAR from a word-per-pixel source to packed BGR bytes.  One warp row-chunk =
@@ -407,10 +427,11 @@ struct ResizeArgs {
 };
 constexpr int kResizeSmemWords = kResizeBand + 1 + kResizeRows;
 
-// one 128-thread block (4 warps: wy = 0..3) = column group bx, band by of image bz.  kBar = 0: the block is a whole
-// CUDA block (__syncthreads); kBar > 0: it is one of several 128-thread sub-blocks of a larger block and
-// synchronises on named barrier kBar (a compile-time id: a run-time id makes ptxas reserve all 16 barriers).
-template <int kBar>
+// one 128-thread block (4 warps: wy = 0..3) = column group bx, band by of image bz.
+// kWords: the output is one 32-bit word per pixel (B | G << 8 | R << 16; dstride / dst_img still in bytes) instead of
+// packed BGR -- the layout the rotation warp's staged gather (warp_tile_kernel<.., kSrc4>) consumes directly when the
+// front end is chained in front of a stitcher handle (an internal buffer: the caller never sees it).
+template <bool kWords>
 __device__ __forceinline__ void resize4_walk_body(const ResizeArgs &A, uint32_t *__restrict__ smem, int bx, int by, int bz, int wy)
 {
     const uint32_t *__restrict__ src = A.src;
@@ -430,8 +451,7 @@ __device__ __forceinline__ void resize4_walk_body(const ResizeArgs &A, uint32_t 
         const short2 q = __ldg(t.ya + min(ybase + tid - 64, t.dh - 1));
         s_ay[tid - 64] = ((uint32_t)(uint16_t)q.y << 16) | (uint16_t)q.x;
     }
-    if (kBar > 0) asm volatile("bar.sync %0, 128;" ::"n"(kBar) : "memory");
-    else __syncthreads();
+    __syncthreads();
     const int xw = (bx * 4 + wy) * 32;                                  // first column of this warp
     if (xw >= t.dw) return;
     const int x = xw + lane;
@@ -443,7 +463,8 @@ __device__ __forceinline__ void resize4_walk_body(const ResizeArgs &A, uint32_t 
     const int j = lane & 3;
     const uint32_t sel = j == 0 ? 0x4210u : (j == 1 ? 0x5421u : 0x6542u);
     // lanes 4k..4k+2 store the three words of pixels 4k..4k+3; lane 4k+3 stores nothing
-    uint8_t *olane = dst + (size_t)bz * dst_img + (size_t)ybase * dstride + (size_t)xw * 3 + ((lane >> 2) * 3 + j) * 4;
+    uint8_t *olane = dst + (size_t)bz * dst_img + (size_t)ybase * dstride +
+                     (kWords ? (size_t)x * 4 : (size_t)xw * 3 + ((lane >> 2) * 3 + j) * 4);
     const uint32_t *ayp = s_ay;
     const unsigned sstride_bytes = sstride_words * 4u;
 
@@ -467,9 +488,13 @@ __device__ __forceinline__ void resize4_walk_body(const ResizeArgs &A, uint32_t 
             const uint32_t c0_ = (__umulhi(a0_, A0) + 2u + __umulhi(a1_, B0)) >> 2;   \
             const uint32_t c1_ = (__umulhi(a0_, A1) + 2u + __umulhi(a1_, B1)) >> 2;   \
             const uint32_t c2_ = (__umulhi(a0_, A2) + 2u + __umulhi(a1_, B2)) >> 2;   \
-            const uint32_t px_ = __byte_perm(__byte_perm(c0_, c1_, 0x0040), c2_, 0x0410); \
-            const uint32_t nx_ = __shfl_down_sync(0xffffffffu, px_, 1);          \
-            if (j < 3) *reinterpret_cast<uint32_t *>(olane) = __byte_perm(px_, nx_, sel); \
+            const uint32_t px_ = __byte_perm(__byte_perm(c0_, c1_, 0x0040), c2_, 0x4410); \
+            if (kWords) {                                                        \
+                *reinterpret_cast<uint32_t *>(olane) = px_;                      \
+            } else {                                                             \
+                const uint32_t nx_ = __shfl_down_sync(0xffffffffu, px_, 1);      \
+                if (j < 3) *reinterpret_cast<uint32_t *>(olane) = __byte_perm(px_, nx_, sel); \
+            }                                                                    \
             olane += dstride;                                                    \
         }                                                                        \
         RS_HCALC(PA, PB, A0, A1, A2)                                             \
@@ -492,44 +517,11 @@ __device__ __forceinline__ void resize4_walk_body(const ResizeArgs &A, uint32_t 
 #undef RS_FETCH
 }
 
+template <bool kWords>
 __global__ void __launch_bounds__(128, 8) resize4_walk_kernel(const __grid_constant__ ResizeArgs A)
 {
     __shared__ uint32_t smem[kResizeSmemWords];
-    resize4_walk_body<0>(A, smem, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.y);
-}
-
-// EXPERIMENT (PANO_FE_MIXED=1; off by default): horizontal fusion of the two front-end kernels.  cubic5 saturates the
-// L1 data pipes (LSU 84 %, TEX 81 %) at 64 % issue utilisation; resize4_walk saturates the issue slots (76 %) at 34 % L1
-// utilisation, so ONE launch carrying cubic tiles of image chunk k and resize bands of chunk k-1, interleaved in
-// block-index order (nc cubic blocks, then nr blocks that each hold two 128-thread resize sub-blocks on named barriers),
-// keeps both kinds co-resident on every SM.  Bit-identical output (same device code), but MEASURED SLOWER: 0.976 ms per
-// wave against 0.85 ms back to back -- the mix is issue-bound at 74.5 % (ncu) and executes 21 % more instructions than
-// the two kernels apart, so the idle L1 / issue capacity it was meant to use does not exist in practice.
-struct MixArgs {
-    CubicArgs c; ResizeArgs r;
-    int c_imgs, r_imgs;              // images per role in this launch (0 = role absent)
-    int nc, nr;                      // interleave pattern
-};
-
-__global__ void __launch_bounds__(256, 6) undistort_resize_mixed_kernel(const __grid_constant__ MixArgs M)
-{
-    __shared__ __align__(16) uint32_t sm[kCubSmemWords];
-    static_assert(2 * kResizeSmemWords <= kCubSmemWords, "resize sub-blocks share the cubic staging buffer");
-    const int period = M.nc + M.nr;
-    const int g = blockIdx.x / period, k = blockIdx.x - g * period;
-    if (k < M.nc) {
-        const int ci = g * M.nc + k, per_img = M.c.tx * M.c.ty;
-        if (ci >= per_img * M.c_imgs) return;
-        const int bz = ci / per_img, rem = ci - bz * per_img;
-        cubic5_body(M.c, sm, rem % M.c.tx, rem / M.c.tx, bz);
-    } else {
-        const int sub = threadIdx.y >> 2;
-        const int ri = (g * M.nr + (k - M.nc)) * 2 + sub, per_img = M.r.gx * M.r.gy;
-        if (ri >= per_img * M.r_imgs) return;
-        const int bz = ri / per_img, rem = ri - bz * per_img;
-        if (sub == 0) resize4_walk_body<1>(M.r, sm, rem % M.r.gx, rem / M.r.gx, bz, threadIdx.y & 3);
-        else resize4_walk_body<2>(M.r, sm + kResizeSmemWords, rem % M.r.gx, rem / M.r.gx, bz, threadIdx.y & 3);
-    }
+    resize4_walk_body<kWords>(A, smem, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.y);
 }
 
 thread_local std::string g_front_error;
@@ -550,9 +542,9 @@ struct pano_frontend_ctx {
     uint32_t *buf_w = nullptr;                                     // cropped undistorted image, one word per pixel (fast path)
     uint32_t *dmap32 = nullptr;                                    // packed map entries (fast path, sources <= 2043 px)
     bool fast4 = false;
-    bool mixed = getenv("PANO_FE_MIXED") != nullptr;              // experiment: cubic + resize as horizontally fused launches (measured slower, off)
     int4 *cub_tiles = nullptr;                                     // per 128x8 tile of the crop rect: staged footprint (cubic5_kernel)
     int cub_tx = 0, cub_ty = 0;
+    bool cub_tma = false;                                          // every tile footprint fits the TMA boxes (kCubBoxW x kCubBoxH1)
     cudaEvent_t *prof_ev = nullptr;                                // events when profiling: before cubic, between, after resize, [3] before the YUYV conversion
     uint8_t *buf_argb = nullptr;                                   // YUYV ingest: converted 8UC4 frames, max_batch deep
     int in_px() const { return cfg.src_format == PANO_SRC_YUYV ? 2 : 4; }
@@ -718,7 +710,7 @@ int pano_frontend_create(const pano_frontend_config *cfg, pano_frontend_handle *
         const int *rc = cfg->rect;
         const int tx = (rc[2] + kCubTileW - 1) / kCubTileW, ty = (rc[3] + kCubTileH - 1) / kCubTileH;
         std::vector<int4> tl((size_t)tx * ty);
-        bool fits = cfg->cam_src_width % 4 == 0;
+        bool fits = cfg->cam_src_width % 4 == 0, tma_fits = true;
         for (int by = 0; by < ty && fits; ++by)
             for (int bx = 0; bx < tx && fits; ++bx) {
                 int x0 = INT32_MAX, x1 = INT32_MIN, y0 = INT32_MAX, y1 = INT32_MIN;
@@ -732,6 +724,7 @@ int pano_frontend_create(const pano_frontend_config *cfg, pano_frontend_handle *
                 const int ax0 = (x0 >= 0 ? x0 / 4 : -((-x0 + 3) / 4)) * 4;           // floor to a multiple of 4
                 const int w4 = (x1 - ax0) / 4 + 1, rows = y1 - y0 + 1;
                 fits = w4 <= 64 && rows * ((w4 * 4 + 31) & ~31) <= kCubSmemWords && rows * w4 < 1024;
+                tma_fits = tma_fits && w4 * 4 <= kCubBoxW && rows <= kCubBoxH1;
                 tl[(size_t)by * tx + bx] = make_int4(ax0, y0, rows | (w4 << 16), (65536 + w4 - 1) / w4);
             }
         if (getenv("PANO_DEBUG")) fprintf(stderr, "[panob200] cubic tiles %dx%d of %dx%d: %s\n", tx, ty, kCubTileW, kCubTileH, fits ? "staged" : "footprint too large -> untiled kernel");
@@ -742,6 +735,7 @@ int pano_frontend_create(const pano_frontend_config *cfg, pano_frontend_handle *
                 return bail();
             }
             h->cub_tx = tx; h->cub_ty = ty;
+            h->cub_tma = tma_fits;
         }
     }
     *out = h;
@@ -787,10 +781,19 @@ int pano_frontend_in_px(pano_frontend_handle h) { return h ? h->in_px() : 4; }
 // Internal entry (also used by capi.cu when a front end is attached to a stitcher handle):
 // images may be strided (in_img / o_img bytes between consecutive images).
 
+// out_px: 3 = packed BGR (the public layout), 4 = one word per pixel (internal hand-over to the rotation warp; only
+// when pano_frontend_can_words(h))
+bool pano_frontend_can_words(pano_frontend_handle h)
+{
+    static const bool no_words = getenv("PANO_FE_NO_WORDS") != nullptr;   // A/B switch: packed BGR hand-over
+    return h && h->fast4 && h->r_mid.walk && !no_words && !getenv("PANO_NO_RESIZE_WALK");
+}
+
 int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img, uint8_t *out, size_t o_img, int batch,
-                      cudaStream_t st)
+                      cudaStream_t st, int out_px)
 {
     if (!h || !argb || !out || batch < 1) return ffail(h, "pano_frontend_run: bad argument");
+    if (out_px != 3 && !(out_px == 4 && pano_frontend_can_words(h))) return ffail(h, "pano_frontend_run: word output is not available for this geometry");
     FCK(h, cudaSetDevice(h->cfg.device));
     const pano_frontend_config &c = h->cfg;
     const int S = c.max_batch, uw = c.undist_width, uh = c.undist_height;
@@ -813,51 +816,35 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
         // stage 1: camera frame -> undist-sized 3-channel "tmp" (:903-904 / :924-927)
         const uint8_t *cur = src; int cur_c = 4; int cw = c.cam_src_width, chh = c.cam_src_height; size_t cur_img = img_stride;
         auto target = [&](bool last, uint8_t *scratch) { return last ? final_dst : scratch; };
-        if (h->fast4 && (img_stride & 3) == 0) {
+        // the fast path reads the frames as 16-byte vectors (or through a TMA descriptor): base and image stride must be
+        // 16-byte aligned; anything else takes the generic byte-wise kernels below
+        if (h->fast4 && (img_stride & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
             const int *rc = c.rect;
             const size_t w_img = (size_t)rc[2] * rc[3];
             const dim3 cg((rc[2] + 127) / 128, (rc[3] + 7) / 8, nb);
             static const bool tex_w = getenv("PANO_CUBIC_TEX") != nullptr;
             static const bool no_tiled = getenv("PANO_CUBIC_UNTILED") != nullptr;
             static const bool no_walk = getenv("PANO_NO_RESIZE_WALK") != nullptr;
+            static const bool no_tma = getenv("PANO_NO_TMA") != nullptr;        // A/B switch: LDG/STS staging loop
             const uint32_t *src4 = reinterpret_cast<const uint32_t *>(src);
             const uint4 *tab4 = reinterpret_cast<const uint4 *>(h->dtab);
             const bool tiled = h->cub_tiles && h->wtex && !no_tiled;
             const bool walk = h->r_mid.walk && !no_walk && (reinterpret_cast<uintptr_t>(final_dst) & 3) == 0 && (o_img & 3) == 0 && ((uw * 3) & 3) == 0;
-            CubicArgs ca{src4, img_stride / 4, cw, chh, h->dmap32, uw, h->wtex, h->cub_tiles, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img,
-                         h->cub_tx, h->cub_ty};
-            ResizeArgs ra{h->buf_w, w_img, (unsigned)rc[2], final_dst, o_img, (unsigned)(uw * 3), h->r_mid,
+            if (out_px == 4 && !walk) return ffail(h, "pano_frontend_run: word output needs the row-walking resize");
+            CubicArgs ca{};
+            ca.src = src4; ca.src_img_words = img_stride / 4; ca.sw = cw; ca.sh = chh; ca.map = h->dmap32; ca.map_w = uw; ca.wtex = h->wtex;
+            ca.tiles = h->cub_tiles; ca.rx = rc[0]; ca.ry = rc[1]; ca.rw = rc[2]; ca.rh = rc[3]; ca.dst = h->buf_w; ca.dst_img_words = w_img;
+            ca.tx = h->cub_tx; ca.ty = h->cub_ty;
+            const bool tma = tiled && h->cub_tma && !no_tma &&
+                             tma_encode_words3d(&ca.tm0, src4, cw, chh, nb, (size_t)cw * 4, img_stride, kCubBoxW, kCubBoxH0) &&
+                             tma_encode_words3d(&ca.tm1, src4, cw, chh, nb, (size_t)cw * 4, img_stride, kCubBoxW, kCubBoxH1);
+            ResizeArgs ra{h->buf_w, w_img, (unsigned)rc[2], final_dst, o_img, (unsigned)(uw * out_px), h->r_mid,
                           (uw + 127) / 128, (rc[3] + 1 + kResizeBand - 1) / kResizeBand};
-            if (tiled && walk && h->mixed) {
-                // horizontally fused launches: cubic(chunk k) + resize(chunk k - 1), k = 0 .. K
-                if (h->prof_ev) cudaEventRecord(h->prof_ev[0], st);
-                const int C = std::max(1, (nb + 3) / 4), K = (nb + C - 1) / C;
-                const int cper = ca.tx * ca.ty, rper = ra.gx * ra.gy;
-                const int nr_mix = 2, nc_mix = std::max(1, (int)std::lround(2.0 * nr_mix * cper / std::max(1, rper)));
-                for (int k = 0; k <= K; ++k) {
-                    MixArgs M{};
-                    M.c = ca; M.r = ra;
-                    M.c_imgs = k < K ? std::min(C, nb - k * C) : 0;
-                    M.r_imgs = k >= 1 ? std::min(C, nb - (k - 1) * C) : 0;
-                    M.c.src = src4 + (size_t)k * C * (img_stride / 4);
-                    M.c.dst = h->buf_w + (size_t)k * C * w_img;
-                    if (k >= 1) {
-                        M.r.src = h->buf_w + (size_t)(k - 1) * C * w_img;
-                        M.r.dst = final_dst + (size_t)(k - 1) * C * o_img;
-                    }
-                    M.nc = M.c_imgs ? (M.r_imgs ? nc_mix : 1) : 0;
-                    M.nr = M.r_imgs ? (M.c_imgs ? nr_mix : 1) : 0;
-                    const long long cb = (long long)cper * M.c_imgs, rb = ((long long)rper * M.r_imgs + 1) / 2;
-                    const long long groups = std::max(M.nc ? (cb + M.nc - 1) / M.nc : 0, M.nr ? (rb + M.nr - 1) / M.nr : 0);
-                    undistort_resize_mixed_kernel<<<(unsigned)(groups * (M.nc + M.nr)), blk, 0, st>>>(M);
-                }
-                if (h->prof_ev) { cudaEventRecord(h->prof_ev[1], st); cudaEventRecord(h->prof_ev[2], st); }
-                h->launches += K + 1;
-                continue;
-            }
             if (h->prof_ev) cudaEventRecord(h->prof_ev[0], st);
-            if (tiled)
-                cubic5_kernel<<<dim3(h->cub_tx, h->cub_ty, nb), blk, 0, st>>>(ca);
+            if (tma)
+                cubic5_kernel<true><<<dim3(h->cub_tx, h->cub_ty, nb), blk, 0, st>>>(ca);
+            else if (tiled)
+                cubic5_kernel<false><<<dim3(h->cub_tx, h->cub_ty, nb), blk, 0, st>>>(ca);
             else if (h->dmap32 && tex_w)
                 cubic4_kernel<true, true><<<cg, blk, 0, st>>>(src4, img_stride / 4, cw, chh, h->dmap32, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
             else if (h->dmap32)
@@ -865,8 +852,10 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
             else
                 cubic4_kernel<false, false><<<cg, blk, 0, st>>>(src4, img_stride / 4, cw, chh, h->dmap, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
             if (h->prof_ev) cudaEventRecord(h->prof_ev[1], st);
-            if (walk)
-                resize4_walk_kernel<<<dim3(ra.gx, ra.gy, nb), dim3(32, 4), 0, st>>>(ra);
+            if (walk && out_px == 4)
+                resize4_walk_kernel<true><<<dim3(ra.gx, ra.gy, nb), dim3(32, 4), 0, st>>>(ra);
+            else if (walk)
+                resize4_walk_kernel<false><<<dim3(ra.gx, ra.gy, nb), dim3(32, 4), 0, st>>>(ra);
             else
                 resize4_kernel<<<dim3((uw + 127) / 128, (uh + 7) / 8, nb), blk, 0, st>>>(h->buf_w, w_img, rc[2], final_dst, o_img,
                                                                                          uw * 3, h->r_mid);
@@ -874,6 +863,7 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
             h->launches += 2;
             continue;
         }
+        if (out_px != 3) return ffail(h, "pano_frontend_run: word output needs 16-byte aligned camera frames");
         if (c.undistort) {
             if (h->use_r_in) {
                 resize_kernel<4><<<grid2(uw, uh, blk, nb), blk, 0, st>>>(cur, cur_img, cw * 4, h->buf_a, u_img, uw * 3, h->r_in);
@@ -958,20 +948,16 @@ void pano_frontend_backmap(pano_frontend_handle h, double *xs, double *ys, size_
 }
 
 int pano_frontend_launches(pano_frontend_handle h) { return h ? h->launches : 0; }
+int pano_frontend_max_batch(pano_frontend_handle h) { return h ? h->cfg.max_batch : 0; }
 // fast path only, one chunk per call: record events around the two kernels; returns their algorithmic bytes per image
-// true when the fast path runs cubic + resize as horizontally fused launches: the profile then has ONE entry for both
-bool pano_frontend_is_mixed(pano_frontend_handle h)
-{
-    return h && h->fast4 && h->mixed && h->cub_tiles && h->wtex && h->r_mid.walk && !getenv("PANO_CUBIC_UNTILED") && !getenv("PANO_NO_RESIZE_WALK");
-}
-bool pano_frontend_set_prof(pano_frontend_handle h, cudaEvent_t *ev, double *cubic_bytes, double *resize_bytes)
+bool pano_frontend_set_prof(pano_frontend_handle h, cudaEvent_t *ev, double *cubic_bytes, double *resize_bytes, int out_px)
 {
     h->prof_ev = ev;
     if (!h->fast4) return false;
     const pano_frontend_config &c = h->cfg;
     const double rect_px = (double)c.rect[2] * c.rect[3];
     if (cubic_bytes) *cubic_bytes = (double)c.cam_src_width * c.cam_src_height * 4 + rect_px * (h->dmap32 ? 4 : 8) + rect_px * 4;
-    if (resize_bytes) *resize_bytes = rect_px * 4 + (double)c.out_width * c.out_height * 3;
+    if (resize_bytes) *resize_bytes = rect_px * 4 + (double)c.out_width * c.out_height * out_px;
     return true;
 }
 void pano_frontend_sizes(pano_frontend_handle h, int *in_wh, int *out_wh)
@@ -987,7 +973,7 @@ int pano_frontend_process_device(pano_frontend_handle h, const uint8_t *argb, ui
     if (!h) return PANO_ERR;
     const pano_frontend_config &c = h->cfg;
     return pano_frontend_run(h, argb, (size_t)c.cam_src_width * c.cam_src_height * h->in_px(), out,
-                             (size_t)c.out_width * c.out_height * 3, batch, (cudaStream_t)stream);
+                             (size_t)c.out_width * c.out_height * 3, batch, (cudaStream_t)stream, 3);
 }
 
 int pano_frontend_process(pano_frontend_handle h, const uint8_t *argb_host, int stride, uint8_t *out_host, int out_stride)

@@ -1,8 +1,9 @@
 // sm_100a kernels of the per-frame compose path.
 //
 // All kernels are HBM-bound integer/byte work (no dense contraction -> no tensor cores).
-// Internal pyramids are channel-PLANAR int16 with 128-byte aligned rows so that every
-// stencil row is a run of aligned 16-byte vectors; the interleaved BGR layout only exists at
+// Internal pyramids are channel-PLANAR with 128-byte aligned rows so that every stencil row is a
+// run of aligned 16-byte vectors: the per-camera Gaussian levels g[l] as UINT8 (provably in
+// [0, 255]), the collapsed dst pyramid out[l] as int16.  The interleaved BGR layout only exists at
 // the two ends (camera frames in, panorama out).  Exactness rules:
 // integer fixed point everywhere OpenCV uses it; the three float steps
 // (lap*w, sum of w, acc/(w+1e-5f)) use explicit round-to-nearest intrinsics so that neither
@@ -12,6 +13,7 @@
 #include <cstdlib>
 
 #include "pano_dev.h"
+#include "tma.h"
 
 namespace pano {
 
@@ -123,39 +125,36 @@ __global__ void __launch_bounds__(256) warp_kernel(const PanoTables *__restrict_
         const float4 gv = __ldg(reinterpret_cast<const float4 *>(C.gain_map + (size_t)Y * C.map_pitch + X));
         g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
     }
-    short px[3][4];
+    int px[3][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         int v[3];
         bilinear_bgr(src, W, H, sx[j], sy[j], v, spx);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) px[c][j] = (short)apply_gain(v[c], C.gain_mode, g[j], C.gain_scalar);
+        for (int c = 0; c < 3; ++c) px[c][j] = apply_gain(v[c], C.gain_mode, g[j], C.gain_scalar);
     }
-    int16_t *dst = C.g[0] + (size_t)slot * C.g_slot[0] + (size_t)Y * C.g_pitch[0] + X;
+    // planar 8-bit g[0]: 4 pixels of one plane = one aligned word (rows carry >= 24 bytes of padding)
+    uint8_t *dst = C.g[0] + (size_t)slot * C.g_slot[0] + (size_t)Y * C.g_pitch[0] + X;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        uint2 o;
-        o.x = (uint16_t)px[c][0] | ((uint32_t)(uint16_t)px[c][1] << 16);
-        o.y = (uint16_t)px[c][2] | ((uint32_t)(uint16_t)px[c][3] << 16);
-        *reinterpret_cast<uint2 *>(dst + (size_t)c * C.g_plane[0]) = o;
-    }
+    for (int c = 0; c < 3; ++c)
+        *reinterpret_cast<uint32_t *>(dst + (size_t)c * C.g_plane[0]) =
+            (uint32_t)px[c][0] | ((uint32_t)px[c][1] << 8) | ((uint32_t)px[c][2] << 16) | ((uint32_t)px[c][3] << 24);
 }
 
-// ------------------------------------------------------------------ K2: pyrDown int16
+// ------------------------------------------------------------------ K2: pyrDown (8-bit Gaussian levels)
 // cv::pyrDown on CV_16S (MultiBandBlender::feed): 5x5 [1 4 6 4 1]^2, reflect-101,
-// (sum + 128) >> 8.  One thread = 4 x 2 outputs of one plane.
-__device__ __forceinline__ void load_row11(const int16_t *__restrict__ row, int x0, int w, int v[11])
+// (sum + 128) >> 8.  The samples are 8-bit values held as bytes (see pano_dev.h); the arithmetic is the
+// reference's 32-bit integer arithmetic.  Generic form (small / odd levels): one thread = 4 x 2 outputs of one plane.
+__device__ __forceinline__ void load_row11(const uint8_t *__restrict__ row, int x0, int w, int v[11])
 {
-    if (x0 >= 0 && x0 + 10 < w) {
-        // x0 = 8t-2: 4-byte aligned; x0+2 = 8t: 16-byte aligned (rows are 128-byte aligned)
-        const uint32_t a = *reinterpret_cast<const uint32_t *>(row + x0);
-        const uint4 b = *reinterpret_cast<const uint4 *>(row + x0 + 2);
-        v[0] = (short)(a & 0xffff); v[1] = (short)(a >> 16);
-        v[2] = (short)(b.x & 0xffff); v[3] = (short)(b.x >> 16);
-        v[4] = (short)(b.y & 0xffff); v[5] = (short)(b.y >> 16);
-        v[6] = (short)(b.z & 0xffff); v[7] = (short)(b.z >> 16);
-        v[8] = (short)(b.w & 0xffff); v[9] = (short)(b.w >> 16);
-        v[10] = row[x0 + 10];
+    if (x0 >= 2 && x0 + 10 < w) {
+        // x0 = 8t-2: the 16 bytes from x0-2 = 8t-4 are four aligned words (rows are 128-byte aligned)
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(row + x0 - 2);
+        const uint32_t a = wp[0], b = wp[1], c = wp[2], d = wp[3];
+        v[0] = (a >> 16) & 0xff; v[1] = a >> 24;
+        v[2] = b & 0xff; v[3] = (b >> 8) & 0xff; v[4] = (b >> 16) & 0xff; v[5] = b >> 24;
+        v[6] = c & 0xff; v[7] = (c >> 8) & 0xff; v[8] = (c >> 16) & 0xff; v[9] = c >> 24;
+        v[10] = d & 0xff;
     } else {
 #pragma unroll
         for (int j = 0; j < 11; ++j) v[j] = row[reflect101(x0 + j, w)];
@@ -178,8 +177,8 @@ __global__ void __launch_bounds__(256) pyrdown_kernel(const PanoTables *__restri
         const int c0 = (C.rx >> (level + 1)) + blockIdx.x * blockDim.x * 4;
         if (outside_window(T, level + 1, c0, c0 + blockDim.x * 4)) return;
     }
-    const int16_t *src = C.g[level] + (size_t)slot * C.g_slot[level] + (size_t)plane * C.g_plane[level];
-    int16_t *dst = C.g[level + 1] + (size_t)slot * C.g_slot[level + 1] + (size_t)plane * C.g_plane[level + 1];
+    const uint8_t *src = C.g[level] + (size_t)slot * C.g_slot[level] + (size_t)plane * C.g_plane[level];
+    uint8_t *dst = C.g[level + 1] + (size_t)slot * C.g_slot[level + 1] + (size_t)plane * C.g_plane[level + 1];
     const int sp = C.g_pitch[level], dp = C.g_pitch[level + 1];
     int acc0[4] = {0, 0, 0, 0}, acc1[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -200,28 +199,27 @@ __global__ void __launch_bounds__(256) pyrdown_kernel(const PanoTables *__restri
     for (int rr = 0; rr < 2; ++rr) {
         if (oy + rr >= dh) break;
         const int *a = rr ? acc1 : acc0;
-        int16_t *d = dst + (size_t)(oy + rr) * dp + ox;
+        uint8_t *d = dst + (size_t)(oy + rr) * dp + ox;
         if (ox + 3 < dw) {
-            uint2 o;
-            o.x = (uint16_t)(short)((a[0] + 128) >> 8) | ((uint32_t)(uint16_t)(short)((a[1] + 128) >> 8) << 16);
-            o.y = (uint16_t)(short)((a[2] + 128) >> 8) | ((uint32_t)(uint16_t)(short)((a[3] + 128) >> 8) << 16);
-            *reinterpret_cast<uint2 *>(d) = o;
+            *reinterpret_cast<uint32_t *>(d) = (uint32_t)((a[0] + 128) >> 8) | ((uint32_t)((a[1] + 128) >> 8) << 8) |
+                                               ((uint32_t)((a[2] + 128) >> 8) << 16) | ((uint32_t)((a[3] + 128) >> 8) << 24);
         } else {
-            for (int j = 0; j < 4 && ox + j < dw; ++j) d[j] = (short)((a[j] + 128) >> 8);
+            for (int j = 0; j < 4 && ox + j < dw; ++j) d[j] = (uint8_t)((a[j] + 128) >> 8);
         }
     }
 }
 
 // ------------------------------------------------------------------ K3: blend + collapse
 // pyrUp of one coarse plane around coarse pixel (k, m) -> the 2x2 fine block (2k..2k+1, 2m..2m+1)
-__device__ __forceinline__ void pyrup_2x2(const int16_t *__restrict__ p, int pitch, int cw, int ch, int k, int m, int up[4])
+template <typename S>
+__device__ __forceinline__ void pyrup_2x2(const S *__restrict__ p, int pitch, int cw, int ch, int k, int m, int up[4])
 {
     const int k0 = up_index(k - 1, cw), k2 = up_index(k + 1, cw);
     int he[3], ho[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         const int mm = up_index(m - 1 + r, ch);
-        const int16_t *row = p + (size_t)mm * pitch;
+        const S *row = p + (size_t)mm * pitch;
         const int a = row[k0], b = row[k], c = row[k2];
         he[r] = a + 6 * b + c;
         ho[r] = 4 * (b + c);
@@ -260,10 +258,10 @@ __global__ void __launch_bounds__(256) coarsest_kernel(const PanoTables *__restr
         float w;
         if (L == 0 && !C.use_wt0) w = __fmul_rn((float)C.mask0[(size_t)y * C.mask_pitch + x], 1.f / 255.f);
         else w = C.wt[L][(size_t)y * C.wt_pitch[L] + x];
-        const int16_t *g = C.g[L] + (size_t)slot * C.g_slot[L] + (size_t)y * C.g_pitch[L] + x;
+        const uint8_t *g = C.g[L] + (size_t)slot * C.g_slot[L] + (size_t)y * C.g_pitch[L] + x;
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-            acc[c] += trunc_s16(__fmul_rn((float)g[(size_t)c * C.g_plane[L]], w));
+            acc[c] += trunc_s16(__fmul_rn((float)(int)g[(size_t)c * C.g_plane[L]], w));
         wsum = __fadd_rn(wsum, w);
     }
     const float den = __fadd_rn(wsum, 1e-5f);
@@ -315,16 +313,16 @@ __global__ void __launch_bounds__(256) collapse_kernel(const PanoTables *__restr
             const float2 b = *reinterpret_cast<const float2 *>(wrow + C.wt_pitch[L]);
             w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y;
         }
-        const int16_t *gf = C.g[L] + (size_t)slot * C.g_slot[L] + (size_t)y * C.g_pitch[L] + x;
-        const int16_t *gc = C.g[L + 1] + (size_t)slot * C.g_slot[L + 1];
+        const uint8_t *gf = C.g[L] + (size_t)slot * C.g_slot[L] + (size_t)y * C.g_pitch[L] + x;
+        const uint8_t *gc = C.g[L + 1] + (size_t)slot * C.g_slot[L + 1];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             int up[4];
             pyrup_2x2(gc + (size_t)c * C.g_plane[L + 1], C.g_pitch[L + 1], fw >> 1, fh >> 1, x >> 1, y >> 1, up);
-            const int16_t *f = gf + (size_t)c * C.g_plane[L];
-            const uint32_t r0 = *reinterpret_cast<const uint32_t *>(f);
-            const uint32_t r1 = *reinterpret_cast<const uint32_t *>(f + C.g_pitch[L]);
-            const int fine[4] = {(short)(r0 & 0xffff), (short)(r0 >> 16), (short)(r1 & 0xffff), (short)(r1 >> 16)};
+            const uint8_t *f = gf + (size_t)c * C.g_plane[L];
+            const uchar2 r0 = *reinterpret_cast<const uchar2 *>(f);
+            const uchar2 r1 = *reinterpret_cast<const uchar2 *>(f + C.g_pitch[L]);
+            const int fine[4] = {r0.x, r0.y, r1.x, r1.y};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int lap = sat_s16(fine[j] - up[j]);
@@ -369,118 +367,55 @@ __global__ void __launch_bounds__(256) collapse_kernel(const PanoTables *__restr
 }
 
 
-// ================================================================== packed (DP2A) kernels
-// The planar int16 pyramids arrive from memory as 32-bit words holding two neighbouring
-// samples.  IDP.2A (dp2a: two 16-bit x 8-bit products + accumulate) evaluates the separable
-// stencils directly on those words, so no sample is ever unpacked before filtering.
+// ================================================================== packed (IDP) kernels
+// The planar pyramids arrive from memory as 32-bit words: FOUR neighbouring 8-bit Gaussian samples, or two
+// neighbouring int16 samples of the collapsed dst pyramid.  IDP.4A (dp4a: four 8-bit x 8-bit products +
+// accumulate) and IDP.2A (dp2a: two 16-bit x 8-bit products) evaluate the separable stencils directly on
+// those words, so no sample is ever unpacked before filtering.
 #define COEF(lo, hi) (((hi) << 8) | (lo))
+#define COEF4(b0, b1, b2, b3) ((uint32_t)(b0) | ((uint32_t)(b1) << 8) | ((uint32_t)(b2) << 16) | ((uint32_t)(b3) << 24))
 
-// ---- K2': pyrDown, one thread = 8 x 2 outputs of one plane (sw % 4 == 0, sh % 2 == 0)
-__global__ void __launch_bounds__(256) pyrdown8_kernel(const PanoTables *__restrict__ T, int level)
-{
-    const int ncam = T->num_cams;
-    int z = blockIdx.z;
-    const int plane = z % 3; z /= 3;
-    const int cam = z % ncam, slot = z / ncam;
-    const CamTables &C = T->cam[cam];
-    const int sw = C.rw >> level, sh = C.rh >> level;
-    const int dw = sw >> 1, dh = sh >> 1;
-    const int ox = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-    const int oy = (blockIdx.y * blockDim.y + threadIdx.y) * 2;
-    if (ox >= dw || oy >= dh) return;
-    {
-        const int c0 = (C.rx >> (level + 1)) + blockIdx.x * blockDim.x * 8;
-        if (outside_window(T, level + 1, c0, c0 + blockDim.x * 8)) return;
-    }
-    const int sp = C.g_pitch[level], dp = C.g_pitch[level + 1];
-    const int16_t *src = C.g[level] + (size_t)slot * C.g_slot[level] + (size_t)plane * C.g_plane[level];
-    int16_t *dst = C.g[level + 1] + (size_t)slot * C.g_slot[level + 1] + (size_t)plane * C.g_plane[level + 1];
-    const int edge = dw - ox + 1;            // local index of the pair that starts at column sw (reflect-101)
-    int acc0[8], acc1[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { acc0[j] = 0; acc1[j] = 0; }
-#pragma unroll
-    for (int r = 0; r < 7; ++r) {
-        const int sy = reflect101(2 * oy - 2 + r, sh);
-        const int16_t *row = src + sy * sp + 2 * ox;
-        int q[10];
-        const uint4 a = *reinterpret_cast<const uint4 *>(row);
-        const uint4 b = *reinterpret_cast<const uint4 *>(row + 8);
-        q[1] = a.x; q[2] = a.y; q[3] = a.z; q[4] = a.w; q[5] = b.x; q[6] = b.y; q[7] = b.z; q[8] = b.w;
-        q[9] = *reinterpret_cast<const int *>(row + 16);          // rows carry >= 24 samples of padding
-        if (ox > 0) q[0] = *reinterpret_cast<const int *>(row - 2);
-        else q[0] = __byte_perm(q[2], q[1], 0x7610);              // (v[-2], v[-1]) := (v[2], v[1])
-        if (edge <= 9) {
-#pragma unroll
-            for (int k = 1; k <= 9; ++k)
-                if (k == edge) q[k] = q[k - 1];                   // v[sw] := v[sw-2]
-        }
-        const int k0 = (r == 0 || r == 4) ? 1 : ((r == 1 || r == 3) ? 4 : (r == 2 ? 6 : 0));
-        const int k1 = (r == 2 || r == 6) ? 1 : ((r == 3 || r == 5) ? 4 : (r == 4 ? 6 : 0));
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int h = __dp2a_lo(q[j], COEF(1, 4), __dp2a_lo(q[j + 1], COEF(6, 4), __dp2a_lo(q[j + 2], COEF(1, 0), 0)));
-            if (k0) acc0[j] += k0 * h;
-            if (k1) acc1[j] += k1 * h;
-        }
-    }
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-        if (oy + rr >= dh) break;
-        const int *a = rr ? acc1 : acc0;
-        int16_t *d = dst + (oy + rr) * dp + ox;
-        if (ox + 8 <= dw) {
-            uint4 o;
-            o.x = (uint16_t)((a[0] + 128) >> 8) | ((uint32_t)((a[1] + 128) >> 8) << 16);
-            o.y = (uint16_t)((a[2] + 128) >> 8) | ((uint32_t)((a[3] + 128) >> 8) << 16);
-            o.z = (uint16_t)((a[4] + 128) >> 8) | ((uint32_t)((a[5] + 128) >> 8) << 16);
-            o.w = (uint16_t)((a[6] + 128) >> 8) | ((uint32_t)((a[7] + 128) >> 8) << 16);
-            *reinterpret_cast<uint4 *>(d) = o;
-        } else {
-            for (int j = 0; j < 8 && ox + j < dw; ++j) d[j] = (short)((a[j] + 128) >> 8);
-        }
-    }
-}
-
-// ---- K2'': pyrDown as a column walker.  A lane owns 8 output columns and walks DOWN a band of kDownBand
-// output rows.  Every source row is loaded and horizontally filtered exactly once (pyrdown8_kernel above
-// does it 3.5 times per output row): a filtered odd row 2k+1 adds 4x to the two output rows k, k+1 that are
-// in flight, a filtered even row 2k+2 completes row k (weight 1), adds 6x to row k+1 and opens row k+2 --
-// two accumulator sets whose roles swap every step, so nothing is ever copied.  The 16 samples a lane
-// filters come in two 16-byte loads; the two halo pairs come from the neighbouring lanes by shuffle (the
-// edge lanes load theirs), which halves the cache wavefronts of a row.
+// ---- K2': pyrDown as a column walker over 8-bit levels (sw % 4 == 0, sh % 2 == 0).  A lane owns 8 output columns
+// (= 16 source bytes = ONE 16-byte load per source row) and walks DOWN a band of kDownBand output rows.  Every
+// source row is loaded and horizontally filtered exactly once: a filtered odd row 2k+1 adds 4x to the two output
+// rows k, k+1 that are in flight, a filtered even row 2k+2 completes row k (weight 1), adds 6x to row k+1 and opens
+// row k+2 -- two accumulator sets whose roles swap every step, so nothing is ever copied.  The 5-tap row filter is
+// two IDP.4A per output on the words as they sit in memory ([1 4 | 6 4 1] for even, [1 4 6 4 | 1] for odd
+// columns); the two halo words come from the neighbouring lanes by shuffle (the edge lanes load theirs).  Source
+// rows are requested TWO steps (four rows) ahead of their use.
 constexpr int kDownBand = 8;
 
-struct DownRaw { uint4 a, b; int l, r; };      // loads in flight (nothing here depends on their arrival)
-struct DownRow { int q[10]; };
+struct DownRaw { uint4 a; uint32_t l, r; };      // loads in flight (nothing here depends on their arrival)
+struct DownRow { uint32_t q[6]; };               // words 4t-1 .. 4t+4 of the source row (t = lane's output group)
 
-__device__ __forceinline__ void down_fetch(const int16_t *__restrict__ row, int lane, bool lo_edge, DownRaw &d)
+__device__ __forceinline__ void down_fetch(const uint8_t *__restrict__ row, int lane, bool lo_edge, DownRaw &d)
 {
     d.a = *reinterpret_cast<const uint4 *>(row);
-    d.b = *reinterpret_cast<const uint4 *>(row + 8);
     d.l = 0; d.r = 0;
-    if (lane == 0 && !lo_edge) d.l = *reinterpret_cast<const int *>(row - 2);
-    if (lane == 31) d.r = *reinterpret_cast<const int *>(row + 16);            // rows carry >= 24 samples of padding
+    if (lane == 0 && !lo_edge) d.l = *reinterpret_cast<const uint32_t *>(row - 4);
+    if (lane == 31) d.r = *reinterpret_cast<const uint32_t *>(row + 16);      // rows carry >= 24 bytes of padding
 }
 
 __device__ __forceinline__ void down_finish(const DownRaw &w, int lane, bool lo_edge, int edge, DownRow &d)
 {
-    d.q[1] = w.a.x; d.q[2] = w.a.y; d.q[3] = w.a.z; d.q[4] = w.a.w; d.q[5] = w.b.x; d.q[6] = w.b.y; d.q[7] = w.b.z; d.q[8] = w.b.w;
-    const int left = __shfl_up_sync(0xffffffffu, (int)w.b.w, 1), right = __shfl_down_sync(0xffffffffu, (int)w.a.x, 1);
-    d.q[0] = lo_edge ? (int)__byte_perm(d.q[2], d.q[1], 0x7610) : (lane == 0 ? w.l : left);   // (v[-2], v[-1]) := (v[2], v[1])
-    d.q[9] = lane == 31 ? w.r : right;
-    if (edge <= 9) {
+    d.q[1] = w.a.x; d.q[2] = w.a.y; d.q[3] = w.a.z; d.q[4] = w.a.w;
+    const uint32_t left = __shfl_up_sync(0xffffffffu, w.a.w, 1), right = __shfl_down_sync(0xffffffffu, w.a.x, 1);
+    d.q[0] = lo_edge ? __byte_perm(w.a.x, 0u, 0x1200) : (lane == 0 ? w.l : left);   // (v[-2], v[-1]) := (v[2], v[1])
+    d.q[5] = lane == 31 ? w.r : right;
+    if (edge <= 5) {
 #pragma unroll
-        for (int k = 1; k <= 9; ++k)
-            if (k == edge) d.q[k] = d.q[k - 1];                               // v[sw] := v[sw-2]
+        for (int k = 2; k <= 5; ++k)
+            if (k == edge) d.q[k] = __byte_perm(d.q[k - 1], 0u, 0x4442);      // v[sw] := v[sw-2]
     }
 }
 
 __device__ __forceinline__ void down_hfilter(const DownRow &d, int h[8])
 {
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-        h[j] = __dp2a_lo(d.q[j], COEF(1, 4), __dp2a_lo(d.q[j + 1], COEF(6, 4), __dp2a_lo(d.q[j + 2], COEF(1, 0), 0)));
+    for (int i = 0; i < 4; ++i) {
+        h[2 * i] = __dp4a(d.q[i], COEF4(0, 0, 1, 4), __dp4a(d.q[i + 1], COEF4(6, 4, 1, 0), 0u));
+        h[2 * i + 1] = __dp4a(d.q[i + 1], COEF4(1, 4, 6, 4), __dp4a(d.q[i + 2], COEF4(1, 0, 0, 0), 0u));
+    }
 }
 
 __global__ void __launch_bounds__(128) pyrdown8_walk_kernel(const PanoTables *__restrict__ T, int level, int band)
@@ -504,21 +439,23 @@ __global__ void __launch_bounds__(128) pyrdown8_walk_kernel(const PanoTables *__
     const bool live = ox < dw;
     const int oxl = live ? ox : ((dw - 1) >> 3) << 3;                         // idle lanes still load + shuffle (in range)
     const int sp = C.g_pitch[level], dp = C.g_pitch[level + 1];
-    const int16_t *src = C.g[level] + (size_t)slot * C.g_slot[level] + (size_t)plane * C.g_plane[level] + 2 * oxl;
-    int16_t *dst = C.g[level + 1] + (size_t)slot * C.g_slot[level + 1] + (size_t)plane * C.g_plane[level + 1] + ox;
+    const uint8_t *src = C.g[level] + (size_t)slot * C.g_slot[level] + (size_t)plane * C.g_plane[level] + 2 * oxl;
+    uint8_t *dst = C.g[level + 1] + (size_t)slot * C.g_slot[level + 1] + (size_t)plane * C.g_plane[level + 1] + ox;
     const bool lo_edge = oxl == 0;
-    const int edge = dw - oxl + 1;            // local index of the pair that starts at column sw (reflect-101)
+    const int edge = ((dw - oxl) >> 1) + 1;   // local index of the word that starts at column sw (reflect-101)
     const int nrows = min(band, dh - oy0);
 
     int accA[8], accB[8];                     // output rows k and k + 1 (128 = rounding, folded in when a row is opened)
-    DownRaw r0, r1;
+    DownRaw ra0, ra1, rb0, rb1;               // the two source rows of this step (a) and of the next one (b)
     {
         DownRaw a, b, c;
         down_fetch(src + reflect101(2 * oy0 - 2, sh) * sp, lane, lo_edge, a);
         down_fetch(src + reflect101(2 * oy0 - 1, sh) * sp, lane, lo_edge, b);
         down_fetch(src + 2 * oy0 * sp, lane, lo_edge, c);
-        down_fetch(src + reflect101(2 * oy0 + 1, sh) * sp, lane, lo_edge, r0);
-        down_fetch(src + reflect101(2 * oy0 + 2, sh) * sp, lane, lo_edge, r1);
+        down_fetch(src + reflect101(2 * oy0 + 1, sh) * sp, lane, lo_edge, ra0);
+        down_fetch(src + reflect101(2 * oy0 + 2, sh) * sp, lane, lo_edge, ra1);
+        down_fetch(src + reflect101(2 * oy0 + 3, sh) * sp, lane, lo_edge, rb0);
+        down_fetch(src + reflect101(2 * oy0 + 4, sh) * sp, lane, lo_edge, rb1);
         DownRow qa, qb, qc;
         down_finish(a, lane, lo_edge, edge, qa); down_finish(b, lane, lo_edge, edge, qb); down_finish(c, lane, lo_edge, edge, qc);
         int ha[8], hb[8], hc[8];
@@ -526,32 +463,34 @@ __global__ void __launch_bounds__(128) pyrdown8_walk_kernel(const PanoTables *__
 #pragma unroll
         for (int j = 0; j < 8; ++j) { accA[j] = ha[j] + 4 * hb[j] + 6 * hc[j] + 128; accB[j] = hc[j] + 128; }
     }
-    // one step: rows 2k+1 (odd) and 2k+2 (even) finish output row k (in A), advance k+1 (in B) and open k+2 (in A)
-#define DOWN_STEP(i, A, B)                                                                       \
+    // one step: rows 2k+1 (odd) and 2k+2 (even) finish output row k (in A), advance k+1 (in B) and open k+2 (in A);
+    // the slot that held them is refilled with the rows of step i + 2
+#define DOWN_STEP(i, A, B, R0, R1)                                                               \
     {                                                                                            \
         DownRow co, ce;                                                                          \
-        down_finish(r0, lane, lo_edge, edge, co); down_finish(r1, lane, lo_edge, edge, ce);      \
-        if ((i) + 1 < nrows) {                                                                   \
-            down_fetch(src + reflect101(2 * (oy0 + (i)) + 3, sh) * sp, lane, lo_edge, r0);        \
-            down_fetch(src + reflect101(2 * (oy0 + (i)) + 4, sh) * sp, lane, lo_edge, r1);        \
+        down_finish(R0, lane, lo_edge, edge, co); down_finish(R1, lane, lo_edge, edge, ce);      \
+        if ((i) + 2 < nrows) {                                                                   \
+            down_fetch(src + reflect101(2 * (oy0 + (i)) + 5, sh) * sp, lane, lo_edge, R0);        \
+            down_fetch(src + reflect101(2 * (oy0 + (i)) + 6, sh) * sp, lane, lo_edge, R1);        \
         }                                                                                        \
         int ho[8], he[8];                                                                        \
         down_hfilter(co, ho); down_hfilter(ce, he);                                              \
-        uint32_t o[4];                                                                           \
-        _Pragma("unroll") for (int j = 0; j < 8; j += 2) {                                       \
+        uint32_t o[2];                                                                           \
+        _Pragma("unroll") for (int j = 0; j < 8; j += 4) {                                       \
             const int v0 = (A[j] + 4 * ho[j] + he[j]) >> 8, v1 = (A[j + 1] + 4 * ho[j + 1] + he[j + 1]) >> 8; \
-            o[j >> 1] = __byte_perm(v0, v1, 0x5410);                                             \
+            const int v2 = (A[j + 2] + 4 * ho[j + 2] + he[j + 2]) >> 8, v3 = (A[j + 3] + 4 * ho[j + 3] + he[j + 3]) >> 8; \
+            o[j >> 2] = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410); \
         }                                                                                        \
         _Pragma("unroll") for (int j = 0; j < 8; ++j) { B[j] += 4 * ho[j] + 6 * he[j]; A[j] = he[j] + 128; } \
         if (live) {                                                                              \
-            int16_t *d = dst + (oy0 + (i)) * dp;                                                 \
-            if (ox + 8 <= dw) *reinterpret_cast<uint4 *>(d) = make_uint4(o[0], o[1], o[2], o[3]); \
-            else for (int j = 0; j < 8 && ox + j < dw; ++j) d[j] = (short)(o[j >> 1] >> (16 * (j & 1))); \
+            uint8_t *d = dst + (oy0 + (i)) * dp;                                                 \
+            if (ox + 8 <= dw) *reinterpret_cast<uint2 *>(d) = make_uint2(o[0], o[1]);            \
+            else for (int j = 0; j < 8 && ox + j < dw; ++j) d[j] = (uint8_t)(o[j >> 2] >> (8 * (j & 3))); \
         }                                                                                        \
     }
     for (int i = 0; i < nrows; i += 2) {
-        DOWN_STEP(i, accA, accB)
-        if (i + 1 < nrows) DOWN_STEP(i + 1, accB, accA)
+        DOWN_STEP(i, accA, accB, ra0, ra1)
+        if (i + 1 < nrows) DOWN_STEP(i + 1, accB, accA, rb0, rb1)
     }
 #undef DOWN_STEP
 }
@@ -599,12 +538,57 @@ __device__ __forceinline__ void up_compute(const UpRaw &r, int up[16])
     }
 }
 
-__device__ __forceinline__ void unpack8(const uint4 v, int o[8])
+// ---- the same pyrUp on an 8-bit Gaussian level: the four coarse samples k0..k0+3 are ONE word (P0); Pm / P2 are the
+// words before / after it (only c[k0-1] = Pm.byte3 and c[k0+4] = P2.byte0 are used).  11 IDP.4A per 8 outputs.
+struct UpRaw8 { uint32_t pm[3], p0[3], p2[3]; };
+
+__device__ __forceinline__ void up8_fetch(const uint8_t *__restrict__ row, bool left, bool right, uint32_t &pm, uint32_t &p0, uint32_t &p2)
 {
-    o[0] = (short)(v.x & 0xffff); o[1] = (int)v.x >> 16;
-    o[2] = (short)(v.y & 0xffff); o[3] = (int)v.y >> 16;
-    o[4] = (short)(v.z & 0xffff); o[5] = (int)v.z >> 16;
-    o[6] = (short)(v.w & 0xffff); o[7] = (int)v.w >> 16;
+    p0 = *reinterpret_cast<const uint32_t *>(row);
+    pm = left ? (p0 << 16) : *reinterpret_cast<const uint32_t *>(row - 4);      // c[-1] := c[1]   (byte 1 -> byte 3)
+    p2 = right ? (p0 >> 24) : *reinterpret_cast<const uint32_t *>(row + 4);     // c[cw] := c[cw-1] (byte 3 -> byte 0)
+}
+
+__device__ __forceinline__ void up_load8(const uint8_t *__restrict__ plane, int pitch, int cw, int ch, int k0, int m, UpRaw8 &r)
+{
+    const int rows[3] = {up_index(m - 1, ch), m, up_index(m + 1, ch)};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) up8_fetch(plane + rows[i] * pitch + k0, k0 == 0, k0 + 4 >= cw, r.pm[i], r.p0[i], r.p2[i]);
+}
+
+__device__ __forceinline__ void up_hrow8(uint32_t Pm, uint32_t P0, uint32_t P2, int h[8])
+{
+    h[0] = __dp4a(P0, COEF4(6, 1, 0, 0), __dp4a(Pm, COEF4(0, 0, 0, 1), 0u));
+    h[1] = __dp4a(P0, COEF4(4, 4, 0, 0), 0u);
+    h[2] = __dp4a(P0, COEF4(1, 6, 1, 0), 0u);
+    h[3] = __dp4a(P0, COEF4(0, 4, 4, 0), 0u);
+    h[4] = __dp4a(P0, COEF4(0, 1, 6, 1), 0u);
+    h[5] = __dp4a(P0, COEF4(0, 0, 4, 4), 0u);
+    h[6] = __dp4a(P0, COEF4(0, 0, 1, 6), __dp4a(P2, COEF4(1, 0, 0, 0), 0u));
+    h[7] = __dp4a(P0, COEF4(0, 0, 0, 4), __dp4a(P2, COEF4(4, 0, 0, 0), 0u));
+}
+
+__device__ __forceinline__ void up_compute8(const UpRaw8 &r, int up[16])
+{
+    int ha[8], hb[8], hc[8];
+    up_hrow8(r.pm[0], r.p0[0], r.p2[0], ha);
+    up_hrow8(r.pm[1], r.p0[1], r.p2[1], hb);
+    up_hrow8(r.pm[2], r.p0[2], r.p2[2], hc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        up[j] = (ha[j] + 6 * hb[j] + hc[j] + 32) >> 6;
+        up[8 + j] = (hb[j] + hc[j] + 8) >> 4;          // == (4*(hb+hc) + 32) >> 6
+    }
+}
+
+// eight 8-bit samples (two words) -> ints
+__device__ __forceinline__ void unpack8(const uint2 v, int o[8])
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        o[j] = (int)__byte_perm(v.x, 0u, 0x4440 + j);
+        o[4 + j] = (int)__byte_perm(v.y, 0u, 0x4440 + j);
+    }
 }
 
 // ---- K3': blend + collapse, one thread = 8 x 2 pixels of ONE plane (threadIdx.z = plane).
@@ -621,7 +605,7 @@ __device__ __forceinline__ void unpack8(const uint4 v, int o[8])
 // chain of dependent global loads through the table struct).
 struct C8Cam {
     int x0, y0, fw, fh;              // camera rect at this level, dst coordinates
-    const int16_t *gf, *gc;          // g[l], g[l+1] (slot 0, plane 0)
+    const uint8_t *gf, *gc;          // g[l], g[l+1] (slot 0, plane 0; 8-bit)
     int pf, pc;                      // pitches
     unsigned plane_f, plane_c;       // plane strides
     size_t slot_f, slot_c;           // slot strides
@@ -676,10 +660,10 @@ __global__ void __launch_bounds__(384, 2) collapse8_kernel(const __grid_constant
             if ((unsigned)x >= (unsigned)fw || (unsigned)y >= (unsigned)fh) continue;
             // the camera is listed for this tile: fetch its pyramid data unconditionally, together
             // with the weights, so that one memory round trip covers all of it
-            UpRaw raw;
-            up_load(C.gc + slot * C.slot_c + plane * C.plane_c, C.pc, fw >> 1, fh >> 1, x >> 1, y >> 1, raw);
-            const int16_t *f = C.gf + slot * C.slot_f + plane * C.plane_f + y * C.pf + x;
-            const uint4 f0 = *reinterpret_cast<const uint4 *>(f), f1 = *reinterpret_cast<const uint4 *>(f + C.pf);
+            UpRaw8 raw;
+            up_load8(C.gc + slot * C.slot_c + plane * C.plane_c, C.pc, fw >> 1, fh >> 1, x >> 1, y >> 1, raw);
+            const uint8_t *f = C.gf + slot * C.slot_f + plane * C.plane_f + y * C.pf + x;
+            const uint2 f0 = *reinterpret_cast<const uint2 *>(f), f1 = *reinterpret_cast<const uint2 *>(f + C.pf);
             float w[16];
             bool ones;
             if (kLevel0 && C.use_mask) {
@@ -708,7 +692,7 @@ __global__ void __launch_bounds__(384, 2) collapse8_kernel(const __grid_constant
                 if (!any) continue;
             }
             int up[16], fine[16];
-            up_compute(raw, up);
+            up_compute8(raw, up);
             unpack8(f0, fine);
             unpack8(f1, fine + 8);
             // Gaussian-pyramid samples of 8-bit frames stay in [0, 255], so |lap| <= 255: the
@@ -817,6 +801,8 @@ __device__ __forceinline__ uint32_t pack_u8x4(int a, int b, int c, int d)
     return lo;                                                                  // a | b<<8 | c<<16 | d<<24, each saturated
 }
 
+struct HRaw8 { uint32_t pm, p0, p2; };
+
 template <bool kLevel0, bool kCam>
 __device__ __forceinline__ void walk_column(const C8Args &A, int cam, int X0, int Yb, int slot, int plane,
                                             uint32_t *__restrict__ smcol)
@@ -829,27 +815,28 @@ __device__ __forceinline__ void walk_column(const C8Args &A, int cam, int X0, in
     const C8Cam &C = A.cam[kCam ? cam : 0];
     const int x = X0 - C.x0, y = Yb - C.y0;
     const int cw = C.fw >> 1, ch = C.fh >> 1, kc = x >> 1, mc = y >> 1, pc = C.pc, pf = C.pf;
-    const int16_t *gc = C.gc + slot * C.slot_c + plane * C.plane_c + kc;
-    const int16_t *gf = C.gf + slot * C.slot_f + plane * C.plane_f + y * pf + x;
+    const uint8_t *gc = C.gc + slot * C.slot_c + plane * C.plane_c + kc;
+    const uint8_t *gf = C.gf + slot * C.slot_f + plane * C.plane_f + y * pf + x;
     const bool cL = kc == 0, cR = kc + 4 >= cw;
 
     int ho[3][8], hc[3][8];
-    HRaw ro, rc;
-    uint4 f0 = make_uint4(0, 0, 0, 0), f1 = f0;
+    HRaw ro;
+    HRaw8 rc = {0u, 0u, 0u};
+    uint2 f0 = make_uint2(0, 0), f1 = f0;
     {
         HRaw a, b;
         hraw_load(oc + up_index(m0 - 1, Hc) * poc, oL, oR, a);
         hraw_load(oc + m0 * poc, oL, oR, b);
         hraw_load(oc + up_index(m0 + 1, Hc) * poc, oL, oR, ro);
         if (kCam) {
-            HRaw c, d;
-            hraw_load(gc + up_index(mc - 1, ch) * pc, cL, cR, c);
-            hraw_load(gc + mc * pc, cL, cR, d);
-            hraw_load(gc + up_index(mc + 1, ch) * pc, cL, cR, rc);
-            f0 = *reinterpret_cast<const uint4 *>(gf);
-            f1 = *reinterpret_cast<const uint4 *>(gf + pf);
-            up_hrow(c.pm, c.p0, c.p1, c.p2, hc[0]);
-            up_hrow(d.pm, d.p0, d.p1, d.p2, hc[1]);
+            HRaw8 c, d;
+            up8_fetch(gc + up_index(mc - 1, ch) * pc, cL, cR, c.pm, c.p0, c.p2);
+            up8_fetch(gc + mc * pc, cL, cR, d.pm, d.p0, d.p2);
+            up8_fetch(gc + up_index(mc + 1, ch) * pc, cL, cR, rc.pm, rc.p0, rc.p2);
+            f0 = *reinterpret_cast<const uint2 *>(gf);
+            f1 = *reinterpret_cast<const uint2 *>(gf + pf);
+            up_hrow8(c.pm, c.p0, c.p2, hc[0]);
+            up_hrow8(d.pm, d.p0, d.p2, hc[1]);
         }
         up_hrow(a.pm, a.p0, a.p1, a.p2, ho[0]);
         up_hrow(b.pm, b.p0, b.p1, b.p2, ho[1]);
@@ -857,14 +844,15 @@ __device__ __forceinline__ void walk_column(const C8Args &A, int cam, int X0, in
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int ia = r % 3, ib = (r + 1) % 3, ic = (r + 2) % 3;
-        const HRaw co = ro, cc = rc;
-        const uint4 c0 = f0, c1 = f1;
+        const HRaw co = ro;
+        const HRaw8 cc = rc;
+        const uint2 c0 = f0, c1 = f1;
         if (r + 1 < R) {                                   // next step's loads first
             hraw_load(oc + up_index(m0 + r + 2, Hc) * poc, oL, oR, ro);
             if (kCam) {
-                hraw_load(gc + up_index(mc + r + 2, ch) * pc, cL, cR, rc);
-                f0 = *reinterpret_cast<const uint4 *>(gf + (2 * r + 2) * pf);
-                f1 = *reinterpret_cast<const uint4 *>(gf + (2 * r + 3) * pf);
+                up8_fetch(gc + up_index(mc + r + 2, ch) * pc, cL, cR, rc.pm, rc.p0, rc.p2);
+                f0 = *reinterpret_cast<const uint2 *>(gf + (2 * r + 2) * pf);
+                f1 = *reinterpret_cast<const uint2 *>(gf + (2 * r + 3) * pf);
             }
         }
         up_hrow(co.pm, co.p0, co.p1, co.p2, ho[ic]);
@@ -875,7 +863,7 @@ __device__ __forceinline__ void walk_column(const C8Args &A, int cam, int X0, in
             res[8 + j] = (ho[ib][j] + ho[ic][j] + 8) >> 4;
         }
         if (kCam) {
-            up_hrow(cc.pm, cc.p0, cc.p1, cc.p2, hc[ic]);
+            up_hrow8(cc.pm, cc.p0, cc.p2, hc[ic]);
             int fine[16];
             unpack8(c0, fine);
             unpack8(c1, fine + 8);
@@ -984,43 +972,48 @@ __global__ void __launch_bounds__(96) collapse_walk_kernel(const __grid_constant
 //     source row are one packed 16|16-bit word (each product <= 1024), so a row of one channel is a single
 //     IDP.2A on the byte pair that PRMT lifts out of the two tap words; B and G share one PRMT.
 // (3) Everything static about the launch arrives as a __grid_constant__ struct (no dependent global loads
-//     in the prologue); all 8 map entries of a thread are requested before the staging loop; the planar
-//     int16 results go out through six precomputed row pointers with immediate offsets.
+//     in the prologue); all 8 map entries of a thread are requested before the staging loop.
+// (1') kTma (word-per-pixel sources: the front end's hand-over buffer, 8UC4 camera frames of the fused variant): the
+//     footprint is not staged by the threads at all -- one elected thread issues cp.async.bulk.tensor box loads
+//     (kWarpBoxH rows x the staged pitch each) that the copy engine lands in shared memory while the block fetches
+//     its map entries.  Out-of-frame parts of a box are zero-filled; those taps have weight 0 by construction.
+// (4) g[0] is planar UINT8.  A thread's 8 results are 32 columns apart (lane = pixel), so the block transposes
+//     them through 6 KB of shared memory: every thread packs the four column groups of a (plane, row) into one
+//     word (6 STS.32), then reads the words of four neighbouring lanes back as one LDS.128, transposes the
+//     4 x 4 bytes with 8 PRMT and stores four pixels of one plane per ST.32 -- 6 global stores per thread
+//     instead of 24, each filling whole 32-byte sectors.
 struct WarpCam {
     const uint32_t *map32;
     const uint2 *map64;
     const int4 *tiles;
     const float *gain_map;
-    int16_t *g0;
+    uint8_t *g0;
     double gain_scalar;
     size_t g_slot;
     int map_pitch, tiles_x, tiles_y, rx, rw, rh, g_pitch, gain_mode;
     unsigned g_plane;
 };
+// TMA boxes of the word-per-pixel staging: kWarpBoxH source rows x (128 + 32 i) words, i = 0 .. kWarpBoxes - 1
+constexpr int kWarpBoxH = 4, kWarpBoxes = 5, kWarpBoxW0 = 128;
 struct WarpArgs {
+    CUtensorMap tm[kWarpBoxes];      // [slots * cameras][H][W] words (kTma only)
     WarpCam cam[kMaxCams];
     int ncam, W, H, win_lo, win_hi, nslots;
 };
 
-template <int kOff>
-__device__ __forceinline__ void st_s16(int16_t *p, int v)
-{
-    asm volatile("st.global.b16 [%0+%1], %2;" ::"l"(p), "n"(kOff), "h"((short)v) : "memory");
-}
-
 // kGain: 0 = no camera has a gain, 1 = per-pixel float maps only (cameras without one use g = 1, which is exact),
 // 2 = generic (scalar double gains or a mix; per-sample mode checks)
+// out[c][h]: the thread's results of plane c, row half h (rows Y0, Y0 + 8), byte k = column group k (Xt + 32 k)
 template <bool kMap64, int kGain, bool kFull, int kPx>
 __device__ __forceinline__ void warp_gather(const WarpCam &C, const uint32_t *__restrict__ sm, const uint8_t *__restrict__ src,
                                             bool staged, int rw, int sbase, int W, int H, const uint32_t (&msx)[8],
-                                            const uint32_t (&msy)[8], int Xt, int Y0, int slot)
+                                            const uint32_t (&msy)[8], int Xt, int Y0, uint32_t (&out)[3][2])
 {
     const int W3 = W * kPx;
-    const int pitch = C.g_pitch, crw = C.rw, crh = C.rh, mp = C.map_pitch;
+    const int crw = C.rw, crh = C.rh, mp = C.map_pitch;
     const bool has_map = C.gain_mode == 1;
-    int16_t *o00 = C.g0 + slot * C.g_slot + Y0 * pitch + Xt;
-    int16_t *o01 = o00 + C.g_plane, *o02 = o01 + C.g_plane;
-    int16_t *o10 = o00 + 8 * pitch, *o11 = o10 + C.g_plane, *o12 = o11 + C.g_plane;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { out[c][0] = 0u; out[c][1] = 0u; }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         if (!kFull && (Y0 + 8 * (k >> 2) >= crh || Xt + 32 * (k & 3) >= crw)) continue;
@@ -1059,25 +1052,18 @@ __device__ __forceinline__ void warp_gather(const WarpCam &C, const uint32_t *__
 #pragma unroll
             for (int c = 0; c < 3; ++c) v[c] = apply_gain(v[c], C.gain_mode, g, C.gain_scalar);
         }
-        // 32 samples = 64 bytes per column group: immediate offsets on the six row pointers
-        if (k < 4) {
-            if ((k & 3) == 0) { st_s16<0>(o00, v[0]); st_s16<0>(o01, v[1]); st_s16<0>(o02, v[2]); }
-            if ((k & 3) == 1) { st_s16<64>(o00, v[0]); st_s16<64>(o01, v[1]); st_s16<64>(o02, v[2]); }
-            if ((k & 3) == 2) { st_s16<128>(o00, v[0]); st_s16<128>(o01, v[1]); st_s16<128>(o02, v[2]); }
-            if ((k & 3) == 3) { st_s16<192>(o00, v[0]); st_s16<192>(o01, v[1]); st_s16<192>(o02, v[2]); }
-        } else {
-            if ((k & 3) == 0) { st_s16<0>(o10, v[0]); st_s16<0>(o11, v[1]); st_s16<0>(o12, v[2]); }
-            if ((k & 3) == 1) { st_s16<64>(o10, v[0]); st_s16<64>(o11, v[1]); st_s16<64>(o12, v[2]); }
-            if ((k & 3) == 2) { st_s16<128>(o10, v[0]); st_s16<128>(o11, v[1]); st_s16<128>(o12, v[2]); }
-            if ((k & 3) == 3) { st_s16<192>(o10, v[0]); st_s16<192>(o11, v[1]); st_s16<192>(o12, v[2]); }
-        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) out[c][k >> 2] += (uint32_t)v[c] << (8 * (k & 3));   // v in [0, 255]
     }
 }
 
-template <bool kMap64, int kGain, bool kSrc4>
+template <bool kMap64, int kGain, bool kSrc4, bool kTma>
 __global__ void __launch_bounds__(256, 5) warp_tile_kernel(const __grid_constant__ WarpArgs A, const uint8_t *__restrict__ frames)
 {
-    __shared__ __align__(16) uint32_t sm[kWarpSmemWords];
+    static_assert(!kTma || kSrc4, "TMA staging needs a word-per-pixel source");
+    __shared__ __align__(128) uint32_t sm[kWarpSmemWords];
+    __shared__ __align__(16) uint32_t so[3 * kWarpTileH * 32];             // [plane][row][lane]: packed column groups
+    __shared__ __align__(8) uint64_t bar;
     const int ncam = A.ncam;
     // Two block orders.  Default: tiles of one (camera, slot) image together (blockIdx.z = cam + ncam * slot).  With gain
     // maps (two 4-byte tables per pixel): frame-set slot fastest (blockIdx.x = slot + nslots * tile column), so that the
@@ -1095,8 +1081,15 @@ __global__ void __launch_bounds__(256, 5) warp_tile_kernel(const __grid_constant
     const uint8_t *src = frames + ((size_t)slot * ncam + cam) * ((size_t)W3 * H);
     const int4 td = __ldg(C.tiles + by * C.tiles_x + bx);   // {x0 (px, %16==0), y0, rows, 16-px groups}
     const int lane = threadIdx.x, ty = threadIdx.y;
-    const int rw = (td.w * 16 + 31) & ~31;                   // staged words per row
     const bool staged = td.z > 0;
+    const int rw = kTma ? max(kWarpBoxW0, (td.w * 16 + 31) & ~31) : ((td.w * 16 + 31) & ~31);   // staged words per row
+    if (kTma && staged && threadIdx.x == 0 && threadIdx.y == 0) {
+        mbar_init(&bar, 1);
+        const int nbox = (td.z + kWarpBoxH - 1) / kWarpBoxH;
+        mbar_expect_tx(&bar, (unsigned)(nbox * kWarpBoxH * rw * 4));
+        const CUtensorMap *tm = &A.tm[(rw - kWarpBoxW0) >> 5];
+        for (int i = 0; i < nbox; ++i) tma_load_3d(sm + i * kWarpBoxH * rw, tm, td.x, td.y + i * kWarpBoxH, slot * ncam + cam, &bar);
+    }
     const int Xt = bx * kWarpTileW + lane;
     const int Y0 = by * kWarpTileH + ty;
     const int mp = C.map_pitch, crw = C.rw, crh = C.rh;
@@ -1119,7 +1112,9 @@ __global__ void __launch_bounds__(256, 5) warp_tile_kernel(const __grid_constant
             }
         }
     }
-    if (staged && kSrc4) {
+    if (kTma) {
+        // nothing to do here: the copy engine is filling sm
+    } else if (staged && kSrc4) {
         // word-per-pixel source (8UC4 camera frames, fused front end): the staged layout IS the source layout --
         // one warp per source row, one lane per 16-byte chunk, conflict-free 16-byte stores
         const int nchunk = 4 * td.w, cmax = W / 4 - 1, c0 = td.x >> 2;
@@ -1165,10 +1160,36 @@ __global__ void __launch_bounds__(256, 5) warp_tile_kernel(const __grid_constant
             }
         }
     }
-    __syncthreads();
+    __syncthreads();                                         // staging done / the mbarrier is initialised
+    if (kTma && staged) mbar_wait(&bar, 0);                  // the boxes have landed
     const int sbase = -(td.y * rw + td.x);
-    if (full) warp_gather<kMap64, kGain, true, kPx>(C, sm, src, staged, rw, sbase, W, H, msx, msy, Xt, Y0, slot);
-    else warp_gather<kMap64, kGain, false, kPx>(C, sm, src, staged, rw, sbase, W, H, msx, msy, Xt, Y0, slot);
+    uint32_t res[3][2];
+    if (full) warp_gather<kMap64, kGain, true, kPx>(C, sm, src, staged, rw, sbase, W, H, msx, msy, Xt, Y0, res);
+    else warp_gather<kMap64, kGain, false, kPx>(C, sm, src, staged, rw, sbase, W, H, msx, msy, Xt, Y0, res);
+    // transpose through shared memory (see (4) above)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        so[(c * kWarpTileH + ty) * 32 + lane] = res[c][0];
+        so[(c * kWarpTileH + ty + 8) * 32 + lane] = res[c][1];
+    }
+    __syncthreads();
+    const int tid = ty * 32 + lane;
+    uint8_t *gbase = C.g0 + slot * C.g_slot + (by * kWarpTileH) * C.g_pitch + bx * kWarpTileW;
+#pragma unroll
+    for (int it = tid; it < 3 * kWarpTileH * 8; it += 256) {
+        const int cr = it >> 3, j = it & 7;                  // (plane, row) and the quad of lanes 4j .. 4j+3
+        const int c = cr >> 4, row = cr & 15;
+        if (!full && by * kWarpTileH + row >= crh) continue;
+        const uint4 q = *reinterpret_cast<const uint4 *>(so + cr * 32 + 4 * j);
+        const uint32_t t0 = __byte_perm(q.x, q.y, 0x5140), t1 = __byte_perm(q.z, q.w, 0x5140);
+        const uint32_t t2 = __byte_perm(q.x, q.y, 0x7362), t3 = __byte_perm(q.z, q.w, 0x7362);
+        const uint32_t o[4] = {__byte_perm(t0, t1, 0x5410), __byte_perm(t0, t1, 0x7632), __byte_perm(t2, t3, 0x5410),
+                               __byte_perm(t2, t3, 0x7632)};      // o[g] = pixels 32 g + 4 j .. + 3
+        uint8_t *d = gbase + c * C.g_plane + row * C.g_pitch + 4 * j;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            if (full || bx * kWarpTileW + 32 * g + 4 * j < crw) *reinterpret_cast<uint32_t *>(d + 32 * g) = o[g];   // rows carry >= 24 bytes of padding
+    }
 }
 
 // ------------------------------------------------------------------ K4: single-pass blenders
@@ -1253,7 +1274,7 @@ __global__ void __launch_bounds__(256) blend_g0_kernel(const PanoTables *__restr
         const CamTables &C = T->cam[i];
         const int y = Y - C.ry, x0 = X0 - C.rx;
         if ((unsigned)y >= (unsigned)C.rh || x0 + 3 < 0 || x0 >= C.rw) continue;
-        const int16_t *g = C.g[0] + (size_t)slot * C.g_slot[0] + (size_t)y * C.g_pitch[0];
+        const uint8_t *g = C.g[0] + (size_t)slot * C.g_slot[0] + (size_t)y * C.g_pitch[0];
         const size_t plane = C.g_plane[0];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -1299,6 +1320,35 @@ __global__ void __launch_bounds__(256) blend_g0_kernel(const PanoTables *__restr
 }
 
 // ------------------------------------------------------------------ strip-split halo columns
+// Halo buffers carry int16 elements for both kinds (the 8-bit Gaussian samples are widened on pack and
+// narrowed on unpack: the messages are a few KB and latency-bound, one layout keeps the exchange code single).
+__device__ __forceinline__ int16_t halo_get(const PanoTables *__restrict__ T, int kind, int level, int cam, int plane, int r, int x, int slot)
+{
+    if (kind == 1) {
+        const bool ok = r < (T->pad_h >> level) && x >= 0 && x < (T->pad_w >> level);
+        return ok ? T->outp[level][(size_t)slot * T->out_slot[level] + (size_t)plane * T->out_plane[level] + (size_t)r * T->out_pitch[level] + x]
+                  : (int16_t)0;
+    }
+    const CamTables &C = T->cam[cam];
+    const int xx = x - (C.rx >> level);
+    const bool ok = r < (C.rh >> level) && xx >= 0 && xx < (C.rw >> level);
+    return ok ? (int16_t)C.g[level][(size_t)slot * C.g_slot[level] + (size_t)plane * C.g_plane[level] + (size_t)r * C.g_pitch[level] + xx]
+              : (int16_t)0;
+}
+
+__device__ __forceinline__ void halo_put(const PanoTables *__restrict__ T, int kind, int level, int cam, int plane, int r, int x, int slot, int16_t v)
+{
+    if (kind == 1) {
+        if (r < (T->pad_h >> level) && x >= 0 && x < (T->pad_w >> level))
+            T->outp[level][(size_t)slot * T->out_slot[level] + (size_t)plane * T->out_plane[level] + (size_t)r * T->out_pitch[level] + x] = v;
+        return;
+    }
+    const CamTables &C = T->cam[cam];
+    const int xx = x - (C.rx >> level);
+    if (r < (C.rh >> level) && xx >= 0 && xx < (C.rw >> level))
+        C.g[level][(size_t)slot * C.g_slot[level] + (size_t)plane * C.g_plane[level] + (size_t)r * C.g_pitch[level] + xx] = (uint8_t)v;
+}
+
 __global__ void __launch_bounds__(256) halo_copy_kernel(const PanoTables *__restrict__ T, int kind, int level, int col,
                                                         int ncols, int16_t *__restrict__ buf, int unpack, int slot, int rows_max)
 {
@@ -1306,27 +1356,9 @@ __global__ void __launch_bounds__(256) halo_copy_kernel(const PanoTables *__rest
     const int plane = blockIdx.y % 3, cam = blockIdx.y / 3;
     if (r >= rows_max) return;
     int16_t *b = buf + (((size_t)cam * 3 + plane) * rows_max + r) * ncols;
-    if (kind == 1) {
-        const int h = T->pad_h >> level, w = T->pad_w >> level;
-        for (int c = 0; c < ncols; ++c) {
-            const int x = col + c;
-            const bool ok = r < h && x >= 0 && x < w;
-            int16_t *p = T->outp[level] + (size_t)slot * T->out_slot[level] + (size_t)plane * T->out_plane[level] +
-                         (size_t)r * T->out_pitch[level] + x;
-            if (unpack) { if (ok) *p = b[c]; }
-            else b[c] = ok ? *p : (int16_t)0;
-        }
-    } else {
-        const CamTables &C = T->cam[cam];
-        const int h = C.rh >> level, w = C.rw >> level, x0 = col - (C.rx >> level);
-        for (int c = 0; c < ncols; ++c) {
-            const int x = x0 + c;
-            const bool ok = r < h && x >= 0 && x < w;
-            int16_t *p = C.g[level] + (size_t)slot * C.g_slot[level] + (size_t)plane * C.g_plane[level] +
-                         (size_t)r * C.g_pitch[level] + x;
-            if (unpack) { if (ok) *p = b[c]; }
-            else b[c] = ok ? *p : (int16_t)0;
-        }
+    for (int c = 0; c < ncols; ++c) {
+        if (unpack) halo_put(T, kind, level, cam, plane, r, col + c, slot, b[c]);
+        else b[c] = halo_get(T, kind, level, cam, plane, r, col + c, slot);
     }
 }
 
@@ -1337,16 +1369,20 @@ __global__ void __launch_bounds__(256) halo_copy_kernel(const PanoTables *__rest
 // flag word (system-scope fence + store).  Before the next phase ONE launch per rank waits for both flags
 // (system-scope acquire loads by one thread per block) and unpacks the received columns into the pyramid halos.
 // Layout of a mailbox slot: [cam][plane][row][ncols] int16, as halo_copy_kernel packs it.
-__device__ __forceinline__ int16_t *halo_elem(const PanoTables *__restrict__ T, int kind, int level, int cam, int plane, int r, int x, bool &ok)
+// Every spin is BOUNDED (kSpinLimit polls, ~seconds): a lost neighbour raises *err instead of hanging the device.
+constexpr unsigned kSpinLimit = 1u << 26;
+
+__device__ __forceinline__ bool wait_flag(const uint32_t *flag, uint32_t seq, unsigned *err)
 {
-    if (kind == 1) {
-        ok = r < (T->pad_h >> level) && x >= 0 && x < (T->pad_w >> level);
-        return T->outp[level] + (size_t)plane * T->out_plane[level] + (size_t)r * T->out_pitch[level] + x;
-    }
-    const CamTables &C = T->cam[cam];
-    const int xx = x - (C.rx >> level);
-    ok = r < (C.rh >> level) && xx >= 0 && xx < (C.rw >> level);
-    return C.g[level] + (size_t)plane * C.g_plane[level] + (size_t)r * C.g_pitch[level] + xx;
+    uint32_t v;
+    unsigned spins = 0;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int32_t)(v - seq) >= 0) return true;                    // sequence numbers only grow
+        __nanosleep(64);
+    } while (++spins < kSpinLimit);
+    atomicExch(err, 1u);
+    return false;
 }
 
 __global__ void p2p_begin_kernel(uint32_t *seq) { ++*seq; }
@@ -1363,11 +1399,7 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const PanoTables *__rest
     const int plane = blockIdx.y % 3, cam = blockIdx.y / 3;
     if (r < rows_max) {
         int16_t *b = S.buf[seq & 1] + (((size_t)cam * 3 + plane) * rows_max + r) * ncols;
-        for (int c = 0; c < ncols; ++c) {
-            bool ok;
-            const int16_t *p = halo_elem(T, kind, level, cam, plane, r, S.col + c, ok);
-            b[c] = ok ? *p : (int16_t)0;                            // b may live in the neighbour's HBM
-        }
+        for (int c = 0; c < ncols; ++c) b[c] = halo_get(T, kind, level, cam, plane, r, S.col + c, 0);   // b may live in the neighbour's HBM
     }
     __threadfence_system();                                         // my stores are ordered before the flag below
     __syncthreads();
@@ -1382,35 +1414,29 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const PanoTables *__rest
 }
 
 __global__ void __launch_bounds__(256) halo_wait_unpack_kernel(const PanoTables *__restrict__ T, int kind, int level, int ncols,
-                                                               HaloSide s0, HaloSide s1, const uint32_t *__restrict__ seq_ptr, int rows_max)
+                                                               HaloSide s0, HaloSide s1, const uint32_t *__restrict__ seq_ptr,
+                                                               unsigned *__restrict__ counters, int rows_max)
 {
     const int side = blockIdx.z;
     const HaloSide S = side ? s1 : s0;
     if (!S.flag) return;
     const uint32_t seq = *seq_ptr;
-    if (threadIdx.x == 0) {
-        uint32_t v;
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(S.flag) : "memory");
-        } while ((int32_t)(v - seq) < 0);                            // sequence numbers only grow
-    }
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) s_ok = wait_flag(S.flag, seq, counters + 2) ? 1 : 0;
     __syncthreads();
+    if (!s_ok) return;
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const int plane = blockIdx.y % 3, cam = blockIdx.y / 3;
     if (r >= rows_max) return;
     const volatile int16_t *b = S.buf[seq & 1] + (((size_t)cam * 3 + plane) * rows_max + r) * ncols;   // written by the neighbour: bypass L1
-    for (int c = 0; c < ncols; ++c) {
-        bool ok;
-        int16_t *p = halo_elem(T, kind, level, cam, plane, r, S.col + c, ok);
-        const int16_t v = b[c];
-        if (ok) *p = v;
-    }
+    for (int c = 0; c < ncols; ++c) halo_put(T, kind, level, cam, plane, r, S.col + c, 0, b[c]);
 }
 
 // push + wait/unpack of one exchange in ONE launch (one kernel boundary less on a latency-bound chain): every block
 // first stores its share of this rank's edge columns into the neighbour's mailbox, the last block of a side raises the
 // neighbour's flag, then the same blocks wait for this rank's own flag of that side and unpack.  All blocks must be
-// co-resident (a spinning block never yields its SM slot), which the launcher guarantees by grid size.
+// co-resident (a spinning block never yields its SM slot): the launcher checks the grid against the occupancy the
+// runtime reports for this kernel (minus a margin) and the caller opts in -- see launch_halo_exchange.
 __global__ void __launch_bounds__(256) halo_exchange_kernel(const PanoTables *__restrict__ T, int kind, int level, int ncols,
                                                             HaloSide p0, HaloSide p1, HaloSide r0, HaloSide r1,
                                                             const uint32_t *__restrict__ seq_ptr, unsigned *__restrict__ counters, int rows_max)
@@ -1424,14 +1450,11 @@ __global__ void __launch_bounds__(256) halo_exchange_kernel(const PanoTables *__
     const size_t slot_off = (((size_t)cam * 3 + plane) * rows_max + r) * ncols;
     if (r < rows_max) {
         int16_t *b = P.buf[seq & 1] + slot_off;
-        for (int c = 0; c < ncols; ++c) {
-            bool ok;
-            const int16_t *p = halo_elem(T, kind, level, cam, plane, r, P.col + c, ok);
-            b[c] = ok ? *p : (int16_t)0;
-        }
+        for (int c = 0; c < ncols; ++c) b[c] = halo_get(T, kind, level, cam, plane, r, P.col + c, 0);
     }
     __threadfence_system();
     __syncthreads();
+    __shared__ int s_ok;
     if (threadIdx.x == 0) {
         const unsigned total = gridDim.x * gridDim.y;
         if (atomicAdd(&counters[side], 1u) == total - 1) {
@@ -1439,20 +1462,12 @@ __global__ void __launch_bounds__(256) halo_exchange_kernel(const PanoTables *__
             __threadfence_system();
             asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.flag), "r"(seq) : "memory");
         }
-        uint32_t v;
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(R.flag) : "memory");
-        } while ((int32_t)(v - seq) < 0);
+        s_ok = wait_flag(R.flag, seq, counters + 2) ? 1 : 0;
     }
     __syncthreads();
-    if (r >= rows_max) return;
+    if (!s_ok || r >= rows_max) return;
     const volatile int16_t *b = R.buf[seq & 1] + slot_off;
-    for (int c = 0; c < ncols; ++c) {
-        bool ok;
-        int16_t *p = halo_elem(T, kind, level, cam, plane, r, R.col + c, ok);
-        const int16_t v = b[c];
-        if (ok) *p = v;
-    }
+    for (int c = 0; c < ncols; ++c) halo_put(T, kind, level, cam, plane, r, R.col + c, 0, b[c]);
 }
 
 // ------------------------------------------------------------------ init-time tables on the device
@@ -1555,7 +1570,8 @@ inline dim3 grid2d(int w, int h, dim3 block, int z) { return dim3((w + block.x -
 void launch_warp(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, const uint8_t *frames, int nslots,
                  cudaStream_t stream)
 {
-    if (kc.warp_tiled) {
+    // the staged kernel reads the frames as 16-byte vectors (or through TMA): an unaligned base takes the generic kernel
+    if (kc.warp_tiled && (reinterpret_cast<uintptr_t>(frames) & 15) == 0) {
         int tx = 0, ty = 0;
         bool gain = false;
         WarpArgs A{};
@@ -1577,8 +1593,13 @@ void launch_warp(const PanoTables *dev, const PanoTables &host, const KernelChoi
         const dim3 block(32, 8);
         const dim3 grid = gv != 0 ? dim3(tx * nslots, ty, host.num_cams) : dim3(tx, ty, host.num_cams * nslots);
         const bool m64 = host.cam[0].map64 != nullptr, s4 = host.src_px == 4;
-#define PANO_WARP_LAUNCH(M, G, S) warp_tile_kernel<M, G, S><<<grid, block, 0, stream>>>(A, frames)
-#define PANO_WARP_PICK_S(M, G) (s4 ? PANO_WARP_LAUNCH(M, G, true) : PANO_WARP_LAUNCH(M, G, false))
+        static const bool no_tma = getenv("PANO_NO_TMA") != nullptr;            // A/B switch: LDG/STS staging loop
+        bool tma = s4 && !no_tma;
+        for (int i = 0; i < kWarpBoxes && tma; ++i)
+            tma = tma_encode_words3d(&A.tm[i], frames, host.src_w, host.src_h, nslots * host.num_cams, (size_t)host.src_w * 4,
+                                     (size_t)host.src_w * host.src_h * 4, kWarpBoxW0 + 32 * i, kWarpBoxH);
+#define PANO_WARP_LAUNCH(M, G, S, T) warp_tile_kernel<M, G, S, T><<<grid, block, 0, stream>>>(A, frames)
+#define PANO_WARP_PICK_S(M, G) (s4 ? (tma ? PANO_WARP_LAUNCH(M, G, true, true) : PANO_WARP_LAUNCH(M, G, true, false)) : PANO_WARP_LAUNCH(M, G, false, false))
 #define PANO_WARP_PICK_G(M) (gv == 0 ? PANO_WARP_PICK_S(M, 0) : (gv == 1 ? PANO_WARP_PICK_S(M, 1) : PANO_WARP_PICK_S(M, 2)))
         if (m64) PANO_WARP_PICK_G(true); else PANO_WARP_PICK_G(false);
 #undef PANO_WARP_PICK_G
@@ -1606,16 +1627,11 @@ void launch_pyrdown(const PanoTables *dev, const PanoTables &host, const KernelC
         maxh = max(maxh, ((host.cam[i].rh >> level) + 1) / 2);
     }
     const dim3 block(32, 8);
-    if (kc.pyrdown8[level]) {
-        static const bool no_walk = getenv("PANO_NO_DOWN_WALK") != nullptr;
-        if (!no_walk) {
-            static const int band = getenv("PANO_DOWN_BAND") ? atoi(getenv("PANO_DOWN_BAND")) : kDownBand;
-            const dim3 wb(32, 4), wg((maxw + 255) / 256, (maxh + 4 * band - 1) / (4 * band), host.num_cams * nslots * 3);
-            pyrdown8_walk_kernel<<<wg, wb, 0, stream>>>(dev, level, band);
-            return;
-        }
-        const dim3 grid8 = grid2d((maxw + 7) / 8, (maxh + 1) / 2, block, host.num_cams * nslots * 3);
-        pyrdown8_kernel<<<grid8, block, 0, stream>>>(dev, level);
+    static const bool no_walk = getenv("PANO_NO_DOWN_WALK") != nullptr;       // A/B switch: the generic kernel everywhere
+    if (kc.pyrdown8[level] && !no_walk) {
+        static const int band = getenv("PANO_DOWN_BAND") ? atoi(getenv("PANO_DOWN_BAND")) : kDownBand;
+        const dim3 wb(32, 4), wg((maxw + 255) / 256, (maxh + 4 * band - 1) / (4 * band), host.num_cams * nslots * 3);
+        pyrdown8_walk_kernel<<<wg, wb, 0, stream>>>(dev, level, band);
         return;
     }
     const dim3 grid = grid2d((maxw + 3) / 4, (maxh + 1) / 2, block, host.num_cams * nslots * 3);
@@ -1708,6 +1724,16 @@ void launch_halo_push(const PanoTables *dev, const PanoTables &host, int kind, i
     halo_push_kernel<<<grid, block, 0, stream>>>(dev, kind, level, ncols, left, right, seq, counters, rows);
 }
 
+// Most blocks of halo_exchange_kernel that are certainly co-resident on `device`: what the runtime reports for this
+// kernel's register / shared-memory footprint, minus a quarter as margin for other work sharing the device.
+int halo_exchange_resident_limit(int device)
+{
+    int per_sm = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, halo_exchange_kernel, 256, 0) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
+    return per_sm * sms * 3 / 4;
+}
+
 bool launch_halo_exchange(const PanoTables *dev, const PanoTables &host, int kind, int level, int ncols, const HaloSide push[2],
                           const HaloSide recv[2], const uint32_t *seq, unsigned *counters, int max_resident_blocks, cudaStream_t stream)
 {
@@ -1719,11 +1745,11 @@ bool launch_halo_exchange(const PanoTables *dev, const PanoTables &host, int kin
 }
 
 void launch_halo_wait_unpack(const PanoTables *dev, const PanoTables &host, int kind, int level, int ncols, const HaloSide &left,
-                             const HaloSide &right, const uint32_t *seq, cudaStream_t stream)
+                             const HaloSide &right, const uint32_t *seq, unsigned *counters, cudaStream_t stream)
 {
     const int rows = halo_rows(host, kind, level);
     const dim3 block(256), grid((rows + 255) / 256, 3 * (kind == 1 ? 1 : host.num_cams), 2);
-    halo_wait_unpack_kernel<<<grid, block, 0, stream>>>(dev, kind, level, ncols, left, right, seq, rows);
+    halo_wait_unpack_kernel<<<grid, block, 0, stream>>>(dev, kind, level, ncols, left, right, seq, counters, rows);
 }
 
 void launch_weight_pyrdown(const void *src, bool from_mask, int spitch, int sw, int sh, float *dst, int dpitch,

@@ -11,8 +11,10 @@ constexpr int kMaxCams = 8;
 constexpr int kMaxLevels = 10;  // num_bands + 1 <= kMaxLevels
 
 // One camera's static tables and per-wave pyramid workspace.  All "pitch" values are in
-// ELEMENTS of the array they describe.  Pyramid planes are channel-planar int16:
-// g[l] -> [slot][3 planes][h_l rows][g_pitch[l]].
+// ELEMENTS of the array they describe.  Gaussian pyramid planes are channel-planar UINT8
+// (every Gaussian level of an 8-bit frame is provably in [0, 255]: level 0 is the warped image after
+// the saturating gain, cv::pyrDown is a convex combination with (S + 128) >> 8), rows 128-byte aligned:
+// g[l] -> [slot][3 planes][h_l rows][g_pitch[l]].  Only the collapsed dst pyramid out[l] needs 16 bits.
 struct CamTables {
     // feed rect of MultiBandBlender::feed at level 0, in padded-dst coordinates
     // (for feather / no-blend: the image rect itself, borders = 0)
@@ -38,7 +40,7 @@ struct CamTables {
     int wt_pitch[kMaxLevels];
     int use_wt0;  // 1: level-0 weights come from wt[0] (caller override / feather) instead of mask0
     // pyramid workspace
-    int16_t *g[kMaxLevels];
+    uint8_t *g[kMaxLevels];
     int g_pitch[kMaxLevels];
     size_t g_plane[kMaxLevels];  // elements per plane
     size_t g_slot[kMaxLevels];   // elements per frame-set slot (= 3 planes)
@@ -112,8 +114,8 @@ void launch_tile_stats(const void *data, bool is_mask, int pitch, int w, int h, 
 
 // strip-split halo columns: pack / unpack `ncols` dst columns starting at dst column `col`
 // (level `level`) of either every camera's g[level] (kind 0) or out[level] (kind 1) into / from a
-// dense buffer laid out [cam][plane][row][ncols] int16 (cameras that do not cover the column
-// contribute zeros and ignore the incoming data).
+// dense buffer laid out [cam][plane][row][ncols] int16 (8-bit Gaussian samples are widened; cameras that do not
+// cover the column contribute zeros and ignore the incoming data).
 void launch_halo_copy(const PanoTables *dev, const PanoTables &host, int kind, int level, int col, int ncols,
                       int16_t *buf, bool unpack, int slot, cudaStream_t stream);
 size_t halo_elems(const PanoTables &host, int kind, int level, int ncols);
@@ -129,9 +131,12 @@ void launch_p2p_begin(uint32_t *seq, cudaStream_t stream);
 void launch_halo_push(const PanoTables *dev, const PanoTables &host, int kind, int level, int ncols, const HaloSide &left,
                       const HaloSide &right, const uint32_t *seq, unsigned *counters, cudaStream_t stream);
 // both halves in one launch; false (nothing launched) when the grid would exceed max_resident_blocks
+// (halo_exchange_resident_limit: the runtime's occupancy for the kernel x SMs, minus a margin)
+int halo_exchange_resident_limit(int device);
 bool launch_halo_exchange(const PanoTables *dev, const PanoTables &host, int kind, int level, int ncols, const HaloSide push[2],
                           const HaloSide recv[2], const uint32_t *seq, unsigned *counters, int max_resident_blocks, cudaStream_t stream);
+// counters: [0], [1] block-completion counters of the two sides, [2] error flag raised by a spin that ran out
 void launch_halo_wait_unpack(const PanoTables *dev, const PanoTables &host, int kind, int level, int ncols, const HaloSide &left,
-                             const HaloSide &right, const uint32_t *seq, cudaStream_t stream);
+                             const HaloSide &right, const uint32_t *seq, unsigned *counters, cudaStream_t stream);
 
 }  // namespace pano

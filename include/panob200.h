@@ -115,7 +115,12 @@ int pano_process(pano_handle h, const uint8_t *const *frames, const int *strides
                  uint8_t *out, int out_stride);
 /* Same for `batch` frame-sets already resident in DEVICE memory, packed
  * [batch][num_images][src_height][src_width][3]; out packed [batch][cut_h][cut_w][3].
- * Asynchronous on `stream` (a cudaStream_t; NULL = legacy default stream). */
+ * Asynchronous on `stream` (a cudaStream_t; NULL = legacy default stream).
+ * Alignment: a 16-byte aligned frames_dev takes the staged 16-byte-vector / TMA kernels; any other address is
+ * accepted and runs the generic byte-wise gather (slower, same bytes).
+ * Concurrency: a handle owns ONE set of pyramid workspaces -- calls on the same handle must be issued on one
+ * stream at a time (or be ordered by the caller); use one handle per concurrent stream, as the reference uses one
+ * ocvStitcher per thread (src/master.cpp:314-318). */
 int pano_process_device(pano_handle h, const uint8_t *frames_dev, uint8_t *out_dev, int batch, void *stream);
 /* Host-memory batch (packed as above): H2D, compose and D2H are pipelined on internal
  * streams.  Pinned host memory gives full PCIe rate.  Synchronous. */
@@ -160,6 +165,10 @@ int pano_strip_p2p_push(pano_handle h, int phase, void *stream);
 int pano_strip_p2p_wait_unpack(pano_handle h, int phase, void *stream);
 int pano_strip_p2p_prepare(pano_handle h, const uint8_t *frames_dev, uint8_t *pano_dev, void *stream);   /* builds the graph only */
 int pano_strip_run_p2p(pano_handle h, const uint8_t *frames_dev, uint8_t *pano_dev, void *stream);
+/* Every device-side wait of the exchange is bounded (about a second of polling); a neighbour that never publishes
+ * raises an error flag instead of hanging the GPU.  Synchronises the handle's device; PANO_ERR if the flag was set
+ * (and clears it). */
+int pano_strip_p2p_check(pano_handle h);
 
 /* Per-kernel device time of the last pano_process_device call made while profiling was
  * enabled (CUDA events on the launching stream).  names: up to max entries. */
@@ -196,7 +205,8 @@ int pano_frontend_destroy(pano_frontend_handle h);
 const char *pano_frontend_last_error(pano_frontend_handle h);
 /* m_mapx / m_mapy as prepareUndistorMap builds them (include/nvcam.hpp:823-833) */
 int pano_frontend_get_maps(pano_frontend_handle h, float *mapx, float *mapy);
-/* frames: [batch][cam_src_height][cam_src_width][4 (2 for YUYV)] -> out [batch][out_height][out_width][3] */
+/* frames: [batch][cam_src_height][cam_src_width][4 (2 for YUYV)] -> out [batch][out_height][out_width][3].
+ * A 16-byte aligned argb_dev takes the tiled (TMA-staged) kernels; other addresses run the generic ones. */
 int pano_frontend_process_device(pano_frontend_handle h, const uint8_t *argb_dev, uint8_t *out_dev,
                                  int batch, void *stream);
 int pano_frontend_process(pano_frontend_handle h, const uint8_t *argb_host, int stride,
@@ -234,7 +244,8 @@ int pano_host_linear_exact_axis(int ssize, int dsize, int *ofs, int *c1);
  * pano_process / pano_process_device / pano_process_batch take the 8UC4 camera frames
  * ([batch][num_images][cam_src_height][cam_src_width][4]) and run nvCam's pixel pipeline on the
  * device first -- the loop of src/master.cpp:300-318 (getFrame x N, then process) as one call.
- * f == NULL detaches.  Attach before the first host-memory process call. */
+ * f == NULL detaches.  Re-callable at any time: the host staging buffers are re-sized when the caller-side frame
+ * format changes; a failing call leaves the handle untouched. */
 int pano_attach_frontend(pano_handle h, int cam, pano_frontend_handle f);
 
 /* ---------------------------------------------------------------- two-ring epilogue (caller step after process)

@@ -545,12 +545,13 @@ def test_strip_split_equals_single_gpu(nranks, mode):
         assert not np.array_equal(panob200.strips.assemble(ranks, panos).cpu().numpy(), want)
 
 
-@pytest.mark.parametrize("nranks,concurrent", [(2, False), (4, False), (8, False), (2, True), (4, True)])
+@pytest.mark.parametrize("nranks,concurrent", [(2, False), (4, False), (8, False)])
 def test_strip_split_peer_memory_exchange(nranks, concurrent):
     """Halo exchange through peer-memory mailboxes (push kernel stores into the neighbour's mailbox and raises a flag,
-    wait/unpack kernel consumes it).  Ranks are handles on one GPU: in lockstep on one stream, or concurrently on one
-    stream per rank, where the wait kernels really spin on flags raised by other streams.  Three consecutive frame-sets
-    (sequence numbers, slot parity) must each equal the undivided panorama byte for byte."""
+    wait/unpack kernel consumes it).  Ranks are handles on ONE GPU stepped in lockstep on one stream: every push
+    precedes the matching wait, so no kernel ever spins (kernels that wait on one another must not share a GPU --
+    B200_PROFILING.md; the truly concurrent exchange is covered on real GPUs by test_strip_split_multi_gpu_torchrun).
+    Three consecutive frame-sets (sequence numbers, slot parity) must each equal the undivided panorama byte for byte."""
     import torch
     t, imgs, want, frames, ranks, panos = _strip_setup(nranks, "exchange")
     panob200.strips.p2p_setup_local(ranks)
