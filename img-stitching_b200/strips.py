@@ -199,3 +199,122 @@ def assemble(ranks, panos):
         c0, c1 = r.own_output_columns()
         out[:, c0:c1] = p[:, c0:c1]
     return out
+
+
+# ---------------------------------------------------------------------------------- BASELINE config 4 measurement
+def ring_calibration(n, width, height, focal, step_deg):
+    """Synthetic cylindrical ring of BASELINE config 4: shared K (f, width/2, height/2), R_i = R_y((i - (n-1)/2) * step)."""
+    import numpy as np
+    f = np.float32(focal)
+    K = np.array([[f, 0, width / 2.0], [0, f, height / 2.0], [0, 0, 1]], np.float32)
+    Rs = []
+    for i in range(n):
+        a = np.radians((i - (n - 1) / 2.0) * step_deg)
+        c, s = np.cos(a), np.sin(a)
+        Rs.append(np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]], np.float32))
+    return [K.copy() for _ in range(n)], Rs, float(f)
+
+
+def soft_band_masks(stitcher):
+    """Seam-like soft masks without a seam finder: each camera keeps the central vertical band of its warped footprint
+    with a linear 0..255 ramp, min-ed with the warped validity mask the handle holds after initTables()."""
+    import numpy as np
+    out = []
+    for i, (w, h) in enumerate(stitcher.m_sizes):
+        x = np.arange(w)
+        lo, hi = int(w * 0.18), int(w * 0.82)
+        ramp = np.clip(np.minimum(x - lo, hi - x) * 12 + 128, 0, 255).astype(np.uint8)
+        out.append(np.minimum(np.broadcast_to(ramp[None, :], (h, w)), stitcher.get_mask(i)).astype(np.uint8))
+    return out
+
+
+def bench_config4(rank, world, local, small=False, steps=10, warmup=3, modes=("exchange", "p2p", "redundant")):
+    """ONE 8-camera cylindrical 7-band panorama (8 x 3840x2160; small: 8 x 960x540, 5 bands) split into `world` column
+    strips, one per rank of an initialised torch.distributed NCCL job.  Every rank checks its own columns against the
+    undivided panorama (computed locally by a second handle), then each halo mode is timed on the device, max over
+    ranks: "exchange" = NCCL point-to-point, "p2p" = peer-memory mailboxes, "redundant" = recomputed halo.
+    Returns the record on every rank."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from . import stitcher as stm
+    dev = torch.device("cuda", local)
+    W, H, nb, focal = (960, 540, 5, 750.0) if small else (3840, 2160, 7, 3000.0)
+    Ks, Rs, scale = ring_calibration(8, W, H, focal, 40.0)
+
+    masks = None
+
+    def make():
+        nonlocal masks
+        st = stm.ocvStitcher(stm.StitcherConfig(width=W, height=H, num_images=8, Ks=Ks, Rs=Rs, warped_image_scale=scale,
+                                                warp="cylindrical", blender="multiband", num_bands=nb, device=local))
+        if st.initTables() != 0:
+            raise capi.PanoError(st.last_error)
+        if masks is None:
+            masks = soft_band_masks(st)
+        for i, m in enumerate(masks):
+            st.set_mask(i, m)
+        return st
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(4242)                                  # every rank generates the SAME frame-set
+    low = torch.rand((8, 3, H // 32 + 2, W // 32 + 2), generator=g, device=dev)
+    up = torch.nn.functional.interpolate(low, size=(H, W), mode="bilinear", align_corners=False) * 255.0
+    frames = up.clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    del low, up
+    ref = make()
+    ow, oh = ref.out_size
+    want = torch.empty((1, oh, ow, 3), dtype=torch.uint8, device=dev)
+    ref.process_device(frames.unsqueeze(0), want)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ref.process_device(frames.unsqueeze(0), want)
+    e1.record()
+    torch.cuda.synchronize()
+    single_ms = e0.elapsed_time(e1) / steps
+    res = {}
+    r = None
+    for mode in modes:
+        r = StripRank(make(), rank, world, "exchange" if mode == "p2p" else mode)
+        pano = torch.zeros((oh, ow, 3), dtype=torch.uint8, device=dev)
+        if mode == "p2p":
+            p2p_setup_distributed(r)
+            side = torch.cuda.Stream(dev)            # a capturable stream: the frame is replayed as a CUDA graph
+
+            def run(bufs=None, r=r, pano=pano, side=side):
+                side.wait_stream(torch.cuda.current_stream(dev))
+                compose_p2p(r, frames, pano, side.cuda_stream)
+                torch.cuda.current_stream(dev).wait_stream(side)
+        else:
+            def run(bufs=None, r=r, pano=pano):
+                return compose_nccl(r, frames, pano, bufs)
+        bufs = run()
+        torch.cuda.synchronize()
+        c0, c1 = r.own_output_columns()
+        ok = bool(torch.equal(pano[:, c0:c1], want[0][:, c0:c1]))
+        for _ in range(warmup):
+            run(bufs)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record()
+        for _ in range(steps):
+            run(bufs)
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        if mode == "p2p":
+            ok = ok and r.lib.pano_strip_p2p_check(r.h) == 0
+        tt = torch.tensor([e0.elapsed_time(e1) / steps, 0.0 if ok else 1.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        res[mode] = {"ms_per_panorama": float(tt[0]), "all_ranks_match_undivided": bool(tt[1] == 0.0),
+                     "halo_bytes_per_rank_side": int(sum(r.halo_bytes(p) for p in range(r.phases)))}
+    t1 = torch.tensor([single_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t1, op=dist.ReduceOp.MAX)
+    return {"workload": "config4%s: 8x%dx%d cylindrical ring, %d bands, one panorama split into %d column strips"
+                        % (" (small)" if small else "", W, H, nb, world),
+            "n_gpus": world, "single_gpu_ms_per_panorama": float(t1[0]), "modes": res,
+            "halo_modes": {"exchange": "NCCL point-to-point (batch_isend_irecv)", "p2p": "peer-memory mailboxes over NVLink, frame replayed as a CUDA graph",
+                           "redundant": "no exchange, halo recomputed"},
+            "strips": sharding.strip_columns(r.padded[0], nb, world)}

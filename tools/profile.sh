@@ -5,7 +5,7 @@
 set -u
 TAG=${1:-r1}
 mkdir -p gpurun_out
-CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 1"   # default shape: 64 frame-sets per step, one wave
+CMD="python bench.py --steps 1 --warmup 3 --waves-per-step 1 --no-cpu-baseline --no-also --e2e-steps 1"   # default shape: one wave of 64 frame-sets
 $CMD > gpurun_out/${TAG}_plain.json 2> gpurun_out/${TAG}_plain.err || { echo "plain run failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
 $CMD > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on \
