@@ -11,6 +11,6 @@ from . import capi  # noqa: F401
 from .capi import PanoError, build_library, library_path  # noqa: F401
 from .stitcher import ocvStitcher, StitcherConfig  # noqa: F401
 from .nvcam import nvCamFrontEnd  # noqa: F401
-from .ring import RingComposer  # noqa: F401
+from .ring import FitCanvas, RingComposer  # noqa: F401
 from . import sharding  # noqa: F401
 from . import strips  # noqa: F401

@@ -51,6 +51,11 @@ class pano_ring_config(C.Structure):
                 ("mode", C.c_int), ("finalcut", C.c_int), ("bar", C.c_int), ("device", C.c_int)]
 
 
+class pano_fit_config(C.Structure):
+    _fields_ = [("in_width", C.c_int), ("in_height", C.c_int), ("canvas_width", C.c_int), ("canvas_height", C.c_int),
+                ("device", C.c_int)]
+
+
 class pano_frontend_config(C.Structure):
     _fields_ = [("cam_src_width", C.c_int), ("cam_src_height", C.c_int),
                 ("undist_width", C.c_int), ("undist_height", C.c_int),
@@ -105,6 +110,15 @@ _SIGS = {
     "pano_frontend_get_maps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pano_frontend_process_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "pano_frontend_process": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "pano_host_seam_scale": (C.c_double, [C.c_int, C.c_int]),
+    "pano_host_seam_input": (C.c_int, [C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pano_fit_create": (C.c_int, [C.POINTER(pano_fit_config), C.POINTER(C.c_void_p)]),
+    "pano_fit_destroy": (C.c_int, [C.c_void_p]),
+    "pano_fit_last_error": (C.c_char_p, [C.c_void_p]),
+    "pano_fit_geometry": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
+    "pano_fit_compose_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "pano_fit_compose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "pano_attach_frontend": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "pano_set_frontend_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "pano_ring_create": (C.c_int, [C.POINTER(pano_ring_config), C.POINTER(C.c_void_p)]),
@@ -174,6 +188,18 @@ def host_warp_roi(kind, scale, K, R, w, h):
     roi = (C.c_int * 4)()
     check(lib().pano_host_warp_roi(kind, scale, ptr(K), ptr(R), w, h, roi))
     return tuple(roi)
+
+
+def host_seam_input(kind, scale, K, R, frame):
+    """One camera's seam-finder input (pano_host_seam_input): -> (roi, image_warped, mask_warped)."""
+    K = np.ascontiguousarray(K, np.float32); R = np.ascontiguousarray(R, np.float32)
+    frame = np.ascontiguousarray(frame, np.uint8)
+    h, w = frame.shape[:2]
+    roi = (C.c_int * 4)()
+    check(lib().pano_host_seam_input(kind, C.c_float(scale), ptr(K), ptr(R), None, w, h, 0, roi, None, None))
+    iw = np.empty((roi[3], roi[2], 3), np.uint8); mw = np.empty((roi[3], roi[2]), np.uint8)
+    check(lib().pano_host_seam_input(kind, C.c_float(scale), ptr(K), ptr(R), ptr(frame), w, h, frame.strides[0], roi, ptr(iw), ptr(mw)))
+    return tuple(roi), iw, mw
 
 
 def host_build_maps(kind, scale, K, R, w, h):

@@ -334,7 +334,25 @@ int buildWeights(pano_ctx *h, int cam)
     const Rect &img = h->rois[cam];
     const FeedRect &fr = h->feed[cam];
     const std::vector<uint8_t> &m = h->mask[cam];
+    static const bool host_weights = getenv("PANO_HOST_WEIGHTS") != nullptr;    // A/B switch: the host builders
     if (h->blender == PANO_BLEND_FEATHER) {
+        if (!host_weights) {
+            // device build: the mask goes up once (1 byte per pixel instead of a 4-byte weight map), the separable exact
+            // L1 distance transform + sharpness + clamp run as two kernels
+            uint8_t *m0d = (uint8_t *)h->cam_mask0[cam];
+            int *tmp = nullptr;
+            CK(h, cudaMalloc((void **)&tmp, (size_t)img.w * img.h * sizeof(int)));
+            cudaError_t e = cudaMemcpy2DAsync(m0d, C.mask_pitch, m.data(), img.w, img.w, img.h, cudaMemcpyHostToDevice, nullptr);
+            if (e == cudaSuccess) {
+                launch_feather_weight(m0d, C.mask_pitch, img.w, img.h, h->cfg.sharpness, tmp, (float *)h->cam_wt[cam][0], C.wt_pitch[0], nullptr);
+                e = cudaStreamSynchronize(nullptr);
+            }
+            if (e == cudaSuccess) e = cudaGetLastError();
+            cudaFree(tmp);
+            if (e != cudaSuccess) return fail(h, "feather weight build failed: %s", cudaGetErrorString(e));
+            C.use_wt0 = 1;
+            return PANO_OK;
+        }
         std::vector<float> w((size_t)img.w * img.h);
         featherWeight(m.data(), img.w, img.h, img.w, h->cfg.sharpness, w.data());
         if (upload2d(h, (float *)h->cam_wt[cam][0], C.wt_pitch[0], w.data(), img.w, img.w, img.h)) return PANO_ERR;
@@ -342,7 +360,6 @@ int buildWeights(pano_ctx *h, int cam)
         return PANO_OK;
     }
     const int W = fr.rect.w, H = fr.rect.h;
-    static const bool host_weights = getenv("PANO_HOST_WEIGHTS") != nullptr;    // A/B switch: the host builder below
     if (!host_weights) {
         // device build: upload the mask into the zeroed feed rect (copyMakeBorder CONSTANT), then the float pyrDown
         // chain and the walker-tile statistics run as kernels; only the few-KB statistics come back

@@ -363,10 +363,11 @@ void cubicTable(int16_t *tab)
 }
 
 void resizeAxis(int ssize, int dsize, bool clamp_frac, std::vector<int> &ofs,
-                std::vector<int16_t> &a0, std::vector<int16_t> &a1)
+                std::vector<int16_t> &a0, std::vector<int16_t> &a1, double inv_scale_in)
 {
     ofs.resize(dsize); a0.resize(dsize); a1.resize(dsize);
-    const double inv_scale = static_cast<double>(dsize) / ssize;
+    // cv::resize called with dsize derives inv_scale from the sizes; called with fx / fy it keeps the caller's factor
+    const double inv_scale = inv_scale_in > 0 ? inv_scale_in : static_cast<double>(dsize) / ssize;
     const double scale = 1.0 / inv_scale;
     for (int d = 0; d < dsize; ++d) {
         float f = static_cast<float>((d + 0.5) * scale - 0.5);
@@ -384,10 +385,11 @@ void resizeAxis(int ssize, int dsize, bool clamp_frac, std::vector<int> &ofs,
 
 // OpenCV resize.cpp, interpolationLinear<uchar>::getCoeffs: softdouble arithmetic == IEEE double operations;
 // ufixedpoint16(x) = cvRound(x * 256) (round half to even); outside the source range the edge sample is replicated.
-void linearExactAxis(int ssize, int dsize, std::vector<int> &ofs, std::vector<int> &c1)
+// inv_scale <= 0: cv::resize was given dsize (inv_scale = dsize / ssize); otherwise the caller's fx / fy is used as is.
+void linearExactAxis(int ssize, int dsize, std::vector<int> &ofs, std::vector<int> &c1, double inv_scale_in)
 {
     ofs.assign(dsize, 0); c1.assign(dsize, 0);
-    const double inv_scale = static_cast<double>(dsize) / ssize;
+    const double inv_scale = inv_scale_in > 0 ? inv_scale_in : static_cast<double>(dsize) / ssize;
     const double scale = 1.0 / inv_scale;
     for (int d = 0; d < dsize; ++d) {
         const double fval = scale * (d + 0.5) - 0.5;
@@ -401,6 +403,74 @@ void linearExactAxis(int ssize, int dsize, std::vector<int> &ofs, std::vector<in
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------- seam-finder inputs (init-time, host)
+// cv::resize(src, dst, Size(), fx, fy, INTER_LINEAR_EXACT) on 8-bit images (include/ocvstitcher.hpp:988, 1228): the
+// horizontal pass accumulates in 8.8 fixed point, the vertical pass in 16.16, the result is rounded half up.
+void resizeLinearExactU8(const uint8_t *src, int w, int h, int stride, int ch, double fx, double fy, int dw, int dh,
+                         uint8_t *dst, int dstride)
+{
+    std::vector<int> xo, xc, yo, yc;
+    linearExactAxis(w, dw, xo, xc, fx);
+    linearExactAxis(h, dh, yo, yc, fy);
+    std::vector<uint32_t> row0(static_cast<size_t>(dw) * ch), row1(static_cast<size_t>(dw) * ch);
+    auto hrow = [&](int y, std::vector<uint32_t> &out) {
+        const uint8_t *s = src + static_cast<size_t>(y) * stride;
+        for (int x = 0; x < dw; ++x) {
+            const int x0 = xo[x], x1 = std::min(x0 + 1, w - 1), c1 = xc[x];
+            for (int c = 0; c < ch; ++c) out[static_cast<size_t>(x) * ch + c] = s[x0 * ch + c] * (256 - c1) + s[x1 * ch + c] * c1;
+        }
+    };
+    int have0 = -1, have1 = -1;
+    for (int y = 0; y < dh; ++y) {
+        const int y0 = yo[y], y1 = std::min(y0 + 1, h - 1), c1 = yc[y];
+        if (have0 != y0) { if (have1 == y0) { row0.swap(row1); std::swap(have0, have1); } else { hrow(y0, row0); have0 = y0; } }
+        if (have1 != y1) { hrow(y1, row1); have1 = y1; }
+        uint8_t *d = dst + static_cast<size_t>(y) * dstride;
+        const std::vector<uint32_t> &b = (y1 == y0) ? row0 : row1;
+        for (int i = 0; i < dw * ch; ++i) d[i] = static_cast<uint8_t>((row0[i] * (256 - c1) + b[i] * c1 + 32768u) >> 16);
+    }
+}
+
+// cv::remap(INTER_LINEAR, BORDER_REFLECT) on 8-bit images through float maps: 1/32-pixel coordinates,
+// weights (32-fy | fy) x (32-fx | fx), (sum + 512) >> 10 == OpenCV's 15-bit table form.
+void remapBilinearReflectU8(const uint8_t *src, int w, int h, int stride, int ch, const float *xmap, const float *ymap,
+                            int mw, int mh, uint8_t *dst, int dstride)
+{
+    auto refl = [](int p, int n) {
+        if (n == 1) return 0;
+        while (static_cast<unsigned>(p) >= static_cast<unsigned>(n)) p = p < 0 ? -p - 1 : 2 * n - 1 - p;
+        return p;
+    };
+    for (int y = 0; y < mh; ++y)
+        for (int x = 0; x < mw; ++x) {
+            const FixedCoord f = toFixed(xmap[static_cast<size_t>(y) * mw + x], ymap[static_cast<size_t>(y) * mw + x]);
+            const int x0 = refl(f.ix, w), x1 = refl(f.ix + 1, w), y0 = refl(f.iy, h), y1 = refl(f.iy + 1, h);
+            const int w00 = (32 - f.fy) * (32 - f.fx), w01 = (32 - f.fy) * f.fx, w10 = f.fy * (32 - f.fx), w11 = f.fy * f.fx;
+            const uint8_t *r0 = src + static_cast<size_t>(y0) * stride, *r1 = src + static_cast<size_t>(y1) * stride;
+            uint8_t *d = dst + static_cast<size_t>(y) * dstride + static_cast<size_t>(x) * ch;
+            for (int c = 0; c < ch; ++c)
+                d[c] = static_cast<uint8_t>((w00 * r0[x0 * ch + c] + w01 * r0[x1 * ch + c] + w10 * r1[x0 * ch + c] + w11 * r1[x1 * ch + c] + 512) >> 10);
+        }
+}
+
+// warp of an all-255 mask with INTER_NEAREST / BORDER_CONSTANT (:1013-1017, 1085, 1241): 255 where the rounded source
+// position lies inside the frame
+void warpedFullMask(const float *xmap, const float *ymap, int mw, int mh, int src_w, int src_h, uint8_t *dst, int dstride)
+{
+    for (int y = 0; y < mh; ++y)
+        for (int x = 0; x < mw; ++x) {
+            const int ix = clampS16(roundEven(xmap[static_cast<size_t>(y) * mw + x]));
+            const int iy = clampS16(roundEven(ymap[static_cast<size_t>(y) * mw + x]));
+            dst[static_cast<size_t>(y) * dstride + x] = (static_cast<unsigned>(ix) < static_cast<unsigned>(src_w) &&
+                                                        static_cast<unsigned>(iy) < static_cast<unsigned>(src_h)) ? 255 : 0;
+        }
+}
+
+double seamWorkAspect(int src_w, int src_h)
+{
+    return std::min(1.0, std::sqrt(1e5 / (static_cast<double>(src_w) * src_h)));      // include/ocvstitcher.hpp:298
 }
 
 }  // namespace pano

@@ -64,10 +64,21 @@ void undistortMaps(const double K[9], const double D[4], const double newK[9], i
 void cubicTable(int16_t *tab);
 // cv::resize INTER_LINEAR u8 coefficient tables for one axis
 void resizeAxis(int ssize, int dsize, bool clamp_frac, std::vector<int> &ofs,
-                std::vector<int16_t> &a0, std::vector<int16_t> &a1);
+                std::vector<int16_t> &a0, std::vector<int16_t> &a1, double inv_scale = 0.0);
 
 // cv::resize INTER_LINEAR_EXACT coefficient table for one axis (8UC1 path: ufixedpoint16, 8 fractional bits):
 // sample d reads src[ofs[d]] * (256 - c1[d]) + src[min(ofs[d] + 1, ssize - 1)] * c1[d]
-void linearExactAxis(int ssize, int dsize, std::vector<int> &ofs, std::vector<int> &c1);
+void linearExactAxis(int ssize, int dsize, std::vector<int> &ofs, std::vector<int> &c1, double inv_scale = 0.0);
+
+// ---- the seam finder's inputs (initSeam :985-1017, updateMask :1228-1242; init-time, host) ----------------
+double seamWorkAspect(int src_w, int src_h);
+// cv::resize(src, dst, Size(), fx, fy, INTER_LINEAR_EXACT), 8-bit, `ch` interleaved channels; dw x dh = cvRound(w * fx) x cvRound(h * fy)
+void resizeLinearExactU8(const uint8_t *src, int w, int h, int stride, int ch, double fx, double fy, int dw, int dh,
+                         uint8_t *dst, int dstride);
+// cv::remap(INTER_LINEAR, BORDER_REFLECT) through float maps
+void remapBilinearReflectU8(const uint8_t *src, int w, int h, int stride, int ch, const float *xmap, const float *ymap,
+                            int mw, int mh, uint8_t *dst, int dstride);
+// warp of an all-255 mask, INTER_NEAREST / BORDER_CONSTANT
+void warpedFullMask(const float *xmap, const float *ymap, int mw, int mh, int src_w, int src_h, uint8_t *dst, int dstride);
 
 }  // namespace pano

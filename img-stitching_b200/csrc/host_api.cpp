@@ -1,5 +1,6 @@
 // Host-only entry points of the C ABI: the init-time table builders, callable without a CUDA
 // device (used by callers that want geometry before creating a handle, and by the CPU tests).
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -112,6 +113,38 @@ int pano_host_linear_exact_axis(int ssize, int dsize, int *ofs, int *c1)
     linearExactAxis(ssize, dsize, o, c);
     std::memcpy(ofs, o.data(), sizeof(int) * dsize);
     std::memcpy(c1, c.data(), sizeof(int) * dsize);
+    return PANO_OK;
+}
+
+double pano_host_seam_scale(int src_w, int src_h) { return (src_w > 0 && src_h > 0) ? seamWorkAspect(src_w, src_h) : 0.0; }
+
+int pano_host_seam_input(int warp_kind, float warped_image_scale, const float *K, const float *R, const uint8_t *frame, int src_w,
+                         int src_h, int stride, int *roi, uint8_t *image_warped, uint8_t *mask_warped)
+{
+    if (!K || !R || !roi || src_w < 2 || src_h < 2) return PANO_ERR;
+    // include/ocvstitcher.hpp:988-1017: resize by seam_work_aspect, K scaled in float, warper at float(scale * aspect)
+    const double aspect = seamWorkAspect(src_w, src_h);
+    const int sw = (int)std::nearbyint(src_w * aspect), sh = (int)std::nearbyint(src_h * aspect);   // saturate_cast<int>(double) == cvRound
+    if (sw < 1 || sh < 1) return PANO_ERR;
+    float Ks[9];
+    std::memcpy(Ks, K, sizeof Ks);
+    const float swa = (float)aspect;
+    Ks[0] *= swa; Ks[2] *= swa; Ks[4] *= swa; Ks[5] *= swa;
+    RotationWarper w(warp_kind, static_cast<float>(warped_image_scale * aspect));
+    w.setCamera(Ks, R);
+    const Rect r = w.warpRoi(sw, sh);
+    roi[0] = r.x; roi[1] = r.y; roi[2] = r.w; roi[3] = r.h;
+    if (!image_warped && !mask_warped) return PANO_OK;
+    if (r.w <= 0 || r.h <= 0) return PANO_ERR;
+    std::vector<float> xm((size_t)r.w * r.h), ym((size_t)r.w * r.h);
+    w.buildMaps(sw, sh, r, xm.data(), ym.data());
+    if (mask_warped) warpedFullMask(xm.data(), ym.data(), r.w, r.h, sw, sh, mask_warped, r.w);
+    if (image_warped) {
+        if (!frame || stride < 3 * src_w) return PANO_ERR;
+        std::vector<uint8_t> small((size_t)sw * sh * 3);
+        resizeLinearExactU8(frame, src_w, src_h, stride, 3, aspect, aspect, sw, sh, small.data(), 3 * sw);
+        remapBilinearReflectU8(small.data(), sw, sh, 3 * sw, 3, xm.data(), ym.data(), r.w, r.h, image_warped, 3 * r.w);
+    }
     return PANO_OK;
 }
 

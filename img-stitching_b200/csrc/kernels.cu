@@ -1533,6 +1533,51 @@ __global__ void __launch_bounds__(256) seam_mask_kernel(const uint8_t *__restric
     dst[(size_t)y * w + x] = (uint8_t)(v & full[(size_t)y * w + x]);
 }
 
+// FeatherBlender::feed's weight map (src/stitching_detailed.cpp:865-869 -> cv::distanceTransform(mask, DIST_L1, 3), then
+// min(d * sharpness, 1)), which the reference recomputes for every frame although it only depends on the mask.  The 3x3
+// chamfer with costs (1, 2) IS the exact city-block distance to the nearest zero pixel, and that distance is separable:
+// d(x, y) = min_x' (|x - x'| + V(x', y)) with V the distance to the nearest zero inside column x'.  Two kernels of two
+// min-plus scans each: down + up every column (one thread per column, coalesced), then right + left every row.  Values
+// are capped at BIG like the host builder (pano::featherWeight), whose output this reproduces bit for bit.
+constexpr int kDistBig = 0x7fffffff >> 2;
+
+__global__ void __launch_bounds__(128) feather_cols_kernel(const uint8_t *__restrict__ mask, int mpitch, int w, int h, int *__restrict__ tmp)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    int d = kDistBig;
+    for (int y = 0; y < h; ++y) {
+        d = mask[(size_t)y * mpitch + x] ? min(d + 1, kDistBig) : 0;
+        tmp[(size_t)y * w + x] = d;
+    }
+    d = kDistBig;
+    for (int y = h - 1; y >= 0; --y) {
+        d = mask[(size_t)y * mpitch + x] ? min(d + 1, kDistBig) : 0;
+        const size_t i = (size_t)y * w + x;
+        tmp[i] = min(tmp[i], d);
+    }
+}
+
+__global__ void __launch_bounds__(128) feather_rows_kernel(int *__restrict__ tmp, int w, int h, float sharpness, float *__restrict__ out, int opitch)
+{
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= h) return;
+    int *row = tmp + (size_t)y * w;
+    int d = kDistBig;
+    for (int x = 0; x < w; ++x) {
+        d = min(row[x], min(d + 1, kDistBig));
+        row[x] = d;
+    }
+    d = kDistBig;
+    float *o = out + (size_t)y * opitch;
+    for (int x = w - 1; x >= 0; --x) {
+        d = min(row[x], min(d + 1, kDistBig));
+        const float dist = d >= kDistBig / 2 ? 3.402823466e+38f : (float)d;
+        const float v = __fmul_rn(dist, sharpness);
+        o[x] = v > 1.f ? 1.f : v;
+    }
+}
+
 // Per walker tile (kWalkTileW x kWalkTileH of the padded dst at this level) of one camera's weight level: is any
 // weight non-zero, and how many are exactly one (`one` = 255 for the 8-bit level-0 mask, 1.0f for float levels)?
 // The host turns these into the collapse work lists (PanoTables::walk_list / gen_list).  One block = one tile.
@@ -1758,6 +1803,12 @@ void launch_weight_pyrdown(const void *src, bool from_mask, int spitch, int sw, 
     const dim3 block(32, 8), grid = grid2d((sw + 1) / 2, (sh + 1) / 2, block, 1);
     if (from_mask) weight_pyrdown_kernel<true><<<grid, block, 0, stream>>>(src, spitch, sw, sh, dst, dpitch);
     else weight_pyrdown_kernel<false><<<grid, block, 0, stream>>>(src, spitch, sw, sh, dst, dpitch);
+}
+
+void launch_feather_weight(const uint8_t *mask, int mpitch, int w, int h, float sharpness, int *tmp, float *out, int opitch, cudaStream_t stream)
+{
+    feather_cols_kernel<<<(w + 127) / 128, 128, 0, stream>>>(mask, mpitch, w, h, tmp);
+    feather_rows_kernel<<<(h + 127) / 128, 128, 0, stream>>>(tmp, w, h, sharpness, out, opitch);
 }
 
 void launch_seam_mask(const uint8_t *seam, int sw, int sh, int spitch, const int *xo, const int *xc, const int *yo, const int *yc,

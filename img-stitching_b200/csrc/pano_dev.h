@@ -109,6 +109,9 @@ void launch_weight_pyrdown(const void *src, bool from_mask, int spitch, int sw, 
 // m_blenderMask from the seam finder's low-resolution mask (dilate -> INTER_LINEAR_EXACT -> AND full mask), tight w x h
 void launch_seam_mask(const uint8_t *seam, int sw, int sh, int spitch, const int *xo, const int *xc, const int *yo, const int *yc,
                       const uint8_t *full, uint8_t *dst, int w, int h, cudaStream_t stream);
+// FeatherBlender weight map of one camera: min(distanceTransform(mask, DIST_L1, 3) * sharpness, 1); tmp = w * h ints
+void launch_feather_weight(const uint8_t *mask, int mpitch, int w, int h, float sharpness, int *tmp, float *out, int opitch,
+                           cudaStream_t stream);
 void launch_tile_stats(const void *data, bool is_mask, int pitch, int w, int h, int ox, int oy, int tiles_x, int tiles_y,
                        uint8_t *nz, int *ones, cudaStream_t stream);
 

@@ -5,9 +5,13 @@
 //   src/panocamimpl.cpp:354-360   both cropped to Rect(0, finalcut, min width, min height - 2*finalcut);
 //                                 cv::vconcat; cv::rectangle(ret, Rect(0, height - 2, width, 4), 0, -1);
 // ONE kernel writes the stacked frame: every output byte is written once (resized / copied / bar), nothing is staged.
+// The display step that follows it in the renderer, nvrenderAlpha::fit2final (src/nvrenderAlpha.cpp:153-189), is the
+// second kernel here (pano_fit_*): the stacked frame scaled by fitscale = min(1, canvas_w / cols) with
+// cv::resize(.., Size(), fitscale, fitscale) and pasted centred on the black 1920x1080 canvas.
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <string>
@@ -85,6 +89,50 @@ __global__ void __launch_bounds__(256) ring_kernel(const uint8_t *__restrict__ u
     } else {
         for (int i = 0; i < 3 * npx; ++i) d[i] = px[i];
     }
+}
+
+struct FitArgs {
+    int canvas_w, canvas_h;    // output
+    int ox, oy, w, h;          // paste rectangle inside the canvas
+    int in_w, in_h;
+    int mode;                  // 0 copy (fitscale == 1), 1 cv::resize INTER_LINEAR, 2 the 2x2 average cv::resize switches to at exactly 1/2
+    const int *xofs, *yofs;
+    const short2 *xa, *ya;
+};
+
+// one thread = one canvas pixel (the canvas is 2 Mpx: a streaming kernel far from any limit)
+__global__ void __launch_bounds__(256) fit_kernel(const uint8_t *__restrict__ in, size_t in_img, int in_stride,
+                                                  uint8_t *__restrict__ out, size_t out_img, int out_stride, FitArgs a)
+{
+    const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (X >= a.canvas_w || Y >= a.canvas_h) return;
+    uint8_t *d = out + (size_t)blockIdx.z * out_img + (size_t)Y * out_stride + (size_t)X * 3;
+    const int x = X - a.ox, y = Y - a.oy;
+    int v[3] = {0, 0, 0};                                            // canvas.setTo(0) (src/nvrenderAlpha.cpp:11)
+    if ((unsigned)x < (unsigned)a.w && (unsigned)y < (unsigned)a.h) {
+        const uint8_t *s = in + (size_t)blockIdx.z * in_img;
+        if (a.mode == 0) {
+            const uint8_t *p = s + (size_t)y * in_stride + (size_t)x * 3;
+            v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
+        } else if (a.mode == 2) {
+            const uint8_t *p = s + (size_t)(2 * y) * in_stride + (size_t)(2 * x) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] = (p[c] + p[3 + c] + p[in_stride + c] + p[in_stride + 3 + c] + 2) >> 2;
+        } else {
+            const int yo = a.yofs[y];
+            const int sy0 = min(max(yo, 0), a.in_h - 1), sy1 = min(max(yo + 1, 0), a.in_h - 1);
+            const short2 ay = a.ya[y], ax = a.xa[x];
+            const int sx0 = a.xofs[x], sx1 = min(sx0 + 1, a.in_w - 1);
+            const uint8_t *r0 = s + (size_t)sy0 * in_stride, *r1 = s + (size_t)sy1 * in_stride;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int t0 = __ldg(r0 + sx0 * 3 + c) * ax.x + __ldg(r0 + sx1 * 3 + c) * ax.y;
+                const int t1 = __ldg(r1 + sx0 * 3 + c) * ax.x + __ldg(r1 + sx1 * 3 + c) * ax.y;
+                v[c] = sat_u8((((ay.x * (t0 >> 4)) >> 16) + ((ay.y * (t1 >> 4)) >> 16) + 2) >> 2);
+            }
+        }
+    }
+    d[0] = (uint8_t)v[0]; d[1] = (uint8_t)v[1]; d[2] = (uint8_t)v[2];
 }
 
 }  // namespace
@@ -235,6 +283,143 @@ int pano_ring_compose(pano_ring_handle h, const uint8_t *up_host, int up_stride,
     if (pano_ring_compose_device(h, h->st_up, (int)ur, h->st_down, (int)dr, h->st_out, (int)orow, 1, nullptr)) return PANO_ERR;
     if (cudaMemcpy2D(out_host, out_stride, h->st_out, orow, orow, a.out_h, cudaMemcpyDeviceToHost) != cudaSuccess)
         return rfail(h, "D2H copy failed");
+    return PANO_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------- fit2final
+struct pano_fit_ctx {
+    pano_fit_config cfg{};
+    FitArgs args{};
+    double fitscale = 1.0;
+    std::string err;
+    std::vector<void *> owned;
+    uint8_t *st_in = nullptr, *st_out = nullptr;
+};
+
+namespace {
+thread_local std::string g_fit_error;
+int ffail2(pano_fit_ctx *h, const char *msg) { if (h) h->err = msg; else g_fit_error = msg; return PANO_ERR; }
+template <typename T>
+bool fupload(pano_fit_ctx *h, const std::vector<T> &v, const T **dst)
+{
+    void *p = nullptr;
+    if (cudaMalloc(&p, std::max<size_t>(1, v.size()) * sizeof(T)) != cudaSuccess) return false;
+    h->owned.push_back(p);
+    if (cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    *dst = static_cast<const T *>(p);
+    return true;
+}
+}  // namespace
+
+extern "C" {
+
+const char *pano_fit_last_error(pano_fit_handle h) { return h ? h->err.c_str() : g_fit_error.c_str(); }
+
+int pano_fit_create(const pano_fit_config *cfg, pano_fit_handle *out)
+{
+    if (!cfg || !out) return ffail2(nullptr, "pano_fit_create: null argument");
+    *out = nullptr;
+    if (cfg->in_width < 1 || cfg->in_height < 1 || cfg->canvas_width < 1 || cfg->canvas_height < 1) return ffail2(nullptr, "pano_fit_create: bad sizes");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return ffail2(nullptr, "no CUDA device: this library has no CPU path");
+    if (cfg->device < 0 || cfg->device >= ndev) return ffail2(nullptr, "bad device ordinal");
+    pano_fit_ctx *h = new pano_fit_ctx();
+    h->cfg = *cfg;
+    auto bail = [&](const char *msg) { g_fit_error = msg; pano_fit_destroy(h); return PANO_ERR; };
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return bail("cudaSetDevice failed");
+    FitArgs &a = h->args;
+    a.canvas_w = cfg->canvas_width; a.canvas_h = cfg->canvas_height; a.in_w = cfg->in_width; a.in_h = cfg->in_height;
+    if (cfg->in_width == cfg->canvas_width && cfg->in_height == cfg->canvas_height) {
+        a.ox = a.oy = 0; a.w = a.canvas_w; a.h = a.canvas_h; a.mode = 0;          // input.copyTo(canvas)  (:156-160)
+        *out = h;
+        return PANO_OK;
+    }
+    // :166-181 -- fitscale only shrinks, and only by the width
+    h->fitscale = cfg->in_width > cfg->canvas_width ? cfg->canvas_width * 1.0 / cfg->in_width : 1.0;
+    a.w = (int)std::nearbyint(cfg->in_width * h->fitscale);          // cv::resize: dsize = saturate_cast<int>(ssize * fx)
+    a.h = (int)std::nearbyint(cfg->in_height * h->fitscale);
+    a.ox = (cfg->canvas_width - a.w) / 2;
+    a.oy = (cfg->canvas_height - a.h) / 2;
+    if (a.w < 1 || a.h < 1 || a.ox < 0 || a.oy < 0 || a.ox + a.w > a.canvas_w || a.oy + a.h > a.canvas_h)
+        return bail("pano_fit_create: the scaled frame does not fit the canvas (cv::Mat::operator()(Rect) would assert, :187)");
+    if (a.w == cfg->in_width && a.h == cfg->in_height) {
+        a.mode = 0;                                                   // cv::resize with equal sizes is a copy
+    } else {
+        const double sx = 1.0 / h->fitscale;
+        const int isx = (int)std::nearbyint(sx);
+        const bool area_fast = std::abs(sx - isx) < 2.220446049250313e-16 && isx == 2 && a.w * 2 == cfg->in_width && a.h * 2 == cfg->in_height;
+        if (area_fast) {
+            a.mode = 2;                                               // INTER_LINEAR at exactly 1/2 runs as the 2x2 INTER_AREA average
+        } else {
+            a.mode = 1;
+            std::vector<int> xo, yo;
+            std::vector<int16_t> xa0, xa1, ya0, ya1;
+            resizeAxis(cfg->in_width, a.w, true, xo, xa0, xa1, h->fitscale);
+            resizeAxis(cfg->in_height, a.h, false, yo, ya0, ya1, h->fitscale);
+            std::vector<short2> xa(xo.size()), ya(yo.size());
+            for (size_t i = 0; i < xo.size(); ++i) xa[i] = make_short2(xa0[i], xa1[i]);
+            for (size_t i = 0; i < yo.size(); ++i) ya[i] = make_short2(ya0[i], ya1[i]);
+            if (!fupload(h, xo, &a.xofs) || !fupload(h, yo, &a.yofs) || !fupload(h, xa, &a.xa) || !fupload(h, ya, &a.ya))
+                return bail("fit table upload failed");
+        }
+    }
+    *out = h;
+    return PANO_OK;
+}
+
+int pano_fit_destroy(pano_fit_handle h)
+{
+    if (!h) return PANO_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    for (void *p : h->owned) cudaFree(p);
+    delete h;
+    return PANO_OK;
+}
+
+int pano_fit_geometry(pano_fit_handle h, int *rect, double *fitscale)
+{
+    if (!h) return PANO_ERR;
+    if (rect) { rect[0] = h->args.ox; rect[1] = h->args.oy; rect[2] = h->args.w; rect[3] = h->args.h; }
+    if (fitscale) *fitscale = h->fitscale;
+    return PANO_OK;
+}
+
+int pano_fit_compose_device(pano_fit_handle h, const uint8_t *in_dev, int in_stride, uint8_t *canvas_dev, int canvas_stride, int batch, void *stream)
+{
+    if (!h || !in_dev || !canvas_dev || batch < 1) return ffail2(h, "pano_fit_compose_device: bad argument");
+    const FitArgs &a = h->args;
+    if (in_stride < 3 * a.in_w || canvas_stride < 3 * a.canvas_w) return ffail2(h, "pano_fit_compose_device: stride too small");
+    if (cudaSetDevice(h->cfg.device) != cudaSuccess) return ffail2(h, "cudaSetDevice failed");
+    const dim3 block(64, 4), grid((a.canvas_w + 63) / 64, (a.canvas_h + 3) / 4, batch);
+    fit_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in_dev, (size_t)in_stride * a.in_h, in_stride, canvas_dev,
+                                                         (size_t)canvas_stride * a.canvas_h, canvas_stride, a);
+    if (cudaGetLastError() != cudaSuccess) return ffail2(h, "fit_kernel launch failed");
+    return PANO_OK;
+}
+
+int pano_fit_compose(pano_fit_handle h, const uint8_t *in_host, int in_stride, uint8_t *canvas_host, int canvas_stride)
+{
+    if (!h || !in_host || !canvas_host) return ffail2(h, "pano_fit_compose: bad argument");
+    const FitArgs &a = h->args;
+    if (in_stride < 3 * a.in_w || canvas_stride < 3 * a.canvas_w) return ffail2(h, "pano_fit_compose: stride too small");
+    if (cudaSetDevice(h->cfg.device) != cudaSuccess) return ffail2(h, "cudaSetDevice failed");
+    const size_t ir = (size_t)3 * a.in_w, orow = (size_t)3 * a.canvas_w;
+    if (!h->st_in) {
+        void *p[2] = {nullptr, nullptr};
+        if (cudaMalloc(&p[0], ir * a.in_h) != cudaSuccess || cudaMalloc(&p[1], orow * a.canvas_h) != cudaSuccess) {
+            for (void *q : p) cudaFree(q);
+            return ffail2(h, "staging allocation failed");
+        }
+        for (void *q : p) h->owned.push_back(q);
+        h->st_in = (uint8_t *)p[0]; h->st_out = (uint8_t *)p[1];
+    }
+    if (cudaMemcpy2D(h->st_in, ir, in_host, in_stride, ir, a.in_h, cudaMemcpyHostToDevice) != cudaSuccess) return ffail2(h, "H2D copy failed");
+    if (pano_fit_compose_device(h, h->st_in, (int)ir, h->st_out, (int)orow, 1, nullptr)) return PANO_ERR;
+    if (cudaMemcpy2D(canvas_host, canvas_stride, h->st_out, orow, orow, a.canvas_h, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return ffail2(h, "D2H copy failed");
     return PANO_OK;
 }
 

@@ -8,17 +8,25 @@
 //   reference                                   here
 //   ---------                                   ----
 //   init(std::string& cfgPath)   :262           init(const StitcherParams&)   (yaml parsing stays in the app)
-//   calibration(vector<Mat>&)    :592           calibration(masks)            fixed-parameter modes 2/3 only
+//   calibration(vector<Mat>&)    :592           calibration(imgs, seamFinder) fixed-parameter modes 2/3 only (initSeam); the
+//                                               seam search is the application's callback (it owns OpenCV), everything
+//                                               around it -- low-res resize + warps, dilate / upsample / AND, weights --
+//                                               is the library's.  calibration(masks) takes finished m_blenderMask images.
 //   process(vector<Mat>&, Mat&)  :1141          process(frames, out)
-//   updateMask(vector<Mat>&)     :1218          updateMask(masks)             masks come from the host seam search
+//   updateMask(vector<Mat>&)     :1218          updateMask(imgs, seamFinder) / updateMask(masks)
+//   panocam::{init,getCamFrame,getPanoFrame}    pano::panocam (include/panocam.h:8-28, src/panocamimpl.cpp:149-360)
+//   nvrenderAlpha::fit2final                    pano::FitCanvas (src/nvrenderAlpha.cpp:153-189)
 #ifndef OCVSTITCHER_B200_HPP
 #define OCVSTITCHER_B200_HPP
 
 #include <cmath>
 #include <ctime>
 #include <fstream>
+#include <functional>
+#include <memory>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "panob200.h"
@@ -43,6 +51,18 @@ struct StitcherParams {  // stStitcherCfg (+ the calibration the reference keeps
     int num_bands = -1;                        // -1: reference rule
     int device = 0, max_batch = 1;
 };
+
+// What initSeam / updateMask hand to seam_finder->find (include/ocvstitcher.hpp:1031-1035, 1243-1245): the low-resolution
+// warped images (8UC3; the reference converts them to CV_32F first), their corners, and the warped all-255 masks, which
+// the finder overwrites with the seam masks.  All tight (step = 3 * width / width).
+struct SeamInputs {
+    std::vector<std::vector<unsigned char>> images, masks;
+    std::vector<int> corners;    // x, y per camera
+    std::vector<int> sizes;      // w, h per camera
+};
+// The application's seam search, e.g. [](pano::SeamInputs &s) { cv::detail::GraphCutSeamFinder(COST_COLOR).find(...); }.
+// Leaving the masks untouched is cv::detail::NoSeamFinder.
+using SeamFinder = std::function<void(SeamInputs &)>;
 
 class ocvStitcher {
 public:
@@ -91,6 +111,42 @@ public:
         h_ = nullptr;
         if (pano_create(&c, &h_) != PANO_OK) { err_ = pano_last_error(nullptr); return RET_ERR; }
         return masks ? updateMask(*masks) : RET_OK;
+    }
+
+    // initSeam (:975-1139) from the frames themselves: geometry + tables, then the seam finder's inputs are built exactly as
+    // the reference builds them (pano_host_seam_input), `finder` searches the seams, and the low-resolution result goes
+    // through the device tail (dilate -> INTER_LINEAR_EXACT -> AND, pano_set_seam_mask).  No Python, no OpenCV in here.
+    int calibration(const std::vector<Image> &imgs, const SeamFinder &finder)
+    {
+        if (calibration(static_cast<const std::vector<Image> *>(nullptr)) != RET_OK) return RET_ERR;
+        return updateMask(imgs, finder);
+    }
+
+    // updateMask (:1218-1261): re-run the seam search on the current frames
+    int updateMask(const std::vector<Image> &imgs, const SeamFinder &finder)
+    {
+        if (!h_ || (int)imgs.size() != p_.num_images) return RET_ERR;
+        SeamInputs s;
+        const int n = p_.num_images;
+        s.images.resize(n); s.masks.resize(n); s.corners.resize(2 * n); s.sizes.resize(2 * n);
+        for (int i = 0; i < n; ++i) {
+            int roi[4];
+            if (imgs[i].width != p_.width || imgs[i].height != p_.height) { err_ = "frame size differs from the configured one"; return RET_ERR; }
+            if (pano_host_seam_input(p_.warp_kind, p_.warped_image_scale, &p_.K[9 * i], &p_.R[9 * i], nullptr, p_.width, p_.height, 0, roi,
+                                     nullptr, nullptr) != PANO_OK) { err_ = "seam geometry failed"; return RET_ERR; }
+            s.corners[2 * i] = roi[0]; s.corners[2 * i + 1] = roi[1]; s.sizes[2 * i] = roi[2]; s.sizes[2 * i + 1] = roi[3];
+            s.images[i].resize((size_t)roi[2] * roi[3] * 3);
+            s.masks[i].resize((size_t)roi[2] * roi[3]);
+            if (pano_host_seam_input(p_.warp_kind, p_.warped_image_scale, &p_.K[9 * i], &p_.R[9 * i], imgs[i].data, p_.width, p_.height,
+                                     imgs[i].step, roi, s.images[i].data(), s.masks[i].data()) != PANO_OK) { err_ = "seam input failed"; return RET_ERR; }
+        }
+        if (finder) finder(s);
+        for (int i = 0; i < n; ++i)
+            if (pano_set_seam_mask(h_, i, s.masks[i].data(), s.sizes[2 * i], s.sizes[2 * i + 1], s.sizes[2 * i]) != PANO_OK) {
+                err_ = pano_last_error(h_);
+                return RET_ERR;
+            }
+        return RET_OK;
     }
 
     int updateMask(const std::vector<Image> &masks)
@@ -273,6 +329,142 @@ public:
 
 private:
     pano_ring_handle h_ = nullptr;
+    std::string err_;
+};
+
+// nvrenderAlpha::fit2final (src/nvrenderAlpha.cpp:153-189): the stacked frame scaled to the display canvas
+class FitCanvas {
+public:
+    FitCanvas() = default;
+    FitCanvas(const FitCanvas &) = delete;
+    FitCanvas &operator=(const FitCanvas &) = delete;
+    ~FitCanvas() { pano_fit_destroy(h_); }
+    int init(int inW, int inH, int canvasW = 1920, int canvasH = 1080, int device = 0)
+    {
+        pano_fit_config c{};
+        c.in_width = inW; c.in_height = inH; c.canvas_width = canvasW; c.canvas_height = canvasH; c.device = device;
+        pano_fit_destroy(h_);
+        h_ = nullptr;
+        if (pano_fit_create(&c, &h_) != PANO_OK) { err_ = pano_fit_last_error(nullptr); return RET_ERR; }
+        return RET_OK;
+    }
+    int fit2final(const Image &input, Image &canvas)
+    {
+        if (!h_) return RET_ERR;
+        if (pano_fit_compose(h_, input.data, input.step, canvas.data, canvas.step) != PANO_OK) { err_ = pano_fit_last_error(h_); return RET_ERR; }
+        return RET_OK;
+    }
+    const std::string &lastError() const { return err_; }
+
+private:
+    pano_fit_handle h_ = nullptr;
+    std::string err_;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// The SDK facade's pixel path (include/panocam.h:8-28; src/panocamimpl.cpp:149-155 construction, :199-257 init,
+// :300-360 getPanoFrame): 2 x num_images cameras, an upper- and a lower-ring stitcher, finalcut crop + vconcat + 4-row
+// separator.  Capture (V4L2 / UDP ingest of the slave board), detect, imgEnhancement, render, drawCross, saveAndSend and
+// the licence / CAN status byte are outside the compose path: the application hands camera frames in with
+// setCamFrame(id, frame) where the reference's nvCam threads would have produced them.
+struct PanoCamParams {
+    int num_images = 4;                 // cameras per ring (USED_CAMERA_NUM = 2 * num_images)
+    CamParams cam;                      // one camera model for the rig, like the reference's camcfgs[] (same sizes / intrinsics)
+    StitcherParams stitcher[2];         // [0] upper ring (id 1), [1] lower ring (id 2)
+    int finalcut = 0;                   // rows dropped above and below each ring (panocamimpl's finalcut)
+};
+
+class panocam {
+public:
+    panocam() = default;
+    panocam(const panocam &) = delete;
+    panocam &operator=(const panocam &) = delete;
+
+    // panocam::init, first half (src/panocamimpl.cpp:149-155): the camera pipeline; frames can be handed in afterwards
+    int init(const PanoCamParams &p)
+    {
+        p_ = p;
+        if (p.num_images < 1) { err_ = "bad camera count"; return RET_ERR; }
+        if (cam_.init(p.cam) != RET_OK) { err_ = "front end: " + cam_.lastError(); return RET_ERR; }
+        frames_.assign(2 * p.num_images, Image{nullptr, 0, 0, 0});
+        return RET_OK;
+    }
+
+    // panocam::init, second half (src/panocamimpl.cpp:199-257: getFrame x 8, stitchers[k]->init(imgs)): both stitchers
+    // calibrated with fixed parameters on the current camera frames (setCamFrame every camera first) -- the seam search
+    // is `finder` (nullptr = NoSeamFinder) -- then the front end is chained in and the ring composer sized.
+    int calibration(const SeamFinder &finder = nullptr)
+    {
+        const int n = p_.num_images, W = p_.cam.outPutWidth, H = p_.cam.outPutHeight;
+        std::vector<std::vector<unsigned char>> buf(2 * n, std::vector<unsigned char>((size_t)W * H * 3));
+        std::vector<Image> first(2 * n);
+        for (int i = 0; i < 2 * n; ++i) {
+            first[i] = Image{buf[i].data(), W, H, W * 3};
+            if (getCamFrame(i, first[i]) != RET_OK) { err_ = "setCamFrame() every camera before calibration(): " + err_; return RET_ERR; }
+        }
+        for (int r = 0; r < 2; ++r) {
+            if (st_[r].init(p_.stitcher[r]) != RET_OK ||
+                st_[r].calibration(std::vector<Image>(first.begin() + r * n, first.begin() + (r + 1) * n), finder) != RET_OK ||
+                st_[r].attachFrontEnd(cam_.handle()) != RET_OK) { err_ = st_[r].lastError(); return RET_ERR; }
+            pano_[r].assign((size_t)st_[r].outWidth() * st_[r].outHeight() * 3, 0);
+        }
+        if (rc_.init(st_[0].outWidth(), st_[0].outHeight(), st_[1].outWidth(), st_[1].outHeight(), PANO_RING_CROP, p_.finalcut) != RET_OK) {
+            err_ = "ring composer: " + rc_.lastError();
+            return RET_ERR;
+        }
+        return RET_OK;
+    }
+
+    // stands in for the capture threads: the latest camera frame of camera `id` (8UC4, or 8UC2 with cam.yuyv); the
+    // buffer must stay valid until getPanoFrame returns
+    int setCamFrame(int id, const Image &frame)
+    {
+        if (id < 0 || id >= (int)frames_.size()) return RET_ERR;
+        frames_[id] = frame;
+        return RET_OK;
+    }
+    // panocam::getCamFrame (src/panocam.cpp): camera `id`'s stitcher input (undistorted, cropped, resized), outPutWidth x outPutHeight x 3
+    int getCamFrame(int id, Image &frame)
+    {
+        if (id < 0 || id >= (int)frames_.size() || !frames_[id].data) return RET_ERR;
+        if (cam_.getFrame(frames_[id], frame) != RET_OK) { err_ = cam_.lastError(); return RET_ERR; }
+        return RET_OK;
+    }
+    int outWidth() const { return rc_.outWidth(); }
+    int outHeight() const { return rc_.outHeight(); }
+    // panocam::getPanoFrame (src/panocamimpl.cpp:300-360): both rings composed on two threads like the reference's t1 / t2,
+    // then cropped by finalcut, stacked and separated by the 4-row bar.  ret: outWidth() x outHeight() x 3
+    int getPanoFrame(Image &ret)
+    {
+        const int n = p_.num_images;
+        for (const Image &f : frames_)
+            if (!f.data) { err_ = "setCamFrame() every camera first"; return RET_ERR; }
+        int rcode[2] = {RET_ERR, RET_ERR};
+        Image out[2];
+        std::thread t[2];
+        for (int r = 0; r < 2; ++r) {
+            out[r] = Image{pano_[r].data(), st_[r].outWidth(), st_[r].outHeight(), st_[r].outWidth() * 3};
+            t[r] = std::thread([this, r, n, &rcode, &out]() {
+                rcode[r] = st_[r].process(std::vector<Image>(frames_.begin() + r * n, frames_.begin() + (r + 1) * n), out[r]);
+            });
+        }
+        t[0].join();
+        t[1].join();
+        for (int r = 0; r < 2; ++r)
+            if (rcode[r] != RET_OK) { err_ = st_[r].lastError(); return RET_ERR; }
+        if (rc_.compose(out[0], out[1], ret) != RET_OK) { err_ = rc_.lastError(); return RET_ERR; }
+        return RET_OK;
+    }
+    ocvStitcher &stitcher(int ring) { return st_[ring]; }
+    const std::string &lastError() const { return err_; }
+
+private:
+    PanoCamParams p_;
+    nvCamFrontEnd cam_;
+    ocvStitcher st_[2];
+    RingComposer rc_;
+    std::vector<Image> frames_;
+    std::vector<unsigned char> pano_[2];
     std::string err_;
 };
 

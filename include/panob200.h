@@ -240,6 +240,17 @@ int pano_host_resize_axis(int ssize, int dsize, int clamp_frac, int *ofs, int16_
 /* cv::resize's INTER_LINEAR_EXACT axis table (8.8 fixed point; pano_set_seam_mask): weight of src[ofs+1] is c1/256 */
 int pano_host_linear_exact_axis(int ssize, int dsize, int *ofs, int *c1);
 
+/* The seam finder's inputs for ONE camera exactly as initSeam / updateMask build them (include/ocvstitcher.hpp:985-1017,
+ * 1228-1242): the frame resized by seam_work_aspect = min(1, sqrt(1e5 / (w*h))) with INTER_LINEAR_EXACT, warped at that
+ * scale (K scaled in float32, warper scale float(scale * aspect), INTER_LINEAR / BORDER_REFLECT), and the all-255 mask
+ * warped with INTER_NEAREST / BORDER_CONSTANT.  roi = x,y,w,h of the low-resolution warp (corner = what the seam finder
+ * gets as corners[i]); image_warped: roi.h x roi.w x 3 (tight), mask_warped: roi.h x roi.w; both may be NULL (geometry
+ * only).  The seam search itself (cv::detail::GraphCutSeamFinder::find) stays with the application; its result goes
+ * to pano_set_seam_mask.  Host only, init-time. */
+double pano_host_seam_scale(int src_w, int src_h);
+int pano_host_seam_input(int warp_kind, float warped_image_scale, const float *K, const float *R, const uint8_t *frame, int src_w,
+                         int src_h, int stride, int *roi, uint8_t *image_warped, uint8_t *mask_warped);
+
 /* Chain a front end in front of a stitcher handle (cam = -1: every camera): from then on
  * pano_process / pano_process_device / pano_process_batch take the 8UC4 camera frames
  * ([batch][num_images][cam_src_height][cam_src_width][4]) and run nvCam's pixel pipeline on the
@@ -276,6 +287,28 @@ int pano_ring_compose_device(pano_ring_handle h, const uint8_t *up_dev, int up_s
 /* one pair in HOST memory; synchronous */
 int pano_ring_compose(pano_ring_handle h, const uint8_t *up_host, int up_stride, const uint8_t *down_host, int down_stride,
                       uint8_t *out_host, int out_stride);
+
+/* ---------------------------------------------------------------- fit to the display canvas (caller step after the epilogue)
+ * nvrenderAlpha::fit2final (src/nvrenderAlpha.cpp:153-189): a frame that already has the canvas size is copied;
+ * otherwise fitscale = in_width > canvas_width ? canvas_width * 1.0 / in_width : 1, the frame is scaled with
+ * cv::resize(input, tmp, Size(), fitscale, fitscale) [INTER_LINEAR, dsize = cvRound(size * fitscale), coordinates mapped
+ * with 1 / fitscale] and pasted at ((canvas_w - w) / 2, (canvas_h - h) / 2) of the canvas, which is black elsewhere
+ * (canvas.setTo(0), :11).  One kernel writes the whole canvas; bit-exact with the OpenCV calls.  The reference's canvas
+ * is 1920 x 1080 (nvbufferWidth x nvbufferHeight). */
+typedef struct pano_fit_ctx *pano_fit_handle;
+typedef struct pano_fit_config {
+    int in_width, in_height;           /* the stacked frame (8UC3) */
+    int canvas_width, canvas_height;   /* nvbufferWidth, nvbufferHeight */
+    int device;
+} pano_fit_config;
+int pano_fit_create(const pano_fit_config *cfg, pano_fit_handle *out);
+int pano_fit_destroy(pano_fit_handle h);
+const char *pano_fit_last_error(pano_fit_handle h);
+/* rect: offsetX, offsetY, w, h of the pasted frame (:176-181) */
+int pano_fit_geometry(pano_fit_handle h, int *rect, double *fitscale);
+int pano_fit_compose_device(pano_fit_handle h, const uint8_t *in_dev, int in_stride, uint8_t *canvas_dev, int canvas_stride,
+                            int batch, void *stream);
+int pano_fit_compose(pano_fit_handle h, const uint8_t *in_host, int in_stride, uint8_t *canvas_host, int canvas_stride);
 
 /* How an attached front end is evaluated.
  * PANO_FRONTEND_SEQUENTIAL (default, the parity mode): the reference's own order -- undistort (INTER_CUBIC) ->

@@ -138,6 +138,27 @@ def ring_epilogue(up, down, mode="resize", finalcut=0, bar=None):
     return ret
 
 
+def fit2final(frame, canvas_size=(1920, 1080)):
+    """nvrenderAlpha::fit2final (src/nvrenderAlpha.cpp:153-189): copy when the sizes agree, else scale by
+    fitscale = canvas_w / cols (only when wider than the canvas) with cv::resize(.., Size(), fitscale, fitscale) and paste
+    centred on the zeroed canvas (:11).  Exactly 1/2 takes cv::resize's 2x2-average branch."""
+    frame = np.ascontiguousarray(frame, np.uint8)
+    cw, ch = canvas_size
+    if frame.shape[1] == cw and frame.shape[0] == ch:
+        return frame.copy()
+    fitscale = cw * 1.0 / frame.shape[1] if frame.shape[1] > cw else 1.0
+    if fitscale == 0.5 and frame.shape[1] % 2 == 0 and frame.shape[0] % 2 == 0:
+        f = frame.astype(np.int32)
+        tmp = ((f[0::2, 0::2] + f[0::2, 1::2] + f[1::2, 0::2] + f[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+    else:
+        tmp = orc.resize_bilinear_scaled_u8(frame, fitscale, fitscale) if fitscale != 1.0 else frame
+    h, w = tmp.shape[:2]
+    ox, oy = (cw - w) // 2, (ch - h) // 2
+    canvas = np.zeros((ch, cw, 3), np.uint8)
+    canvas[oy:oy + h, ox:ox + w] = tmp
+    return canvas
+
+
 def dilate3x3_u8(m):
     """cv::dilate(src, dst, Mat()) -- 3x3 rectangle, anchor at the centre, border pixels ignored
     (include/ocvstitcher.hpp:1095, 1251)."""

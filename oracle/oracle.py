@@ -126,6 +126,16 @@ def resize_bilinear_u8(src, dsize):
     return dst
 
 
+def resize_bilinear_scaled_u8(src, fx, fy):
+    """cv2.resize(src, None, fx=fx, fy=fy) [INTER_LINEAR]"""
+    src, ch = _img3(src)
+    dw, dh = int(np.rint(src.shape[1] * fx)), int(np.rint(src.shape[0] * fy))
+    dst = np.empty((dh, dw) + ((ch,) if src.ndim == 3 else ()), np.uint8)
+    lib().orc_resize_bilinear_scaled_u8(_p(src), C.c_int(src.shape[1]), C.c_int(src.shape[0]), C.c_int(ch),
+                                        C.c_size_t(src.strides[0]), _p(dst), C.c_int(dw), C.c_int(dh), C.c_double(fx), C.c_double(fy))
+    return dst
+
+
 def init_undistort_map(K, D, newK, w, h):
     K = np.ascontiguousarray(K, np.float64).reshape(9)
     D = np.ascontiguousarray(list(D)[:4], np.float64)

@@ -26,6 +26,7 @@ ocvStitcher = pkg.ocvStitcher
 StitcherConfig = pkg.StitcherConfig
 nvCamFrontEnd = pkg.nvCamFrontEnd
 RingComposer = pkg.RingComposer
+FitCanvas = pkg.FitCanvas
 sharding = pkg.sharding
 strips = pkg.strips
 PanoError = pkg.PanoError

@@ -161,3 +161,71 @@ def test_cxx_two_ring_pipeline_bit_exact(tmp_path):
     assert np.allclose(np.asarray(Ks2), np.asarray(g["Ks"], np.float32), rtol=1e-5)
     assert np.allclose(np.asarray(Rs2), np.asarray(g["Rs"], np.float32), rtol=1e-5, atol=1e-6)
     assert abs(sc2 - g["scales"][0]) < 1e-2
+
+
+# ------------------------------------------------------------------ the SDK facade from C++ (include/panocam.h:8-28)
+
+def facade_setup(tmp_path, W=480, H=270, nb=3, finalcut=6, canvas=(640, 360)):
+    g = rig_setup(tmp_path, W, H, nb)
+    inp = str(tmp_path / "facade.bin")
+    with open(inp, "wb") as f:
+        f.write(struct.pack("<11i", 4, W, H, nb, *g["rect"], finalcut, *canvas))
+        f.write(np.concatenate([g["K"].reshape(-1), np.asarray(g["D"], np.float64)[:4], g["newK"].reshape(-1)]).astype(np.float64).tobytes())
+        f.write(np.asarray(g["scales"], np.float32).tobytes())
+        f.write(np.asarray(g["Ks"], np.float32).tobytes())
+        f.write(np.asarray(g["Rs"], np.float32).tobytes())
+        for r in range(2):
+            for im in g["frames"][r]:
+                f.write(np.ascontiguousarray(im, np.uint8).tobytes())
+    g.update(inp=inp, finalcut=finalcut, canvas=canvas)
+    return g
+
+
+def test_cxx_facade_compiles_and_fails_loudly_without_a_device(tmp_path):
+    import torch
+    exe = build_demo(tmp_path, "panocam_demo")
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present: covered by the gpu test")
+    g = facade_setup(tmp_path)
+    r = subprocess.run([exe, g["inp"], str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CUDA device" in r.stderr, (r.returncode, r.stderr)
+
+
+@pytest.mark.gpu
+def test_cxx_facade_pano_frame_bit_exact(tmp_path):
+    """pano::panocam from C++: init -> setCamFrame x 8 -> calibration(seam finder callback) -> getPanoFrame -> fit2final.
+    The seam-finder inputs, the device tail of the masks, both rings' compose, the finalcut crop + bar and the canvas fit
+    are restated with the oracle; the stacked frame and the canvas must match byte for byte."""
+    import panob200
+    from oracle import oracle as orc
+    exe = build_demo(tmp_path, "panocam_demo")
+    g = facade_setup(tmp_path)
+    outp = str(tmp_path / "out.bin")
+    r = subprocess.run([exe, g["inp"], outp], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    W, H = g["W"], g["H"]
+    mx, my = orc.init_undistort_map(g["K"], g["D"], g["newK"], W, H)
+    panos = []
+    for ring in range(2):
+        bgr = [compose.front_end(f, (W, H), mx, my, g["rect"], (W, H)) for f in g["frames"][ring]]
+        t = compose.build_tables(g["Ks"], g["Rs"], g["scales"][ring], (W, H), "spherical")
+        masks = []
+        for i in range(4):
+            # the application's stand-in seam finder on the library's low-resolution inputs (pinned vs cv2 in test_host_tables)
+            _, _, low = panob200.capi.host_seam_input(panob200.capi.WARP_SPHERICAL, g["scales"][ring], g["Ks"][i], g["Rs"][i], bgr[i])
+            w = low.shape[1]
+            low = low.copy()
+            low[:, :w // 5] = 0
+            low[:, w - w // 5:] = 0
+            masks.append(compose.seam_mask_tail(low, t.warped_masks[i]))
+        t.blend_masks = masks
+        panos.append(compose.process(t, bgr, "multiband", g["nb"]))
+    want = compose.ring_epilogue(panos[0], panos[1], "crop", finalcut=g["finalcut"])
+    raw = open(outp, "rb").read()
+    w, h = struct.unpack("<2i", raw[:8])
+    assert (w, h) == (want.shape[1], want.shape[0])
+    got = np.frombuffer(raw, np.uint8, count=w * h * 3, offset=8).reshape(h, w, 3)
+    assert np.array_equal(got, want), util.report("c++ facade getPanoFrame", got, want)
+    cw, ch = g["canvas"]
+    canvas = np.frombuffer(raw, np.uint8, offset=8 + w * h * 3).reshape(ch, cw, 3)
+    assert np.array_equal(canvas, compose.fit2final(want, (cw, ch))), "fit2final canvas differs"

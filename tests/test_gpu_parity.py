@@ -83,6 +83,38 @@ def test_feather_no_gain_golden_bit_exact():
     assert_equal("gain+multiband", st.process(imgs), g["pano_gain_multiband"])
 
 
+def test_feather_weights_built_on_device():
+    """FeatherBlender weight maps (distanceTransform(mask, DIST_L1, 3) * sharpness, clamped at 1) are built by two scan
+    kernels at every mask refresh: bit-identical to the host builder and to cv2's distanceTransform + threshold."""
+    Ks, Rs, scale = calib.rig("2222", 320)
+    st = make(Ks, Rs, scale, 320, 180, "spherical", "feather", 0, sharp=0.037)
+    assert st.initTables() == 0, st.last_error
+    rng = np.random.default_rng(5)
+    masks = []
+    for i, (w, h) in enumerate(st.m_sizes):
+        m = st.get_mask(i).copy()
+        if i == 1:
+            m[:] = 255                                            # no zero pixel anywhere: every weight saturates to 1
+        elif i == 2:
+            m[rng.integers(0, h, 40), rng.integers(0, w, 40)] = 0   # isolated holes
+        elif i == 3:
+            m[:, : w // 3] = 0
+            m[h // 2, :] = 0
+        masks.append(m)
+        st.set_mask(i, m)
+    for i, m in enumerate(masks):
+        got = st.weight_level(i, 0)
+        want = panob200.capi.host_feather_weight(m, 0.037)
+        assert np.array_equal(got, want), "camera %d: device feather weights differ from the host builder" % i
+        try:
+            import cv2
+        except ImportError:
+            continue
+        w = cv2.distanceTransform(m, cv2.DIST_L1, 3)
+        _, w = cv2.threshold(w * np.float32(0.037), 1.0, 1.0, cv2.THRESH_TRUNC)
+        assert np.array_equal(got, w), "camera %d: device feather weights differ from cv2" % i
+
+
 # ------------------------------------------------------------------ against the oracle
 
 def oracle_case(Ks, Rs, scale, W, H, warp, blender, nb, seed, masks="soft", cut=None, gains=None, sharp=0.05):
@@ -568,6 +600,28 @@ def test_strip_split_peer_memory_exchange(nranks, concurrent):
         assert_equal("p2p strip split %d ranks, frame %d" % (nranks, k), got, ref)
 
 
+def test_strip_split_multi_gpu_torchrun():
+    """The strip split on REAL GPUs, one process per GPU under torchrun (skipped with fewer than two devices): NCCL
+    point-to-point halos, peer-memory mailboxes (kernels of different GPUs really wait on one another here) and the
+    redundant halo must all reproduce the undivided panorama on every rank."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two CUDA devices")
+    world = 4 if n >= 4 else 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(util.ROOT, "tools", "strip_split_nccl.py"), "--small", "--steps", "3"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    rec = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert rec["n_gpus"] == world
+    for mode in ("exchange", "p2p", "redundant"):
+        assert rec["modes"][mode]["all_ranks_match_undivided"], (mode, rec)
+
+
 # ------------------------------------------------------------------ nvCam front end
 
 def test_front_end_golden_bit_exact():
@@ -632,6 +686,26 @@ def test_ring_epilogue_bit_exact(mode, up, down, fc):
     for b in range(2):
         assert_equal("ring device %d" % b, out[b].cpu().numpy(), want[b])
     rc.close()
+
+
+@pytest.mark.parametrize("size", [(5336, 1792), (2500, 700), (3840, 1000), (1920, 1080), (1000, 500), (3840, 2160), (2007, 333)])
+def test_fit2final_bit_exact(size):
+    """nvrenderAlpha::fit2final (src/nvrenderAlpha.cpp:153-189): scale by fitscale + centred paste on the black canvas as one
+    kernel, against the oracle restatement (itself pinned against the cv2 calls in tests/test_oracle_vs_cv2.py)."""
+    import torch
+    w, h = size
+    frames = np.stack([util.synth_frame(h, w, 60 + b) for b in range(2)])
+    fc = panob200.FitCanvas((w, h))
+    want = [compose.fit2final(frames[b]) for b in range(2)]
+    assert_equal("fit2final host", fc.fit2final(frames[0]), want[0])
+    out = torch.empty((2, 1080, 1920, 3), dtype=torch.uint8, device="cuda")
+    fc.fit2final_device(torch.from_numpy(frames).cuda(), out)
+    torch.cuda.synchronize()
+    for b in range(2):
+        assert_equal("fit2final device %d" % b, out[b].cpu().numpy(), want[b])
+    fc.close()
+    with pytest.raises(panob200.PanoError):
+        panob200.FitCanvas((1000, 1200))                 # taller than the canvas: the reference's ROI would assert
 
 
 # ------------------------------------------------------------------ YUYV ingest (SURVEY 8f-3)

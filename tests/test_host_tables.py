@@ -10,6 +10,13 @@ from oracle import oracle as orc
 
 capi = panob200.capi
 
+try:
+    import cv2  # noqa: F401
+    HAVE_CV2 = True
+except ImportError:
+    HAVE_CV2 = False
+needs_cv2 = pytest.mark.skipif(not HAVE_CV2, reason="cv2 is the comparison target")
+
 
 def rot_y(a):
     c, s = np.cos(a), np.sin(a)
@@ -176,3 +183,30 @@ def test_linear_exact_axis_matches_oracle_restatement():
         o, c = capi.host_linear_exact_axis(ss, ds)
         wo, wc = compose.linear_exact_axis(ss, ds)
         assert np.array_equal(o, wo) and np.array_equal(c, wc), (ss, ds)
+
+
+@needs_cv2
+@pytest.mark.parametrize("warp,size", [("spherical", (1920, 1080)), ("spherical", (960, 540)), ("cylindrical", (1280, 720))])
+def test_seam_finder_inputs_equal_cv2(warp, size):
+    """pano_host_seam_input == the low-resolution resize + warps of initSeam / updateMask through cv2
+    (include/ocvstitcher.hpp:985-1017, 1228-1242): corners, warped images and warped masks bit for bit."""
+    import math
+    import cv2
+    W, H = size
+    Ks, Rs, scale = calib.rig("2222", W)
+    imgs = util.synth_set(4, H, W, 77)
+    swa = min(1.0, math.sqrt(1e5 / (H * W)))
+    assert panob200.capi.lib().pano_host_seam_scale(W, H) == swa
+    sw = cv2.PyRotationWarper(warp, np.float32(scale * swa))
+    kind = panob200.capi.WARP_SPHERICAL if warp == "spherical" else panob200.capi.WARP_CYLINDRICAL
+    for i in range(4):
+        K = Ks[i].astype(np.float32).copy()
+        f = np.float32(swa)
+        K[0, 0] *= f; K[0, 2] *= f; K[1, 1] *= f; K[1, 2] *= f
+        small = cv2.resize(imgs[i], None, fx=swa, fy=swa, interpolation=cv2.INTER_LINEAR_EXACT)
+        corner, want_img = sw.warp(small, K, Rs[i], cv2.INTER_LINEAR, cv2.BORDER_REFLECT)
+        _, want_mask = sw.warp(np.full(small.shape[:2], 255, np.uint8), K, Rs[i], cv2.INTER_NEAREST, cv2.BORDER_CONSTANT)
+        roi, got_img, got_mask = panob200.capi.host_seam_input(kind, scale, Ks[i], Rs[i], imgs[i])
+        assert tuple(roi[:2]) == tuple(corner) and (roi[3], roi[2]) == want_img.shape[:2]
+        assert np.array_equal(got_mask, want_mask)
+        assert np.array_equal(got_img, want_img), util.report("seam input %d" % i, got_img, want_img)

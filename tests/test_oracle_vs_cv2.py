@@ -6,7 +6,7 @@ import pytest
 
 import util
 from golden import calib
-from oracle import oracle as orc, cv2_reference as ref  # noqa: F401  (cv2_reference imports cv2)
+from oracle import compose, oracle as orc, cv2_reference as ref  # noqa: F401  (cv2_reference imports cv2)
 
 cv2 = pytest.importorskip("cv2")
 
@@ -205,3 +205,19 @@ def test_yuyv_ingest_vs_cv2_cvtcolor():
     a = np.zeros((1, 2 * n, 2), np.uint8)
     a[0, 0::2, 0] = yy.ravel(); a[0, 1::2, 0] = 255 - yy.ravel(); a[0, 0::2, 1] = uu.ravel(); a[0, 1::2, 1] = vv.ravel()
     eq(compose.yuyv_to_bgra(a), cv2.cvtColor(a, cv2.COLOR_YUV2BGRA_YUYV), "yuv sweep")
+
+
+@pytest.mark.parametrize("size", [(5336, 1792), (2500, 700), (3840, 1000), (1920, 1080), (1000, 500), (3840, 2160)])
+def test_fit2final_oracle_equals_cv2(size):
+    """nvrenderAlpha::fit2final (src/nvrenderAlpha.cpp:153-189) restated vs the cv2 calls it makes."""
+    w, h = size
+    f = util.synth_frame(h, w, 5)
+    if (w, h) == (1920, 1080):
+        want = f.copy()
+    else:
+        fs = 1920 * 1.0 / w if w > 1920 else 1
+        tmp = cv2.resize(f, None, fx=fs, fy=fs)
+        want = np.zeros((1080, 1920, 3), np.uint8)
+        ox, oy = (1920 - tmp.shape[1]) // 2, (1080 - tmp.shape[0]) // 2
+        want[oy:oy + tmp.shape[0], ox:ox + tmp.shape[1]] = tmp
+    assert np.array_equal(compose.fit2final(f), want)
