@@ -92,6 +92,11 @@ _SIGS = {
     "pano_strip_halo_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
     "pano_strip_halo_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "pano_strip_halo_unpack": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "pano_strip_set_window_hybrid": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "pano_strip_run_phases": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pano_strip_level_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "pano_strip_level_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "pano_strip_level_unpack_all": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "pano_strip_p2p_create": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]),
     "pano_strip_p2p_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "pano_strip_p2p_connect_local": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),

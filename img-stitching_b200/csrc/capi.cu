@@ -1334,7 +1334,63 @@ int pano_strip_set_window(pano_handle h, int x0, int x1, int margin)
     return PANO_OK;
 }
 
+// Hybrid decomposition: below `split_level` every rank computes its strip widened by 3 * 2^split_level level-0 columns (the
+// redundant-halo rule of a split_level-band pyramid); from split_level up every rank computes the FULL width, which costs
+// 4^-split_level of the work and needs the neighbours' data exactly once: the all-gather of g[split_level].
+int pano_strip_set_window_hybrid(pano_handle h, int x0, int x1, int split_level)
+{
+    if (!h) return PANO_ERR;
+    if (h->blender != PANO_BLEND_MULTIBAND || split_level < 1 || split_level > h->nb)
+        return fail(h, "pano_strip_set_window_hybrid: split level must lie in [1, %d]", h->nb);
+    if (pano_strip_set_window(h, x0, x1, 3 * (1 << split_level))) return PANO_ERR;
+    for (int l = split_level; l <= h->nb; ++l) { h->host.win_lo[l] = 0; h->host.win_hi[l] = INT_MAX; }
+    h->tables_dirty = true;
+    return PANO_OK;
+}
+
 int pano_strip_phase_count(pano_handle h) { return h ? phaseCount(h) : 0; }
+
+int pano_strip_run_phases(pano_handle h, int first, int last, const uint8_t *frames_dev, uint8_t *pano_dev, void *stream)
+{
+    if (!h || first < 0 || last > phaseCount(h) || first > last || !frames_dev || !pano_dev) return fail(h, "pano_strip_run_phases: bad argument");
+    CK(h, cudaSetDevice(h->device));
+    if (syncTables(h)) return PANO_ERR;
+    if (first == 0) h->last_launches = 0;
+    for (int p = first; p < last; ++p)
+        if (runPhase(h, p, frames_dev, pano_dev, 1, (cudaStream_t)stream)) return PANO_ERR;
+    CK(h, cudaGetLastError());
+    return PANO_OK;
+}
+
+size_t pano_strip_level_bytes(pano_handle h, int level, int ncols)
+{
+    if (!h || level < 0 || level > h->nb || ncols < 1) return 0;
+    return halo_elems(h->host, 0, level, ncols) * sizeof(int16_t);
+}
+
+int pano_strip_level_pack(pano_handle h, int level, int col, int ncols, void *buf_dev, void *stream)
+{
+    if (!h || !buf_dev || level < 0 || level > h->nb || ncols < 1) return fail(h, "pano_strip_level_pack: bad argument");
+    CK(h, cudaSetDevice(h->device));
+    if (syncTables(h)) return PANO_ERR;
+    launch_halo_copy(h->dev, h->host, 0, level, col, ncols, (int16_t *)buf_dev, false, 0, (cudaStream_t)stream);
+    ++h->last_launches;
+    CK(h, cudaGetLastError());
+    return PANO_OK;
+}
+
+int pano_strip_level_unpack_all(pano_handle h, int level, const void *gathered_dev, int chunk_cols, const int *lo, const int *n,
+                                int nranks, int self, void *stream)
+{
+    if (!h || !gathered_dev || !lo || !n || level < 0 || level > h->nb || nranks < 1 || nranks > 16 || self < 0 || self >= nranks)
+        return fail(h, "pano_strip_level_unpack_all: bad argument");
+    CK(h, cudaSetDevice(h->device));
+    if (syncTables(h)) return PANO_ERR;
+    launch_level_unpack_all(h->dev, h->host, level, (const int16_t *)gathered_dev, chunk_cols, lo, n, nranks, self, (cudaStream_t)stream);
+    ++h->last_launches;
+    CK(h, cudaGetLastError());
+    return PANO_OK;
+}
 
 int pano_strip_run_phase(pano_handle h, int phase, const uint8_t *frames_dev, uint8_t *pano_dev, void *stream)
 {

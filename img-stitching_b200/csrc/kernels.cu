@@ -1402,6 +1402,22 @@ __global__ void __launch_bounds__(256) halo_copy_kernel(const PanoTables *__rest
     }
 }
 
+// Hybrid strip split: after the ranks all-gathered their own columns of camera-pyramid level `level` (one dense chunk
+// per rank, laid out like halo_copy_kernel packs it with ncols = chunk_cols), ONE launch scatters every other rank's chunk
+// into this rank's g[level].  blockIdx.z = source rank.
+struct GatherCols { int lo[16], n[16]; };
+__global__ void __launch_bounds__(256) level_unpack_all_kernel(const PanoTables *__restrict__ T, int level, const int16_t *__restrict__ buf,
+                                                               int chunk_cols, size_t chunk_elems, GatherCols gc, int self, int rows_max)
+{
+    const int src = blockIdx.z;
+    if (src == self) return;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int plane = blockIdx.y % 3, cam = blockIdx.y / 3;
+    if (r >= rows_max) return;
+    const int16_t *b = buf + (size_t)src * chunk_elems + (((size_t)cam * 3 + plane) * rows_max + r) * chunk_cols;
+    for (int c = 0; c < gc.n[src]; ++c) halo_put(T, 0, level, cam, plane, r, gc.lo[src] + c, 0, b[c]);
+}
+
 // ---- halo exchange over PEER MEMORY (NVLink / NVSwitch), no library collective on the data path.
 // Every rank owns a mailbox in its own HBM that its neighbours can address (CUDA IPC mapping).  After a phase, ONE
 // launch packs this rank's edge columns for both neighbours and stores them straight into the neighbours' mailboxes
@@ -1821,6 +1837,16 @@ void launch_halo_copy(const PanoTables *dev, const PanoTables &host, int kind, i
     const int rows = halo_rows(host, kind, level);
     const dim3 block(256), grid((rows + 255) / 256, 3 * (kind == 1 ? 1 : host.num_cams));
     halo_copy_kernel<<<grid, block, 0, stream>>>(dev, kind, level, col, ncols, buf, unpack ? 1 : 0, slot, rows);
+}
+
+void launch_level_unpack_all(const PanoTables *dev, const PanoTables &host, int level, const int16_t *buf, int chunk_cols,
+                             const int *lo, const int *n, int nranks, int self, cudaStream_t stream)
+{
+    GatherCols gc{};
+    for (int i = 0; i < nranks && i < 16; ++i) { gc.lo[i] = lo[i]; gc.n[i] = n[i]; }
+    const int rows = halo_rows(host, 0, level);
+    const dim3 block(256), grid((rows + 255) / 256, 3 * host.num_cams, nranks);
+    level_unpack_all_kernel<<<grid, block, 0, stream>>>(dev, level, buf, chunk_cols, halo_elems(host, 0, level, chunk_cols), gc, self, rows);
 }
 
 void launch_p2p_begin(uint32_t *seq, cudaStream_t stream) { p2p_begin_kernel<<<1, 1, 0, stream>>>(seq); }

@@ -122,6 +122,9 @@ void launch_tile_stats(const void *data, bool is_mask, int pitch, int w, int h, 
 void launch_halo_copy(const PanoTables *dev, const PanoTables &host, int kind, int level, int col, int ncols,
                       int16_t *buf, bool unpack, int slot, cudaStream_t stream);
 size_t halo_elems(const PanoTables &host, int kind, int level, int ncols);
+// hybrid strip split: scatter the all-gathered level-`level` chunks of the other ranks (<= 16) into g[level]
+void launch_level_unpack_all(const PanoTables *dev, const PanoTables &host, int level, const int16_t *buf, int chunk_cols,
+                             const int *lo, const int *n, int nranks, int self, cudaStream_t stream);
 
 // Peer-memory halo exchange (no collective library on the data path): one side of one exchange.
 //   push:        col = first of this rank's own edge columns, buf = slot in the NEIGHBOUR's mailbox, flag = word in the

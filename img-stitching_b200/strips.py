@@ -13,6 +13,9 @@ phase that produces pyramid data a neighbour needs, the ranks exchange the edge 
                       no kernel ever waits on another);
 * `mode="redundant"` -- no exchange at all: each rank widens its window by 3*2^nb columns and
                       recomputes the halo (SURVEY 8e option B).
+* `mode="hybrid"`    -- thin redundant halos (3*2^split columns) below pyramid level `split`, the full width above it,
+                      and ONE all-gather of the camera pyramids' level `split` per panorama (`compose_hybrid`): the 2 nb
+                      latency-bound neighbour exchanges collapse into a single collective of a few hundred KB.
 """
 import ctypes as C
 
@@ -22,15 +25,21 @@ from . import capi, sharding
 class StripRank:
     """One rank's share: an initialised `ocvStitcher` + its column window."""
 
-    def __init__(self, stitcher, rank, world, mode="exchange"):
+    def __init__(self, stitcher, rank, world, mode="exchange", split=None):
         self.st, self.rank, self.world, self.mode = stitcher, rank, world, mode
         self.lib = capi.lib()
         self.h = stitcher._h
         nb, padded, _ = stitcher.blend_geometry()
         self.nb, self.padded = nb, padded
-        self.x0, self.x1 = sharding.strip_columns(padded[0], nb, world)[rank]
-        margin = 8 if mode == "exchange" else 3 * (1 << nb)
-        capi.check(self.lib.pano_strip_set_window(self.h, self.x0, self.x1, margin), self.h)
+        self.strips = sharding.strip_columns(padded[0], nb, world)
+        self.x0, self.x1 = self.strips[rank]
+        self.split = None
+        if mode == "hybrid":
+            self.split = max(1, min(nb, split if split is not None else nb - 2))
+            capi.check(self.lib.pano_strip_set_window_hybrid(self.h, self.x0, self.x1, self.split), self.h)
+        else:
+            margin = 8 if mode == "exchange" else 3 * (1 << nb)
+            capi.check(self.lib.pano_strip_set_window(self.h, self.x0, self.x1, margin), self.h)
         self.phases = self.lib.pano_strip_phase_count(self.h)
         self.has_left, self.has_right = rank > 0, rank < world - 1
 
@@ -94,6 +103,54 @@ def compose_nccl(rank_obj, frames, pano, bufs=None):
         if r.has_right:
             r.unpack(p, 1, b["rr"], stream)
     return bufs
+
+
+def compose_hybrid(rank_obj, frames, pano, bufs=None, gather=None):
+    """One frame-set on this rank in hybrid mode.  `gather(send, recv)` all-gathers the ranks' chunks (default:
+    torch.distributed.all_gather_into_tensor on the current stream, i.e. ncclAllGather); returns the reusable buffers."""
+    import torch
+    r = rank_obj
+    L = r.split
+    stream = torch.cuda.current_stream(frames.device).cuda_stream
+    lo = [x0 >> L for x0, _ in r.strips]
+    n = [(x1 >> L) - (x0 >> L) for x0, x1 in r.strips]
+    cmax = max(n)
+    if bufs is None:
+        nbytes = int(r.lib.pano_strip_level_bytes(r.h, L, cmax))
+        bufs = {"send": torch.empty(nbytes, dtype=torch.uint8, device=frames.device),
+                "recv": torch.empty(nbytes * r.world, dtype=torch.uint8, device=frames.device),
+                "lo": (C.c_int * r.world)(*lo), "n": (C.c_int * r.world)(*n)}
+    capi.check(r.lib.pano_strip_run_phases(r.h, 0, L, capi.ptr(frames), capi.ptr(pano), C.c_void_p(stream)), r.h)
+    capi.check(r.lib.pano_strip_level_pack(r.h, L, lo[r.rank], cmax, capi.ptr(bufs["send"]), C.c_void_p(stream)), r.h)
+    if gather is None:
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(bufs["recv"], bufs["send"])
+    else:
+        gather(bufs["send"], bufs["recv"])
+    capi.check(r.lib.pano_strip_level_unpack_all(r.h, L, capi.ptr(bufs["recv"]), cmax, bufs["lo"], bufs["n"], r.world, r.rank,
+                                                 C.c_void_p(stream)), r.h)
+    capi.check(r.lib.pano_strip_run_phases(r.h, L, r.phases, capi.ptr(frames), capi.ptr(pano), C.c_void_p(stream)), r.h)
+    return bufs
+
+
+def compose_hybrid_local(ranks, frames, panos):
+    """All hybrid ranks inside ONE process/GPU in lockstep (tests): the all-gather is a device copy of every rank's chunk."""
+    import torch
+    L = ranks[0].split
+    stream = torch.cuda.current_stream(frames.device).cuda_stream
+    world = len(ranks)
+    lo = [x0 >> L for x0, _ in ranks[0].strips]
+    n = [(x1 >> L) - (x0 >> L) for x0, x1 in ranks[0].strips]
+    cmax = max(n)
+    nbytes = int(ranks[0].lib.pano_strip_level_bytes(ranks[0].h, L, cmax))
+    recv = torch.empty(nbytes * world, dtype=torch.uint8, device=frames.device)
+    for r, pano in zip(ranks, panos):
+        capi.check(r.lib.pano_strip_run_phases(r.h, 0, L, capi.ptr(frames), capi.ptr(pano), C.c_void_p(stream)), r.h)
+        capi.check(r.lib.pano_strip_level_pack(r.h, L, lo[r.rank], cmax, capi.ptr(recv[r.rank * nbytes:]), C.c_void_p(stream)), r.h)
+    lo_c, n_c = (C.c_int * world)(*lo), (C.c_int * world)(*n)
+    for r, pano in zip(ranks, panos):
+        capi.check(r.lib.pano_strip_level_unpack_all(r.h, L, capi.ptr(recv), cmax, lo_c, n_c, world, r.rank, C.c_void_p(stream)), r.h)
+        capi.check(r.lib.pano_strip_run_phases(r.h, L, r.phases, capi.ptr(frames), capi.ptr(pano), C.c_void_p(stream)), r.h)
 
 
 def compose_local(ranks, frames, panos):
@@ -228,7 +285,7 @@ def soft_band_masks(stitcher):
     return out
 
 
-def bench_config4(rank, world, local, small=False, steps=10, warmup=3, modes=("exchange", "p2p", "redundant")):
+def bench_config4(rank, world, local, small=False, steps=10, warmup=3, modes=("exchange", "p2p", "redundant", "hybrid")):
     """ONE 8-camera cylindrical 7-band panorama (8 x 3840x2160; small: 8 x 960x540, 5 bands) split into `world` column
     strips, one per rank of an initialised torch.distributed NCCL job.  Every rank checks its own columns against the
     undivided panorama (computed locally by a second handle), then each halo mode is timed on the device, max over
@@ -279,7 +336,14 @@ def bench_config4(rank, world, local, small=False, steps=10, warmup=3, modes=("e
     for mode in modes:
         r = StripRank(make(), rank, world, "exchange" if mode == "p2p" else mode)
         pano = torch.zeros((oh, ow, 3), dtype=torch.uint8, device=dev)
-        if mode == "p2p":
+        if mode == "hybrid":
+            def run(bufs=None, r=r, pano=pano):
+                return compose_hybrid(r, frames, pano, bufs)
+        elif mode == "redundant":
+            def run(bufs=None, r=r, pano=pano):      # every phase from ONE library call (no exchange in between)
+                capi.check(r.lib.pano_strip_run_phases(r.h, 0, r.phases, capi.ptr(frames), capi.ptr(pano),
+                                                       C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), r.h)
+        elif mode == "p2p":
             p2p_setup_distributed(r)
             side = torch.cuda.Stream(dev)            # a capturable stream: the frame is replayed as a CUDA graph
 
@@ -310,11 +374,16 @@ def bench_config4(rank, world, local, small=False, steps=10, warmup=3, modes=("e
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         res[mode] = {"ms_per_panorama": float(tt[0]), "all_ranks_match_undivided": bool(tt[1] == 0.0),
                      "halo_bytes_per_rank_side": int(sum(r.halo_bytes(p) for p in range(r.phases)))}
+        if mode == "hybrid":
+            L = r.split
+            res[mode].update(split_level=L, redundant_margin_px=3 * (1 << L),
+                             all_gather_bytes_per_rank=int(r.lib.pano_strip_level_bytes(r.h, L, max((x1 >> L) - (x0 >> L) for x0, x1 in r.strips))))
     t1 = torch.tensor([single_ms], dtype=torch.float64, device=dev)
     dist.all_reduce(t1, op=dist.ReduceOp.MAX)
     return {"workload": "config4%s: 8x%dx%d cylindrical ring, %d bands, one panorama split into %d column strips"
                         % (" (small)" if small else "", W, H, nb, world),
             "n_gpus": world, "single_gpu_ms_per_panorama": float(t1[0]), "modes": res,
-            "halo_modes": {"exchange": "NCCL point-to-point (batch_isend_irecv)", "p2p": "peer-memory mailboxes over NVLink, frame replayed as a CUDA graph",
-                           "redundant": "no exchange, halo recomputed"},
+            "halo_modes": {"exchange": "NCCL point-to-point (batch_isend_irecv) after each of the 2 nb phases", "p2p": "peer-memory mailboxes over NVLink, frame replayed as a CUDA graph",
+                           "redundant": "no exchange, halo of 3 * 2^nb columns recomputed",
+                           "hybrid": "thin redundant halo (3 * 2^split columns) below level `split`, full width above, ONE ncclAllGather of g[split] per panorama"},
             "strips": sharding.strip_columns(r.padded[0], nb, world)}

@@ -143,6 +143,23 @@ size_t pano_strip_halo_bytes(pano_handle h, int phase);
 int pano_strip_halo_pack(pano_handle h, int phase, int side, void *buf_dev, void *stream);
 int pano_strip_halo_unpack(pano_handle h, int phase, int side, const void *buf_dev, void *stream);
 
+/* ---- hybrid split: thin redundant halos below `split_level`, full width above it, ONE all-gather per panorama.
+ * Levels < split_level: the rank computes its strip widened by 3 * 2^split_level level-0 columns (no exchange); levels
+ * >= split_level: every rank computes the whole width (4^-split_level of the work), which needs the other ranks' columns of
+ * the camera pyramids g[split_level] exactly once.  Per frame-set:
+ *   pano_strip_run_phases(h, 0, split_level, ..)                      warp + pyrDown into levels 1 .. split_level
+ *   pano_strip_level_pack(h, split_level, x0 >> split_level, n, buf)  own columns -> dense chunk ([cam][plane][row][n] int16)
+ *   all-gather of the chunks (e.g. ncclAllGather; chunk_cols = the widest strip)
+ *   pano_strip_level_unpack_all(h, split_level, gathered, ..)         every other rank's chunk -> g[split_level]
+ *   pano_strip_run_phases(h, split_level, pano_strip_phase_count(h), ..)
+ * Bit-identical to the undivided panorama on the rank's own columns. */
+int pano_strip_set_window_hybrid(pano_handle h, int x0, int x1, int split_level);
+int pano_strip_run_phases(pano_handle h, int first, int last, const uint8_t *frames_dev, uint8_t *pano_dev, void *stream);
+size_t pano_strip_level_bytes(pano_handle h, int level, int ncols);
+int pano_strip_level_pack(pano_handle h, int level, int col, int ncols, void *buf_dev, void *stream);
+int pano_strip_level_unpack_all(pano_handle h, int level, const void *gathered_dev, int chunk_cols, const int *lo, const int *n,
+                                int nranks, int self, void *stream);
+
 /* ---- the same exchange over PEER MEMORY (NVLink / NVSwitch) instead of a collective library: every rank owns a
  * mailbox in its HBM; after a phase ONE kernel packs the rank's edge columns and stores them straight into both
  * neighbours' mailboxes (P2P stores), then publishes the frame's sequence number in the neighbour's flag word

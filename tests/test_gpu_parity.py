@@ -577,6 +577,32 @@ def test_strip_split_equals_single_gpu(nranks, mode):
         assert not np.array_equal(panob200.strips.assemble(ranks, panos).cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("nranks,split", [(2, 3), (4, 3), (8, 2), (8, 4), (3, 1), (4, 5)])
+def test_strip_split_hybrid_equals_single_gpu(nranks, split):
+    """Hybrid decomposition (thin redundant halo below `split`, full width above, one all-gather of g[split]): ranks
+    emulated in lockstep on one GPU must reproduce the undivided panorama byte for byte, for split levels from 1 to nb."""
+    import torch
+    Ks, Rs, scale = calib.ring(8, 960, 540, 65.2, 40.0)
+    t = compose.build_tables(Ks, Rs, scale, (960, 540), "cylindrical")
+    t.blend_masks = util.soft_masks(t)
+    imgs = [util.synth_frame(540, 960, 700 + i, cell=32) for i in range(8)]
+    ref_st = make(Ks, Rs, scale, 960, 540, "cylindrical", "multiband", 5)
+    assert ref_st.initTables(t.blend_masks) == 0, ref_st.last_error
+    want = ref_st.process(imgs)
+    frames = torch.from_numpy(np.stack(imgs)).cuda()
+    ranks, panos = [], []
+    for r in range(nranks):
+        st = make(Ks, Rs, scale, 960, 540, "cylindrical", "multiband", 5)
+        assert st.initTables(t.blend_masks) == 0, st.last_error
+        ranks.append(panob200.strips.StripRank(st, r, nranks, "hybrid", split=split))
+        panos.append(torch.full(want.shape, 77, dtype=torch.uint8, device="cuda"))
+    for _ in range(2):                                       # twice: stale data of the first frame must not matter
+        panob200.strips.compose_hybrid_local(ranks, frames, panos)
+    torch.cuda.synchronize()
+    got = panob200.strips.assemble(ranks, panos).cpu().numpy()
+    assert_equal("hybrid strip split %d ranks, split level %d" % (nranks, split), got, want)
+
+
 @pytest.mark.parametrize("nranks,concurrent", [(2, False), (4, False), (8, False)])
 def test_strip_split_peer_memory_exchange(nranks, concurrent):
     """Halo exchange through peer-memory mailboxes (push kernel stores into the neighbour's mailbox and raises a flag,
@@ -618,7 +644,7 @@ def test_strip_split_multi_gpu_torchrun():
     assert r.returncode == 0, r.stderr[-3000:]
     rec = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert rec["n_gpus"] == world
-    for mode in ("exchange", "p2p", "redundant"):
+    for mode in ("exchange", "p2p", "redundant", "hybrid"):
         assert rec["modes"][mode]["all_ranks_match_undivided"], (mode, rec)
 
 
