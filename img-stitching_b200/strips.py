@@ -336,13 +336,19 @@ def bench_config4(rank, world, local, small=False, steps=10, warmup=3, modes=("e
     for mode in modes:
         r = StripRank(make(), rank, world, "exchange" if mode == "p2p" else mode)
         pano = torch.zeros((oh, ow, 3), dtype=torch.uint8, device=dev)
-        if mode == "hybrid":
-            def run(bufs=None, r=r, pano=pano):
-                return compose_hybrid(r, frames, pano, bufs)
-        elif mode == "redundant":
-            def run(bufs=None, r=r, pano=pano):      # every phase from ONE library call (no exchange in between)
-                capi.check(r.lib.pano_strip_run_phases(r.h, 0, r.phases, capi.ptr(frames), capi.ptr(pano),
-                                                       C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), r.h)
+        if mode in ("hybrid", "redundant"):
+            side = torch.cuda.Stream(dev)            # a capturable stream: phase ranges are replayed as CUDA graphs
+
+            def run(bufs=None, r=r, pano=pano, side=side, mode=mode):
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):        # NCCL's all-gather follows torch's current stream
+                    if mode == "hybrid":
+                        bufs = compose_hybrid(r, frames, pano, bufs)
+                    else:                            # every phase from ONE library call (no exchange in between)
+                        capi.check(r.lib.pano_strip_run_phases(r.h, 0, r.phases, capi.ptr(frames), capi.ptr(pano),
+                                                               C.c_void_p(side.cuda_stream)), r.h)
+                torch.cuda.current_stream(dev).wait_stream(side)
+                return bufs
         elif mode == "p2p":
             p2p_setup_distributed(r)
             side = torch.cuda.Stream(dev)            # a capturable stream: the frame is replayed as a CUDA graph
