@@ -97,8 +97,6 @@ struct pano_ctx {
     int *d_stat_ones = nullptr;
     std::vector<void *> owned;                    // device allocations to free
     std::vector<void *> cam_mask0, cam_gain;      // per camera, re-uploadable
-    std::vector<void *> cam_dist;                 // feather: clamped integer distances (CamTables::dist), per camera
-    int dist_cap = 0, dist_bytes = 0;             // smallest d with float(d) * sharpness >= 1, and the element size that holds it
     std::vector<std::vector<void *>> cam_wt;      // per camera per level
 
     // peer-memory halo exchange (pano_strip_p2p_*): own mailbox (flags + halo slots), the neighbours' mapped mailboxes
@@ -333,41 +331,6 @@ int buildCamMap(pano_ctx *h, int cam, const float *xm, const float *ym, int W, i
     return PANO_OK;
 }
 
-// A float feather weight map that is min(d * sharpness, 1) of integer distances d (what FeatherBlender builds) is also kept
-// as the clamped distances (CamTables::dist): the streaming blend then reads 1 (2) bytes per pixel and rebuilds the very
-// same float.  Any other map (an arbitrary caller override) keeps the float path.
-int compactFeather(pano_ctx *h, int cam, const float *w, int width, int height)
-{
-    CamTables &C = h->host.cam[cam];
-    C.dist = nullptr; C.dist_bytes = 0;
-    if (!h->cam_dist[cam] || h->dist_bytes == 0) return PANO_OK;
-    const float sh = h->cfg.sharpness;
-    const int cap = h->dist_cap, eb = h->dist_bytes;
-    std::vector<uint8_t> d8;
-    std::vector<uint16_t> d16;
-    if (eb == 1) d8.assign((size_t)C.dist_pitch * height, 0); else d16.assign((size_t)C.dist_pitch * height, 0);
-    for (int y = 0; y < height; ++y)
-        for (int x = 0; x < width; ++x) {
-            const float v = w[(size_t)y * width + x];
-            int d = -1;
-            if (v == 1.f) d = cap;
-            else if (v >= 0.f && v < 1.f) {
-                const int c = (int)lrintf(v / sh);
-                for (int k = c - 1; k <= c + 1 && d < 0; ++k) {
-                    if (k < 0 || k > cap) continue;
-                    volatile float r = (float)k * sh;
-                    if ((r > 1.f ? 1.f : r) == v) d = k;
-                }
-            }
-            if (d < 0) return PANO_OK;                                  // not a distance map: float path
-            if (eb == 1) d8[(size_t)y * C.dist_pitch + x] = (uint8_t)d; else d16[(size_t)y * C.dist_pitch + x] = (uint16_t)d;
-        }
-    CK(h, cudaMemcpy(h->cam_dist[cam], eb == 1 ? (const void *)d8.data() : (const void *)d16.data(),
-                     (size_t)C.dist_pitch * height * eb, cudaMemcpyHostToDevice));
-    C.dist = h->cam_dist[cam]; C.dist_bytes = eb;
-    return PANO_OK;
-}
-
 int buildWeights(pano_ctx *h, int cam)
 {
     CamTables &C = h->host.cam[cam];
@@ -384,22 +347,20 @@ int buildWeights(pano_ctx *h, int cam)
             CK(h, cudaMalloc((void **)&tmp, (size_t)img.w * img.h * sizeof(int)));
             cudaError_t e = cudaMemcpy2DAsync(m0d, C.mask_pitch, m.data(), img.w, img.w, img.h, cudaMemcpyHostToDevice, nullptr);
             if (e == cudaSuccess) {
-                launch_feather_weight(m0d, C.mask_pitch, img.w, img.h, h->cfg.sharpness, tmp, (float *)h->cam_wt[cam][0], C.wt_pitch[0],
-                                      h->cam_dist[cam], h->cam_dist[cam] ? h->dist_bytes : 0, C.dist_pitch, h->dist_cap, nullptr);
+                launch_feather_weight(m0d, C.mask_pitch, img.w, img.h, h->cfg.sharpness, tmp, (float *)h->cam_wt[cam][0], C.wt_pitch[0], nullptr);
                 e = cudaStreamSynchronize(nullptr);
             }
             if (e == cudaSuccess) e = cudaGetLastError();
             cudaFree(tmp);
             if (e != cudaSuccess) return fail(h, "feather weight build failed: %s", cudaGetErrorString(e));
             C.use_wt0 = 1;
-            C.dist = h->cam_dist[cam]; C.dist_bytes = h->cam_dist[cam] ? h->dist_bytes : 0;
             return PANO_OK;
         }
         std::vector<float> w((size_t)img.w * img.h);
         featherWeight(m.data(), img.w, img.h, img.w, h->cfg.sharpness, w.data());
         if (upload2d(h, (float *)h->cam_wt[cam][0], C.wt_pitch[0], w.data(), img.w, img.w, img.h)) return PANO_ERR;
         C.use_wt0 = 1;
-        return compactFeather(h, cam, w.data(), img.w, img.h);
+        return PANO_OK;
     }
     const int W = fr.rect.w, H = fr.rect.h;
     if (!host_weights) {
@@ -556,7 +517,7 @@ double blendG0Bytes(const pano_ctx *h, int slots)
     double b = (double)h->out_bytes();
     for (int i = 0; i < h->n; ++i) {
         const CamTables &C = h->host.cam[i];
-        b += (double)C.rw * C.rh * (3 + (h->blender == PANO_BLEND_FEATHER ? (C.dist_bytes ? C.dist_bytes : 4) : 1));
+        b += (double)C.rw * C.rh * (3 + (h->blender == PANO_BLEND_FEATHER ? 4 : 1));
     }
     return b * slots;
 }
@@ -586,7 +547,7 @@ int runPhase(pano_ctx *h, int p, const uint8_t *frames_dev, uint8_t *out_dev, in
             launch_warp(h->dev, h->host, h->kc, frames_dev, slots, st);
             L.end();
             L.begin("blend_warped", blendG0Bytes(h, slots));
-            launch_blend_g0(h->dev, h->host, h->blender, h->cfg.sharpness, out_dev, slots, st);
+            launch_blend_g0(h->dev, h->host, h->blender, out_dev, slots, st);
             L.end();
         } else {
             L.begin("direct_blend", directBytes(h, slots));
@@ -850,18 +811,7 @@ int pano_create(const pano_config *cfg, pano_handle *out)
 
     // ---- per-camera device tables ----
     const int S = h->cfg.max_batch;
-    h->cam_mask0.assign(n, nullptr); h->cam_gain.assign(n, nullptr); h->cam_dist.assign(n, nullptr);
-    if (h->blender == PANO_BLEND_FEATHER) {
-        // FeatherBlender weight = min(d * sharpness, 1): every distance from dist_cap on saturates to exactly 1.0f
-        volatile float sh = cfg->sharpness;
-        for (int d = 1; d <= 65535; ++d) {
-            volatile float v = (float)d * sh;
-            if (v >= 1.f) { h->dist_cap = d; break; }
-        }
-        h->dist_bytes = h->dist_cap == 0 ? 0 : (h->dist_cap <= 255 ? 1 : 2);
-        static const bool no_dist = getenv("PANO_FEATHER_FLOAT") != nullptr;        // A/B switch: float weight maps
-        if (no_dist) h->dist_bytes = 0;
-    }
+    h->cam_mask0.assign(n, nullptr); h->cam_gain.assign(n, nullptr);
     h->cam_wt.assign(n, std::vector<void *>(kMaxLevels, nullptr));
     for (int i = 0; i < n; ++i) {
         CamTables &C = T.cam[i];
@@ -875,13 +825,6 @@ int pano_create(const pano_config *cfg, pano_handle *out)
         uint8_t *m0 = nullptr;
         if (devAlloc(h, &m0, (size_t)C.mask_pitch * C.rh + 16)) return bail(0);     // + slack: 4-byte funnel loads may touch the next word
         h->cam_mask0[i] = m0; C.mask0 = m0;
-        C.dist = nullptr; C.dist_bytes = 0; C.dist_pitch = 0;
-        if (h->blender == PANO_BLEND_FEATHER && h->dist_bytes > 0) {
-            C.dist_pitch = roundUp(C.rw + 8, 128);
-            uint8_t *d = nullptr;
-            if (devAlloc(h, &d, (size_t)C.dist_pitch * C.rh * h->dist_bytes + 16)) return bail(0);
-            h->cam_dist[i] = d;
-        }
         const int wl0 = (h->blender == PANO_BLEND_MULTIBAND) ? 0 : 0;
         for (int l = wl0; l <= h->nb; ++l) {
             C.wt_pitch[l] = roundUp(std::max(1, C.rw >> l), 32);
@@ -1136,7 +1079,7 @@ int pano_set_feather_weight(pano_handle h, int cam, const float *w, int width, i
     if (upload2d(h, (float *)h->cam_wt[cam][0], C.wt_pitch[0], w, width, width, height)) return PANO_ERR;
     C.use_wt0 = 1;
     h->tables_dirty = true;
-    return compactFeather(h, cam, w, width, height);
+    return PANO_OK;
 }
 
 int pano_set_gain_map(pano_handle h, int cam, const float *gain, int width, int height)

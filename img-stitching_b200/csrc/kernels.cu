@@ -1301,22 +1301,12 @@ __global__ void __launch_bounds__(256) direct_blend_kernel(const PanoTables *__r
 
 
 // ---- K4': the same blenders as a streaming pass over the WARPED images.  The warp itself (remap + gain +
-// convertTo(CV_16S)) is then the staged tile kernel of the multiband path (warp_tile_kernel -> planar u8 g[0]), which gathers
+// convertTo(CV_16S)) is then the staged tile kernel of the multiband path (warp_tile_kernel -> planar g[0]), which gathers
 // 3x faster than the per-pixel byte loads above; this kernel does what FeatherBlender::feed / blend (weight, accumulate,
 // normalise), Blender::blend (mask), convertTo(CV_8U) and the crop do.  Same operations in the same camera order as
-// direct_blend_kernel -> identical bytes.  One thread = 4 consecutive panorama pixels; where the four pixels lie inside a
-// camera's image the three planes (and the 1-byte weight source) arrive as funnel-shifted aligned words.
-// Feather weights: min(d * sharpness, 1) rebuilt from the clamped integer distance (CamTables::dist) with the builder's own
-// two float operations when the camera has it (4 -> 1 byte per pixel), else read from wt[0].
-__device__ __forceinline__ uint32_t load4_u8(const uint8_t *__restrict__ p)       // 4 bytes at any alignment (rows are padded)
-{
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-    return __funnelshift_r(__ldg(w), __ldg(w + 1), (uint32_t)(a & 3) * 8u);
-}
-
+// direct_blend_kernel -> identical bytes.  One thread = 4 consecutive panorama pixels.
 template <bool kFeather>
-__global__ void __launch_bounds__(256) blend_g0_kernel(const PanoTables *__restrict__ T, float sharpness, uint8_t *__restrict__ pano)
+__global__ void __launch_bounds__(256) blend_g0_kernel(const PanoTables *__restrict__ T, uint8_t *__restrict__ pano)
 {
     const int cx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, cy = blockIdx.y * blockDim.y + threadIdx.y;
     const int slot = blockIdx.z;
@@ -1334,56 +1324,19 @@ __global__ void __launch_bounds__(256) blend_g0_kernel(const PanoTables *__restr
         if ((unsigned)y >= (unsigned)C.rh || x0 + 3 < 0 || x0 >= C.rw) continue;
         const uint8_t *g = C.g[0] + (size_t)slot * C.g_slot[0] + (size_t)y * C.g_pitch[0];
         const size_t plane = C.g_plane[0];
-        const bool inside = npx == 4 && x0 >= 0 && x0 + 3 < C.rw;
-        uint32_t p0 = 0, p1 = 0, p2 = 0, ws = 0;
-        float wf[4] = {0.f, 0.f, 0.f, 0.f};
-        if (inside) {
-            p0 = load4_u8(g + x0); p1 = load4_u8(g + plane + x0); p2 = load4_u8(g + 2 * plane + x0);
-            if (kFeather) {
-                if (C.dist_bytes == 1) {
-                    ws = load4_u8(static_cast<const uint8_t *>(C.dist) + (size_t)y * C.dist_pitch + x0);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) wf[j] = fminf(__fmul_rn((float)((ws >> (8 * j)) & 0xffu), sharpness), 1.f);
-                } else if (C.dist_bytes == 2) {
-                    const uint16_t *dp = static_cast<const uint16_t *>(C.dist) + (size_t)y * C.dist_pitch + x0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) wf[j] = fminf(__fmul_rn((float)__ldg(dp + j), sharpness), 1.f);
-                } else {
-                    const float *wp = C.wt[0] + (size_t)y * C.wt_pitch[0] + x0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) wf[j] = __ldg(wp + j);
-                }
-            } else {
-                ws = load4_u8(C.mask0 + (size_t)y * C.mask_pitch + x0);
-            }
-        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int x = x0 + j;
-            int v0, v1, v2;
-            float w = 0.f;
-            int mk = 0;
-            if (inside) {
-                v0 = (p0 >> (8 * j)) & 0xff; v1 = (p1 >> (8 * j)) & 0xff; v2 = (p2 >> (8 * j)) & 0xff;
-                w = wf[j];
-                mk = (ws >> (8 * j)) & 0xff;
-            } else {
-                if (j >= npx || (unsigned)x >= (unsigned)C.rw) continue;
-                v0 = g[x]; v1 = g[plane + x]; v2 = g[2 * plane + x];
-                if (kFeather) {
-                    if (C.dist_bytes == 1) w = fminf(__fmul_rn((float)static_cast<const uint8_t *>(C.dist)[(size_t)y * C.dist_pitch + x], sharpness), 1.f);
-                    else if (C.dist_bytes == 2) w = fminf(__fmul_rn((float)static_cast<const uint16_t *>(C.dist)[(size_t)y * C.dist_pitch + x], sharpness), 1.f);
-                    else w = __ldg(C.wt[0] + (size_t)y * C.wt_pitch[0] + x);
-                } else {
-                    mk = __ldg(C.mask0 + (size_t)y * C.mask_pitch + x);
-                }
-            }
+            if (j >= npx || (unsigned)x >= (unsigned)C.rw) continue;
+            const int v0 = g[x], v1 = g[plane + x], v2 = g[2 * plane + x];
             if (kFeather) {
+                const float w = __ldg(C.wt[0] + (size_t)y * C.wt_pitch[0] + x);
                 acc[j][0] += trunc_s16(__fmul_rn((float)v0, w));
                 acc[j][1] += trunc_s16(__fmul_rn((float)v1, w));
                 acc[j][2] += trunc_s16(__fmul_rn((float)v2, w));
                 wsum[j] = __fadd_rn(wsum[j], w);
             } else {             // no blending: later images overwrite where their mask is set
+                const int mk = __ldg(C.mask0 + (size_t)y * C.mask_pitch + x);
                 if (mk) { acc[j][0] = v0; acc[j][1] = v1; acc[j][2] = v2; }
                 any[j] |= mk;
             }
@@ -1669,8 +1622,7 @@ __global__ void __launch_bounds__(128) feather_cols_kernel(const uint8_t *__rest
     }
 }
 
-__global__ void __launch_bounds__(128) feather_rows_kernel(int *__restrict__ tmp, int w, int h, float sharpness, float *__restrict__ out, int opitch,
-                                                           void *__restrict__ dist, int dist_bytes, int dist_pitch, int dist_cap)
+__global__ void __launch_bounds__(128) feather_rows_kernel(int *__restrict__ tmp, int w, int h, float sharpness, float *__restrict__ out, int opitch)
 {
     const int y = blockIdx.x * blockDim.x + threadIdx.x;
     if (y >= h) return;
@@ -1684,11 +1636,9 @@ __global__ void __launch_bounds__(128) feather_rows_kernel(int *__restrict__ tmp
     float *o = out + (size_t)y * opitch;
     for (int x = w - 1; x >= 0; --x) {
         d = min(row[x], min(d + 1, kDistBig));
-        const float fd = d >= kDistBig / 2 ? 3.402823466e+38f : (float)d;
-        const float v = __fmul_rn(fd, sharpness);
+        const float dist = d >= kDistBig / 2 ? 3.402823466e+38f : (float)d;
+        const float v = __fmul_rn(dist, sharpness);
         o[x] = v > 1.f ? 1.f : v;
-        if (dist_bytes == 1) static_cast<uint8_t *>(dist)[(size_t)y * dist_pitch + x] = (uint8_t)min(d, dist_cap);
-        else if (dist_bytes == 2) static_cast<uint16_t *>(dist)[(size_t)y * dist_pitch + x] = (uint16_t)min(d, dist_cap);
     }
 }
 
@@ -1953,11 +1903,10 @@ void launch_weight_pyrdown(const void *src, bool from_mask, int spitch, int sw, 
     else weight_pyrdown_kernel<false><<<grid, block, 0, stream>>>(src, spitch, sw, sh, dst, dpitch);
 }
 
-void launch_feather_weight(const uint8_t *mask, int mpitch, int w, int h, float sharpness, int *tmp, float *out, int opitch,
-                           void *dist, int dist_bytes, int dist_pitch, int dist_cap, cudaStream_t stream)
+void launch_feather_weight(const uint8_t *mask, int mpitch, int w, int h, float sharpness, int *tmp, float *out, int opitch, cudaStream_t stream)
 {
     feather_cols_kernel<<<(w + 127) / 128, 128, 0, stream>>>(mask, mpitch, w, h, tmp);
-    feather_rows_kernel<<<(h + 127) / 128, 128, 0, stream>>>(tmp, w, h, sharpness, out, opitch, dist, dist_bytes, dist_pitch, dist_cap);
+    feather_rows_kernel<<<(h + 127) / 128, 128, 0, stream>>>(tmp, w, h, sharpness, out, opitch);
 }
 
 void launch_seam_mask(const uint8_t *seam, int sw, int sh, int spitch, const int *xo, const int *xc, const int *yo, const int *yc,
@@ -1975,13 +1924,12 @@ void launch_tile_stats(const void *data, bool is_mask, int pitch, int w, int h, 
     else tile_stats_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float *>(data), pitch, w, h, ox, oy, 1.0f, nz, ones);
 }
 
-void launch_blend_g0(const PanoTables *dev, const PanoTables &host, int blender, float sharpness, uint8_t *pano, int nslots,
-                     cudaStream_t stream)
+void launch_blend_g0(const PanoTables *dev, const PanoTables &host, int blender, uint8_t *pano, int nslots, cudaStream_t stream)
 {
     const dim3 block(32, 8);
     const dim3 grid = grid2d((host.cut_w + 3) / 4, host.cut_h, block, nslots);
-    if (blender == 1) blend_g0_kernel<true><<<grid, block, 0, stream>>>(dev, sharpness, pano);
-    else blend_g0_kernel<false><<<grid, block, 0, stream>>>(dev, sharpness, pano);
+    if (blender == 1) blend_g0_kernel<true><<<grid, block, 0, stream>>>(dev, pano);
+    else blend_g0_kernel<false><<<grid, block, 0, stream>>>(dev, pano);
 }
 
 void launch_direct_blend(const PanoTables *dev, const PanoTables &host, int blender, const uint8_t *frames,

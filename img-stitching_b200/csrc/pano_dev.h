@@ -39,11 +39,6 @@ struct CamTables {
     const float *wt[kMaxLevels];
     int wt_pitch[kMaxLevels];
     int use_wt0;  // 1: level-0 weights come from wt[0] (caller override / feather) instead of mask0
-    // FeatherBlender: wt[0] = min(d * sharpness, 1) of an integer city-block distance d, so the streaming blend reads the
-    // distance clamped at dist_cap (1 or 2 bytes per pixel instead of 4) and rebuilds the weight with the same two float
-    // operations.  dist_bytes = 0: not available (a caller-supplied weight map that is not of that form) -> wt[0]
-    const void *dist;
-    int dist_bytes, dist_pitch;   // pitch in elements
     // pyramid workspace
     uint8_t *g[kMaxLevels];
     int g_pitch[kMaxLevels];
@@ -102,8 +97,7 @@ void launch_coarsest(const PanoTables *dev, const PanoTables &host, uint8_t *pan
 int launch_collapse(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, int level, uint8_t *pano,
                     int nslots, cudaStream_t stream);
 // feather / no-blend as two passes: launch_warp (staged gather -> g[0]) + this streaming blend over the warped images
-void launch_blend_g0(const PanoTables *dev, const PanoTables &host, int blender, float sharpness, uint8_t *pano, int nslots,
-                     cudaStream_t stream);
+void launch_blend_g0(const PanoTables *dev, const PanoTables &host, int blender, uint8_t *pano, int nslots, cudaStream_t stream);
 void launch_direct_blend(const PanoTables *dev, const PanoTables &host, int blender, const uint8_t *frames,
                          uint8_t *pano, int nslots, cudaStream_t stream);
 
@@ -115,10 +109,9 @@ void launch_weight_pyrdown(const void *src, bool from_mask, int spitch, int sw, 
 // m_blenderMask from the seam finder's low-resolution mask (dilate -> INTER_LINEAR_EXACT -> AND full mask), tight w x h
 void launch_seam_mask(const uint8_t *seam, int sw, int sh, int spitch, const int *xo, const int *xc, const int *yo, const int *yc,
                       const uint8_t *full, uint8_t *dst, int w, int h, cudaStream_t stream);
-// FeatherBlender weight map of one camera: min(distanceTransform(mask, DIST_L1, 3) * sharpness, 1); tmp = w * h ints;
-// dist (optional): the same distance clamped at dist_cap as dist_bytes-byte integers
+// FeatherBlender weight map of one camera: min(distanceTransform(mask, DIST_L1, 3) * sharpness, 1); tmp = w * h ints
 void launch_feather_weight(const uint8_t *mask, int mpitch, int w, int h, float sharpness, int *tmp, float *out, int opitch,
-                           void *dist, int dist_bytes, int dist_pitch, int dist_cap, cudaStream_t stream);
+                           cudaStream_t stream);
 void launch_tile_stats(const void *data, bool is_mask, int pitch, int w, int h, int ox, int oy, int tiles_x, int tiles_y,
                        uint8_t *nz, int *ones, cudaStream_t stream);
 
