@@ -20,6 +20,8 @@ Frame-sets are sharded across ranks with no data-path collective (weak scaling: 
   parity     the first GPU panoramas against the CPU arm's panoramas computed from the same bytes in this run
   cpu_baseline  cv2-driven reference call sequence on the host cores: faithful (maps rebuilt per call, the reference's
              behaviour) and cached-maps variants
+  also.config5  BASELINE config 5: ONE 256-frame-set batch sharded over the ranks (strong scaling), device-resident and
+             streamed from pinned host memory
   strip_split   (N > 1) BASELINE config 4: one 8 x 4K cylindrical 7-band panorama split into N column strips, halos by
              NCCL point-to-point / peer-memory mailboxes / recomputed
 
@@ -457,6 +459,47 @@ def time_e2e(b, host_in, host_out, steps, barrier):
     return dt
 
 
+def time_config5(b, host_in, host_out, world, stream, barrier, steps):
+    """BASELINE config 5: ONE 256-frame-set batch sharded over the ranks (strong scaling: 256 / world frame-sets per rank per
+    step), device-resident and streamed from pinned host memory.  -> (device ms, host-streamed s, frame-sets per rank)"""
+    import torch
+    st, frames, out = b["st"], b["frames"], b["out"]
+    per = max(1, 256 // world)
+    B = frames.shape[0]
+    chunks = [min(B, per - o) for o in range(0, per, B)]
+
+    def dev_step():
+        for n in chunks:
+            st.process_device(frames[:n], out[:n], stream.cuda_stream)
+
+    def host_step():
+        for n in chunks:
+            st.process_batch(host_in[:n], host_out[:n])
+
+    for _ in range(3):
+        dev_step()
+    torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        dev_step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    host_step()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        host_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    barrier()
+    return ms, dt, per
+
+
 def pcie_ceiling(host_in, host_out, dev_in, dev_out, barrier, seconds=0.6):
     """Raw rate of this rank's pinned buffers over PCIe with BOTH directions busy (what the e2e pipeline needs), all
     ranks copying at the same time.  -> (h2d GB/s, d2h GB/s) of this rank."""
@@ -644,6 +687,14 @@ def main():
             latency, lat_pano = time_latency(b)
             latency["matches_device_path"] = bool(np.array_equal(lat_pano, out[(200 - 1) % min(4, B)].cpu().numpy())) if B >= 4 else None
         barrier()
+        c5_steps = max(4, args.steps)
+        c5_ms, c5_s, c5_per = time_config5(b, host_in, host_out, world, stream, barrier, c5_steps)
+        c5_ms, c5_s = allmax([c5_ms, c5_s * 1000.0])
+        also["config5"] = {"workload": "config5: ONE 256-frame-set batch of the default workload sharded over the ranks (strong scaling)",
+                           "frame_sets_per_batch": c5_per * world, "frame_sets_per_rank": c5_per, "steps": c5_steps, "scaling": "strong",
+                           "value": c5_per * world * c5_steps / (c5_ms / 1000.0), "unit": UNIT, "ms_per_batch": c5_ms / c5_steps,
+                           "host_streamed": {"value": c5_per * world * c5_steps / (c5_s / 1000.0), "unit": UNIT,
+                                             "ms_per_batch": c5_s / c5_steps, "api": "pano_process_batch"}}
         if args.workload != "config1":
             del host_in, host_out
             b1 = build("config1", local_rank, dev, B, args.max_batch, 1234 + rank)

@@ -88,6 +88,7 @@ _SIGS = {
     "pano_process_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "pano_strip_set_window": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "pano_strip_phase_count": (C.c_int, [C.c_void_p]),
+    "pano_strip_cameras": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "pano_strip_run_phase": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pano_strip_halo_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
     "pano_strip_halo_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -1363,6 +1363,18 @@ int pano_strip_set_window_hybrid(pano_handle h, int x0, int x1, int split_level)
     return PANO_OK;
 }
 
+// A camera is read by a strip only where its warped ROI meets the level-0 window: the warp skips every other tile, the
+// pyramid kernels every other column, and above a hybrid split level the data comes from the all-gather.
+int pano_strip_cameras(pano_handle h, int *needed)
+{
+    if (!h || !needed) return fail(h, "pano_strip_cameras: bad argument");
+    for (int i = 0; i < h->host.num_cams; ++i) {
+        const auto &C = h->host.cam[i];
+        needed[i] = !(C.rx + C.rw <= h->host.win_lo[0] || C.rx >= h->host.win_hi[0]);
+    }
+    return PANO_OK;
+}
+
 int pano_strip_phase_count(pano_handle h) { return h ? phaseCount(h) : 0; }
 
 int pano_strip_run_phases(pano_handle h, int first, int last, const uint8_t *frames_dev, uint8_t *pano_dev, void *stream)

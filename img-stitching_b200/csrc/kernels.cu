@@ -636,11 +636,11 @@ template <bool kLevel0>
 __global__ void __launch_bounds__(384, 2) collapse8_kernel(const __grid_constant__ C8Args A, uint8_t *__restrict__ pano)
 {
     __shared__ __align__(16) uint8_t tile[kWalkTileH][kWalkTileW * 3];
-    // block = one 64 x 32 tile of the work list: threadIdx.z = plane, a warp = 64 pixels x 4 row pairs
+    // block = one kWalkTileW x kWalkTileH tile of the work list: threadIdx.z = plane, a warp = kWalkTileW pixels x 32 / kWalkLanesX row pairs
     const int plane = threadIdx.z;
     const uint32_t td = __ldg(A.list + blockIdx.x);
     const int tx = td & 0xfffu, ty = (td >> 12) & 0xfffu;
-    const int xl = threadIdx.x & 7, rp = threadIdx.y * 4 + (threadIdx.x >> 3);
+    const int xl = threadIdx.x % kWalkLanesX, rp = threadIdx.y * (32 / kWalkLanesX) + threadIdx.x / kWalkLanesX;
     const int X0 = tx * kWalkTileW + xl * 8, Y0 = ty * kWalkTileH + rp * 2;
     const int slot = blockIdx.y;
     const int Wf = A.Wf, Hf = A.Hf;
@@ -762,7 +762,9 @@ __global__ void __launch_bounds__(384, 2) collapse8_kernel(const __grid_constant
     __syncthreads();
     if (!in_window) return;
     const int tid = (threadIdx.z * 4 + threadIdx.y) * 32 + threadIdx.x;   // one 16-byte chunk of the tile each
-    const int row = tid / 12, col = (tid % 12) * 16;
+    constexpr int kChunks = kWalkTileW * 3 / 16;                           // 16-byte chunks per tile row
+    static_assert(kChunks * 16 == kWalkTileW * 3 && kChunks * kWalkTileH == 384, "one 16-byte chunk per thread");
+    const int row = tid / kChunks, col = (tid % kChunks) * 16;
     const int Y = ty * kWalkTileH + row - A.cut_y;
     if ((unsigned)Y >= (unsigned)A.cut_h) return;
     const int xbyte = (tx * kWalkTileW - A.cut_x) * 3 + col;               // byte offset inside the output row
@@ -911,16 +913,18 @@ __device__ __forceinline__ void walk_column(const C8Args &A, int cam, int X0, in
 template <bool kLevel0, int kMinBlocks>
 __global__ void __launch_bounds__(96, kMinBlocks) collapse_walk_kernel(const __grid_constant__ C8Args A, uint8_t *__restrict__ pano)
 {
-    __shared__ __align__(16) uint32_t sm[kLevel0 ? 3 * kWalkTileH * (kWalkTileW / 4) : 4];   // [plane][row][16 words]
+    // [plane][band][2R rows][W/4 words] + kPad words per band, so that the bands of a half-warp store to different banks
+    constexpr int kRowW = kWalkTileW / 4, kBands = 32 / kWalkLanesX, kPad = kRowW, kBandW = 2 * kWalkR * kRowW + kPad;
+    __shared__ __align__(16) uint32_t sm[kLevel0 ? 3 * kBands * kBandW : 4];
     const int lane = threadIdx.x, plane = threadIdx.y, slot = blockIdx.y;
     const uint32_t td = __ldg(A.list + blockIdx.x);
     const int tx = td & 0xfffu, ty = (td >> 12) & 0xfffu, cls = td >> 24;
     if (tx * kWalkTileW + kWalkTileW <= A.win_lo || tx * kWalkTileW >= A.win_hi) return;      // strip split (block-uniform)
-    const int band = lane >> 3, xl = lane & 7;
+    const int band = lane / kWalkLanesX, xl = lane % kWalkLanesX;
     const int X0 = tx * kWalkTileW + xl * 8, Yb = ty * kWalkTileH + band * (2 * kWalkR);
     bool active = X0 < A.Wf && Yb < A.Hf;
     if (kLevel0) active = active && Yb + 2 * kWalkR > A.cut_y && Yb < A.cut_y + A.cut_h;
-    uint32_t *smcol = sm + (plane * kWalkTileH + band * (2 * kWalkR)) * (kWalkTileW / 4) + xl * 2;
+    uint32_t *smcol = sm + (plane * kBands + band) * kBandW + xl * 2;
     if (active) {
         if (cls == kWalkEmpty) {
             if (kLevel0) {
@@ -944,9 +948,10 @@ __global__ void __launch_bounds__(96, kMinBlocks) collapse_walk_kernel(const __g
         if ((unsigned)Y >= (unsigned)A.cut_h) continue;
         const int Xc = tx * kWalkTileW + q * 4 - A.cut_x;
         if (Xc + 4 <= 0 || Xc >= A.cut_w) continue;
-        const uint32_t b = sm[row * (kWalkTileW / 4) + q];
-        const uint32_t gch = sm[(kWalkTileH + row) * (kWalkTileW / 4) + q];
-        const uint32_t rch = sm[(2 * kWalkTileH + row) * (kWalkTileW / 4) + q];
+        const int si = (row / (2 * kWalkR)) * kBandW + (row % (2 * kWalkR)) * kRowW + q;
+        const uint32_t b = sm[si];
+        const uint32_t gch = sm[kBands * kBandW + si];
+        const uint32_t rch = sm[2 * kBands * kBandW + si];
         const uint32_t x01 = __byte_perm(b, gch, 0x5140);            // b0 g0 b1 g1
         const uint32_t x23 = __byte_perm(b, gch, 0x7362);            // b2 g2 b3 g3
         const uint32_t w0 = __byte_perm(x01, rch, 0x2410);           // b0 g0 r0 b1

@@ -79,7 +79,8 @@ struct PanoTables {
 constexpr int kWarpTileW = 128, kWarpTileH = 16;      // output pixels per warp-kernel block
 constexpr int kWarpSmemWords = 7168;                  // staged source footprint, one 32-bit word per pixel (28 KB)
 
-constexpr int kWalkTileW = 64, kWalkR = 4, kWalkTileH = 8 * kWalkR;   // walker tile: 4 bands x 2R fine rows
+// walker tile: kWalkLanesX lanes of 8 pixels across, 32 / kWalkLanesX bands of 2R fine rows down (one warp per plane)
+constexpr int kWalkTileW = 64, kWalkR = 4, kWalkLanesX = kWalkTileW / 8, kWalkTileH = (32 / kWalkLanesX) * 2 * kWalkR;
 constexpr int kWalkEmpty = 0xff;
 
 struct KernelChoice {

@@ -43,6 +43,14 @@ class StripRank:
         self.phases = self.lib.pano_strip_phase_count(self.h)
         self.has_left, self.has_right = rank > 0, rank < world - 1
 
+    def cameras(self):
+        """Indices of the cameras whose warped ROI meets this rank's window: the only frames the rank has to hold
+        (the rest of the `frames` buffer is never read)."""
+        n = self.st.m_cfg.num_images
+        need = (C.c_int * n)()
+        capi.check(self.lib.pano_strip_cameras(self.h, need), self.h)
+        return [i for i in range(n) if need[i]]
+
     def halo_bytes(self, phase):
         return 0 if self.mode != "exchange" else int(self.lib.pano_strip_halo_bytes(self.h, phase))
 
@@ -137,20 +145,22 @@ def compose_hybrid_local(ranks, frames, panos):
     """All hybrid ranks inside ONE process/GPU in lockstep (tests): the all-gather is a device copy of every rank's chunk."""
     import torch
     L = ranks[0].split
-    stream = torch.cuda.current_stream(frames.device).cuda_stream
+    device = (frames[0] if isinstance(frames, (list, tuple)) else frames).device
+    stream = torch.cuda.current_stream(device).cuda_stream
     world = len(ranks)
     lo = [x0 >> L for x0, _ in ranks[0].strips]
     n = [(x1 >> L) - (x0 >> L) for x0, x1 in ranks[0].strips]
     cmax = max(n)
     nbytes = int(ranks[0].lib.pano_strip_level_bytes(ranks[0].h, L, cmax))
     recv = torch.empty(nbytes * world, dtype=torch.uint8, device=frames.device)
+    per_rank = list(frames) if isinstance(frames, (list, tuple)) else [frames] * world      # each rank may hold its own cameras only
     for r, pano in zip(ranks, panos):
-        capi.check(r.lib.pano_strip_run_phases(r.h, 0, L, capi.ptr(frames), capi.ptr(pano), C.c_void_p(stream)), r.h)
+        capi.check(r.lib.pano_strip_run_phases(r.h, 0, L, capi.ptr(per_rank[r.rank]), capi.ptr(pano), C.c_void_p(stream)), r.h)
         capi.check(r.lib.pano_strip_level_pack(r.h, L, lo[r.rank], cmax, capi.ptr(recv[r.rank * nbytes:]), C.c_void_p(stream)), r.h)
     lo_c, n_c = (C.c_int * world)(*lo), (C.c_int * world)(*n)
     for r, pano in zip(ranks, panos):
         capi.check(r.lib.pano_strip_level_unpack_all(r.h, L, capi.ptr(recv), cmax, lo_c, n_c, world, r.rank, C.c_void_p(stream)), r.h)
-        capi.check(r.lib.pano_strip_run_phases(r.h, L, r.phases, capi.ptr(frames), capi.ptr(pano), C.c_void_p(stream)), r.h)
+        capi.check(r.lib.pano_strip_run_phases(r.h, L, r.phases, capi.ptr(per_rank[r.rank]), capi.ptr(pano), C.c_void_p(stream)), r.h)
 
 
 def compose_local(ranks, frames, panos):
@@ -158,11 +168,13 @@ def compose_local(ranks, frames, panos):
     with device-to-device copies.  Bit-identical to the NCCL path by construction: same phases,
     same pack/unpack kernels, same bytes."""
     import torch
-    stream = torch.cuda.current_stream(frames.device).cuda_stream
-    allbufs = [_buffers(torch, r, frames.device) for r in ranks]
+    per_rank = list(frames) if isinstance(frames, (list, tuple)) else [frames] * len(ranks)
+    device = per_rank[0].device
+    stream = torch.cuda.current_stream(device).cuda_stream
+    allbufs = [_buffers(torch, r, device) for r in ranks]
     for p in range(ranks[0].phases):
         for r, pano in zip(ranks, panos):
-            r.run_phase(p, frames, pano, stream)
+            r.run_phase(p, per_rank[r.rank], pano, stream)
         if p not in allbufs[0]:
             continue
         for i, r in enumerate(ranks):
@@ -318,6 +330,7 @@ def bench_config4(rank, world, local, small=False, steps=10, warmup=3, modes=("e
     low = torch.rand((8, 3, H // 32 + 2, W // 32 + 2), generator=g, device=dev)
     up = torch.nn.functional.interpolate(low, size=(H, W), mode="bilinear", align_corners=False) * 255.0
     frames = up.clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    frames_all = frames
     del low, up
     ref = make()
     ow, oh = ref.out_size
@@ -336,10 +349,15 @@ def bench_config4(rank, world, local, small=False, steps=10, warmup=3, modes=("e
     for mode in modes:
         r = StripRank(make(), rank, world, "exchange" if mode == "p2p" else mode)
         pano = torch.zeros((oh, ow, 3), dtype=torch.uint8, device=dev)
+        # the rank holds only the cameras its window meets (pano_strip_cameras); the others are noise it must never read
+        need = r.cameras()
+        frames = torch.full_like(frames_all, 0x5a)
+        for i in need:
+            frames[i] = frames_all[i]
         if mode in ("hybrid", "redundant"):
             side = torch.cuda.Stream(dev)            # a capturable stream: phase ranges are replayed as CUDA graphs
 
-            def run(bufs=None, r=r, pano=pano, side=side, mode=mode):
+            def run(bufs=None, r=r, pano=pano, side=side, mode=mode, frames=frames):
                 side.wait_stream(torch.cuda.current_stream(dev))
                 with torch.cuda.stream(side):        # NCCL's all-gather follows torch's current stream
                     if mode == "hybrid":
@@ -353,12 +371,12 @@ def bench_config4(rank, world, local, small=False, steps=10, warmup=3, modes=("e
             p2p_setup_distributed(r)
             side = torch.cuda.Stream(dev)            # a capturable stream: the frame is replayed as a CUDA graph
 
-            def run(bufs=None, r=r, pano=pano, side=side):
+            def run(bufs=None, r=r, pano=pano, side=side, frames=frames):
                 side.wait_stream(torch.cuda.current_stream(dev))
                 compose_p2p(r, frames, pano, side.cuda_stream)
                 torch.cuda.current_stream(dev).wait_stream(side)
         else:
-            def run(bufs=None, r=r, pano=pano):
+            def run(bufs=None, r=r, pano=pano, frames=frames):
                 return compose_nccl(r, frames, pano, bufs)
         bufs = run()
         torch.cuda.synchronize()
@@ -376,9 +394,10 @@ def bench_config4(rank, world, local, small=False, steps=10, warmup=3, modes=("e
         dist.barrier()
         if mode == "p2p":
             ok = ok and r.lib.pano_strip_p2p_check(r.h) == 0
-        tt = torch.tensor([e0.elapsed_time(e1) / steps, 0.0 if ok else 1.0], dtype=torch.float64, device=dev)
+        tt = torch.tensor([e0.elapsed_time(e1) / steps, 0.0 if ok else 1.0, float(len(need))], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         res[mode] = {"ms_per_panorama": float(tt[0]), "all_ranks_match_undivided": bool(tt[1] == 0.0),
+                     "cameras_held_per_rank_max": int(tt[2]),
                      "halo_bytes_per_rank_side": int(sum(r.halo_bytes(p) for p in range(r.phases)))}
         if mode == "hybrid":
             L = r.split

@@ -138,6 +138,9 @@ int pano_process_batch(pano_handle h, const uint8_t *frames_host, uint8_t *out_h
  * side: 0 = left neighbour, 1 = right neighbour.  One frame-set per call sequence. */
 int pano_strip_set_window(pano_handle h, int x0, int x1, int margin);
 int pano_strip_phase_count(pano_handle h);
+/* needed[i] = 1 when camera i's warped ROI meets the window set by pano_strip_set_window*: the frames of the other cameras
+ * are never read by this rank (their part of `frames_dev` may hold anything), so a rank uploads only the cameras it needs. */
+int pano_strip_cameras(pano_handle h, int *needed);
 int pano_strip_run_phase(pano_handle h, int phase, const uint8_t *frames_dev, uint8_t *pano_dev, void *stream);
 size_t pano_strip_halo_bytes(pano_handle h, int phase);
 int pano_strip_halo_pack(pano_handle h, int phase, int side, void *buf_dev, void *stream);

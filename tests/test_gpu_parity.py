@@ -603,6 +603,45 @@ def test_strip_split_hybrid_equals_single_gpu(nranks, split):
     assert_equal("hybrid strip split %d ranks, split level %d" % (nranks, split), got, want)
 
 
+@pytest.mark.parametrize("nranks,mode", [(4, "exchange"), (8, "redundant"), (8, "hybrid")])
+def test_strip_rank_reads_only_its_cameras(nranks, mode):
+    """pano_strip_cameras: a rank only needs the frames of the cameras whose warped ROI meets its window.  Every rank gets
+    its own frame buffer in which all OTHER cameras hold noise; the assembled panorama must still equal the undivided one,
+    and with 8 ranks no rank may need all 8 cameras of the ring."""
+    import torch
+    t, imgs, want, frames, ranks, panos = _strip_setup(nranks, mode)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    per_rank = []
+    for r in ranks:
+        need = r.cameras()
+        assert need and all(0 <= i < 8 for i in need)
+        if nranks == 8:
+            assert len(need) < 8, "rank %d claims every camera: %r" % (r.rank, need)
+        fr = torch.randint(0, 256, frames.shape, dtype=torch.uint8, device="cuda", generator=g)
+        for i in need:
+            fr[i] = frames[i]
+        per_rank.append(fr)
+    if mode == "hybrid":
+        panob200.strips.compose_hybrid_local(ranks, per_rank, panos)
+    else:
+        panob200.strips.compose_local(ranks, per_rank, panos)
+    torch.cuda.synchronize()
+    got = panob200.strips.assemble(ranks, panos).cpu().numpy()
+    assert_equal("strip split with per-rank cameras %d/%s" % (nranks, mode), got, want)
+    # and the list is tight: noise in a NEEDED camera changes that rank's columns
+    r = ranks[nranks // 2]
+    bad = per_rank[r.rank].clone()
+    mid = r.cameras()[len(r.cameras()) // 2]
+    bad[mid] = 255 - bad[mid]
+    if mode == "redundant":
+        p2 = torch.zeros_like(panos[0])
+        for ph in range(r.phases):
+            r.run_phase(ph, bad, p2, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        c0, c1 = r.own_output_columns()
+        assert not torch.equal(p2[:, c0:c1], panos[r.rank][:, c0:c1])
+
+
 @pytest.mark.parametrize("nranks,concurrent", [(2, False), (4, False), (8, False)])
 def test_strip_split_peer_memory_exchange(nranks, concurrent):
     """Halo exchange through peer-memory mailboxes (push kernel stores into the neighbour's mailbox and raises a flag,
