@@ -19,6 +19,7 @@
 
 #include "../../include/panob200.h"
 #include "geometry.hpp"
+#include "pdl.h"
 #include "tma.h"
 
 using namespace pano;
@@ -102,6 +103,7 @@ __device__ __forceinline__ uint2 yuyv_pair(uint32_t w)      // bytes Y0 U Y1 V -
 __global__ void __launch_bounds__(256) yuyv_to_bgra_kernel(const uint4 *__restrict__ src, size_t src_img16, uint4 *__restrict__ dst,
                                                            size_t dst_img16, size_t n16)
 {
+    pdl_enter();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n16) return;
     const uint4 s = __ldg(src + (size_t)blockIdx.y * src_img16 + i);
@@ -343,6 +345,7 @@ __device__ __forceinline__ void cubic5_body(const CubicArgs &A, uint32_t *__rest
 template <bool kTma>
 __global__ void __launch_bounds__(256) cubic5_kernel(const __grid_constant__ CubicArgs A)
 {
+    pdl_enter();
     __shared__ __align__(128) uint32_t sm[kCubSmemWords];
     __shared__ __align__(8) uint64_t bar;
     cubic5_body<kTma>(A, sm, &bar, blockIdx.x, blockIdx.y, blockIdx.z);
@@ -520,6 +523,7 @@ __device__ __forceinline__ void resize4_walk_body(const ResizeArgs &A, uint32_t 
 template <bool kWords>
 __global__ void __launch_bounds__(128, 8) resize4_walk_kernel(const __grid_constant__ ResizeArgs A)
 {
+    pdl_enter();
     __shared__ uint32_t smem[kResizeSmemWords];
     resize4_walk_body<kWords>(A, smem, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.y);
 }
@@ -769,8 +773,8 @@ int pano_frontend_convert(pano_frontend_handle h, const uint8_t *yuyv, size_t in
     const pano_frontend_config &c = h->cfg;
     const size_t npx = (size_t)c.cam_src_width * c.cam_src_height, out_img = npx * 4;
     if (npx % 8 == 0 && in_img % 16 == 0 && (reinterpret_cast<uintptr_t>(yuyv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0)
-        yuyv_to_bgra_kernel<<<dim3((unsigned)((npx / 8 + 255) / 256), count), 256, 0, st>>>(
-            reinterpret_cast<const uint4 *>(yuyv), in_img / 16, reinterpret_cast<uint4 *>(dst), out_img / 16, npx / 8);
+        launch_chain(yuyv_to_bgra_kernel, dim3((unsigned)((npx / 8 + 255) / 256), count), dim3(256), st,
+                     reinterpret_cast<const uint4 *>(yuyv), in_img / 16, reinterpret_cast<uint4 *>(dst), out_img / 16, npx / 8);
     else
         yuyv_to_bgra_pair_kernel<<<dim3((unsigned)((npx / 2 + 255) / 256), count), 256, 0, st>>>(yuyv, in_img, dst, out_img, npx / 2);
     FCK(h, cudaGetLastError());
@@ -842,9 +846,9 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
                           (uw + 127) / 128, (rc[3] + 1 + kResizeBand - 1) / kResizeBand};
             if (h->prof_ev) cudaEventRecord(h->prof_ev[0], st);
             if (tma)
-                cubic5_kernel<true><<<dim3(h->cub_tx, h->cub_ty, nb), blk, 0, st>>>(ca);
+                launch_chain(cubic5_kernel<true>, dim3(h->cub_tx, h->cub_ty, nb), blk, st, ca);
             else if (tiled)
-                cubic5_kernel<false><<<dim3(h->cub_tx, h->cub_ty, nb), blk, 0, st>>>(ca);
+                launch_chain(cubic5_kernel<false>, dim3(h->cub_tx, h->cub_ty, nb), blk, st, ca);
             else if (h->dmap32 && tex_w)
                 cubic4_kernel<true, true><<<cg, blk, 0, st>>>(src4, img_stride / 4, cw, chh, h->dmap32, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
             else if (h->dmap32)
@@ -853,9 +857,9 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
                 cubic4_kernel<false, false><<<cg, blk, 0, st>>>(src4, img_stride / 4, cw, chh, h->dmap, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
             if (h->prof_ev) cudaEventRecord(h->prof_ev[1], st);
             if (walk && out_px == 4)
-                resize4_walk_kernel<true><<<dim3(ra.gx, ra.gy, nb), dim3(32, 4), 0, st>>>(ra);
+                launch_chain(resize4_walk_kernel<true>, dim3(ra.gx, ra.gy, nb), dim3(32, 4), st, ra);
             else if (walk)
-                resize4_walk_kernel<false><<<dim3(ra.gx, ra.gy, nb), dim3(32, 4), 0, st>>>(ra);
+                launch_chain(resize4_walk_kernel<false>, dim3(ra.gx, ra.gy, nb), dim3(32, 4), st, ra);
             else
                 resize4_kernel<<<dim3((uw + 127) / 128, (uh + 7) / 8, nb), blk, 0, st>>>(h->buf_w, w_img, rc[2], final_dst, o_img,
                                                                                          uw * 3, h->r_mid);

@@ -13,6 +13,7 @@
 #include <cstdlib>
 
 #include "pano_dev.h"
+#include "pdl.h"
 #include "tma.h"
 
 namespace pano {
@@ -96,6 +97,7 @@ __device__ __forceinline__ int apply_gain_map(int v, float g)
 template <bool kMap64>
 __global__ void __launch_bounds__(256) warp_kernel(const PanoTables *__restrict__ T, const uint8_t *__restrict__ frames)
 {
+    pdl_enter();
     const int ncam = T->num_cams;
     const int cam = blockIdx.z % ncam, slot = blockIdx.z / ncam;
     const CamTables &C = T->cam[cam];
@@ -202,6 +204,7 @@ __device__ __forceinline__ void pyrdown_item(const PanoTables *__restrict__ T, i
 
 __global__ void __launch_bounds__(256) pyrdown_kernel(const PanoTables *__restrict__ T, int level)
 {
+    pdl_enter();
     const int ncam = T->num_cams;
     int z = blockIdx.z;
     const int plane = z % 3; z /= 3;
@@ -278,6 +281,7 @@ __device__ __forceinline__ void coarsest_item(const PanoTables *__restrict__ T, 
 
 __global__ void __launch_bounds__(256) coarsest_kernel(const PanoTables *__restrict__ T, uint8_t *__restrict__ pano)
 {
+    pdl_enter();
     if (outside_window(T, T->nb, blockIdx.x * blockDim.x, (blockIdx.x + 1) * blockDim.x)) return;
     coarsest_item(T, pano, blockIdx.z, blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y * blockDim.y + threadIdx.y);
 }
@@ -371,6 +375,7 @@ __device__ __forceinline__ void collapse_item(const PanoTables *__restrict__ T, 
 
 __global__ void __launch_bounds__(256) collapse_kernel(const PanoTables *__restrict__ T, int L, uint8_t *__restrict__ pano)
 {
+    pdl_enter();
     if (outside_window(T, L, 2 * blockIdx.x * blockDim.x, 2 * (blockIdx.x + 1) * blockDim.x)) return;
     collapse_item(T, L, pano, blockIdx.z, blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y * blockDim.y + threadIdx.y);
 }
@@ -429,6 +434,7 @@ __device__ __forceinline__ void down_hfilter(const DownRow &d, int h[8])
 template <int kMinBlocks>
 __global__ void __launch_bounds__(128, kMinBlocks) pyrdown8_walk_kernel(const PanoTables *__restrict__ T, int level, int band)
 {
+    pdl_enter();
     const int ncam = T->num_cams;
     int z = blockIdx.z;
     const int plane = z % 3; z /= 3;
@@ -635,6 +641,7 @@ struct C8Args {
 template <bool kLevel0>
 __global__ void __launch_bounds__(384, 2) collapse8_kernel(const __grid_constant__ C8Args A, uint8_t *__restrict__ pano)
 {
+    pdl_enter();
     __shared__ __align__(16) uint8_t tile[kWalkTileH][kWalkTileW * 3];
     // block = one kWalkTileW x kWalkTileH tile of the work list: threadIdx.z = plane, a warp = kWalkTileW pixels x 32 / kWalkLanesX row pairs
     const int plane = threadIdx.z;
@@ -913,6 +920,7 @@ __device__ __forceinline__ void walk_column(const C8Args &A, int cam, int X0, in
 template <bool kLevel0, int kMinBlocks>
 __global__ void __launch_bounds__(96, kMinBlocks) collapse_walk_kernel(const __grid_constant__ C8Args A, uint8_t *__restrict__ pano)
 {
+    pdl_enter();
     // [plane][band][2R rows][W/4 words] + kPad words per band, so that the bands of a half-warp store to different banks
     constexpr int kRowW = kWalkTileW / 4, kBands = 32 / kWalkLanesX, kPad = kRowW, kBandW = 2 * kWalkR * kRowW + kPad;
     __shared__ __align__(16) uint32_t sm[kLevel0 ? 3 * kBands * kBandW : 4];
@@ -1100,6 +1108,7 @@ __device__ __forceinline__ void warp_gather(const WarpCam &C, const uint32_t *__
 template <bool kMap64, int kGain, bool kSrc4, bool kTma, int kMinBlocks = (kTma ? 6 : 5)>
 __global__ void __launch_bounds__(256, kMinBlocks) warp_tile_kernel(const __grid_constant__ WarpArgs A, const uint8_t *__restrict__ frames)
 {
+    pdl_enter();
     __shared__ __align__(128) uint32_t sm[kWarpSmemWords + 4];             // + slack: the packed gather's third word of a row may lie one past the box
     __shared__ __align__(16) uint32_t so[3 * kWarpTileH * 32];             // [plane][row][lane]: packed column groups
     __shared__ __align__(8) uint64_t bar;
@@ -1253,6 +1262,7 @@ template <bool kMap64>
 __global__ void __launch_bounds__(256) direct_blend_kernel(const PanoTables *__restrict__ T, int blender,
                                                            const uint8_t *__restrict__ frames, uint8_t *__restrict__ pano)
 {
+    pdl_enter();
     const int cx = blockIdx.x * blockDim.x + threadIdx.x, cy = blockIdx.y * blockDim.y + threadIdx.y;
     const int slot = blockIdx.z;
     if (cx >= T->cut_w || cy >= T->cut_h) return;
@@ -1313,6 +1323,7 @@ __global__ void __launch_bounds__(256) direct_blend_kernel(const PanoTables *__r
 template <bool kFeather>
 __global__ void __launch_bounds__(256) blend_g0_kernel(const PanoTables *__restrict__ T, uint8_t *__restrict__ pano)
 {
+    pdl_enter();
     const int cx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, cy = blockIdx.y * blockDim.y + threadIdx.y;
     const int slot = blockIdx.z;
     if (cx0 >= T->cut_w || cy >= T->cut_h) return;
@@ -1718,7 +1729,7 @@ void launch_warp(const PanoTables *dev, const PanoTables &host, const KernelChoi
                 tma = tma_encode_words3d(&A.tm[i], frames, host.src_w * 3 / 4, host.src_h, nslots * host.num_cams, (size_t)host.src_w * 3,
                                          (size_t)host.src_w * host.src_h * 3, kWarpPackW0 + kWarpPackStep * i, kWarpBoxH);
         }
-#define PANO_WARP_LAUNCH(M, G, S, T) warp_tile_kernel<M, G, S, T><<<grid, block, 0, stream>>>(A, frames)
+#define PANO_WARP_LAUNCH(M, G, S, T) launch_chain(warp_tile_kernel<M, G, S, T>, grid, block, stream, A, frames)
 #define PANO_WARP_PICK_S(M, G) (s4 ? (tma ? PANO_WARP_LAUNCH(M, G, true, true) : PANO_WARP_LAUNCH(M, G, true, false)) \
                                    : (tma ? PANO_WARP_LAUNCH(M, G, false, true) : PANO_WARP_LAUNCH(M, G, false, false)))
 #define PANO_WARP_PICK_G(M) (gv == 0 ? PANO_WARP_PICK_S(M, 0) : (gv == 1 ? PANO_WARP_PICK_S(M, 1) : PANO_WARP_PICK_S(M, 2)))
@@ -1735,8 +1746,8 @@ void launch_warp(const PanoTables *dev, const PanoTables &host, const KernelChoi
     }
     const dim3 block(32, 8);
     const dim3 grid = grid2d((maxw + 3) / 4, maxh, block, host.num_cams * nslots);
-    if (host.cam[0].map64) warp_kernel<true><<<grid, block, 0, stream>>>(dev, frames);
-    else warp_kernel<false><<<grid, block, 0, stream>>>(dev, frames);
+    if (host.cam[0].map64) launch_chain(warp_kernel<true>, grid, block, stream, dev, frames);
+    else launch_chain(warp_kernel<false>, grid, block, stream, dev, frames);
 }
 
 void launch_pyrdown(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, int level, int nslots,
@@ -1756,20 +1767,20 @@ void launch_pyrdown(const PanoTables *dev, const PanoTables &host, const KernelC
         const int band = band_env > 0 ? band_env : (maxh >= 400 ? 32 : 16);
         const dim3 wb(32, 4), wg((maxw + 255) / 256, (maxh + 4 * band - 1) / (4 * band), host.num_cams * nslots * 3);
         static const int occ = getenv("PANO_DOWN_OCC") ? atoi(getenv("PANO_DOWN_OCC")) : 0;      // tuning knob: min blocks per SM (0 = compiler's choice)
-        if (occ >= 8) pyrdown8_walk_kernel<8><<<wg, wb, 0, stream>>>(dev, level, band);
-        else if (occ >= 6) pyrdown8_walk_kernel<6><<<wg, wb, 0, stream>>>(dev, level, band);
-        else pyrdown8_walk_kernel<0><<<wg, wb, 0, stream>>>(dev, level, band);
+        if (occ >= 8) launch_chain(pyrdown8_walk_kernel<8>, wg, wb, stream, dev, level, band);
+        else if (occ >= 6) launch_chain(pyrdown8_walk_kernel<6>, wg, wb, stream, dev, level, band);
+        else launch_chain(pyrdown8_walk_kernel<0>, wg, wb, stream, dev, level, band);
         return;
     }
     const dim3 grid = grid2d((maxw + 3) / 4, (maxh + 1) / 2, block, host.num_cams * nslots * 3);
-    pyrdown_kernel<<<grid, block, 0, stream>>>(dev, level);
+    launch_chain(pyrdown_kernel, grid, block, stream, dev, level);
 }
 
 void launch_coarsest(const PanoTables *dev, const PanoTables &host, uint8_t *pano, int nslots, cudaStream_t stream)
 {
     const dim3 block(32, 8);
     const dim3 grid = grid2d(host.pad_w >> host.nb, host.pad_h >> host.nb, block, nslots);
-    coarsest_kernel<<<grid, block, 0, stream>>>(dev, pano);
+    launch_chain(coarsest_kernel, grid, block, stream, dev, pano);
 }
 
 int launch_collapse(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, int level, uint8_t *pano,
@@ -1806,28 +1817,28 @@ int launch_collapse(const PanoTables *dev, const PanoTables &host, const KernelC
             static const int occ_env = getenv("PANO_WALK_OCC") ? atoi(getenv("PANO_WALK_OCC")) : -1;
             const int occ = occ_env >= 0 ? occ_env : (level == 0 ? 8 : 0);
             if (level == 0) {
-                if (occ >= 10) collapse_walk_kernel<true, 10><<<wg, wb, 0, stream>>>(A, pano);
-                else if (occ >= 8) collapse_walk_kernel<true, 8><<<wg, wb, 0, stream>>>(A, pano);
-                else collapse_walk_kernel<true, 0><<<wg, wb, 0, stream>>>(A, pano);
+                if (occ >= 10) launch_chain(collapse_walk_kernel<true, 10>, wg, wb, stream, A, pano);
+                else if (occ >= 8) launch_chain(collapse_walk_kernel<true, 8>, wg, wb, stream, A, pano);
+                else launch_chain(collapse_walk_kernel<true, 0>, wg, wb, stream, A, pano);
             } else {
-                if (occ >= 10) collapse_walk_kernel<false, 10><<<wg, wb, 0, stream>>>(A, pano);
-                else if (occ >= 8) collapse_walk_kernel<false, 8><<<wg, wb, 0, stream>>>(A, pano);
-                else collapse_walk_kernel<false, 0><<<wg, wb, 0, stream>>>(A, pano);
+                if (occ >= 10) launch_chain(collapse_walk_kernel<false, 10>, wg, wb, stream, A, pano);
+                else if (occ >= 8) launch_chain(collapse_walk_kernel<false, 8>, wg, wb, stream, A, pano);
+                else launch_chain(collapse_walk_kernel<false, 0>, wg, wb, stream, A, pano);
             }
             ++launches;
         }
         if (host.gen_n[L] > 0) {
             A.list = host.gen_list[L];
             const dim3 block(32, 4, 3), grid(host.gen_n[L], nslots);
-            if (level == 0) collapse8_kernel<true><<<grid, block, 0, stream>>>(A, pano);
-            else collapse8_kernel<false><<<grid, block, 0, stream>>>(A, pano);
+            if (level == 0) launch_chain(collapse8_kernel<true>, grid, block, stream, A, pano);
+            else launch_chain(collapse8_kernel<false>, grid, block, stream, A, pano);
             ++launches;
         }
         return launches;
     }
     const dim3 block(32, 8);
     const dim3 grid = grid2d(host.pad_w >> (level + 1), host.pad_h >> (level + 1), block, nslots);
-    collapse_kernel<<<grid, block, 0, stream>>>(dev, level, pano);
+    launch_chain(collapse_kernel, grid, block, stream, dev, level, pano);
     return 1;
 }
 
@@ -1933,8 +1944,8 @@ void launch_blend_g0(const PanoTables *dev, const PanoTables &host, int blender,
 {
     const dim3 block(32, 8);
     const dim3 grid = grid2d((host.cut_w + 3) / 4, host.cut_h, block, nslots);
-    if (blender == 1) blend_g0_kernel<true><<<grid, block, 0, stream>>>(dev, pano);
-    else blend_g0_kernel<false><<<grid, block, 0, stream>>>(dev, pano);
+    if (blender == 1) launch_chain(blend_g0_kernel<true>, grid, block, stream, dev, pano);
+    else launch_chain(blend_g0_kernel<false>, grid, block, stream, dev, pano);
 }
 
 void launch_direct_blend(const PanoTables *dev, const PanoTables &host, int blender, const uint8_t *frames,
@@ -1942,8 +1953,8 @@ void launch_direct_blend(const PanoTables *dev, const PanoTables &host, int blen
 {
     const dim3 block(32, 8);
     const dim3 grid = grid2d(host.cut_w, host.cut_h, block, nslots);
-    if (host.cam[0].map64) direct_blend_kernel<true><<<grid, block, 0, stream>>>(dev, blender, frames, pano);
-    else direct_blend_kernel<false><<<grid, block, 0, stream>>>(dev, blender, frames, pano);
+    if (host.cam[0].map64) launch_chain(direct_blend_kernel<true>, grid, block, stream, dev, blender, frames, pano);
+    else launch_chain(direct_blend_kernel<false>, grid, block, stream, dev, blender, frames, pano);
 }
 
 }  // namespace pano

@@ -152,7 +152,7 @@ def compose_hybrid_local(ranks, frames, panos):
     n = [(x1 >> L) - (x0 >> L) for x0, x1 in ranks[0].strips]
     cmax = max(n)
     nbytes = int(ranks[0].lib.pano_strip_level_bytes(ranks[0].h, L, cmax))
-    recv = torch.empty(nbytes * world, dtype=torch.uint8, device=frames.device)
+    recv = torch.empty(nbytes * world, dtype=torch.uint8, device=device)
     per_rank = list(frames) if isinstance(frames, (list, tuple)) else [frames] * world      # each rank may hold its own cameras only
     for r, pano in zip(ranks, panos):
         capi.check(r.lib.pano_strip_run_phases(r.h, 0, L, capi.ptr(per_rank[r.rank]), capi.ptr(pano), C.c_void_p(stream)), r.h)
