@@ -246,16 +246,39 @@ FeedRect multibandFeedRect(const Rect &roi, int pw, int ph, int nb, const Rect &
 
 // ------------------------------------------------------------------------- weights
 
+// cv::pyrDown on CV_32F with the evaluation order of OpenCV 4.x's universal-intrinsics build with 4-lane float vectors
+// (x86-64 SSE baseline, NEON): modules/imgproc/src/pyramids.cpp evaluates the SAME 1-4-6-4-1 sums in two different
+// orders depending on the column -- the vector bodies (PyrDownVecH / PyrDownVecV: c*6 + ((b+d)*4 + (a+e)) and
+// (r1+r3+r2)*4 + (r0+r4+(r2+r2))) and the scalar loops around them (c*6 + (b+d)*4 + a + e, left to right) -- and
+// float addition is not associative, so bit-exact weights need the column rule as well:
+//   horizontal: dst column 0 and every column from hv_end on are scalar (left border, vector tail, right border), the
+//               vector body runs in groups of 4 from column 1 while a whole group fits below
+//               width0 = min((sw - 3) / 2 + 1, dw);
+//   vertical:   groups of 4 from column 0 while a whole group fits below dw, scalar tail.
+// Pinned against cv2 4.13 over all sizes from 1 x 1 to 48 x 48 and the bench shapes (tests/test_host_tables.py).
+void pyrDownColumnRule(int sw, int *hv_end, int *vv_end)
+{
+    const int dw = (sw + 1) / 2;
+    const int width0 = std::min((sw - 3) / 2 + 1, dw);
+    const int groups = width0 >= 5 ? (width0 - 5) / 4 + 1 : 0;
+    *hv_end = 1 + 4 * groups;
+    *vv_end = dw & ~3;
+}
+
 void pyrDownF32(const float *src, int sw, int sh, float *dst)
 {
     const int dw = (sw + 1) / 2, dh = (sh + 1) / 2;
+    int hv_end, vv_end;
+    pyrDownColumnRule(sw, &hv_end, &vv_end);
     std::vector<float> hrow(static_cast<size_t>(dw) * sh);
     for (int y = 0; y < sh; ++y) {
         const float *s = src + static_cast<size_t>(y) * sw;
         for (int x = 0; x < dw; ++x) {
             const float a = s[reflect101(2 * x - 2, sw)], b = s[reflect101(2 * x - 1, sw)], c = s[2 * x],
                         d = s[reflect101(2 * x + 1, sw)], e = s[reflect101(2 * x + 2, sw)];
-            hrow[static_cast<size_t>(y) * dw + x] = c * 6 + (b + d) * 4 + a + e;
+            float &h = hrow[static_cast<size_t>(y) * dw + x];
+            if (x >= 1 && x < hv_end) h = c * 6 + ((b + d) * 4 + (a + e));
+            else h = c * 6 + (b + d) * 4 + a + e;
         }
     }
     for (int y = 0; y < dh; ++y) {
@@ -264,8 +287,11 @@ void pyrDownF32(const float *src, int sw, int sh, float *dst)
         const float *r2 = &hrow[static_cast<size_t>(2 * y) * dw];
         const float *r3 = &hrow[static_cast<size_t>(reflect101(2 * y + 1, sh)) * dw];
         const float *r4 = &hrow[static_cast<size_t>(reflect101(2 * y + 2, sh)) * dw];
-        for (int x = 0; x < dw; ++x)
-            dst[static_cast<size_t>(y) * dw + x] = (r2[x] * 6 + (r1[x] + r3[x]) * 4 + r0[x] + r4[x]) * (1.f / 256.f);
+        float *o = dst + static_cast<size_t>(y) * dw;
+        for (int x = 0; x < dw; ++x) {
+            if (x < vv_end) o[x] = ((r1[x] + r3[x] + r2[x]) * 4 + (r0[x] + r4[x] + (r2[x] + r2[x]))) * (1.f / 256.f);
+            else o[x] = (r2[x] * 6 + (r1[x] + r3[x]) * 4 + r0[x] + r4[x]) * (1.f / 256.f);
+        }
     }
 }
 

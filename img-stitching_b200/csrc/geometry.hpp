@@ -52,7 +52,10 @@ int multibandPrepare(const Rect &dst_roi, int num_bands, int &padded_w, int &pad
 FeedRect multibandFeedRect(const Rect &dst_roi, int padded_w, int padded_h, int nb, const Rect &img_roi);
 
 // ---- weights ----------------------------------------------------------------------------
-// cv::pyrDown on CV_32F (plain evaluation order; cv2's SIMD build may differ by 1 ulp)
+// cv::pyrDown on CV_32F, bit-exact with OpenCV 4.x's 4-lane universal-intrinsics build: the vector bodies and the
+// scalar border / tail loops of pyramids.cpp sum in different orders, pyrDownColumnRule says which columns get which
+// (horizontal pass: vector order for 1 <= x < hv_end; vertical pass: vector order for x < vv_end)
+void pyrDownColumnRule(int sw, int *hv_end, int *vv_end);
 void pyrDownF32(const float *src, int sw, int sh, float *dst);
 // cv::distanceTransform(mask, DIST_L1, 3) followed by min(d*sharpness, 1)
 void featherWeight(const uint8_t *mask, int w, int h, int stride, float sharpness, float *out);

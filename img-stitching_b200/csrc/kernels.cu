@@ -1554,8 +1554,9 @@ __global__ void __launch_bounds__(256) halo_exchange_kernel(const PanoTables *__
 // MultiBandBlender::feed's weight pyramid -- convertTo(CV_32F, 1/255) + cv::pyrDown chain on CV_32F -- which the
 // reference recomputes for every frame although it only depends on the masks (ocvstitcher.hpp:1202).  Here it is
 // rebuilt whenever a mask changes (pano_set_mask: initSeam :1101, updateMask :1257).  The evaluation order is
-// exactly that of pano::pyrDownF32 (geometry.cpp) -- explicit round-to-nearest operations, no contraction -- so
-// the device and the host builder agree bit for bit.  One thread = one output weight.
+// exactly that of pano::pyrDownF32 (geometry.cpp), i.e. of OpenCV's pyramids.cpp including its per-column choice between
+// the vector-body order and the scalar border / tail order (pyrDownColumnRule) -- explicit round-to-nearest operations,
+// no contraction -- so the device, the host builder and cv2 agree bit for bit.  One thread = one output weight.
 template <bool kFromMask>
 __global__ void __launch_bounds__(256) weight_pyrdown_kernel(const void *__restrict__ src, int spitch, int sw, int sh,
                                                              float *__restrict__ dst, int dpitch)
@@ -1563,6 +1564,10 @@ __global__ void __launch_bounds__(256) weight_pyrdown_kernel(const void *__restr
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     const int dw = (sw + 1) / 2, dh = (sh + 1) / 2;
     if (x >= dw || y >= dh) return;
+    // pyrDownColumnRule (geometry.cpp): which summation order OpenCV uses in this column
+    const int width0 = min((sw - 3) / 2 + 1, dw);
+    const int hv_end = 1 + 4 * (width0 >= 5 ? (width0 - 5) / 4 + 1 : 0);
+    const bool h_vec = x >= 1 && x < hv_end, v_vec = x < (dw & ~3);
     int cx[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) cx[k] = reflect101(2 * x - 2 + k, sw);
@@ -1576,9 +1581,12 @@ __global__ void __launch_bounds__(256) weight_pyrdown_kernel(const void *__restr
             if (kFromMask) v[k] = __fmul_rn((float)__ldg(static_cast<const uint8_t *>(src) + row + cx[k]), 1.f / 255.f);
             else v[k] = __ldg(static_cast<const float *>(src) + row + cx[k]);
         }
-        hv[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v[2], 6.f), __fmul_rn(__fadd_rn(v[1], v[3]), 4.f)), v[0]), v[4]);
+        if (h_vec) hv[r] = __fadd_rn(__fmul_rn(v[2], 6.f), __fadd_rn(__fmul_rn(__fadd_rn(v[1], v[3]), 4.f), __fadd_rn(v[0], v[4])));
+        else hv[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v[2], 6.f), __fmul_rn(__fadd_rn(v[1], v[3]), 4.f)), v[0]), v[4]);
     }
-    const float o = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(hv[2], 6.f), __fmul_rn(__fadd_rn(hv[1], hv[3]), 4.f)), hv[0]), hv[4]);
+    float o;
+    if (v_vec) o = __fadd_rn(__fmul_rn(__fadd_rn(__fadd_rn(hv[1], hv[3]), hv[2]), 4.f), __fadd_rn(__fadd_rn(hv[0], hv[4]), __fadd_rn(hv[2], hv[2])));
+    else o = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(hv[2], 6.f), __fmul_rn(__fadd_rn(hv[1], hv[3]), 4.f)), hv[0]), hv[4]);
     dst[(size_t)y * dpitch + x] = __fmul_rn(o, 1.f / 256.f);
 }
 

@@ -47,7 +47,8 @@ class StitcherConfig:
     num_bands: Optional[int] = None          # pin the band count (BASELINE config 1 pins 5)
     sharpness: Optional[float] = None        # feather; None -> 1/blend_width (stitching_detailed.cpp:868)
     seam: str = "gc_color"                   # 'gc_color' (:1033) | 'no' (:1034)
-    exact_weights: bool = True               # upload cv2-built float weight pyramids (bit-exact parity)
+    exact_weights: bool = False              # True: upload cv2-built float weight tables over the device-built ones (cross-check
+                                             # only: the device builders are bit-exact with cv2 4.x, tests/test_gpu_parity.py)
     device: int = 0
     max_batch: int = 1
 

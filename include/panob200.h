@@ -92,8 +92,9 @@ int pano_set_seam_mask(pano_handle h, int cam, const uint8_t *seam, int width, i
 /* m_blenderMask[cam] as the handle currently holds it (sizes[cam] large) */
 int pano_get_mask(pano_handle h, int cam, uint8_t *mask, int stride);
 /* Optional: override the float weight pyramid level the library derives from the mask
- * (MultiBandBlender::feed builds it with cv::pyrDown on CV_32F, which is only ~1-ulp
- * reproducible outside OpenCV).  level in [0, num_bands]; size = feed rect >> level. */
+ * (MultiBandBlender::feed builds it with cv::pyrDown on CV_32F; the library's own builder follows
+ * OpenCV 4.x's per-column summation order and is bit-exact with it, so this is only needed for
+ * tables that come from elsewhere).  level in [0, num_bands]; size = feed rect >> level. */
 int pano_set_weight_level(pano_handle h, int cam, int level, const float *w, int width, int height);
 /* The weight level the compose currently uses for camera `cam` (feed rect >> level large, float32): the library's
  * own pyramid (built on the device at every pano_set_mask) or the caller's override.  Multiband: level in

@@ -157,10 +157,14 @@ def test_undistort_maps_match_oracle():
 
 def test_float_pyrdown_and_feather_weight():
     rng = np.random.default_rng(3)
-    for w, h in [(64, 32), (33, 17), (5, 3), (1, 1), (128, 7)]:
+    for w, h in [(64, 32), (33, 17), (5, 3), (1, 1), (128, 7)] + [(w, 9) for w in range(1, 40)]:
         a = rng.random((h, w), np.float32)
         assert np.array_equal(capi.host_pyrdown_f32(a), orc.pyrdown_f32(a))
     cv2 = pytest.importorskip("cv2")
+    # ... and against cv2 itself (per-column summation order of pyramids.cpp, geometry.cpp pyrDownColumnRule)
+    for w, h in [(w, h) for w in range(1, 30) for h in (1, 2, 5, 8)] + [(1920, 1080), (5400, 968), (517, 301)]:
+        a = rng.integers(0, 256, (h, w)).astype(np.float32) * np.float32(1.0 / 255.0)
+        assert np.array_equal(capi.host_pyrdown_f32(a), cv2.pyrDown(a)), (w, h)
     m = np.zeros((90, 140), np.uint8)
     m[10:70, 20:120] = 255
     m[30:40, 50:60] = 0
