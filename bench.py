@@ -564,7 +564,9 @@ def time_latency(b, calls=200):
            "calls": calls, "pano_process_ms_p50": float(np.percentile(tq, 50)), "pano_process_ms_p99": float(np.percentile(tq, 99)),
            "pano_process_ms_min": float(tq.min()), "panoramas_per_s": float(1000.0 / tq.mean()), "host_buffers": "pinned",
            "pageable_host_buffers": {"pano_process_ms_p50": float(np.percentile(tp, 50)), "pano_process_ms_p99": float(np.percentile(tp, 99)),
-                                     "panoramas_per_s": float(1000.0 / tp.mean())},
+                                     "panoramas_per_s": float(1000.0 / tp.mean()),
+                                     "how": ("the CUDA driver's own staging of pageable memory (PANO_NO_HOST_STAGING=1)" if os.environ.get("PANO_NO_HOST_STAGING")
+                                             else "library worker threads -> pinned bounce buffers, chunked so that DMA overlaps the host copies")},
            "device_ms_per_frame_set": e0.elapsed_time(e1) / 50.0, "launches_per_call": launches,
            "h2d_bytes_per_call": int(fr[0].numel()), "d2h_bytes_per_call": int(ret.size)}
     return rec, ret

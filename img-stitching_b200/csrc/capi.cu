@@ -15,6 +15,7 @@
 
 #include "../../include/panob200.h"
 #include "geometry.hpp"
+#include "host_pool.hpp"
 #include "pano_dev.h"
 
 using namespace pano;
@@ -45,6 +46,8 @@ struct ProfEntry {
 constexpr int kPipeDepth = 4;
 
 }  // namespace
+
+constexpr int kBounceBands = 4;      // row bands of the panorama / chunks per camera frame on the pageable-buffer path
 
 struct pano_ctx {
     pano_config cfg{};
@@ -88,6 +91,11 @@ struct pano_ctx {
     std::vector<PhaseGraph> phase_graphs;
     cudaGraphExec_t graph1 = nullptr;             // pano_process: the kernel chain of ONE frame-set (stage_in[0] -> stage_out[0])
     int graph1_launches = 0;
+    // pano_process with PAGEABLE host buffers: pinned bounce buffers filled / drained by worker threads (host_pool.hpp)
+    HostPool *pool = nullptr;
+    uint8_t *pin_in = nullptr, *pin_out = nullptr;
+    size_t pin_in_bytes = 0, pin_out_bytes = 0;
+    cudaEvent_t ev_band[kBounceBands] = {};
     int strip_x0 = 0, strip_x1 = 0;               // own dst columns (level 0, padded coords); full width = no split
     // walker tiles (kWalkTileW x kWalkTileH): [level][cam][tile] -> any non-zero weight / count of weights == 1
     std::vector<std::vector<std::vector<uint8_t>>> walk_nz;
@@ -219,7 +227,7 @@ int uploadTileLists(pano_ctx *h)
         const bool walk_ok = (T.unit_norm_exact & 1) && !no_walk;
         const int wf = h->pad_w >> l, hf = h->pad_h >> l, wtx = walkTilesX(h, l), wty = walkTilesY(h, l);
         std::vector<uint32_t> walk, gen;
-        size_t n_unit = 0, n_empty = 0;
+        size_t n_unit = 0, n_empty = 0, n_gen_by_cams[4] = {0, 0, 0, 0};
         for (int ty = 0; ty < wty; ++ty) {
             if (l == 0 && (ty * kWalkTileH >= T.cut_y + T.cut_h || (ty + 1) * kWalkTileH <= T.cut_y)) continue;
             for (int tx = 0; tx < wtx; ++tx) {
@@ -234,7 +242,7 @@ int uploadTileLists(pano_ctx *h)
                 if (walk_ok && ncam == 0) { walk.push_back(pos | ((uint32_t)kWalkEmpty << 24)); ++n_empty; }
                 else if (walk_ok && ncam == 1 && h->walk_ones[l][cam][t] == npx &&
                          (l > 0 || T.cam[cam].use_wt0 || (T.unit_norm_exact & 2))) { walk.push_back(pos | ((uint32_t)(1 + cam) << 24)); ++n_unit; }
-                else gen.push_back(pos | (mask << 24));
+                else { gen.push_back(pos | (mask << 24)); ++n_gen_by_cams[std::min(ncam, 3)]; }
             }
         }
         if (!walk.empty()) CK(h, cudaMemcpy(h->d_walk_list[l], walk.data(), walk.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -242,8 +250,9 @@ int uploadTileLists(pano_ctx *h)
         T.walk_list[l] = h->d_walk_list[l]; T.walk_n[l] = (int)walk.size();
         T.gen_list[l] = h->d_gen_list[l]; T.gen_n[l] = (int)gen.size();
         if (getenv("PANO_DEBUG"))
-            fprintf(stderr, "[panob200] level %d: %dx%d tiles of %dx%d: unit-weight %zu, empty %zu, generic %zu\n", l, wtx, wty,
-                    kWalkTileW, kWalkTileH, n_unit, n_empty, gen.size());
+            fprintf(stderr, "[panob200] level %d: %dx%d tiles of %dx%d: unit-weight %zu, empty %zu, generic %zu (cameras with weight: "
+                            "0: %zu, 1: %zu, 2: %zu, 3+: %zu)\n", l, wtx, wty, kWalkTileW, kWalkTileH, n_unit, n_empty, gen.size(),
+                    n_gen_by_cams[0], n_gen_by_cams[1], n_gen_by_cams[2], n_gen_by_cams[3]);
     }
     return PANO_OK;
 }
@@ -911,6 +920,11 @@ int pano_destroy(pano_handle h)
     if (h->p2p_graph) cudaGraphExecDestroy(h->p2p_graph);
     if (h->graph1) cudaGraphExecDestroy(h->graph1);
     for (auto &g : h->phase_graphs) cudaGraphExecDestroy(g.exec);
+    if (h->pool) host_pool_destroy(h->pool);
+    if (h->pin_in) cudaFreeHost(h->pin_in);
+    if (h->pin_out) cudaFreeHost(h->pin_out);
+    for (auto &e : h->ev_band)
+        if (e) cudaEventDestroy(e);
     for (int s = 0; s < 2; ++s)
         if (h->peer_mail[s] && h->peer_ipc[s]) cudaIpcCloseMemHandle(h->peer_mail[s]);
     for (void *p : h->owned) cudaFree(p);
@@ -1242,6 +1256,41 @@ int pano_process_device(pano_handle h, const uint8_t *frames_dev, uint8_t *out_d
     return PANO_OK;
 }
 
+namespace {
+
+// host memory the CUDA driver can DMA from directly (cudaHostAlloc / cudaHostRegister / managed); anything else is pageable
+bool isPinned(const void *p)
+{
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return a.type != cudaMemoryTypeUnregistered;
+}
+
+int ensureBounce(pano_ctx *h, size_t in_bytes, size_t out_bytes)
+{
+    if (!h->pool) {
+        static const int nthreads = getenv("PANO_HOST_THREADS") ? std::max(1, atoi(getenv("PANO_HOST_THREADS"))) : 4;
+        h->pool = host_pool_create(nthreads);
+    }
+    if (in_bytes > h->pin_in_bytes) {
+        if (h->pin_in) cudaFreeHost(h->pin_in);
+        h->pin_in = nullptr; h->pin_in_bytes = 0;
+        CK(h, cudaHostAlloc((void **)&h->pin_in, in_bytes, cudaHostAllocDefault));
+        h->pin_in_bytes = in_bytes;
+    }
+    if (out_bytes > h->pin_out_bytes) {
+        if (h->pin_out) cudaFreeHost(h->pin_out);
+        h->pin_out = nullptr; h->pin_out_bytes = 0;
+        CK(h, cudaHostAlloc((void **)&h->pin_out, out_bytes, cudaHostAllocDefault));
+        h->pin_out_bytes = out_bytes;
+    }
+    for (auto &e : h->ev_band)
+        if (!e) CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return PANO_OK;
+}
+
+}  // namespace
+
 int pano_process(pano_handle h, const uint8_t *const *frames, const int *strides, uint8_t *out, int out_stride)
 {
     if (!h || !frames || !out) return fail(h, "pano_process: bad argument");
@@ -1255,11 +1304,43 @@ int pano_process(pano_handle h, const uint8_t *const *frames, const int *strides
         W3 = in_wh[0] * pano_frontend_in_px(h->front[0]); H = in_wh[1]; fbytes = h->in_frame_bytes;
     }
     if (out_stride < h->host.cut_w * 3) return fail(h, "pano_process: out_stride too small");
-    for (int i = 0; i < h->n; ++i) {
-        const int st = strides ? strides[i] : W3;
-        if (!frames[i] || st < W3) return fail(h, "pano_process: bad frame %d", i);
-        CK(h, cudaMemcpy2DAsync(h->stage_in[0] + (size_t)i * fbytes, W3, frames[i], st, W3, H,
-                                cudaMemcpyHostToDevice, h->s_compute));
+    for (int i = 0; i < h->n; ++i)
+        if (!frames[i] || (strides ? strides[i] : W3) < W3) return fail(h, "pano_process: bad frame %d", i);
+    // Pageable buffers (what the reference's cv::Mat frames are) must not reach the driver: its internal staging copy is
+    // single-threaded (~12 GB/s).  Worker threads move them through pinned bounce buffers chunk by chunk instead, each
+    // chunk's DMA starting as soon as it has landed (PANO_NO_HOST_STAGING=1: the driver's path, for A/B).
+    static const bool no_bounce = getenv("PANO_NO_HOST_STAGING") != nullptr;
+    bool pageable_in = false;
+    for (int i = 0; i < h->n && !no_bounce; ++i) pageable_in = pageable_in || !isPinned(frames[i]);
+    const bool pageable_out = !no_bounce && !isPinned(out);
+    const size_t out_row = (size_t)h->host.cut_w * 3;
+    if ((pageable_in || pageable_out) && ensureBounce(h, fbytes * h->n, out_row * h->host.cut_h)) return PANO_ERR;
+    if (pageable_in) {
+        static const bool stream_in = getenv("PANO_HOST_NO_STREAM") == nullptr;      // A/B: plain memcpy into the bounce buffer
+        int ticket[kMaxCams][kBounceBands];
+        const int band = (H + kBounceBands - 1) / kBounceBands;
+        for (int i = 0; i < h->n; ++i)
+            for (int k = 0; k < kBounceBands; ++k) {
+                const int r0 = std::min(H, k * band), nr = std::min(H, r0 + band) - r0;
+                const int st = strides ? strides[i] : W3;
+                ticket[i][k] = host_pool_copy2d(h->pool, h->pin_in + (size_t)i * fbytes + (size_t)r0 * W3, W3,
+                                                frames[i] + (size_t)r0 * st, st, W3, nr, stream_in);
+            }
+        cudaError_t e = cudaSuccess;
+        for (int i = 0; i < h->n; ++i)
+            for (int k = 0; k < kBounceBands; ++k) {
+                host_pool_wait(h->pool, ticket[i][k]);
+                const int r0 = std::min(H, k * band), nr = std::min(H, r0 + band) - r0;
+                const size_t off = (size_t)i * fbytes + (size_t)r0 * W3;
+                if (e == cudaSuccess && nr > 0)
+                    e = cudaMemcpyAsync(h->stage_in[0] + off, h->pin_in + off, (size_t)nr * W3, cudaMemcpyHostToDevice, h->s_compute);
+            }
+        host_pool_wait_all(h->pool);
+        CK(h, e);
+    } else {
+        for (int i = 0; i < h->n; ++i)
+            CK(h, cudaMemcpy2DAsync(h->stage_in[0] + (size_t)i * fbytes, W3, frames[i], strides ? strides[i] : W3, W3, H,
+                                    cudaMemcpyHostToDevice, h->s_compute));
     }
     if (h->profiling) clearProf(h);
     // The drop-in call (one frame-set per process(), src/replay.cpp:284-292): the ~20 launches of the kernel chain are
@@ -1288,8 +1369,30 @@ int pano_process(pano_handle h, const uint8_t *const *frames, const int *strides
         CK(h, cudaGraphLaunch(h->graph1, h->s_compute));
         h->last_launches = h->graph1_launches;
     }
-    CK(h, cudaMemcpy2DAsync(out, out_stride, h->stage_out[0], (size_t)h->host.cut_w * 3, (size_t)h->host.cut_w * 3,
-                            h->host.cut_h, cudaMemcpyDeviceToHost, h->s_compute));
+    if (pageable_out) {
+        // the panorama comes back in row bands: band k is copied out of the pinned buffer by a worker while band k + 1 is in flight
+        static const bool stream_out = getenv("PANO_HOST_STREAM_OUT") != nullptr;     // A/B: streaming stores into the caller's panorama
+        const int rows = h->host.cut_h, band = (rows + kBounceBands - 1) / kBounceBands;
+        cudaError_t e = cudaSuccess;
+        for (int k = 0; k < kBounceBands && e == cudaSuccess; ++k) {
+            const int r0 = std::min(rows, k * band), nr = std::min(rows, r0 + band) - r0;
+            if (nr > 0) e = cudaMemcpyAsync(h->pin_out + (size_t)r0 * out_row, h->stage_out[0] + (size_t)r0 * out_row, (size_t)nr * out_row,
+                                            cudaMemcpyDeviceToHost, h->s_compute);
+            if (e == cudaSuccess) e = cudaEventRecord(h->ev_band[k], h->s_compute);
+        }
+        for (int k = 0; k < kBounceBands && e == cudaSuccess; ++k) {
+            const int r0 = std::min(rows, k * band), nr = std::min(rows, r0 + band) - r0;
+            e = cudaEventSynchronize(h->ev_band[k]);
+            if (e == cudaSuccess && nr > 0)
+                host_pool_copy2d(h->pool, out + (size_t)r0 * out_stride, (size_t)out_stride, h->pin_out + (size_t)r0 * out_row, out_row, out_row, nr,
+                                 stream_out);
+        }
+        host_pool_wait_all(h->pool);
+        CK(h, e);
+        CK(h, cudaStreamSynchronize(h->s_compute));
+        return PANO_OK;
+    }
+    CK(h, cudaMemcpy2DAsync(out, out_stride, h->stage_out[0], out_row, out_row, h->host.cut_h, cudaMemcpyDeviceToHost, h->s_compute));
     CK(h, cudaStreamSynchronize(h->s_compute));
     return PANO_OK;
 }

@@ -176,6 +176,50 @@ def test_wide_source_uses_64bit_map_entries():
     assert_equal("map64", st.process(imgs), want)
 
 
+def test_process_from_pageable_strided_and_pinned_buffers():
+    """pano_process takes whatever host memory the caller has: pageable frames with row padding (a cv::Mat ROI) go through
+    the library's pinned bounce buffers and worker threads, pinned ones straight to the copy engine; the panorama may land
+    in a padded pageable buffer as well.  All variants must give the same bytes as the oracle."""
+    import ctypes as C
+    import torch
+    Ks, Rs, scale = calib.rig("2222", 320)
+    t, st, imgs, want = oracle_case(Ks, Rs, scale, 320, 180, "spherical", "multiband", 3, seed=11)
+    assert_equal("contiguous pageable", st.process(imgs), want)
+    lib, capi = panob200.capi.lib(), panob200.capi
+    ow, oh = st.out_size
+    # (a) every frame is a window of a wider, taller pageable array; the output is a window too
+    big = [np.full((180 + 7, 320 + 13, 3), 201, np.uint8) for _ in imgs]
+    views = []
+    for b, im in zip(big, imgs):
+        v = b[3:183, 5:325]
+        v[...] = im
+        views.append(v)
+    out_big = np.full((oh + 4, ow + 9, 3), 66, np.uint8)
+    out_v = out_big[2:2 + oh, 4:4 + ow]
+    fp = (C.c_void_p * 4)(*[v.ctypes.data for v in views])
+    sp = (C.c_int * 4)(*[v.strides[0] for v in views])
+    capi.check(lib.pano_process(st._h, fp, sp, C.c_void_p(out_v.ctypes.data), out_v.strides[0]), st._h)
+    assert_equal("strided pageable in / out", np.ascontiguousarray(out_v), want)
+    frame = out_big.copy()
+    frame[2:2 + oh, 4:4 + ow] = 66
+    assert np.all(frame == 66), "bytes outside the output window were touched"
+    # (b) pinned frames and a pinned panorama
+    pin = [torch.from_numpy(im).pin_memory() for im in imgs]
+    pout = torch.empty((oh, ow, 3), dtype=torch.uint8).pin_memory()
+    fp = (C.c_void_p * 4)(*[p_.data_ptr() for p_ in pin])
+    capi.check(lib.pano_process(st._h, fp, None, C.c_void_p(pout.data_ptr()), ow * 3), st._h)
+    assert_equal("pinned in / out", pout.numpy(), want)
+    # (c) mixed: pinned frames, pageable panorama; then the reverse
+    ret = np.empty((oh, ow, 3), np.uint8)
+    capi.check(lib.pano_process(st._h, fp, None, capi.ptr(ret), ow * 3), st._h)
+    assert_equal("pinned in, pageable out", ret, want)
+    fp2 = (C.c_void_p * 4)(*[im.ctypes.data for im in imgs])
+    pout.zero_()
+    capi.check(lib.pano_process(st._h, fp2, None, C.c_void_p(pout.data_ptr()), ow * 3), st._h)
+    assert_equal("pageable in, pinned out", pout.numpy(), want)
+    st.close()
+
+
 def test_mask_update_at_runtime():
     Ks, Rs, scale = calib.rig("2222", 240)
     t, st, imgs, want = oracle_case(Ks, Rs, scale, 240, 135, "spherical", "multiband", 3, seed=4)
