@@ -712,6 +712,12 @@ def main():
             ms1m, e1m = allmax([ms1, e1s * 1000.0])
             lat1 = time_latency(b1, 100)[0] if rank == 0 else None
             barrier()
+            # config 5 as SURVEY 8(d) words it: config-1 tables, one 256-frame-set batch over the ranks
+            k5_ms, k5_s, k5_per = time_config5(b1, hi, ho, world, stream, barrier, c5_steps)
+            k5_ms, k5_s = allmax([k5_ms, k5_s * 1000.0])
+            also["config5"]["config1_tables"] = {"value": k5_per * world * c5_steps / (k5_ms / 1000.0), "unit": UNIT,
+                                                 "ms_per_batch": k5_ms / c5_steps,
+                                                 "host_streamed": {"value": k5_per * world * c5_steps / (k5_s / 1000.0), "unit": UNIT}}
             peak, peak_src = peaks()
             r1 = roofline_record(acc1, min(B, args.max_batch), peak, peak_src)
             also["config1"] = {"workload": WORKLOADS["config1"], "value": world * B * WAVES * max(2, args.steps // 4) / (ms1m / 1000.0),
