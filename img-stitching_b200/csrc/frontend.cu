@@ -520,6 +520,110 @@ __device__ __forceinline__ void resize4_walk_body(const ResizeArgs &A, uint32_t 
 #undef RS_FETCH
 }
 
+// plain multiply-high: written as PTX so that the compiler does not fold the following add into IMAD.HI's 64-bit
+// accumulator operand (which needs a zeroed register pair per use and ends up longer)
+__device__ __forceinline__ uint32_t mul_hi(uint32_t a, uint32_t b)
+{
+    uint32_t d;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+
+// The same walk with TWO adjacent output columns per lane (word output only: the chained hot path).  The kernel is
+// issue-bound, and a third of its instructions do not depend on the column at all (row-coefficient fetch, loop control,
+// the first-output-row table, the row address, the store): with two pixels per lane they are paid once per pixel pair,
+// the pair leaves as one 8-byte store, and the row base is a warp-uniform pointer indexed with 32-bit lane offsets.
+// requires dw % 64 == 0 and 8-byte aligned dst rows (checked at launch).
+__device__ __forceinline__ void resize4_walk2_body(const ResizeArgs &A, uint32_t *__restrict__ smem, int bx, int by, int bz, int wy)
+{
+    const ResizeTab &t = A.t;
+    int *s_yb = reinterpret_cast<int *>(smem);
+    uint32_t *s_ay = smem + kResizeBand + 1;
+    const int lane = threadIdx.x, tid = wy * 32 + lane;
+    const int sh = t.sh;
+    const int v0 = by * kResizeBand - 1;
+    const int nv = min(kResizeBand, sh - v0);
+    const int ybase = __ldg(t.ybeg + v0 + 1);
+    if (tid <= nv) s_yb[tid] = __ldg(t.ybeg + v0 + 1 + tid);
+    if (tid >= 64) {
+        const short2 q = __ldg(t.ya + min(ybase + tid - 64, t.dh - 1));
+        s_ay[tid - 64] = ((uint32_t)(uint16_t)q.y << 16) | (uint16_t)q.x;
+    }
+    __syncthreads();
+    const int xw = (bx * 4 + wy) * 64;
+    if (xw >= t.dw) return;
+    const int x = xw + 2 * lane;
+    const int2 xo = __ldg(reinterpret_cast<const int2 *>(t.xofs + x));
+    const int2 axq = __ldg(reinterpret_cast<const int2 *>(t.xa + x));      // two short2 (a0 | a1 << 16): exactly the dp2a operand
+    // word indices of the four taps in row 0 of this image, relative to A.src: 32-bit (checked at launch)
+    const unsigned img0 = (unsigned)bz * (unsigned)A.src_img_words;
+    const unsigned xa0 = img0 + xo.x, xa1 = img0 + min((unsigned)xo.x + 1u, (unsigned)t.sw - 1u);
+    const unsigned xb0 = img0 + xo.y, xb1 = img0 + min((unsigned)xo.y + 1u, (unsigned)t.sw - 1u);
+    const int axa = axq.x, axb = axq.y;
+    const uint32_t *__restrict__ simg = A.src;
+    const unsigned sstride_words = A.sstride_words, dstride = A.dstride;
+    uint8_t *olane = A.dst + (size_t)bz * A.dst_img + (size_t)ybase * dstride + (size_t)x * 4;
+    const uint32_t *ayp = s_ay;
+
+    // word indices stay 32-bit (the launcher checks that the whole batch has fewer than 2^32 words): one add + one
+    // widening multiply-add per load instead of a 64-bit add chain
+#define RS2_FETCH(v, P)                                                          \
+    {                                                                            \
+        const unsigned ri_ = (unsigned)min(max((v), 0), sh - 1) * sstride_words; \
+        P[0] = __ldg(simg + (ri_ + xa0)); P[1] = __ldg(simg + (ri_ + xa1));      \
+        P[2] = __ldg(simg + (ri_ + xb0)); P[3] = __ldg(simg + (ri_ + xb1));      \
+    }
+#define RS2_HCALC(P, H)                                                          \
+    {                                                                            \
+        const uint32_t bga_ = __byte_perm(P[0], P[1], 0x5140u), bgb_ = __byte_perm(P[2], P[3], 0x5140u); \
+        H[0] = (uint32_t)dp2a_su(axa, bga_, 0) >> 4;                             \
+        H[1] = (uint32_t)dp2a_su_hi(axa, bga_, 0) >> 4;                          \
+        H[2] = (uint32_t)dp2a_su(axa, __byte_perm(P[0], P[1], 0x0062u), 0) >> 4; \
+        H[3] = (uint32_t)dp2a_su(axb, bgb_, 0) >> 4;                             \
+        H[4] = (uint32_t)dp2a_su_hi(axb, bgb_, 0) >> 4;                          \
+        H[5] = (uint32_t)dp2a_su(axb, __byte_perm(P[2], P[3], 0x0062u), 0) >> 4; \
+    }
+#define RS2_STEP(i, HA, HB, P)                                                   \
+    {                                                                            \
+        _Pragma("unroll 1") for (int n_ = s_yb[(i) + 1] - s_yb[(i)]; n_ > 0; --n_) { \
+            const uint32_t w_ = *ayp++;                                          \
+            const uint32_t a0_ = w_ << 16, a1_ = w_ & 0xffff0000u;               \
+            uint32_t c_[6];                                                      \
+            _Pragma("unroll") for (int k_ = 0; k_ < 6; ++k_)                      \
+                c_[k_] = (mul_hi(a0_, HA[k_]) + mul_hi(a1_, HB[k_]) + 2u) >> 2;  \
+            uint2 px_;                                                           \
+            px_.x = __byte_perm(__byte_perm(c_[0], c_[1], 0x0040), c_[2], 0x4410); \
+            px_.y = __byte_perm(__byte_perm(c_[3], c_[4], 0x0040), c_[5], 0x4410); \
+            *reinterpret_cast<uint2 *>(olane) = px_;                             \
+            olane += dstride;                                                    \
+        }                                                                        \
+        RS2_HCALC(P, HA)                                                         \
+        RS2_FETCH(v0 + (i) + 4, P)                                               \
+    }
+
+    uint32_t g[6], hh[6], p0[4], p1[4];
+    {
+        uint32_t a[4], b[4];
+        RS2_FETCH(v0, a) RS2_FETCH(v0 + 1, b)
+        RS2_FETCH(v0 + 2, p0) RS2_FETCH(v0 + 3, p1)
+        RS2_HCALC(a, g) RS2_HCALC(b, hh)
+    }
+    for (int i = 0; i < nv; i += 2) {
+        RS2_STEP(i, g, hh, p0)
+        if (i + 1 < nv) RS2_STEP(i + 1, hh, g, p1)
+    }
+#undef RS2_STEP
+#undef RS2_HCALC
+#undef RS2_FETCH
+}
+
+__global__ void __launch_bounds__(128, 8) resize4_walk2_kernel(const __grid_constant__ ResizeArgs A)
+{
+    pdl_enter();
+    __shared__ uint32_t smem[kResizeSmemWords];
+    resize4_walk2_body(A, smem, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.y);
+}
+
 template <bool kWords>
 __global__ void __launch_bounds__(128, 8) resize4_walk_kernel(const __grid_constant__ ResizeArgs A)
 {
@@ -856,7 +960,11 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
             else
                 cubic4_kernel<false, false><<<cg, blk, 0, st>>>(src4, img_stride / 4, cw, chh, h->dmap, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
             if (h->prof_ev) cudaEventRecord(h->prof_ev[1], st);
-            if (walk && out_px == 4)
+            static const bool one_col = getenv("PANO_RESIZE_ONE_COL") != nullptr;     // A/B switch: one output column per lane
+            if (walk && out_px == 4 && !one_col && uw % 64 == 0 && (reinterpret_cast<uintptr_t>(final_dst) & 7) == 0 && (o_img & 7) == 0 &&
+                w_img * (size_t)nb < ((size_t)1 << 32))
+                launch_chain(resize4_walk2_kernel, dim3((uw + 255) / 256, ra.gy, nb), dim3(32, 4), st, ra);
+            else if (walk && out_px == 4)
                 launch_chain(resize4_walk_kernel<true>, dim3(ra.gx, ra.gy, nb), dim3(32, 4), st, ra);
             else if (walk)
                 launch_chain(resize4_walk_kernel<false>, dim3(ra.gx, ra.gy, nb), dim3(32, 4), st, ra);
