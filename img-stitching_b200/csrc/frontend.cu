@@ -529,12 +529,14 @@ __device__ __forceinline__ uint32_t mul_hi(uint32_t a, uint32_t b)
     return d;
 }
 
-// The same walk with TWO adjacent output columns per lane (word output only: the chained hot path).  The kernel is
-// issue-bound, and a third of its instructions do not depend on the column at all (row-coefficient fetch, loop control,
-// the first-output-row table, the row address, the store): with two pixels per lane they are paid once per pixel pair,
-// the pair leaves as one 8-byte store, and the row base is a warp-uniform pointer indexed with 32-bit lane offsets.
-// requires dw % 64 == 0 and 8-byte aligned dst rows (checked at launch).
-__device__ __forceinline__ void resize4_walk2_body(const ResizeArgs &A, uint32_t *__restrict__ smem, int bx, int by, int bz, int wy)
+// The same walk with kCols (2 or 4) adjacent output columns per lane (word output only: the chained hot path).  The
+// kernel is issue-bound, and a third of its instructions do not depend on the column at all (row-coefficient fetch,
+// loop control, the first-output-row table, the row index, the store address): with several pixels per lane they are
+// paid once per group, the group leaves as one 8- or 16-byte store, and tap addresses are 32-bit word indices (one add
+// + one widening multiply-add per load instead of a 64-bit add chain; the launcher checks the batch has < 2^32 words).
+// requires dw % (32 * kCols) == 0 and dst rows aligned to 4 * kCols bytes (checked at launch).
+template <int kCols>
+__device__ __forceinline__ void resize4_walkn_body(const ResizeArgs &A, uint32_t *__restrict__ smem, int bx, int by, int bz, int wy)
 {
     const ResizeTab &t = A.t;
     int *s_yb = reinterpret_cast<int *>(smem);
@@ -550,78 +552,88 @@ __device__ __forceinline__ void resize4_walk2_body(const ResizeArgs &A, uint32_t
         s_ay[tid - 64] = ((uint32_t)(uint16_t)q.y << 16) | (uint16_t)q.x;
     }
     __syncthreads();
-    const int xw = (bx * 4 + wy) * 64;
+    const int xw = (bx * 4 + wy) * 32 * kCols;
     if (xw >= t.dw) return;
-    const int x = xw + 2 * lane;
-    const int2 xo = __ldg(reinterpret_cast<const int2 *>(t.xofs + x));
-    const int2 axq = __ldg(reinterpret_cast<const int2 *>(t.xa + x));      // two short2 (a0 | a1 << 16): exactly the dp2a operand
-    // word indices of the four taps in row 0 of this image, relative to A.src: 32-bit (checked at launch)
+    const int x = xw + kCols * lane;
+    int xo[kCols], ax[kCols];                       // ax: short2 (a0 | a1 << 16) = exactly the dp2a operand
+    if (kCols == 4) {
+        const int4 q = __ldg(reinterpret_cast<const int4 *>(t.xofs + x)), r = __ldg(reinterpret_cast<const int4 *>(t.xa + x));
+        xo[0] = q.x; xo[1] = q.y; xo[kCols - 2] = q.z; xo[kCols - 1] = q.w;
+        ax[0] = r.x; ax[1] = r.y; ax[kCols - 2] = r.z; ax[kCols - 1] = r.w;
+    } else {
+        const int2 q = __ldg(reinterpret_cast<const int2 *>(t.xofs + x)), r = __ldg(reinterpret_cast<const int2 *>(t.xa + x));
+        xo[0] = q.x; xo[1] = q.y;
+        ax[0] = r.x; ax[1] = r.y;
+    }
+    // word indices of the taps in row 0 of this image, relative to A.src
     const unsigned img0 = (unsigned)bz * (unsigned)A.src_img_words;
-    const unsigned xa0 = img0 + xo.x, xa1 = img0 + min((unsigned)xo.x + 1u, (unsigned)t.sw - 1u);
-    const unsigned xb0 = img0 + xo.y, xb1 = img0 + min((unsigned)xo.y + 1u, (unsigned)t.sw - 1u);
-    const int axa = axq.x, axb = axq.y;
+    unsigned ti[2 * kCols];
+#pragma unroll
+    for (int c = 0; c < kCols; ++c) {
+        ti[2 * c] = img0 + (unsigned)xo[c];
+        ti[2 * c + 1] = img0 + min((unsigned)xo[c] + 1u, (unsigned)t.sw - 1u);
+    }
     const uint32_t *__restrict__ simg = A.src;
     const unsigned sstride_words = A.sstride_words, dstride = A.dstride;
     uint8_t *olane = A.dst + (size_t)bz * A.dst_img + (size_t)ybase * dstride + (size_t)x * 4;
     const uint32_t *ayp = s_ay;
 
-    // word indices stay 32-bit (the launcher checks that the whole batch has fewer than 2^32 words): one add + one
-    // widening multiply-add per load instead of a 64-bit add chain
-#define RS2_FETCH(v, P)                                                          \
-    {                                                                            \
-        const unsigned ri_ = (unsigned)min(max((v), 0), sh - 1) * sstride_words; \
-        P[0] = __ldg(simg + (ri_ + xa0)); P[1] = __ldg(simg + (ri_ + xa1));      \
-        P[2] = __ldg(simg + (ri_ + xb0)); P[3] = __ldg(simg + (ri_ + xb1));      \
-    }
-#define RS2_HCALC(P, H)                                                          \
-    {                                                                            \
-        const uint32_t bga_ = __byte_perm(P[0], P[1], 0x5140u), bgb_ = __byte_perm(P[2], P[3], 0x5140u); \
-        H[0] = (uint32_t)dp2a_su(axa, bga_, 0) >> 4;                             \
-        H[1] = (uint32_t)dp2a_su_hi(axa, bga_, 0) >> 4;                          \
-        H[2] = (uint32_t)dp2a_su(axa, __byte_perm(P[0], P[1], 0x0062u), 0) >> 4; \
-        H[3] = (uint32_t)dp2a_su(axb, bgb_, 0) >> 4;                             \
-        H[4] = (uint32_t)dp2a_su_hi(axb, bgb_, 0) >> 4;                          \
-        H[5] = (uint32_t)dp2a_su(axb, __byte_perm(P[2], P[3], 0x0062u), 0) >> 4; \
-    }
-#define RS2_STEP(i, HA, HB, P)                                                   \
-    {                                                                            \
-        _Pragma("unroll 1") for (int n_ = s_yb[(i) + 1] - s_yb[(i)]; n_ > 0; --n_) { \
-            const uint32_t w_ = *ayp++;                                          \
-            const uint32_t a0_ = w_ << 16, a1_ = w_ & 0xffff0000u;               \
-            uint32_t c_[6];                                                      \
-            _Pragma("unroll") for (int k_ = 0; k_ < 6; ++k_)                      \
-                c_[k_] = (mul_hi(a0_, HA[k_]) + mul_hi(a1_, HB[k_]) + 2u) >> 2;  \
-            uint2 px_;                                                           \
-            px_.x = __byte_perm(__byte_perm(c_[0], c_[1], 0x0040), c_[2], 0x4410); \
-            px_.y = __byte_perm(__byte_perm(c_[3], c_[4], 0x0040), c_[5], 0x4410); \
-            *reinterpret_cast<uint2 *>(olane) = px_;                             \
-            olane += dstride;                                                    \
-        }                                                                        \
-        RS2_HCALC(P, HA)                                                         \
-        RS2_FETCH(v0 + (i) + 4, P)                                               \
-    }
+    auto fetch = [&](int v, uint32_t (&P)[2 * kCols]) {
+        const unsigned ri = (unsigned)min(max(v, 0), sh - 1) * sstride_words;
+#pragma unroll
+        for (int k = 0; k < 2 * kCols; ++k) P[k] = __ldg(simg + (ri + ti[k]));
+    };
+    auto hcalc = [&](const uint32_t (&P)[2 * kCols], uint32_t (&H)[3 * kCols]) {
+#pragma unroll
+        for (int c = 0; c < kCols; ++c) {
+            const uint32_t bg = __byte_perm(P[2 * c], P[2 * c + 1], 0x5140u);
+            H[3 * c] = (uint32_t)dp2a_su(ax[c], bg, 0) >> 4;
+            H[3 * c + 1] = (uint32_t)dp2a_su_hi(ax[c], bg, 0) >> 4;
+            H[3 * c + 2] = (uint32_t)dp2a_su(ax[c], __byte_perm(P[2 * c], P[2 * c + 1], 0x0062u), 0) >> 4;
+        }
+    };
+    // one step: emit the output rows that blend (HA, HB) = rows (v, v + 1), then row v + 2 replaces HA (it is the next
+    // step's HB) and the prefetch slot is refilled with row v + 4
+    auto step = [&](int i, uint32_t (&HA)[3 * kCols], const uint32_t (&HB)[3 * kCols], uint32_t (&P)[2 * kCols]) {
+#pragma unroll 1
+        for (int n = s_yb[i + 1] - s_yb[i]; n > 0; --n) {
+            const uint32_t w = *ayp++;
+            const uint32_t a0 = w << 16, a1 = w & 0xffff0000u;
+            uint32_t px[kCols];
+#pragma unroll
+            for (int c = 0; c < kCols; ++c) {
+                const uint32_t c0 = (mul_hi(a0, HA[3 * c]) + mul_hi(a1, HB[3 * c]) + 2u) >> 2;
+                const uint32_t c1 = (mul_hi(a0, HA[3 * c + 1]) + mul_hi(a1, HB[3 * c + 1]) + 2u) >> 2;
+                const uint32_t c2 = (mul_hi(a0, HA[3 * c + 2]) + mul_hi(a1, HB[3 * c + 2]) + 2u) >> 2;
+                px[c] = __byte_perm(__byte_perm(c0, c1, 0x0040), c2, 0x4410);
+            }
+            if (kCols == 4) *reinterpret_cast<uint4 *>(olane) = make_uint4(px[0], px[1], px[kCols - 2], px[kCols - 1]);
+            else *reinterpret_cast<uint2 *>(olane) = make_uint2(px[0], px[1]);
+            olane += dstride;
+        }
+        hcalc(P, HA);
+        fetch(v0 + i + 4, P);
+    };
 
-    uint32_t g[6], hh[6], p0[4], p1[4];
+    uint32_t g[3 * kCols], hh[3 * kCols], p0[2 * kCols], p1[2 * kCols];
     {
-        uint32_t a[4], b[4];
-        RS2_FETCH(v0, a) RS2_FETCH(v0 + 1, b)
-        RS2_FETCH(v0 + 2, p0) RS2_FETCH(v0 + 3, p1)
-        RS2_HCALC(a, g) RS2_HCALC(b, hh)
+        uint32_t a[2 * kCols], b[2 * kCols];
+        fetch(v0, a); fetch(v0 + 1, b);
+        fetch(v0 + 2, p0); fetch(v0 + 3, p1);
+        hcalc(a, g); hcalc(b, hh);
     }
     for (int i = 0; i < nv; i += 2) {
-        RS2_STEP(i, g, hh, p0)
-        if (i + 1 < nv) RS2_STEP(i + 1, hh, g, p1)
+        step(i, g, hh, p0);
+        if (i + 1 < nv) step(i + 1, hh, g, p1);
     }
-#undef RS2_STEP
-#undef RS2_HCALC
-#undef RS2_FETCH
 }
 
-__global__ void __launch_bounds__(128, 8) resize4_walk2_kernel(const __grid_constant__ ResizeArgs A)
+template <int kCols, int kMinBlocks>
+__global__ void __launch_bounds__(128, kMinBlocks) resize4_walkn_kernel(const __grid_constant__ ResizeArgs A)
 {
     pdl_enter();
     __shared__ uint32_t smem[kResizeSmemWords];
-    resize4_walk2_body(A, smem, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.y);
+    resize4_walkn_body<kCols>(A, smem, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.y);
 }
 
 template <bool kWords>
@@ -960,10 +972,18 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
             else
                 cubic4_kernel<false, false><<<cg, blk, 0, st>>>(src4, img_stride / 4, cw, chh, h->dmap, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
             if (h->prof_ev) cudaEventRecord(h->prof_ev[1], st);
-            static const bool one_col = getenv("PANO_RESIZE_ONE_COL") != nullptr;     // A/B switch: one output column per lane
-            if (walk && out_px == 4 && !one_col && uw % 64 == 0 && (reinterpret_cast<uintptr_t>(final_dst) & 7) == 0 && (o_img & 7) == 0 &&
-                w_img * (size_t)nb < ((size_t)1 << 32))
-                launch_chain(resize4_walk2_kernel, dim3((uw + 255) / 256, ra.gy, nb), dim3(32, 4), st, ra);
+            static const int cols_env = getenv("PANO_RESIZE_COLS") ? atoi(getenv("PANO_RESIZE_COLS")) : 4;     // A/B switch: output columns per lane
+            const bool idx32 = w_img * (size_t)nb < ((size_t)1 << 32);
+            if (walk && out_px == 4 && cols_env == 4 && idx32 && uw % 128 == 0 && (reinterpret_cast<uintptr_t>(final_dst) & 15) == 0 && (o_img & 15) == 0)
+            {
+                static const int occ = getenv("PANO_RESIZE_OCC") ? atoi(getenv("PANO_RESIZE_OCC")) : 7;      // tuning knob: min blocks per SM
+                const dim3 g4((uw + 511) / 512, ra.gy, nb);
+                if (occ >= 7) launch_chain(resize4_walkn_kernel<4, 7>, g4, dim3(32, 4), st, ra);
+                else if (occ == 6) launch_chain(resize4_walkn_kernel<4, 6>, g4, dim3(32, 4), st, ra);
+                else launch_chain(resize4_walkn_kernel<4, 5>, g4, dim3(32, 4), st, ra);
+            }
+            else if (walk && out_px == 4 && cols_env >= 2 && idx32 && uw % 64 == 0 && (reinterpret_cast<uintptr_t>(final_dst) & 7) == 0 && (o_img & 7) == 0)
+                launch_chain(resize4_walkn_kernel<2, 8>, dim3((uw + 255) / 256, ra.gy, nb), dim3(32, 4), st, ra);
             else if (walk && out_px == 4)
                 launch_chain(resize4_walk_kernel<true>, dim3(ra.gx, ra.gy, nb), dim3(32, 4), st, ra);
             else if (walk)
