@@ -61,17 +61,10 @@ for v in by_kernel.values():
 def lvl(name, i):
     v = by_kernel.get(name, [])
     return v[i][1] if i < len(v) else 0.0
-t = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum PER FRAME-SET per kernel from the ncu --set full capture profiles/%s_ncu_full_raw.csv "
-                 "(waves of %d frame-sets: bytes per launch / %d); bench.py multiplies by the frame-sets one launch processes. "
-                 "collapse levels = collapse_walk_kernel + collapse8_kernel of that level" % (tag, sets, sets),
-     "frame_sets_per_captured_launch": sets,
-     "fe_cubic_undistort": lvl("cubic5_kernel", 0) / sets, "fe_resize": lvl("resize4_walk_kernel", 0) / sets,
-     "warp": lvl("warp_tile_kernel", 0) / sets}
-for i in range(4):
-    t["pyrdown_l%d" % i] = lvl("pyrdown8_walk_kernel", i) / sets
-t["collapse_l0"] = (lvl("collapse_walk_kernel<1>", 0) + lvl("collapse8_kernel<1>", 0)) / sets
-for i in range(2):
-    t["collapse_l%d" % (i + 1)] = (lvl("collapse_walk_kernel", i) + lvl("collapse8_kernel", i)) / sets
+# DRAM traffic per frame-set and logical kernel: one implementation, tools/ncu_traffic.py (it follows the launch ORDER of a
+# wave, which is what tells the collapse levels apart)
+t = json.loads(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_traffic.py"), os.path.join(G, tag + "_full.ncu-rep"),
+                               str(sets), "profiles/%s_ncu_full_raw.csv" % tag], capture_output=True, text=True, check=True).stdout)
 json.dump(t, open(os.path.join(P, "traffic.json"), "w"), indent=1)
 print(open(os.path.join(P, tag + "_launch_shares.txt")).read())
 print(json.dumps(t, indent=1))
