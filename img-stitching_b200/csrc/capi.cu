@@ -21,8 +21,11 @@
 using namespace pano;
 
 // internal front-end entry points (frontend.cu)
+struct pano_front_scratch;
 int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img, uint8_t *out, size_t o_img, int batch,
-                      cudaStream_t st, int out_px);
+                      cudaStream_t st, int out_px, pano_front_scratch *scratch);
+pano_front_scratch *pano_frontend_scratch_create(pano_frontend_handle h);
+void pano_frontend_scratch_destroy(pano_front_scratch *s);
 bool pano_frontend_can_words(pano_frontend_handle h);
 int pano_frontend_max_batch(pano_frontend_handle h);
 int pano_frontend_launches(pano_frontend_handle h);
@@ -76,6 +79,9 @@ struct pano_ctx {
     bool tables_dirty = true;
     // optional nvCam front end per camera (pano_attach_frontend): inputs become 8UC4 camera frames
     pano_frontend_handle front[kMaxCams] = {};
+    // this handle's own set of the front ends' intermediate buffers (cameras that share a front end share the set: they
+    // run one after the other on one stream): a front-end handle can then serve several stitchers at the same time
+    pano_front_scratch *front_scratch[kMaxCams] = {};
     bool has_front = false;
     // fused front-end mode (pano_set_frontend_mode): the whole nvCam pipeline is folded into the warp's remap table
     // and the gather reads the 8UC4 camera frames directly -- NOT bit-exact with the sequential path
@@ -91,6 +97,11 @@ struct pano_ctx {
     std::vector<PhaseGraph> phase_graphs;
     cudaGraphExec_t graph1 = nullptr;             // pano_process: the kernel chain of ONE frame-set (stage_in[0] -> stage_out[0])
     int graph1_launches = 0;
+    // pano_process, overlapped form: camera i's chain (front end, warp, pyrDown levels) is replayed as soon as ITS frame has
+    // landed (copies on s_h2d, one event per camera), the tail (coarsest + collapse) after the last one
+    cudaEvent_t ev_cam_in[kMaxCams] = {};
+    cudaGraphExec_t graph_cam[kMaxCams] = {}, graph_tail = nullptr;
+    int graph_split_launches = 0;
     // pano_process with PAGEABLE host buffers: pinned bounce buffers filled / drained by worker threads (host_pool.hpp)
     HostPool *pool = nullptr;
     uint8_t *pin_in = nullptr, *pin_out = nullptr;
@@ -437,11 +448,20 @@ int buildWeights(pano_ctx *h, int cam)
     return PANO_OK;
 }
 
+// the CUDA graphs of pano_process bake in staging pointers, table pointers and launch shapes: they die with any of those
+void dropProcessGraphs(pano_ctx *h)
+{
+    if (h->graph1) { cudaGraphExecDestroy(h->graph1); h->graph1 = nullptr; }
+    for (auto &g : h->graph_cam)
+        if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    if (h->graph_tail) { cudaGraphExecDestroy(h->graph_tail); h->graph_tail = nullptr; }
+}
+
 int syncTables(pano_ctx *h)
 {
     if (!h->tables_dirty) return PANO_OK;
     // captured launch sequences bake table pointers, work-list sizes and grid shapes in: they die with the tables
-    if (h->graph1) { cudaGraphExecDestroy(h->graph1); h->graph1 = nullptr; }
+    dropProcessGraphs(h);
     for (auto &g : h->phase_graphs) cudaGraphExecDestroy(g.exec);
     h->phase_graphs.clear();
     if (uploadTileLists(h)) return PANO_ERR;
@@ -616,7 +636,7 @@ int runFrontEnds(pano_ctx *h, const uint8_t *&frames_dev, int slots, cudaStream_
         for (auto &e : ev) cudaEventCreate(&e);
         const bool yuyv = h->in_frame_bytes4 != h->in_frame_bytes;
         if (pano_frontend_set_prof(h->front[0], ev, &cb, &rb, opx)) {
-            const int rc = pano_frontend_run(h->front[0], frames_dev, h->in_frame_bytes, h->front_out, ofb, slots * h->n, st, opx);
+            const int rc = pano_frontend_run(h->front[0], frames_dev, h->in_frame_bytes, h->front_out, ofb, slots * h->n, st, opx, h->front_scratch[0]);
             pano_frontend_set_prof(h->front[0], nullptr, nullptr, nullptr, opx);
             if (rc) return fail(h, "front end: %s", pano_frontend_last_error(h->front[0]));
             if (yuyv) {
@@ -640,13 +660,13 @@ int runFrontEnds(pano_ctx *h, const uint8_t *&frames_dev, int slots, cudaStream_
     }
     L.begin("front_end", (double)slots * h->n * (h->in_frame_bytes + ofb));
     if (same) {
-        if (pano_frontend_run(h->front[0], frames_dev, h->in_frame_bytes, h->front_out, ofb, slots * h->n, st, opx))
+        if (pano_frontend_run(h->front[0], frames_dev, h->in_frame_bytes, h->front_out, ofb, slots * h->n, st, opx, h->front_scratch[0]))
             return fail(h, "front end: %s", pano_frontend_last_error(h->front[0]));
         h->last_launches += pano_frontend_launches(h->front[0]) - 1;
     } else {
         for (int i = 0; i < h->n; ++i) {
             if (pano_frontend_run(h->front[i], frames_dev + i * h->in_frame_bytes, h->in_frame_bytes * h->n,
-                                  h->front_out + i * ofb, ofb * h->n, slots, st, opx))
+                                  h->front_out + i * ofb, ofb * h->n, slots, st, opx, h->front_scratch[i]))
                 return fail(h, "front end: %s", pano_frontend_last_error(h->front[i]));
             h->last_launches += pano_frontend_launches(h->front[i]);
         }
@@ -676,6 +696,64 @@ int runWave(pano_ctx *h, const uint8_t *frames_dev, uint8_t *out_dev, int slots,
     return PANO_OK;
 }
 
+// ---- pano_process, overlapped form (one frame-set, host frames): everything one camera needs before the cameras meet
+// in the blend -- its front end, its warp, its Gaussian pyramid -- only reads that camera's frame, so it can run while the
+// NEXT camera's frame is still crossing PCIe.  All chains run on ONE stream, in camera order (a camera's chain is ~50 us,
+// its copy ~150 us: the stream is idle most of the time anyway, and a front-end handle shared by the cameras is used
+// by one of them at a time); the tail (coarsest + collapse levels) follows the last chain.
+bool canOverlapCameras(const pano_ctx *h)
+{
+    static const bool off = getenv("PANO_NO_OVERLAP") != nullptr;       // A/B switch: copy everything, then compute
+    const bool full = h->strip_x0 == 0 && h->strip_x1 == h->pad_w;
+    return !off && h->blender == PANO_BLEND_MULTIBAND && h->nb >= 1 && h->n >= 2 && !h->fused && full && !h->profiling;
+}
+
+int runCameraChain(pano_ctx *h, int cam, const uint8_t *stage, cudaStream_t st)
+{
+    const uint8_t *fr = stage;
+    if (h->has_front) {
+        const int opx = h->front_px4 ? 4 : 3;
+        const size_t ofb = h->front_frame_bytes();
+        if (pano_frontend_run(h->front[cam], stage + (size_t)cam * h->in_frame_bytes, h->in_frame_bytes * h->n,
+                              h->front_out + (size_t)cam * ofb, ofb * h->n, 1, st, opx, h->front_scratch[cam]))
+            return fail(h, "front end: %s", pano_frontend_last_error(h->front[cam]));
+        h->last_launches += pano_frontend_launches(h->front[cam]);
+        fr = h->front_out;
+    }
+    launch_warp(h->dev, h->host, h->kc, fr, 1, st, CamRange{cam, 1});
+    for (int l = 0; l < h->nb; ++l) launch_pyrdown(h->dev, h->host, h->kc, l, 1, st, CamRange{cam, 1});
+    h->last_launches += 1 + h->nb;
+    CK(h, cudaGetLastError());
+    return PANO_OK;
+}
+
+int runTail(pano_ctx *h, const uint8_t *stage, uint8_t *out_dev, cudaStream_t st)
+{
+    const uint8_t *fr = h->has_front ? h->front_out : stage;
+    if (runPhases(h, h->nb, phaseCount(h), fr, out_dev, 1, st)) return PANO_ERR;
+    CK(h, cudaGetLastError());
+    return PANO_OK;
+}
+
+// capture what `body` launches on `st` into an executable graph
+template <typename F>
+int captureGraph(pano_ctx *h, cudaStream_t st, cudaGraphExec_t *exec, F body)
+{
+    cudaGraph_t g = nullptr;
+    CK(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = body();
+    const cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (rc || e != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        (void)cudaGetLastError();
+        return rc ? PANO_ERR : fail(h, "pano_process: graph capture failed: %s", cudaGetErrorString(e));
+    }
+    const cudaError_t ei = cudaGraphInstantiate(exec, g, 0);
+    cudaGraphDestroy(g);
+    if (ei != cudaSuccess) { *exec = nullptr; return fail(h, "pano_process: graph instantiation failed: %s", cudaGetErrorString(ei)); }
+    return PANO_OK;
+}
+
 // halo exchanged after phase p: kind (0 = camera pyramids g, 1 = collapsed pyramid out), level, columns
 bool phaseHalo(const pano_ctx *h, int p, int &kind, int &level, int &ncols)
 {
@@ -696,6 +774,7 @@ int ensureStaging(pano_ctx *h)
             CK(h, cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
             CK(h, cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
         }
+        for (auto &e : h->ev_cam_in) CK(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CK(h, cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
         CK(h, cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
         CK(h, cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
@@ -709,6 +788,34 @@ int ensureStaging(pano_ctx *h)
     return PANO_OK;
 }
 
+// One private set of front-end intermediates per DISTINCT front end of this handle (cameras sharing a front end run one
+// after the other on one stream and share the set).  The device must be idle.
+void freeFrontScratch(pano_ctx *h)
+{
+    for (int i = 0; i < kMaxCams; ++i) {
+        pano_front_scratch *s = h->front_scratch[i];
+        if (!s) continue;
+        for (int j = i; j < kMaxCams; ++j)
+            if (h->front_scratch[j] == s) h->front_scratch[j] = nullptr;
+        pano_frontend_scratch_destroy(s);
+    }
+}
+
+int rebuildFrontScratch(pano_ctx *h)
+{
+    freeFrontScratch(h);
+    for (int i = 0; i < h->n; ++i) {
+        if (!h->front[i]) continue;
+        for (int j = 0; j < i && !h->front_scratch[i]; ++j)
+            if (h->front[j] == h->front[i]) h->front_scratch[i] = h->front_scratch[j];
+        if (!h->front_scratch[i]) {
+            h->front_scratch[i] = pano_frontend_scratch_create(h->front[i]);
+            if (!h->front_scratch[i]) return fail(h, "pano_attach_frontend: out of device memory for the front end's intermediate buffers");
+        }
+    }
+    return PANO_OK;
+}
+
 // The staging buffers are sized from set_bytes(), which changes when a front end is attached or detached (8UC4 / YUYV
 // camera frames vs BGR stitcher inputs): release them so that the next host-side call re-creates them at the new size.
 // The device must be idle (callers synchronise first).
@@ -718,7 +825,7 @@ void dropStaging(pano_ctx *h)
         devFree(h, h->stage_in[i]); devFree(h, h->stage_out[i]);
         h->stage_in[i] = nullptr; h->stage_out[i] = nullptr;
     }
-    if (h->graph1) { cudaGraphExecDestroy(h->graph1); h->graph1 = nullptr; }
+    dropProcessGraphs(h);
 }
 
 }  // namespace
@@ -918,7 +1025,10 @@ int pano_destroy(pano_handle h)
     cudaDeviceSynchronize();
     clearProf(h);
     if (h->p2p_graph) cudaGraphExecDestroy(h->p2p_graph);
-    if (h->graph1) cudaGraphExecDestroy(h->graph1);
+    dropProcessGraphs(h);
+    freeFrontScratch(h);
+    for (auto &e : h->ev_cam_in)
+        if (e) cudaEventDestroy(e);
     for (auto &g : h->phase_graphs) cudaGraphExecDestroy(g.exec);
     if (h->pool) host_pool_destroy(h->pool);
     if (h->pin_in) cudaFreeHost(h->pin_in);
@@ -1142,6 +1252,7 @@ int pano_attach_frontend(pano_handle h, int cam, pano_frontend_handle f)
     if (!f) {
         if (h->fused && pano_set_frontend_mode(h, PANO_FRONTEND_SEQUENTIAL)) return PANO_ERR;
         for (int i = 0; i < h->n; ++i) h->front[i] = nullptr;
+        freeFrontScratch(h);
         if (h->has_front) dropStaging(h);         // the caller-side frame-set shrinks or grows: re-size on next use
         h->has_front = false;
         h->front_px4 = false;
@@ -1176,9 +1287,9 @@ int pano_attach_frontend(pano_handle h, int cam, pano_frontend_handle f)
     for (int i = 0; i < h->n; ++i) h->front_px4 = h->front_px4 && pano_frontend_can_words(h->front[i]);
     h->host.src_px = h->front_px4 ? 4 : 3;
     h->tables_dirty = true;
-    if (h->graph1) { cudaGraphExecDestroy(h->graph1); h->graph1 = nullptr; }
+    dropProcessGraphs(h);
     if (h->set_bytes() != old_set) dropStaging(h);
-    return PANO_OK;
+    return rebuildFrontScratch(h);
 }
 
 int pano_set_frontend_mode(pano_handle h, int mode)
@@ -1306,6 +1417,36 @@ int pano_process(pano_handle h, const uint8_t *const *frames, const int *strides
     if (out_stride < h->host.cut_w * 3) return fail(h, "pano_process: out_stride too small");
     for (int i = 0; i < h->n; ++i)
         if (!frames[i] || (strides ? strides[i] : W3) < W3) return fail(h, "pano_process: bad frame %d", i);
+    if (h->profiling) clearProf(h);
+    // The drop-in call (one frame-set per process(), src/replay.cpp:284-292): the ~20 launches of the kernel chain are
+    // captured ONCE (they only touch the handle's own staging buffers and tables) and replayed as CUDA graphs -- one per
+    // camera chain plus the tail when the cameras' chains overlap the copies (canOverlapCameras), one for everything otherwise.
+    static const bool no_graph = getenv("PANO_NO_GRAPH") != nullptr;
+    const bool overlap = canOverlapCameras(h), graphs = !no_graph && !h->profiling;
+    if (overlap && graphs && !h->graph_tail) {
+        h->last_launches = 0;
+        for (int i = 0; i < h->n; ++i)
+            if (captureGraph(h, h->s_compute, &h->graph_cam[i], [&] { return runCameraChain(h, i, h->stage_in[0], h->s_compute); })) {
+                dropProcessGraphs(h);
+                return PANO_ERR;
+            }
+        if (captureGraph(h, h->s_compute, &h->graph_tail, [&] { return runTail(h, h->stage_in[0], h->stage_out[0], h->s_compute); })) {
+            dropProcessGraphs(h);
+            return PANO_ERR;
+        }
+        h->graph_split_launches = h->last_launches;
+    }
+    if (overlap) h->last_launches = graphs ? h->graph_split_launches : 0;
+    cudaStream_t cs = overlap ? h->s_h2d : h->s_compute;          // the stream the input copies go to
+    // camera i's copies are all enqueued on `cs`: its chain may start as soon as they have landed
+    auto camera_ready = [&](int i) -> int {
+        if (!overlap) return PANO_OK;
+        CK(h, cudaEventRecord(h->ev_cam_in[i], cs));
+        CK(h, cudaStreamWaitEvent(h->s_compute, h->ev_cam_in[i], 0));
+        if (graphs) CK(h, cudaGraphLaunch(h->graph_cam[i], h->s_compute));
+        else if (runCameraChain(h, i, h->stage_in[0], h->s_compute)) return PANO_ERR;
+        return PANO_OK;
+    };
     // Pageable buffers (what the reference's cv::Mat frames are) must not reach the driver: its internal staging copy is
     // single-threaded (~12 GB/s).  Worker threads move them through pinned bounce buffers chunk by chunk instead, each
     // chunk's DMA starting as soon as it has landed (PANO_NO_HOST_STAGING=1: the driver's path, for A/B).
@@ -1327,43 +1468,38 @@ int pano_process(pano_handle h, const uint8_t *const *frames, const int *strides
                                                 frames[i] + (size_t)r0 * st, st, W3, nr, stream_in);
             }
         cudaError_t e = cudaSuccess;
-        for (int i = 0; i < h->n; ++i)
+        int rc = PANO_OK;
+        for (int i = 0; i < h->n; ++i) {
             for (int k = 0; k < kBounceBands; ++k) {
                 host_pool_wait(h->pool, ticket[i][k]);
                 const int r0 = std::min(H, k * band), nr = std::min(H, r0 + band) - r0;
                 const size_t off = (size_t)i * fbytes + (size_t)r0 * W3;
-                if (e == cudaSuccess && nr > 0)
-                    e = cudaMemcpyAsync(h->stage_in[0] + off, h->pin_in + off, (size_t)nr * W3, cudaMemcpyHostToDevice, h->s_compute);
+                if (e == cudaSuccess && rc == PANO_OK && nr > 0)
+                    e = cudaMemcpyAsync(h->stage_in[0] + off, h->pin_in + off, (size_t)nr * W3, cudaMemcpyHostToDevice, cs);
             }
-        host_pool_wait_all(h->pool);
+            if (e == cudaSuccess && rc == PANO_OK) rc = camera_ready(i);
+        }
+        host_pool_wait_all(h->pool);      // the workers read the caller's frames: never return while one is still running
         CK(h, e);
+        if (rc) return PANO_ERR;
     } else {
-        for (int i = 0; i < h->n; ++i)
+        for (int i = 0; i < h->n; ++i) {
             CK(h, cudaMemcpy2DAsync(h->stage_in[0] + (size_t)i * fbytes, W3, frames[i], strides ? strides[i] : W3, W3, H,
-                                    cudaMemcpyHostToDevice, h->s_compute));
+                                    cudaMemcpyHostToDevice, cs));
+            if (camera_ready(i)) return PANO_ERR;
+        }
     }
-    if (h->profiling) clearProf(h);
-    // The drop-in call (one frame-set per process(), src/replay.cpp:284-292): the ~20 launches of the kernel chain are
-    // captured ONCE (they only touch the handle's own staging buffers and tables) and replayed as a CUDA graph.
-    static const bool no_graph = getenv("PANO_NO_GRAPH") != nullptr;
-    if (no_graph || h->profiling) {
+    if (overlap) {
+        if (graphs) CK(h, cudaGraphLaunch(h->graph_tail, h->s_compute));
+        else if (runTail(h, h->stage_in[0], h->stage_out[0], h->s_compute)) return PANO_ERR;
+    } else if (!graphs) {
         h->last_launches = 0;
         if (runWave(h, h->stage_in[0], h->stage_out[0], 1, h->s_compute)) return PANO_ERR;
     } else {
         if (!h->graph1) {
-            cudaGraph_t g = nullptr;
             h->last_launches = 0;
-            CK(h, cudaStreamBeginCapture(h->s_compute, cudaStreamCaptureModeThreadLocal));
-            const int rc = runWave(h, h->stage_in[0], h->stage_out[0], 1, h->s_compute);
-            const cudaError_t e = cudaStreamEndCapture(h->s_compute, &g);
-            if (rc || e != cudaSuccess || !g) {
-                if (g) cudaGraphDestroy(g);
-                (void)cudaGetLastError();
-                return rc ? PANO_ERR : fail(h, "pano_process: graph capture failed: %s", cudaGetErrorString(e));
-            }
-            const cudaError_t ei = cudaGraphInstantiate(&h->graph1, g, 0);
-            cudaGraphDestroy(g);
-            if (ei != cudaSuccess) { h->graph1 = nullptr; return fail(h, "pano_process: graph instantiation failed: %s", cudaGetErrorString(ei)); }
+            if (captureGraph(h, h->s_compute, &h->graph1, [&] { return runWave(h, h->stage_in[0], h->stage_out[0], 1, h->s_compute); }))
+                return PANO_ERR;
             h->graph1_launches = h->last_launches;
         }
         CK(h, cudaGraphLaunch(h->graph1, h->s_compute));

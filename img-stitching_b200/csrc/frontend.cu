@@ -648,6 +648,18 @@ thread_local std::string g_front_error;
 
 }  // namespace
 
+// The front end's intermediate images.  A handle has one set of its own (host-buffer API, standalone device calls); a
+// stitcher handle that chains the front end in brings ITS OWN set (pano_frontend_scratch_*), so that one front-end handle
+// -- which otherwise only holds read-only tables -- can serve several stitchers running on different streams / threads
+// at the same time (the SDK facade's two rings share the camera model).
+struct pano_front_scratch {
+    uint8_t *a = nullptr, *b = nullptr, *c = nullptr;  // generic path: undist-sized 3-channel intermediates
+    uint32_t *w = nullptr;                             // fast path: cropped undistorted image, one word per pixel
+    uint8_t *argb = nullptr;                           // YUYV ingest: converted 8UC4 frames
+    int depth = 0;                                     // images each buffer holds
+    int device = 0;
+};
+
 struct pano_frontend_ctx {
     pano_frontend_config cfg{};
     std::string err;
@@ -658,15 +670,13 @@ struct pano_frontend_ctx {
     cudaTextureObject_t wtex = 0;                                  // dtab as a linear uint4 texture
     ResizeTab r_in, r_mid, r_out;       // cam->undist, rect->undist, undist->out
     bool use_r_in = false, use_r_mid = false, use_r_out = false;
-    uint8_t *buf_a = nullptr, *buf_b = nullptr, *buf_c = nullptr;  // intermediates, max_batch deep
-    uint32_t *buf_w = nullptr;                                     // cropped undistorted image, one word per pixel (fast path)
+    pano_front_scratch own;                                        // intermediates, max_batch deep
     uint32_t *dmap32 = nullptr;                                    // packed map entries (fast path, sources <= 2043 px)
     bool fast4 = false;
     int4 *cub_tiles = nullptr;                                     // per 128x8 tile of the crop rect: staged footprint (cubic5_kernel)
     int cub_tx = 0, cub_ty = 0;
     bool cub_tma = false;                                          // every tile footprint fits the TMA boxes (kCubBoxW x kCubBoxH1)
     cudaEvent_t *prof_ev = nullptr;                                // events when profiling: before cubic, between, after resize, [3] before the YUYV conversion
-    uint8_t *buf_argb = nullptr;                                   // YUYV ingest: converted 8UC4 frames, max_batch deep
     int in_px() const { return cfg.src_format == PANO_SRC_YUYV ? 2 : 4; }
     uint8_t *stage_in = nullptr, *stage_out = nullptr;
     int launches = 0;
@@ -698,6 +708,26 @@ int falloc(pano_frontend_ctx *h, T **p, size_t count)
     FCK(h, cudaMalloc((void **)p, std::max<size_t>(1, count) * sizeof(T)));
     h->owned.push_back(*p);
     return PANO_OK;
+}
+
+int scratchAlloc(pano_frontend_ctx *h, pano_front_scratch &s, int depth)
+{
+    const pano_frontend_config &c = h->cfg;
+    const size_t ubytes = (size_t)c.undist_width * c.undist_height * 3 * depth;
+    s.depth = depth;
+    s.device = c.device;
+    if (c.src_format == PANO_SRC_YUYV) FCK(h, cudaMalloc((void **)&s.argb, (size_t)c.cam_src_width * c.cam_src_height * 4 * depth));
+    FCK(h, cudaMalloc((void **)&s.a, ubytes));
+    FCK(h, cudaMalloc((void **)&s.b, ubytes));
+    FCK(h, cudaMalloc((void **)&s.c, ubytes));
+    if (h->fast4) FCK(h, cudaMalloc((void **)&s.w, (size_t)c.rect[2] * c.rect[3] * depth * sizeof(uint32_t)));
+    return PANO_OK;
+}
+
+void scratchFree(pano_front_scratch &s)
+{
+    cudaFree(s.a); cudaFree(s.b); cudaFree(s.c); cudaFree(s.w); cudaFree(s.argb);
+    s = pano_front_scratch();
 }
 
 int makeResize(pano_frontend_ctx *h, ResizeTab &t, int sw, int sh, int dw, int dh)
@@ -807,12 +837,9 @@ int pano_frontend_create(const pano_frontend_config *cfg, pano_frontend_handle *
     }
     h->use_r_out = !(cfg->out_width == uw && cfg->out_height == uh);
     if (h->use_r_out && makeResize(h, h->r_out, uw, uh, cfg->out_width, cfg->out_height)) return bail();
-    if (cfg->src_format == PANO_SRC_YUYV && falloc(h, &h->buf_argb, (size_t)cfg->cam_src_width * cfg->cam_src_height * 4 * S)) return bail();
-    const size_t ubytes = (size_t)uw * uh * 3 * S;
-    if (falloc(h, &h->buf_a, ubytes) || falloc(h, &h->buf_b, ubytes) || falloc(h, &h->buf_c, ubytes)) return bail();
     // fast path: undistort straight from the 8UC4 camera frame, then one resize to the output size
     h->fast4 = cfg->undistort && !h->use_r_in && h->use_r_mid && !h->use_r_out;
-    if (h->fast4 && falloc(h, &h->buf_w, (size_t)cfg->rect[2] * cfg->rect[3] * S)) return bail();
+    if (scratchAlloc(h, h->own, S)) return bail();
     if (h->fast4 && cfg->cam_src_width + 4 <= 2047 && cfg->cam_src_height + 4 <= 2047) {
         std::vector<uint32_t> pm(h->mapx.size());
         for (size_t i = 0; i < pm.size(); ++i) {
@@ -869,6 +896,7 @@ int pano_frontend_destroy(pano_frontend_handle h)
     cudaDeviceSynchronize();
     if (h->wtex) cudaDestroyTextureObject(h->wtex);
     for (void *p : h->owned) cudaFree(p);
+    scratchFree(h->own);
     delete h;
     return PANO_OK;
 }
@@ -882,6 +910,26 @@ int pano_frontend_get_maps(pano_frontend_handle h, float *mapx, float *mapy)
 }
 
 }  // extern "C"
+
+// A private set of the intermediates for a caller that chains this front end into its own stream (capi.cu: one per
+// stitcher handle and distinct front end): as deep as the handle's own (max_batch images).
+pano_front_scratch *pano_frontend_scratch_create(pano_frontend_handle h)
+{
+    if (!h) return nullptr;
+    if (cudaSetDevice(h->cfg.device) != cudaSuccess) return nullptr;
+    pano_front_scratch *s = new pano_front_scratch();
+    if (scratchAlloc(h, *s, h->cfg.max_batch)) { scratchFree(*s); delete s; return nullptr; }
+    return s;
+}
+
+void pano_frontend_scratch_destroy(pano_front_scratch *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    scratchFree(*s);
+    delete s;
+}
+
 
 // YUYV ingest: `count` frames (in_img bytes apart) -> dense 8UC4 frames at dst
 int pano_frontend_convert(pano_frontend_handle h, const uint8_t *yuyv, size_t in_img, uint8_t *dst, int count, cudaStream_t st)
@@ -910,13 +958,14 @@ bool pano_frontend_can_words(pano_frontend_handle h)
 }
 
 int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img, uint8_t *out, size_t o_img, int batch,
-                      cudaStream_t st, int out_px)
+                      cudaStream_t st, int out_px, pano_front_scratch *scratch)
 {
     if (!h || !argb || !out || batch < 1) return ffail(h, "pano_frontend_run: bad argument");
+    const pano_front_scratch &B = scratch ? *scratch : h->own;      // the caller's set of intermediates, or the handle's own
     if (out_px != 3 && !(out_px == 4 && pano_frontend_can_words(h))) return ffail(h, "pano_frontend_run: word output is not available for this geometry");
     FCK(h, cudaSetDevice(h->cfg.device));
     const pano_frontend_config &c = h->cfg;
-    const int S = c.max_batch, uw = c.undist_width, uh = c.undist_height;
+    const int S = B.depth, uw = c.undist_width, uh = c.undist_height;
     const size_t u_img = (size_t)uw * uh * 3;
     const dim3 blk(32, 8);
     h->launches = 0;
@@ -928,9 +977,9 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
         if (c.src_format == PANO_SRC_YUYV) {
             // stage 0 (YUYVCAM builds, :880-886): cv::cvtColor(COLOR_YUV2BGRA_YUYV) into the 8UC4 frame m_argb
             if (h->prof_ev) cudaEventRecord(h->prof_ev[3], st);
-            if (pano_frontend_convert(h, src, in_img, h->buf_argb, nb, st)) return PANO_ERR;
+            if (pano_frontend_convert(h, src, in_img, B.argb, nb, st)) return PANO_ERR;
             ++h->launches;
-            src = h->buf_argb;
+            src = B.argb;
             img_stride = (size_t)c.cam_src_width * c.cam_src_height * 4;
         }
         // stage 1: camera frame -> undist-sized 3-channel "tmp" (:903-904 / :924-927)
@@ -953,12 +1002,12 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
             if (out_px == 4 && !walk) return ffail(h, "pano_frontend_run: word output needs the row-walking resize");
             CubicArgs ca{};
             ca.src = src4; ca.src_img_words = img_stride / 4; ca.sw = cw; ca.sh = chh; ca.map = h->dmap32; ca.map_w = uw; ca.wtex = h->wtex;
-            ca.tiles = h->cub_tiles; ca.rx = rc[0]; ca.ry = rc[1]; ca.rw = rc[2]; ca.rh = rc[3]; ca.dst = h->buf_w; ca.dst_img_words = w_img;
+            ca.tiles = h->cub_tiles; ca.rx = rc[0]; ca.ry = rc[1]; ca.rw = rc[2]; ca.rh = rc[3]; ca.dst = B.w; ca.dst_img_words = w_img;
             ca.tx = h->cub_tx; ca.ty = h->cub_ty;
             const bool tma = tiled && h->cub_tma && !no_tma &&
                              tma_encode_words3d(&ca.tm0, src4, cw, chh, nb, (size_t)cw * 4, img_stride, kCubBoxW, kCubBoxH0) &&
                              tma_encode_words3d(&ca.tm1, src4, cw, chh, nb, (size_t)cw * 4, img_stride, kCubBoxW, kCubBoxH1);
-            ResizeArgs ra{h->buf_w, w_img, (unsigned)rc[2], final_dst, o_img, (unsigned)(uw * out_px), h->r_mid,
+            ResizeArgs ra{B.w, w_img, (unsigned)rc[2], final_dst, o_img, (unsigned)(uw * out_px), h->r_mid,
                           (uw + 127) / 128, (rc[3] + 1 + kResizeBand - 1) / kResizeBand};
             if (h->prof_ev) cudaEventRecord(h->prof_ev[0], st);
             if (tma)
@@ -966,11 +1015,11 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
             else if (tiled)
                 launch_chain(cubic5_kernel<false>, dim3(h->cub_tx, h->cub_ty, nb), blk, st, ca);
             else if (h->dmap32 && tex_w)
-                cubic4_kernel<true, true><<<cg, blk, 0, st>>>(src4, img_stride / 4, cw, chh, h->dmap32, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
+                cubic4_kernel<true, true><<<cg, blk, 0, st>>>(src4, img_stride / 4, cw, chh, h->dmap32, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], B.w, w_img);
             else if (h->dmap32)
-                cubic4_kernel<true, false><<<cg, blk, 0, st>>>(src4, img_stride / 4, cw, chh, h->dmap32, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
+                cubic4_kernel<true, false><<<cg, blk, 0, st>>>(src4, img_stride / 4, cw, chh, h->dmap32, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], B.w, w_img);
             else
-                cubic4_kernel<false, false><<<cg, blk, 0, st>>>(src4, img_stride / 4, cw, chh, h->dmap, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], h->buf_w, w_img);
+                cubic4_kernel<false, false><<<cg, blk, 0, st>>>(src4, img_stride / 4, cw, chh, h->dmap, uw, tab4, h->wtex, rc[0], rc[1], rc[2], rc[3], B.w, w_img);
             if (h->prof_ev) cudaEventRecord(h->prof_ev[1], st);
             static const int cols_env = getenv("PANO_RESIZE_COLS") ? atoi(getenv("PANO_RESIZE_COLS")) : 4;     // A/B switch: output columns per lane
             const bool idx32 = w_img * (size_t)nb < ((size_t)1 << 32);
@@ -989,7 +1038,7 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
             else if (walk)
                 launch_chain(resize4_walk_kernel<false>, dim3(ra.gx, ra.gy, nb), dim3(32, 4), st, ra);
             else
-                resize4_kernel<<<dim3((uw + 127) / 128, (uh + 7) / 8, nb), blk, 0, st>>>(h->buf_w, w_img, rc[2], final_dst, o_img,
+                resize4_kernel<<<dim3((uw + 127) / 128, (uh + 7) / 8, nb), blk, 0, st>>>(B.w, w_img, rc[2], final_dst, o_img,
                                                                                          uw * 3, h->r_mid);
             if (h->prof_ev) cudaEventRecord(h->prof_ev[2], st);
             h->launches += 2;
@@ -998,14 +1047,14 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
         if (out_px != 3) return ffail(h, "pano_frontend_run: word output needs 16-byte aligned camera frames");
         if (c.undistort) {
             if (h->use_r_in) {
-                resize_kernel<4><<<grid2(uw, uh, blk, nb), blk, 0, st>>>(cur, cur_img, cw * 4, h->buf_a, u_img, uw * 3, h->r_in);
+                resize_kernel<4><<<grid2(uw, uh, blk, nb), blk, 0, st>>>(cur, cur_img, cw * 4, B.a, u_img, uw * 3, h->r_in);
                 ++h->launches;
-                cur = h->buf_a; cur_c = 3; cw = uw; chh = uh; cur_img = u_img;
+                cur = B.a; cur_c = 3; cw = uw; chh = uh; cur_img = u_img;
             }
             // stage 2: cubic remap restricted to the crop rect (:909-916)
             const int *rc = c.rect;
             const bool last2 = !h->use_r_mid && !h->use_r_out;
-            uint8_t *d2 = target(last2, h->buf_b);
+            uint8_t *d2 = target(last2, B.b);
             const size_t d2_img = last2 ? o_img : (size_t)rc[2] * rc[3] * 3;
             if (cur_c == 4)
                 cubic_kernel<4><<<grid2(rc[2], rc[3], blk, nb), blk, 0, st>>>(cur, cur_img, cw, chh, cw * 4, h->dmap, uw, h->dtab,
@@ -1017,14 +1066,14 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
             cur = d2; cur_c = 3; cw = rc[2]; chh = rc[3]; cur_img = d2_img;
             // stage 3: resize the crop back to the undistort size (:917)
             if (h->use_r_mid) {
-                uint8_t *d3 = target(!h->use_r_out, h->buf_c);
+                uint8_t *d3 = target(!h->use_r_out, B.c);
                 const size_t d3_img = h->use_r_out ? u_img : o_img;
                 resize_kernel<3><<<grid2(uw, uh, blk, nb), blk, 0, st>>>(cur, cur_img, cw * 3, d3, d3_img, uw * 3, h->r_mid);
                 ++h->launches;
                 cur = d3; cw = uw; chh = uh; cur_img = d3_img;
             }
         } else {
-            uint8_t *d1 = target(!h->use_r_out, h->buf_a);
+            uint8_t *d1 = target(!h->use_r_out, B.a);
             const size_t d1_img = h->use_r_out ? u_img : o_img;
             if (h->use_r_in) {
                 resize_kernel<4><<<grid2(uw, uh, blk, nb), blk, 0, st>>>(cur, cur_img, cw * 4, d1, d1_img, uw * 3, h->r_in);
@@ -1105,7 +1154,7 @@ int pano_frontend_process_device(pano_frontend_handle h, const uint8_t *argb, ui
     if (!h) return PANO_ERR;
     const pano_frontend_config &c = h->cfg;
     return pano_frontend_run(h, argb, (size_t)c.cam_src_width * c.cam_src_height * h->in_px(), out,
-                             (size_t)c.out_width * c.out_height * 3, batch, (cudaStream_t)stream, 3);
+                             (size_t)c.out_width * c.out_height * 3, batch, (cudaStream_t)stream, 3, nullptr);
 }
 
 int pano_frontend_process(pano_frontend_handle h, const uint8_t *argb_host, int stride, uint8_t *out_host, int out_stride)

@@ -95,11 +95,11 @@ __device__ __forceinline__ int apply_gain_map(int v, float g)
 }
 
 template <bool kMap64>
-__global__ void __launch_bounds__(256) warp_kernel(const PanoTables *__restrict__ T, const uint8_t *__restrict__ frames)
+__global__ void __launch_bounds__(256) warp_kernel(const PanoTables *__restrict__ T, const uint8_t *__restrict__ frames, int cam0, int zcams)
 {
     pdl_enter();
     const int ncam = T->num_cams;
-    const int cam = blockIdx.z % ncam, slot = blockIdx.z / ncam;
+    const int cam = cam0 + blockIdx.z % zcams, slot = blockIdx.z / zcams;      // this launch covers cameras [cam0, cam0 + zcams)
     const CamTables &C = T->cam[cam];
     const int X = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int Y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -202,13 +202,12 @@ __device__ __forceinline__ void pyrdown_item(const PanoTables *__restrict__ T, i
     }
 }
 
-__global__ void __launch_bounds__(256) pyrdown_kernel(const PanoTables *__restrict__ T, int level)
+__global__ void __launch_bounds__(256) pyrdown_kernel(const PanoTables *__restrict__ T, int level, int cam0, int zcams)
 {
     pdl_enter();
-    const int ncam = T->num_cams;
     int z = blockIdx.z;
     const int plane = z % 3; z /= 3;
-    const int cam = z % ncam, slot = z / ncam;
+    const int cam = cam0 + z % zcams, slot = z / zcams;
     const int c0 = (T->cam[cam].rx >> (level + 1)) + blockIdx.x * blockDim.x * 4;
     if (outside_window(T, level + 1, c0, c0 + blockDim.x * 4)) return;
     pyrdown_item(T, level, cam, plane, slot, (blockIdx.x * blockDim.x + threadIdx.x) * 4, (blockIdx.y * blockDim.y + threadIdx.y) * 2);
@@ -432,13 +431,12 @@ __device__ __forceinline__ void down_hfilter(const DownRow &d, int h[8])
 }
 
 template <int kMinBlocks>
-__global__ void __launch_bounds__(128, kMinBlocks) pyrdown8_walk_kernel(const PanoTables *__restrict__ T, int level, int band)
+__global__ void __launch_bounds__(128, kMinBlocks) pyrdown8_walk_kernel(const PanoTables *__restrict__ T, int level, int band, int cam0, int zcams)
 {
     pdl_enter();
-    const int ncam = T->num_cams;
     int z = blockIdx.z;
     const int plane = z % 3; z /= 3;
-    const int cam = z % ncam, slot = z / ncam;
+    const int cam = cam0 + z % zcams, slot = z / zcams;
     const CamTables &C = T->cam[cam];
     const int sw = C.rw >> level, sh = C.rh >> level;
     const int dw = sw >> 1, dh = sh >> 1;
@@ -1028,6 +1026,7 @@ struct WarpArgs {
     CUtensorMap tm[kWarpBoxes];      // [slots * cameras][H][W] words (kTma only)
     WarpCam cam[kMaxCams];
     int ncam, W, H, win_lo, win_hi, nslots;
+    int cam0, zcams;                       // this launch covers cameras [cam0, cam0 + zcams)
 };
 
 // kGain: 0 = no camera has a gain, 1 = per-pixel float maps only (cameras without one use g = 1, which is exact),
@@ -1118,8 +1117,8 @@ __global__ void __launch_bounds__(256, kMinBlocks) warp_tile_kernel(const __grid
     // same tile of all slots runs back to back and its table entries come from L2 for all but the first slot --
     // measured 3.44 -> 3.09 ms per 64 frame-sets with gains, but 1.65 -> 1.74 ms without, hence the switch.
     constexpr bool kSlotFast = kGain != 0;
-    const int cam = kSlotFast ? (int)blockIdx.z : (int)(blockIdx.z % ncam);
-    const int slot = kSlotFast ? (int)(blockIdx.x % A.nslots) : (int)(blockIdx.z / ncam);
+    const int cam = A.cam0 + (kSlotFast ? (int)blockIdx.z : (int)(blockIdx.z % A.zcams));
+    const int slot = kSlotFast ? (int)(blockIdx.x % A.nslots) : (int)(blockIdx.z / A.zcams);
     const WarpCam &C = A.cam[cam];
     const int bx = kSlotFast ? (int)(blockIdx.x / A.nslots) : (int)blockIdx.x, by = blockIdx.y;
     if (bx >= C.tiles_x || by >= C.tiles_y) return;
@@ -1701,8 +1700,9 @@ inline dim3 grid2d(int w, int h, dim3 block, int z) { return dim3((w + block.x -
 }  // namespace
 
 void launch_warp(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, const uint8_t *frames, int nslots,
-                 cudaStream_t stream)
+                 cudaStream_t stream, CamRange cams)
 {
+    const int cam0 = cams.count > 0 ? cams.first : 0, zc = cams.count > 0 ? cams.count : host.num_cams;
     // the staged kernel reads the frames as 16-byte vectors (or through TMA): an unaligned base takes the generic kernel
     if (kc.warp_tiled && (reinterpret_cast<uintptr_t>(frames) & 15) == 0) {
         int tx = 0, ty = 0;
@@ -1710,8 +1710,10 @@ void launch_warp(const PanoTables *dev, const PanoTables &host, const KernelChoi
         WarpArgs A{};
         for (int i = 0; i < host.num_cams; ++i) {
             const CamTables &C = host.cam[i];
-            tx = max(tx, C.tiles_x);
-            ty = max(ty, C.tiles_y);
+            if (i >= cam0 && i < cam0 + zc) {
+                tx = max(tx, C.tiles_x);
+                ty = max(ty, C.tiles_y);
+            }
             gain = gain || C.gain_mode != 0;
             WarpCam &d = A.cam[i];
             d.map32 = C.map32; d.map64 = C.map64; d.tiles = C.tiles; d.gain_map = C.gain_map; d.g0 = C.g[0];
@@ -1723,8 +1725,9 @@ void launch_warp(const PanoTables *dev, const PanoTables &host, const KernelChoi
         int gv = 0;              // gain variant: 0 none, 1 float maps only, 2 generic (a scalar gain somewhere)
         for (int i = 0; i < host.num_cams; ++i) gv = max(gv, host.cam[i].gain_mode);
         A.nslots = nslots;
+        A.cam0 = cam0; A.zcams = zc;
         const dim3 block(32, 8);
-        const dim3 grid = gv != 0 ? dim3(tx * nslots, ty, host.num_cams) : dim3(tx, ty, host.num_cams * nslots);
+        const dim3 grid = gv != 0 ? dim3(tx * nslots, ty, zc) : dim3(tx, ty, zc * nslots);
         const bool m64 = host.cam[0].map64 != nullptr, s4 = host.src_px == 4;
         static const bool no_tma = getenv("PANO_NO_TMA") != nullptr;            // A/B switch: LDG/STS staging loop
         static const bool no_tma_bgr = getenv("PANO_NO_TMA_BGR") != nullptr;    // A/B switch: packed-BGR frames through the LDG/STS expansion
@@ -1748,21 +1751,22 @@ void launch_warp(const PanoTables *dev, const PanoTables &host, const KernelChoi
         return;
     }
     int maxw = 0, maxh = 0;
-    for (int i = 0; i < host.num_cams; ++i) {
+    for (int i = cam0; i < cam0 + zc; ++i) {
         maxw = max(maxw, host.cam[i].rw);
         maxh = max(maxh, host.cam[i].rh);
     }
     const dim3 block(32, 8);
-    const dim3 grid = grid2d((maxw + 3) / 4, maxh, block, host.num_cams * nslots);
-    if (host.cam[0].map64) launch_chain(warp_kernel<true>, grid, block, stream, dev, frames);
-    else launch_chain(warp_kernel<false>, grid, block, stream, dev, frames);
+    const dim3 grid = grid2d((maxw + 3) / 4, maxh, block, zc * nslots);
+    if (host.cam[0].map64) launch_chain(warp_kernel<true>, grid, block, stream, dev, frames, cam0, zc);
+    else launch_chain(warp_kernel<false>, grid, block, stream, dev, frames, cam0, zc);
 }
 
 void launch_pyrdown(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, int level, int nslots,
-                    cudaStream_t stream)
+                    cudaStream_t stream, CamRange cams)
 {
+    const int cam0 = cams.count > 0 ? cams.first : 0, zc = cams.count > 0 ? cams.count : host.num_cams;
     int maxw = 0, maxh = 0;
-    for (int i = 0; i < host.num_cams; ++i) {
+    for (int i = cam0; i < cam0 + zc; ++i) {
         maxw = max(maxw, ((host.cam[i].rw >> level) + 1) / 2);
         maxh = max(maxh, ((host.cam[i].rh >> level) + 1) / 2);
     }
@@ -1773,15 +1777,15 @@ void launch_pyrdown(const PanoTables *dev, const PanoTables &host, const KernelC
         // (measured, level 0 / 1 / 2 of config 1: band 8 0.541 / 0.152 / 0.052 ms, 16 0.496 / 0.140 / 0.050, 32 0.482 / 0.141 / 0.061)
         static const int band_env = getenv("PANO_DOWN_BAND") ? atoi(getenv("PANO_DOWN_BAND")) : 0;
         const int band = band_env > 0 ? band_env : (maxh >= 400 ? 32 : 16);
-        const dim3 wb(32, 4), wg((maxw + 255) / 256, (maxh + 4 * band - 1) / (4 * band), host.num_cams * nslots * 3);
+        const dim3 wb(32, 4), wg((maxw + 255) / 256, (maxh + 4 * band - 1) / (4 * band), zc * nslots * 3);
         static const int occ = getenv("PANO_DOWN_OCC") ? atoi(getenv("PANO_DOWN_OCC")) : 0;      // tuning knob: min blocks per SM (0 = compiler's choice)
-        if (occ >= 8) launch_chain(pyrdown8_walk_kernel<8>, wg, wb, stream, dev, level, band);
-        else if (occ >= 6) launch_chain(pyrdown8_walk_kernel<6>, wg, wb, stream, dev, level, band);
-        else launch_chain(pyrdown8_walk_kernel<0>, wg, wb, stream, dev, level, band);
+        if (occ >= 8) launch_chain(pyrdown8_walk_kernel<8>, wg, wb, stream, dev, level, band, cam0, zc);
+        else if (occ >= 6) launch_chain(pyrdown8_walk_kernel<6>, wg, wb, stream, dev, level, band, cam0, zc);
+        else launch_chain(pyrdown8_walk_kernel<0>, wg, wb, stream, dev, level, band, cam0, zc);
         return;
     }
-    const dim3 grid = grid2d((maxw + 3) / 4, (maxh + 1) / 2, block, host.num_cams * nslots * 3);
-    launch_chain(pyrdown_kernel, grid, block, stream, dev, level);
+    const dim3 grid = grid2d((maxw + 3) / 4, (maxh + 1) / 2, block, zc * nslots * 3);
+    launch_chain(pyrdown_kernel, grid, block, stream, dev, level, cam0, zc);
 }
 
 void launch_coarsest(const PanoTables *dev, const PanoTables &host, uint8_t *pano, int nslots, cudaStream_t stream)

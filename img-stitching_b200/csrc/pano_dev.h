@@ -89,10 +89,13 @@ struct KernelChoice {
     bool collapse8[kMaxLevels] = {};         // packed 8x2 collapse usable at this level
 };
 
+// cameras [first, first + count) of every slot; count == 0: all of them.  The per-camera stages (warp, pyrDown levels) can be
+// launched camera by camera, so that a camera's chain starts as soon as ITS frame is in device memory (pano_process)
+struct CamRange { int first = 0, count = 0; };
 void launch_warp(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, const uint8_t *frames, int nslots,
-                 cudaStream_t stream);
+                 cudaStream_t stream, CamRange cams = CamRange());
 void launch_pyrdown(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, int level, int nslots,
-                    cudaStream_t stream);
+                    cudaStream_t stream, CamRange cams = CamRange());
 void launch_coarsest(const PanoTables *dev, const PanoTables &host, uint8_t *pano, int nslots, cudaStream_t stream);
 // returns the number of kernels launched
 int launch_collapse(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, int level, uint8_t *pano,

@@ -277,7 +277,10 @@ int pano_host_seam_input(int warp_kind, float warped_image_scale, const float *K
  * ([batch][num_images][cam_src_height][cam_src_width][4]) and run nvCam's pixel pipeline on the
  * device first -- the loop of src/master.cpp:300-318 (getFrame x N, then process) as one call.
  * f == NULL detaches.  Re-callable at any time: the host staging buffers are re-sized when the caller-side frame
- * format changes; a failing call leaves the handle untouched. */
+ * format changes; a failing call leaves the handle untouched.  The stitcher handle keeps its own copy of the front
+ * end's intermediate buffers, so ONE front-end handle may be attached to several stitcher handles that run on
+ * different threads / streams at the same time (the two rings of src/panocamimpl.cpp share the camera model); the
+ * front end's own host-buffer calls (pano_frontend_process*) remain one thread at a time. */
 int pano_attach_frontend(pano_handle h, int cam, pano_frontend_handle f);
 
 /* ---------------------------------------------------------------- two-ring epilogue (caller step after process)
