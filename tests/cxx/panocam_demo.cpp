@@ -59,8 +59,14 @@ int main(int argc, char **argv)
     if (cam.calibration(finder) != pano::RET_OK) { fprintf(stderr, "calibration failed: %s\n", cam.lastError().c_str()); return 3; }
     std::vector<unsigned char> ret((size_t)cam.outWidth() * cam.outHeight() * 3);
     pano::Image ret_img{ret.data(), cam.outWidth(), cam.outHeight(), cam.outWidth() * 3};
-    for (int rep = 0; rep < 2; ++rep)       // twice: the second call replays the captured graphs
+    // repeatedly: later calls replay the captured graphs, and the two rings -- two threads, two streams, ONE shared
+    // front-end handle -- must give the same bytes every time whatever their relative timing
+    std::vector<unsigned char> first;
+    for (int rep = 0; rep < 24; ++rep) {
         if (cam.getPanoFrame(ret_img) != pano::RET_OK) { fprintf(stderr, "getPanoFrame failed: %s\n", cam.lastError().c_str()); return 4; }
+        if (rep == 0) first = ret;
+        else if (ret != first) { fprintf(stderr, "getPanoFrame call %d differs from the first call\n", rep); return 5; }
+    }
     pano::FitCanvas fit;
     if (fit.init(ret_img.width, ret_img.height, hdr[9], hdr[10]) != pano::RET_OK) { fprintf(stderr, "fit: %s\n", fit.lastError().c_str()); return 3; }
     std::vector<unsigned char> canvas((size_t)hdr[9] * hdr[10] * 3);
