@@ -46,6 +46,16 @@ __device__ __forceinline__ bool outside_window(const PanoTables *__restrict__ T,
     return c1 <= T->win_lo[l] || c0 >= T->win_hi[l];
 }
 
+// ---- conversions without the quarter-rate conversion pipe (I2F / F2I issue at 16 lanes per clock per SM; the feather blend
+// needs ~15 of them per pixel and was bound by exactly that pipe).  All exact on the stated ranges:
+// u in [0, 2^23): (float)u == (2^23 + u) - 2^23, with 2^23 + u assembled in the mantissa by one integer OR / byte permute
+__device__ __forceinline__ float small_uint_to_float(uint32_t u) { return __fadd_rn(__uint_as_float(0x4B000000u | u), -8388608.f); }
+// byte j of word v -> float: one PRMT places the byte in the low mantissa byte of 0x4B000000
+template <int j>
+__device__ __forceinline__ float byte_to_float(uint32_t v) { return __fadd_rn(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7440 + j)), -8388608.f); }
+// f in [0, 2^22): (int)f (truncation) == low mantissa bits of f + 2^23 added with round-toward-zero
+__device__ __forceinline__ int trunc_small_nonneg(float f) { return __float_as_int(__fadd_rz(f, 8388608.f)) & 0x7fffff; }
+
 // ------------------------------------------------------------------ K1: rotation warp
 // cv::remap(INTER_LINEAR, BORDER_REFLECT) of blender_warper->warp (ocvstitcher.hpp:1171)
 // + compensator->apply (stitching_detailed.cpp:841) + convertTo(CV_16S) (:1180)
@@ -1320,11 +1330,14 @@ __global__ void __launch_bounds__(256) direct_blend_kernel(const PanoTables *__r
 // normalise), Blender::blend (mask), convertTo(CV_8U) and the crop do.  Same operations in the same camera order as
 // direct_blend_kernel -> identical bytes.  One thread = 4 consecutive panorama pixels.
 template <bool kFeather>
-__global__ void __launch_bounds__(256) blend_g0_kernel(const PanoTables *__restrict__ T, uint8_t *__restrict__ pano)
+__global__ void __launch_bounds__(256) blend_g0_kernel(const PanoTables *__restrict__ T, uint8_t *__restrict__ pano, int nslots)
 {
     pdl_enter();
-    const int cx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, cy = blockIdx.y * blockDim.y + threadIdx.y;
-    const int slot = blockIdx.z;
+    // frame-set slot fastest (blockIdx.x = slot + nslots * column block): the same panorama tile of all slots runs back to
+    // back, so the static per-camera weight maps (4 bytes per pixel, more than a slot's whole image data) come from L2
+    // for every slot but the first
+    const int slot = blockIdx.x % nslots, bx = blockIdx.x / nslots;
+    const int cx0 = (bx * blockDim.x + threadIdx.x) * 4, cy = blockIdx.y * blockDim.y + threadIdx.y;
     if (cx0 >= T->cut_w || cy >= T->cut_h) return;
     const int npx = min(4, T->cut_w - cx0);
     const int X0 = cx0 + T->cut_x, Y = cy + T->cut_y, ncam = T->num_cams;
@@ -1339,6 +1352,59 @@ __global__ void __launch_bounds__(256) blend_g0_kernel(const PanoTables *__restr
         if ((unsigned)y >= (unsigned)C.rh || x0 + 3 < 0 || x0 >= C.rw) continue;
         const uint8_t *g = C.g[0] + (size_t)slot * C.g_slot[0] + (size_t)y * C.g_pitch[0];
         const size_t plane = C.g_plane[0];
+        // The 4 pixels of this thread sit at camera columns x0 .. x0 + 3, and x0 & 3 is the SAME for every thread of the
+        // grid (cx0 is a multiple of 4): where the group lies inside the image its three planes come in as aligned words
+        // -- two per plane, funnel-shifted by that camera-wide byte offset -- instead of twelve single-byte loads.
+        const int sh = x0 & 3, xa = x0 - sh;
+        if (npx == 4 && xa >= 0 && x0 + 4 <= C.rw && xa + 8 <= C.g_pitch[0]) {
+            uint32_t pv[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const uint32_t lo = *reinterpret_cast<const uint32_t *>(g + c * plane + xa);
+                const uint32_t hi = sh ? *reinterpret_cast<const uint32_t *>(g + c * plane + xa + 4) : 0u;
+                pv[c] = __funnelshift_r(lo, hi, 8 * sh);
+            }
+            if (kFeather) {
+                const float *wr = C.wt[0] + (size_t)y * C.wt_pitch[0] + x0;
+                float w[4];
+                if (sh == 0 && (C.wt_pitch[0] & 3) == 0) {
+                    const float4 q = __ldg(reinterpret_cast<const float4 *>(wr));
+                    w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) w[j] = __ldg(wr + j);
+                }
+                // weights in [0, 1] (every builder's output; anything else takes the plain conversions): products are in
+                // [0, 255], so truncation and the short wrap are the mantissa tricks above
+                const bool tame = w[0] >= 0.f && w[0] <= 1.f && w[1] >= 0.f && w[1] <= 1.f && w[2] >= 0.f && w[2] <= 1.f && w[3] >= 0.f && w[3] <= 1.f;
+                if (tame) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        acc[0][c] += trunc_small_nonneg(__fmul_rn(byte_to_float<0>(pv[c]), w[0]));
+                        acc[1][c] += trunc_small_nonneg(__fmul_rn(byte_to_float<1>(pv[c]), w[1]));
+                        acc[2][c] += trunc_small_nonneg(__fmul_rn(byte_to_float<2>(pv[c]), w[2]));
+                        acc[3][c] += trunc_small_nonneg(__fmul_rn(byte_to_float<3>(pv[c]), w[3]));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            acc[j][c] += trunc_s16(__fmul_rn((float)((pv[c] >> (8 * j)) & 0xffu), w[j]));
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) wsum[j] = __fadd_rn(wsum[j], w[j]);
+            } else {
+                const uint8_t *mr = C.mask0 + (size_t)y * C.mask_pitch + x0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int mk = __ldg(mr + j);
+                    if (mk) { acc[j][0] = (pv[0] >> (8 * j)) & 0xffu; acc[j][1] = (pv[1] >> (8 * j)) & 0xffu; acc[j][2] = (pv[2] >> (8 * j)) & 0xffu; }
+                    any[j] |= mk;
+                }
+            }
+            continue;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int x = x0 + j;
@@ -1361,11 +1427,37 @@ __global__ void __launch_bounds__(256) blend_g0_kernel(const PanoTables *__restr
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         if (kFeather) {
+            // (short)(sum / (weight sum + 1e-5f)) for the three channels of a pixel: ONE approximate reciprocal of the shared
+            // denominator, refined by a Newton step (relative error < 2^-22), gives q' = sum * y within 3 ulp of the true
+            // quotient Q; the reference's value is trunc(RN(Q)), which equals trunc(q') unless Q lies within a few ulp of an
+            // integer.  For q' < 256 (3 ulp < 2^-13) the test is on the fraction: inside [2^-11, 1 - 2^-11] the truncation
+            // is settled; otherwise -- ~0.1 % of the values, sums outside [0, 32767], quotients >= 256 -- the pixel's three
+            // IEEE divisions are done as the reference does them.  floor(q') comes from one round-toward-zero add of 2^23.
             const float den = __fadd_rn(wsum[j], 1e-5f);
             const bool valid = wsum[j] > 1e-5f;
+            int r[3] = {0, 0, 0};
+            if (valid) {
+                float y;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(den));
+                y = __fmaf_rn(y, __fmaf_rn(-den, y, 1.0f), y);
+                bool settled = true;
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-                px[3 * j + c] = valid ? (uint8_t)sat_u8(trunc_s16(__fdiv_rn((float)wrap_s16(acc[j][c]), den))) : (uint8_t)0;
+                for (int c = 0; c < 3; ++c) {
+                    const int a = acc[j][c];
+                    const float q = __fmul_rn(small_uint_to_float((uint32_t)a & 0x7fffu), y);
+                    const float t = __fadd_rz(q, 8388608.f);                        // 2^23 + floor(q) for q < 2^23
+                    const float frac = __fadd_rn(q, -__fadd_rn(t, -8388608.f));     // exact: q - floor(q)
+                    const bool ok = (fabsf(__fadd_rn(frac, -0.5f)) <= 0.49951171875f && q < 256.f && (unsigned)a < 32768u) || a == 0;
+                    settled = settled && ok;
+                    r[c] = __float_as_int(t) & 0xff;
+                }
+                if (!settled) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) r[c] = sat_u8(trunc_s16(__fdiv_rn((float)wrap_s16(acc[j][c]), den)));
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) px[3 * j + c] = (uint8_t)r[c];
         } else {
 #pragma unroll
             for (int c = 0; c < 3; ++c) px[3 * j + c] = any[j] ? (uint8_t)sat_u8(acc[j][c]) : (uint8_t)0;
@@ -1955,9 +2047,10 @@ void launch_tile_stats(const void *data, bool is_mask, int pitch, int w, int h, 
 void launch_blend_g0(const PanoTables *dev, const PanoTables &host, int blender, uint8_t *pano, int nslots, cudaStream_t stream)
 {
     const dim3 block(32, 8);
-    const dim3 grid = grid2d((host.cut_w + 3) / 4, host.cut_h, block, nslots);
-    if (blender == 1) launch_chain(blend_g0_kernel<true>, grid, block, stream, dev, pano);
-    else launch_chain(blend_g0_kernel<false>, grid, block, stream, dev, pano);
+    dim3 grid = grid2d((host.cut_w + 3) / 4, host.cut_h, block, 1);
+    grid.x *= nslots;
+    if (blender == 1) launch_chain(blend_g0_kernel<true>, grid, block, stream, dev, pano, nslots);
+    else launch_chain(blend_g0_kernel<false>, grid, block, stream, dev, pano, nslots);
 }
 
 void launch_direct_blend(const PanoTables *dev, const PanoTables &host, int blender, const uint8_t *frames,
