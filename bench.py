@@ -20,6 +20,7 @@ Frame-sets are sharded across ranks with no data-path collective (weak scaling: 
   parity     the first GPU panoramas against the CPU arm's panoramas computed from the same bytes in this run
   cpu_baseline  cv2-driven reference call sequence on the host cores: faithful (maps rebuilt per call, the reference's
              behaviour) and cached-maps variants
+  also.config3  BASELINE config 3 (imx424 rig, BlocksGainCompensator gains + FeatherBlender), device-resident
   also.config5  BASELINE config 5: ONE 256-frame-set batch sharded over the ranks (strong scaling), device-resident and
              streamed from pinned host memory
   strip_split   (N > 1) BASELINE config 4: one 8 x 4K cylindrical 7-band panorama split into N column strips, halos by
@@ -729,6 +730,23 @@ def main():
                                            for k, v in r1["kernels"].items()}}
             b1["st"].close()
             del b1, hi, ho
+        if args.workload != "config3":
+            # BASELINE config 3 (imx424 rig, block gains + FeatherBlender) in the same process, device-resident
+            try:
+                b3 = build("config3", local_rank, dev, B, args.max_batch, 1234 + rank)
+                for _ in range(3):
+                    b3["st"].process_device(b3["frames"], b3["out"], stream.cuda_stream)
+                s3 = max(2, args.steps // 4)
+                ms3, _ = time_device(b3, s3, WAVES, stream, barrier)
+                acc3 = profile_kernels(b3, stream)
+                ms3m, = allmax([ms3])
+                also["config3"] = {"workload": WORKLOADS["config3"], "value": world * B * WAVES * s3 / (ms3m / 1000.0), "unit": UNIT,
+                                   "ms_per_wave": ms3m / (WAVES * s3), "gpu_launches_per_wave": b3["st"].last_launch_count(),
+                                   "kernels_ms_per_launch": {k: v["ms"] / v["launches"] for k, v in acc3.items()}}
+                b3["st"].close()
+                del b3
+            except Exception as e:                   # a side record must not take the headline down
+                also["config3"] = {"error": repr(e)[:300]}
         if world > 1:
             from panob200 import pkg
             try:

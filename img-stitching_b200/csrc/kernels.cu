@@ -1329,10 +1329,21 @@ __global__ void __launch_bounds__(256) direct_blend_kernel(const PanoTables *__r
 // 3x faster than the per-pixel byte loads above; this kernel does what FeatherBlender::feed / blend (weight, accumulate,
 // normalise), Blender::blend (mask), convertTo(CV_8U) and the crop do.  Same operations in the same camera order as
 // direct_blend_kernel -> identical bytes.  One thread = 4 consecutive panorama pixels.
+// per-camera descriptors travel as kernel parameters (constant bank): reading them from the table in global memory puts a
+// dependent load in front of every camera's pixel loads
+struct BlendCam {
+    const uint8_t *g0; const float *wt0; const uint8_t *mask0;
+    size_t g_slot, g_plane;
+    int rx, ry, rw, rh, g_pitch, wt_pitch, mask_pitch, pad_;
+};
+struct BlendArgs { BlendCam cam[kMaxCams]; int num_cams, cut_x, cut_y, cut_w, cut_h, nslots; };
+
 template <bool kFeather>
-__global__ void __launch_bounds__(256) blend_g0_kernel(const PanoTables *__restrict__ T, uint8_t *__restrict__ pano, int nslots)
+__global__ void __launch_bounds__(256) blend_g0_kernel(const __grid_constant__ BlendArgs A, uint8_t *__restrict__ pano)
 {
     pdl_enter();
+    const BlendArgs *T = &A;
+    const int nslots = A.nslots;
     // frame-set slot fastest (blockIdx.x = slot + nslots * column block): the same panorama tile of all slots runs back to
     // back, so the static per-camera weight maps (4 bytes per pixel, more than a slot's whole image data) come from L2
     // for every slot but the first
@@ -1347,16 +1358,16 @@ __global__ void __launch_bounds__(256) blend_g0_kernel(const PanoTables *__restr
 #pragma unroll
     for (int j = 0; j < 4; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = 0; wsum[j] = 0.f; any[j] = 0; }
     for (int i = 0; i < ncam; ++i) {
-        const CamTables &C = T->cam[i];
+        const BlendCam &C = A.cam[i];
         const int y = Y - C.ry, x0 = X0 - C.rx;
         if ((unsigned)y >= (unsigned)C.rh || x0 + 3 < 0 || x0 >= C.rw) continue;
-        const uint8_t *g = C.g[0] + (size_t)slot * C.g_slot[0] + (size_t)y * C.g_pitch[0];
-        const size_t plane = C.g_plane[0];
+        const uint8_t *g = C.g0 + (size_t)slot * C.g_slot + (size_t)y * C.g_pitch;
+        const size_t plane = C.g_plane;
         // The 4 pixels of this thread sit at camera columns x0 .. x0 + 3, and x0 & 3 is the SAME for every thread of the
         // grid (cx0 is a multiple of 4): where the group lies inside the image its three planes come in as aligned words
         // -- two per plane, funnel-shifted by that camera-wide byte offset -- instead of twelve single-byte loads.
         const int sh = x0 & 3, xa = x0 - sh;
-        if (npx == 4 && xa >= 0 && x0 + 4 <= C.rw && xa + 8 <= C.g_pitch[0]) {
+        if (npx == 4 && xa >= 0 && x0 + 4 <= C.rw && xa + 8 <= C.g_pitch) {
             uint32_t pv[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -1365,9 +1376,9 @@ __global__ void __launch_bounds__(256) blend_g0_kernel(const PanoTables *__restr
                 pv[c] = __funnelshift_r(lo, hi, 8 * sh);
             }
             if (kFeather) {
-                const float *wr = C.wt[0] + (size_t)y * C.wt_pitch[0] + x0;
+                const float *wr = C.wt0 + (size_t)y * C.wt_pitch + x0;
                 float w[4];
-                if (sh == 0 && (C.wt_pitch[0] & 3) == 0) {
+                if (sh == 0 && (C.wt_pitch & 3) == 0) {
                     const float4 q = __ldg(reinterpret_cast<const float4 *>(wr));
                     w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
                 } else {
@@ -1411,7 +1422,7 @@ __global__ void __launch_bounds__(256) blend_g0_kernel(const PanoTables *__restr
             if (j >= npx || (unsigned)x >= (unsigned)C.rw) continue;
             const int v0 = g[x], v1 = g[plane + x], v2 = g[2 * plane + x];
             if (kFeather) {
-                const float w = __ldg(C.wt[0] + (size_t)y * C.wt_pitch[0] + x);
+                const float w = __ldg(C.wt0 + (size_t)y * C.wt_pitch + x);
                 acc[j][0] += trunc_s16(__fmul_rn((float)v0, w));
                 acc[j][1] += trunc_s16(__fmul_rn((float)v1, w));
                 acc[j][2] += trunc_s16(__fmul_rn((float)v2, w));
@@ -2049,8 +2060,17 @@ void launch_blend_g0(const PanoTables *dev, const PanoTables &host, int blender,
     const dim3 block(32, 8);
     dim3 grid = grid2d((host.cut_w + 3) / 4, host.cut_h, block, 1);
     grid.x *= nslots;
-    if (blender == 1) launch_chain(blend_g0_kernel<true>, grid, block, stream, dev, pano, nslots);
-    else launch_chain(blend_g0_kernel<false>, grid, block, stream, dev, pano, nslots);
+    BlendArgs A{};
+    for (int i = 0; i < host.num_cams; ++i) {
+        const CamTables &C = host.cam[i];
+        BlendCam &d = A.cam[i];
+        d.g0 = C.g[0]; d.wt0 = C.wt[0]; d.mask0 = C.mask0; d.g_slot = C.g_slot[0]; d.g_plane = C.g_plane[0];
+        d.rx = C.rx; d.ry = C.ry; d.rw = C.rw; d.rh = C.rh; d.g_pitch = C.g_pitch[0]; d.wt_pitch = C.wt_pitch[0]; d.mask_pitch = C.mask_pitch;
+    }
+    A.num_cams = host.num_cams; A.cut_x = host.cut_x; A.cut_y = host.cut_y; A.cut_w = host.cut_w; A.cut_h = host.cut_h; A.nslots = nslots;
+    (void)dev;
+    if (blender == 1) launch_chain(blend_g0_kernel<true>, grid, block, stream, A, pano);
+    else launch_chain(blend_g0_kernel<false>, grid, block, stream, A, pano);
 }
 
 void launch_direct_blend(const PanoTables *dev, const PanoTables &host, int blender, const uint8_t *frames,
