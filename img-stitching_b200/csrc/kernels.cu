@@ -212,9 +212,12 @@ __device__ __forceinline__ void pyrdown_item(const PanoTables *__restrict__ T, i
     }
 }
 
-__global__ void __launch_bounds__(256) pyrdown_kernel(const PanoTables *__restrict__ T, int level, int cam0, int zcams)
+// (the small / generic kernels take the whole table -- 4.7 KB -- as a __grid_constant__ parameter: every descriptor read is then
+// a constant-bank access instead of a global load in front of the first data load; these kernels are latency-bound)
+__global__ void __launch_bounds__(256) pyrdown_kernel(const __grid_constant__ PanoTables TT, int level, int cam0, int zcams)
 {
     pdl_enter();
+    const PanoTables *T = &TT;
     int z = blockIdx.z;
     const int plane = z % 3; z /= 3;
     const int cam = cam0 + z % zcams, slot = z / zcams;
@@ -288,9 +291,10 @@ __device__ __forceinline__ void coarsest_item(const PanoTables *__restrict__ T, 
     }
 }
 
-__global__ void __launch_bounds__(256) coarsest_kernel(const PanoTables *__restrict__ T, uint8_t *__restrict__ pano)
+__global__ void __launch_bounds__(256) coarsest_kernel(const __grid_constant__ PanoTables TT, uint8_t *__restrict__ pano)
 {
     pdl_enter();
+    const PanoTables *T = &TT;
     if (outside_window(T, T->nb, blockIdx.x * blockDim.x, (blockIdx.x + 1) * blockDim.x)) return;
     coarsest_item(T, pano, blockIdx.z, blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y * blockDim.y + threadIdx.y);
 }
@@ -382,9 +386,10 @@ __device__ __forceinline__ void collapse_item(const PanoTables *__restrict__ T, 
 }
 
 
-__global__ void __launch_bounds__(256) collapse_kernel(const PanoTables *__restrict__ T, int L, uint8_t *__restrict__ pano)
+__global__ void __launch_bounds__(256) collapse_kernel(const __grid_constant__ PanoTables TT, int L, uint8_t *__restrict__ pano)
 {
     pdl_enter();
+    const PanoTables *T = &TT;
     if (outside_window(T, L, 2 * blockIdx.x * blockDim.x, 2 * (blockIdx.x + 1) * blockDim.x)) return;
     collapse_item(T, L, pano, blockIdx.z, blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y * blockDim.y + threadIdx.y);
 }
@@ -441,9 +446,10 @@ __device__ __forceinline__ void down_hfilter(const DownRow &d, int h[8])
 }
 
 template <int kMinBlocks>
-__global__ void __launch_bounds__(128, kMinBlocks) pyrdown8_walk_kernel(const PanoTables *__restrict__ T, int level, int band, int cam0, int zcams)
+__global__ void __launch_bounds__(128, kMinBlocks) pyrdown8_walk_kernel(const __grid_constant__ PanoTables TT, int level, int band, int cam0, int zcams)
 {
     pdl_enter();
+    const PanoTables *T = &TT;
     int z = blockIdx.z;
     const int plane = z % 3; z /= 3;
     const int cam = cam0 + z % zcams, slot = z / zcams;
@@ -1882,20 +1888,20 @@ void launch_pyrdown(const PanoTables *dev, const PanoTables &host, const KernelC
         const int band = band_env > 0 ? band_env : (maxh >= 400 ? 32 : 16);
         const dim3 wb(32, 4), wg((maxw + 255) / 256, (maxh + 4 * band - 1) / (4 * band), zc * nslots * 3);
         static const int occ = getenv("PANO_DOWN_OCC") ? atoi(getenv("PANO_DOWN_OCC")) : 0;      // tuning knob: min blocks per SM (0 = compiler's choice)
-        if (occ >= 8) launch_chain(pyrdown8_walk_kernel<8>, wg, wb, stream, dev, level, band, cam0, zc);
-        else if (occ >= 6) launch_chain(pyrdown8_walk_kernel<6>, wg, wb, stream, dev, level, band, cam0, zc);
-        else launch_chain(pyrdown8_walk_kernel<0>, wg, wb, stream, dev, level, band, cam0, zc);
+        if (occ >= 8) launch_chain(pyrdown8_walk_kernel<8>, wg, wb, stream, host, level, band, cam0, zc);
+        else if (occ >= 6) launch_chain(pyrdown8_walk_kernel<6>, wg, wb, stream, host, level, band, cam0, zc);
+        else launch_chain(pyrdown8_walk_kernel<0>, wg, wb, stream, host, level, band, cam0, zc);
         return;
     }
     const dim3 grid = grid2d((maxw + 3) / 4, (maxh + 1) / 2, block, zc * nslots * 3);
-    launch_chain(pyrdown_kernel, grid, block, stream, dev, level, cam0, zc);
+    launch_chain(pyrdown_kernel, grid, block, stream, host, level, cam0, zc);
 }
 
 void launch_coarsest(const PanoTables *dev, const PanoTables &host, uint8_t *pano, int nslots, cudaStream_t stream)
 {
     const dim3 block(32, 8);
     const dim3 grid = grid2d(host.pad_w >> host.nb, host.pad_h >> host.nb, block, nslots);
-    launch_chain(coarsest_kernel, grid, block, stream, dev, pano);
+    launch_chain(coarsest_kernel, grid, block, stream, host, pano);
 }
 
 int launch_collapse(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, int level, uint8_t *pano,
@@ -1953,7 +1959,7 @@ int launch_collapse(const PanoTables *dev, const PanoTables &host, const KernelC
     }
     const dim3 block(32, 8);
     const dim3 grid = grid2d(host.pad_w >> (level + 1), host.pad_h >> (level + 1), block, nslots);
-    launch_chain(collapse_kernel, grid, block, stream, dev, level, pano);
+    launch_chain(collapse_kernel, grid, block, stream, host, level, pano);
     return 1;
 }
 
