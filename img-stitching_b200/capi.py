@@ -154,8 +154,11 @@ def lib():
     """The loaded shared library (built on first use if stale).  Raises if unavailable."""
     global _lib
     if _lib is None:
-        build_library()
-        l = C.CDLL(_LIB)
+        path = os.environ.get("PANOB200_LIB")          # A/B runs of two builds of the library; default: the in-tree build
+        if not path:
+            build_library()
+            path = _LIB
+        l = C.CDLL(path)
         for name, (res, args) in _SIGS.items():
             fn = getattr(l, name)  # AttributeError if the .so lacks a declared symbol
             fn.restype, fn.argtypes = res, args
