@@ -801,21 +801,6 @@ void freeFrontScratch(pano_ctx *h)
     }
 }
 
-int rebuildFrontScratch(pano_ctx *h)
-{
-    freeFrontScratch(h);
-    for (int i = 0; i < h->n; ++i) {
-        if (!h->front[i]) continue;
-        for (int j = 0; j < i && !h->front_scratch[i]; ++j)
-            if (h->front[j] == h->front[i]) h->front_scratch[i] = h->front_scratch[j];
-        if (!h->front_scratch[i]) {
-            h->front_scratch[i] = pano_frontend_scratch_create(h->front[i]);
-            if (!h->front_scratch[i]) return fail(h, "pano_attach_frontend: out of device memory for the front end's intermediate buffers");
-        }
-    }
-    return PANO_OK;
-}
-
 // The staging buffers are sized from set_bytes(), which changes when a front end is attached or detached (8UC4 / YUYV
 // camera frames vs BGR stitcher inputs): release them so that the next host-side call re-creates them at the new size.
 // The device must be idle (callers synchronise first).
@@ -1273,11 +1258,38 @@ int pano_attach_frontend(pano_handle h, int cam, pano_frontend_handle f)
         if (!replaces_all) return fail(h, "pano_attach_frontend: all cameras must share one frame size and format");
     }
     if (!h->front_out && devAlloc(h, &h->front_out, h->front_out_bytes() * h->n * h->cfg.max_batch, false)) return PANO_ERR;
+    // the new assignment and its intermediate-buffer sets (one per distinct front end; a set that is still needed is kept)
+    // are built on the side: running out of device memory here leaves the handle as it was
+    pano_frontend_handle nf[kMaxCams] = {};
+    pano_front_scratch *ns[kMaxCams] = {};
+    for (int i = 0; i < h->n; ++i) nf[i] = (cam < 0 || cam == i || !h->front[i]) ? f : h->front[i];   // every camera needs one once the input format changes
+    for (int i = 0; i < h->n; ++i) {
+        for (int j = 0; j < i && !ns[i]; ++j)
+            if (nf[j] == nf[i]) ns[i] = ns[j];
+        for (int j = 0; j < h->n && !ns[i]; ++j)
+            if (h->front[j] == nf[i] && h->front_scratch[j]) ns[i] = h->front_scratch[j];
+        if (!ns[i]) ns[i] = pano_frontend_scratch_create(nf[i]);
+        if (!ns[i]) {
+            for (int k = 0; k < i; ++k) {
+                bool fresh = ns[k] != nullptr;
+                for (int j = 0; j < h->n; ++j) fresh = fresh && ns[k] != h->front_scratch[j];
+                for (int j = 0; j < k; ++j) fresh = fresh && ns[k] != ns[j];
+                if (fresh) pano_frontend_scratch_destroy(ns[k]);
+            }
+            return fail(h, "pano_attach_frontend: out of device memory for the front end's intermediate buffers");
+        }
+    }
     const size_t old_set = h->set_bytes();
-    for (int i = 0; i < h->n; ++i)
-        if (cam < 0 || cam == i) h->front[i] = f;
-    for (int i = 0; i < h->n; ++i)
-        if (!h->front[i]) h->front[i] = f;      // every camera needs one once the input format changes
+    for (int i = 0; i < kMaxCams; ++i) {          // release the sets nobody uses any more, then install
+        pano_front_scratch *o = h->front_scratch[i];
+        if (!o) continue;
+        bool kept = false;
+        for (int j = 0; j < h->n; ++j) kept = kept || ns[j] == o;
+        for (int j = i; j < kMaxCams; ++j)
+            if (h->front_scratch[j] == o) h->front_scratch[j] = nullptr;
+        if (!kept) pano_frontend_scratch_destroy(o);
+    }
+    for (int i = 0; i < h->n; ++i) { h->front[i] = nf[i]; h->front_scratch[i] = ns[i]; }
     h->in_frame_bytes = in_bytes;
     h->in_frame_bytes4 = (size_t)in_wh[0] * in_wh[1] * 4;
     h->has_front = true;
@@ -1289,7 +1301,7 @@ int pano_attach_frontend(pano_handle h, int cam, pano_frontend_handle f)
     h->tables_dirty = true;
     dropProcessGraphs(h);
     if (h->set_bytes() != old_set) dropStaging(h);
-    return rebuildFrontScratch(h);
+    return PANO_OK;
 }
 
 int pano_set_frontend_mode(pano_handle h, int mode)
