@@ -732,10 +732,16 @@ def main():
             del b1, hi, ho
         if args.workload != "config3":
             # BASELINE config 3 (imx424 rig, block gains + FeatherBlender) in the same process, device-resident
+            b3, err3 = None, None
             try:
                 b3 = build("config3", local_rank, dev, B, args.max_batch, 1234 + rank)
                 for _ in range(3):
                     b3["st"].process_device(b3["frames"], b3["out"], stream.cuda_stream)
+                torch.cuda.synchronize()
+            except (Exception, SystemExit) as e:     # a side record must not take the headline down
+                err3 = repr(e)[:300]
+            # the timing below is collective (barriers): every rank takes part or none does
+            if allmax([0.0 if err3 is None else 1.0])[0] == 0.0:
                 s3 = max(2, args.steps // 4)
                 ms3, _ = time_device(b3, s3, WAVES, stream, barrier)
                 acc3 = profile_kernels(b3, stream)
@@ -743,10 +749,11 @@ def main():
                 also["config3"] = {"workload": WORKLOADS["config3"], "value": world * B * WAVES * s3 / (ms3m / 1000.0), "unit": UNIT,
                                    "ms_per_wave": ms3m / (WAVES * s3), "gpu_launches_per_wave": b3["st"].last_launch_count(),
                                    "kernels_ms_per_launch": {k: v["ms"] / v["launches"] for k, v in acc3.items()}}
+            else:
+                also["config3"] = {"error": err3 or "another rank failed to initialise config 3"}
+            if b3 is not None:
                 b3["st"].close()
-                del b3
-            except Exception as e:                   # a side record must not take the headline down
-                also["config3"] = {"error": repr(e)[:300]}
+            del b3
         if world > 1:
             from panob200 import pkg
             try:
