@@ -63,8 +63,8 @@ WORKLOADS = {
 # what ncu shows as the on-chip limiter of each hot kernel (profiles/r2*_ncu_summary.txt): the HBM
 # roofline is the denominator the task asks for, but the exact-arithmetic gathers are not DRAM-limited
 LIMITERS = {
-    "fe_cubic_undistort": "L1 data pipes: LSU wavefronts (16 shared-memory taps per pixel at ~1.8 wavefronts each) + TEX (32-byte weight entry per pixel)",
-    "fe_resize": "issue slots (exact cv::resize fixed point, ~60 instructions per pixel)",
+    "fe_cubic_undistort": "L1 data pipes: TEX wavefronts 94 % (the 32-byte weight entry per pixel: 15 wavefronts per 16-byte fetch) + LSU wavefronts 77 % (16 shared-memory taps per pixel at ~1.8 wavefronts each)",
+    "fe_resize": "memory latency at 38 % occupancy (72 registers, four output columns per lane), issue slots 57 %, DRAM 65 %",
     "warp": "L1 LSU wavefronts (4 shared-memory taps per pixel at ~2 wavefronts each) + issue slots",
     "pyrdown_l0": "memory latency at ~30 % occupancy (92 registers)",
     "collapse_l0": "issue slots + memory latency at ~40 % occupancy",
