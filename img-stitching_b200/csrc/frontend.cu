@@ -717,10 +717,31 @@ int scratchAlloc(pano_frontend_ctx *h, pano_front_scratch &s, int depth)
     s.depth = depth;
     s.device = c.device;
     if (c.src_format == PANO_SRC_YUYV) FCK(h, cudaMalloc((void **)&s.argb, (size_t)c.cam_src_width * c.cam_src_height * 4 * depth));
+    if (h->fast4) FCK(h, cudaMalloc((void **)&s.w, (size_t)c.rect[2] * c.rect[3] * depth * sizeof(uint32_t)));
+    // the three undist-sized intermediates of the generic path (3 x 1.6 GB at 256 x 1080p) are only needed where the fast
+    // path does not apply (no undistortion, extra resizes) or is refused (camera frames not 16-byte aligned): scratchGeneric
+    if (!h->fast4) {
+        FCK(h, cudaMalloc((void **)&s.a, ubytes));
+        FCK(h, cudaMalloc((void **)&s.b, ubytes));
+        FCK(h, cudaMalloc((void **)&s.c, ubytes));
+    }
+    return PANO_OK;
+}
+
+// first use of the generic path with a set that was created for the fast path: allocate now (not possible inside a
+// stream capture -- the caller's frames then have to be 16-byte aligned)
+int scratchGeneric(pano_frontend_ctx *h, pano_front_scratch &s, cudaStream_t st)
+{
+    if (s.a) return PANO_OK;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+        (void)cudaGetLastError();
+        return ffail(h, "pano_frontend_run: camera frames must be 16-byte aligned here (the byte-wise path needs buffers that cannot be allocated inside a stream capture)");
+    }
+    const size_t ubytes = (size_t)h->cfg.undist_width * h->cfg.undist_height * 3 * s.depth;
     FCK(h, cudaMalloc((void **)&s.a, ubytes));
     FCK(h, cudaMalloc((void **)&s.b, ubytes));
     FCK(h, cudaMalloc((void **)&s.c, ubytes));
-    if (h->fast4) FCK(h, cudaMalloc((void **)&s.w, (size_t)c.rect[2] * c.rect[3] * depth * sizeof(uint32_t)));
     return PANO_OK;
 }
 
@@ -961,7 +982,7 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
                       cudaStream_t st, int out_px, pano_front_scratch *scratch)
 {
     if (!h || !argb || !out || batch < 1) return ffail(h, "pano_frontend_run: bad argument");
-    const pano_front_scratch &B = scratch ? *scratch : h->own;      // the caller's set of intermediates, or the handle's own
+    pano_front_scratch &B = scratch ? *scratch : h->own;            // the caller's set of intermediates, or the handle's own
     if (out_px != 3 && !(out_px == 4 && pano_frontend_can_words(h))) return ffail(h, "pano_frontend_run: word output is not available for this geometry");
     FCK(h, cudaSetDevice(h->cfg.device));
     const pano_frontend_config &c = h->cfg;
@@ -1045,6 +1066,7 @@ int pano_frontend_run(pano_frontend_handle h, const uint8_t *argb, size_t in_img
             continue;
         }
         if (out_px != 3) return ffail(h, "pano_frontend_run: word output needs 16-byte aligned camera frames");
+        if (scratchGeneric(h, B, st)) return PANO_ERR;
         if (c.undistort) {
             if (h->use_r_in) {
                 resize_kernel<4><<<grid2(uw, uh, blk, nb), blk, 0, st>>>(cur, cur_img, cw * 4, B.a, u_img, uw * 3, h->r_in);
