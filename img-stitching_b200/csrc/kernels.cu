@@ -652,8 +652,8 @@ struct C8Args {
     const uint32_t *list;            // this launch's tile list (PanoTables::walk_list / gen_list)
 };
 
-template <bool kLevel0>
-__global__ void __launch_bounds__(384, 2) collapse8_kernel(const __grid_constant__ C8Args A, uint8_t *__restrict__ pano)
+template <bool kLevel0, int kMinBlocks>
+__global__ void __launch_bounds__(384, kMinBlocks) collapse8_kernel(const __grid_constant__ C8Args A, uint8_t *__restrict__ pano)
 {
     pdl_enter();
     __shared__ __align__(16) uint8_t tile[kWalkTileH][kWalkTileW * 3];
@@ -1951,8 +1951,17 @@ int launch_collapse(const PanoTables *dev, const PanoTables &host, const KernelC
         if (host.gen_n[L] > 0) {
             A.list = host.gen_list[L];
             const dim3 block(32, 4, 3), grid(host.gen_n[L], nslots);
-            if (level == 0) launch_chain(collapse8_kernel<true>, grid, block, stream, A, pano);
-            else launch_chain(collapse8_kernel<false>, grid, block, stream, A, pano);
+            static const int occ8 = getenv("PANO_C8_OCC") ? atoi(getenv("PANO_C8_OCC")) : 2;     // tuning knob: min blocks per SM
+            if (occ8 <= 1) {
+                if (level == 0) launch_chain(collapse8_kernel<true, 1>, grid, block, stream, A, pano);
+                else launch_chain(collapse8_kernel<false, 1>, grid, block, stream, A, pano);
+            } else if (occ8 >= 3) {
+                if (level == 0) launch_chain(collapse8_kernel<true, 3>, grid, block, stream, A, pano);
+                else launch_chain(collapse8_kernel<false, 3>, grid, block, stream, A, pano);
+            } else {
+                if (level == 0) launch_chain(collapse8_kernel<true, 2>, grid, block, stream, A, pano);
+                else launch_chain(collapse8_kernel<false, 2>, grid, block, stream, A, pano);
+            }
             ++launches;
         }
         return launches;
