@@ -97,6 +97,7 @@ struct pano_ctx {
     std::vector<PhaseGraph> phase_graphs;
     cudaGraphExec_t graph1 = nullptr;             // pano_process: the kernel chain of ONE frame-set (stage_in[0] -> stage_out[0])
     int graph1_launches = 0;
+    SideStream side{};                              // second stream for the seam-tile kernel of a collapse level (launch_collapse)
     // pano_process, overlapped form: camera i's chain (front end, warp, pyrDown levels) is replayed as soon as ITS frame has
     // landed (copies on s_h2d, one event per camera), the tail (coarsest + collapse) after the last one
     cudaEvent_t ev_cam_in[kMaxCams] = {};
@@ -604,7 +605,7 @@ int runPhase(pano_ctx *h, int p, const uint8_t *frames_dev, uint8_t *out_dev, in
     } else {
         const int l = 2 * nb - p;
         L.begin(kCol[l], collapseBytes(h, l, slots));
-        h->last_launches += launch_collapse(h->dev, h->host, h->kc, l, out_dev, slots, st) - 1;
+        h->last_launches += launch_collapse(h->dev, h->host, h->kc, l, out_dev, slots, st, h->side.st ? &h->side : nullptr) - 1;
         L.end();
     }
     return PANO_OK;
@@ -996,6 +997,9 @@ int pano_create(const pano_config *cfg, pano_handle *out)
         T.unit_norm_exact = (ok ? 1 : 0) | (p == 1.0f ? 2 : 0);
     }
     if (devAlloc(h, &h->dev, 1)) return bail(0);
+    if (cudaStreamCreateWithFlags(&h->side.st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->side.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->side.join, cudaEventDisableTiming) != cudaSuccess) return bail(0);
     for (int i = 0; i < n; ++i)
         if (buildWeights(h, i)) return bail(0);
     h->tables_dirty = true;
@@ -1012,6 +1016,9 @@ int pano_destroy(pano_handle h)
     if (h->p2p_graph) cudaGraphExecDestroy(h->p2p_graph);
     dropProcessGraphs(h);
     freeFrontScratch(h);
+    if (h->side.st) cudaStreamDestroy(h->side.st);
+    if (h->side.fork) cudaEventDestroy(h->side.fork);
+    if (h->side.join) cudaEventDestroy(h->side.join);
     for (auto &e : h->ev_cam_in)
         if (e) cudaEventDestroy(e);
     for (auto &g : h->phase_graphs) cudaGraphExecDestroy(g.exec);

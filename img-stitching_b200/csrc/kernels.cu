@@ -1885,7 +1885,12 @@ void launch_pyrdown(const PanoTables *dev, const PanoTables &host, const KernelC
         // rows per warp: tall levels amortise the 3-row warm-up of a band over 32 rows, small ones keep more warps busy
         // (measured, level 0 / 1 / 2 of config 1: band 8 0.541 / 0.152 / 0.052 ms, 16 0.496 / 0.140 / 0.050, 32 0.482 / 0.141 / 0.061)
         static const int band_env = getenv("PANO_DOWN_BAND") ? atoi(getenv("PANO_DOWN_BAND")) : 0;
-        const int band = band_env > 0 ? band_env : (maxh >= 400 ? 32 : 16);
+        int band = band_env > 0 ? band_env : (maxh >= 400 ? 32 : 16);
+        // With ONE frame-set in flight (pano_process, a strip of the strip split) the grid is a few hundred blocks and the
+        // kernel's duration is one warp's walk down its band: shorter bands until the grid fills the GPU (4 blocks per SM)
+        // -- measured per level at one frame-set: 17 us at 16-32 rows per warp.  Waves of many slots never get here.
+        if (band_env <= 0)
+            while (band > 8 && (size_t)((maxw + 255) / 256) * ((maxh + 4 * band - 1) / (4 * band)) * zc * nslots * 3 < (size_t)148 * 4) band >>= 1;
         const dim3 wb(32, 4), wg((maxw + 255) / 256, (maxh + 4 * band - 1) / (4 * band), zc * nslots * 3);
         static const int occ = getenv("PANO_DOWN_OCC") ? atoi(getenv("PANO_DOWN_OCC")) : 0;      // tuning knob: min blocks per SM (0 = compiler's choice)
         if (occ >= 8) launch_chain(pyrdown8_walk_kernel<8>, wg, wb, stream, host, level, band, cam0, zc);
@@ -1905,7 +1910,7 @@ void launch_coarsest(const PanoTables *dev, const PanoTables &host, uint8_t *pan
 }
 
 int launch_collapse(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, int level, uint8_t *pano,
-                    int nslots, cudaStream_t stream)
+                    int nslots, cudaStream_t stream, const SideStream *side)
 {
     if (kc.collapse8[level]) {
         const int wf = host.pad_w >> level, hf = host.pad_h >> level;
@@ -1930,6 +1935,14 @@ int launch_collapse(const PanoTables *dev, const PanoTables &host, const KernelC
         A.cut_x = host.cut_x; A.cut_y = host.cut_y; A.cut_w = host.cut_w; A.cut_h = host.cut_h;
         A.flags = host.unit_norm_exact;
         int launches = 0;
+        static const bool no_fork = getenv("PANO_NO_FORK") != nullptr;      // A/B switch: the two kernels of a level one after the other
+        const bool fork = side && side->st && !no_fork && nslots <= 2 && host.walk_n[L] > 0 && host.gen_n[L] > 0;
+        cudaStream_t gen_stream = stream;
+        if (fork) {
+            cudaEventRecord(side->fork, stream);
+            cudaStreamWaitEvent(side->st, side->fork, 0);
+            gen_stream = side->st;
+        }
         if (host.walk_n[L] > 0) {
             A.list = host.walk_list[L];
             const dim3 wb(32, 3), wg(host.walk_n[L], nslots);
@@ -1953,16 +1966,20 @@ int launch_collapse(const PanoTables *dev, const PanoTables &host, const KernelC
             const dim3 block(32, 4, 3), grid(host.gen_n[L], nslots);
             static const int occ8 = getenv("PANO_C8_OCC") ? atoi(getenv("PANO_C8_OCC")) : 2;     // tuning knob: min blocks per SM
             if (occ8 <= 1) {
-                if (level == 0) launch_chain(collapse8_kernel<true, 1>, grid, block, stream, A, pano);
-                else launch_chain(collapse8_kernel<false, 1>, grid, block, stream, A, pano);
+                if (level == 0) launch_chain(collapse8_kernel<true, 1>, grid, block, gen_stream, A, pano);
+                else launch_chain(collapse8_kernel<false, 1>, grid, block, gen_stream, A, pano);
             } else if (occ8 >= 3) {
-                if (level == 0) launch_chain(collapse8_kernel<true, 3>, grid, block, stream, A, pano);
-                else launch_chain(collapse8_kernel<false, 3>, grid, block, stream, A, pano);
+                if (level == 0) launch_chain(collapse8_kernel<true, 3>, grid, block, gen_stream, A, pano);
+                else launch_chain(collapse8_kernel<false, 3>, grid, block, gen_stream, A, pano);
             } else {
-                if (level == 0) launch_chain(collapse8_kernel<true, 2>, grid, block, stream, A, pano);
-                else launch_chain(collapse8_kernel<false, 2>, grid, block, stream, A, pano);
+                if (level == 0) launch_chain(collapse8_kernel<true, 2>, grid, block, gen_stream, A, pano);
+                else launch_chain(collapse8_kernel<false, 2>, grid, block, gen_stream, A, pano);
             }
             ++launches;
+        }
+        if (fork) {
+            cudaEventRecord(side->join, side->st);
+            cudaStreamWaitEvent(stream, side->join, 0);
         }
         return launches;
     }

@@ -98,8 +98,12 @@ void launch_pyrdown(const PanoTables *dev, const PanoTables &host, const KernelC
                     cudaStream_t stream, CamRange cams = CamRange());
 void launch_coarsest(const PanoTables *dev, const PanoTables &host, uint8_t *pano, int nslots, cudaStream_t stream);
 // returns the number of kernels launched
+// side: a second stream + two events of the caller.  With one or two frame-set slots in flight the two kernels of a level
+// (walker tiles, seam tiles -- disjoint outputs, same inputs) are a few microseconds each and mostly launch + drain: they
+// then run side by side (fork / join through the events; capturable).  nullptr, or more slots: one after the other.
+struct SideStream { cudaStream_t st; cudaEvent_t fork, join; };
 int launch_collapse(const PanoTables *dev, const PanoTables &host, const KernelChoice &kc, int level, uint8_t *pano,
-                    int nslots, cudaStream_t stream);
+                    int nslots, cudaStream_t stream, const SideStream *side = nullptr);
 // feather / no-blend as two passes: launch_warp (staged gather -> g[0]) + this streaming blend over the warped images
 void launch_blend_g0(const PanoTables *dev, const PanoTables &host, int blender, uint8_t *pano, int nslots, cudaStream_t stream);
 void launch_direct_blend(const PanoTables *dev, const PanoTables &host, int blender, const uint8_t *frames,
